@@ -1,0 +1,96 @@
+/* b200bwa -- C-ABI of the B200-native BWA-MEM engine (drop-in for the `mem` path of SparkBWA's libbwa.so).
+ *
+ * Every entry point uses plain C types only.  Reference interfaces replaced (paths relative to
+ * citiususc/SparkBWA, `bwa/` = src/main/native/bwa-0.7.15/):
+ *
+ *   Java_com_github_sparkbwa_BwaJni_bwa_1jni   src/main/native/bwa_jni.c:29, declared in
+ *                                              src/main/native/com_github_sparkbwa_BwaJni.h:15-16;
+ *                                              bound by java/com/github/sparkbwa/BwaJni.java:59
+ *   b200bwa_main                               bwa/main.c:61 (`int main(int argc, char *argv[])`), `mem` only
+ *   b200bwa_mem                                bwa/fastmap.c:115 (`int main_mem(int argc, char *argv[])`)
+ *   b200bwa_index_load / _align_batch / ...    bwa/bwa.c:252 (bwa_idx_load_from_disk) and
+ *                                              bwa/bwamem.c:1172 (mem_process_seqs) -- the library-level
+ *                                              calls a host program (bwa/example.c) would make
+ *
+ * Error behaviour: nothing in this library calls exit()/abort() (the reference's err_fatal does,
+ * bwa/utils.c:90-122, and would take an executor JVM down); failures return non-zero and the
+ * message is available from b200bwa_last_error().  There is no CPU fallback: without a usable
+ * CUDA device every aligning call fails.
+ */
+#ifndef B200BWA_H
+#define B200BWA_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* argv-compatible with `bwa` (argv[0] = program name, argv[1] = "mem", then bwa-mem options,
+ * index prefix, reads [, mates]).  SAM goes to stdout.  Other sub-commands return 1. */
+int b200bwa_main(int argc, char** argv);
+
+/* Same, but the SAM text is written to `out_path` (what the JNI glue achieves with
+ * "-f <out>" + freopen, bwa_jni.c:74-135) without touching the process-wide stdout. */
+int b200bwa_main_to(int argc, char** argv, const char* out_path);
+
+/* argv as main_mem sees it: argv[0] = "mem". out_path may be NULL (stdout). */
+int b200bwa_mem(int argc, char** argv, const char* out_path);
+
+/* Last error message of the calling thread's most recent failing call ("" if none). */
+const char* b200bwa_last_error(void);
+
+/* ---- library-level API (device-resident index, batches in host memory) -------------------- */
+
+typedef struct b200bwa_index b200bwa_index_t; /* opaque: FM-index image resident in HBM */
+
+/* Loads <prefix>.bwt/.sa/.pac/.ann/.amb[/.alt] and uploads them to `device`.  NULL on failure. */
+b200bwa_index_t* b200bwa_index_load(const char* prefix, int device);
+void b200bwa_index_free(b200bwa_index_t* idx);
+
+/* Sets bwa-mem options from an option string as given to `-w` of SparkBWA / the bwa command line
+ * (e.g. "-t 4 -K 10000000 -M"); NULL or "" = defaults.  Returns 0 on success. */
+int b200bwa_set_options(b200bwa_index_t* idx, const char* mem_options);
+
+/* Aligns one batch held in HOST memory and returns the SAM records (no header) in a malloc'ed
+ * buffer the caller frees with b200bwa_free.
+ *   n_reads          number of reads; paired-end batches are interleaved (mate1, mate2, ...) and even
+ *   seq/qual         concatenated bases (ASCII) / qualities; qual may be NULL (FASTA)
+ *   seq_off[n+1]     start of read i in seq/qual (seq_off[n] = total)
+ *   names            NUL-separated read names, one per read (the /1 /2 suffix already trimmed)
+ *   n_processed      absolute index of the first read of this batch within the whole run
+ *   paired           non-zero: paired-end
+ * Returns 0 on success. */
+int b200bwa_align_batch(b200bwa_index_t* idx, int n_reads, const char* seq, const char* qual,
+                        const int64_t* seq_off, const char* names, int64_t n_processed, int paired,
+                        char** sam_out, size_t* sam_len);
+void b200bwa_free(void* p);
+
+/* Writes the SAM header (@SQ lines, -R/-H lines, @PG) for this index into a malloc'ed buffer. */
+int b200bwa_sam_header(b200bwa_index_t* idx, const char* cmdline, char** out, size_t* out_len);
+
+/* Device timing of the last b200bwa_align_batch on this index, milliseconds (CUDA events). */
+typedef struct {
+  float h2d, seed, sa, chain, extend, pestat, finalize, gather, d2h, total;
+  int launches;
+  int64_t n_seed_tasks, n_regs, sam_bytes;
+} b200bwa_times_t;
+int b200bwa_last_times(b200bwa_index_t* idx, b200bwa_times_t* t);
+
+/* Benchmark helpers: keep a batch resident in HBM and run only the device pipeline. */
+int b200bwa_upload_batch(b200bwa_index_t* idx, int n_reads, const char* seq, const char* qual,
+                         const int64_t* seq_off, const char* names, int64_t n_processed);
+int b200bwa_run_resident(b200bwa_index_t* idx, int paired, int want_sam, char** sam_out, size_t* sam_len);
+
+/* Multi-GPU plumbing: device pointers/sizes of the index image, and adoption of an image that a
+ * peer already placed in this GPU's memory (e.g. by ncclBroadcast). */
+int b200bwa_index_device_image(b200bwa_index_t* idx, void** bwt, size_t* bwt_bytes, void** sa, size_t* sa_bytes,
+                               void** pac, size_t* pac_bytes);
+b200bwa_index_t* b200bwa_index_adopt(const char* prefix, int device, const void* d_bwt, const void* d_sa,
+                                     const void* d_pac);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -1,0 +1,415 @@
+// Chain -> alignment regions: reference fetch, seed extension driver, de-duplication and patching.
+//
+// Restates bwa/bntseq.c:349-446 (bns_pos2rid, bns_intv2rid, bns_get_seq, bns_fetch_seq),
+// bwa/bwamem.c:621-628 (cal_max_gap), :632-786 (mem_chain2aln), :406-435 (mem_patch_reg),
+// :437-489 (mem_sort_dedup_patch) and bwa/bwa.c:111-197 (bwa_gen_cigar2: band choice, gap-free
+// shortcut, NM/MD).  Floating point appears only as IEEE double/float +,-,*,/ without contraction.
+#pragma once
+#include "b2_types.h"
+#include "b2_sort.cuh"
+#include "b2_ksw.cuh"
+
+// Per-task bump scratch (stack discipline via mark/reset).
+struct B2Scratch {
+  uint8_t* base;
+  size_t cap, used;
+  int overflow;
+  B2_HD inline void* alloc(size_t bytes, size_t align = 8) {
+    size_t o = (used + align - 1) & ~(align - 1);
+    if (o + bytes > cap) { overflow = 1; o = 0; if (bytes > cap) return base; }
+    used = o + bytes;
+    return base + o;
+  }
+  B2_HD inline size_t mark() const { return used; }
+  B2_HD inline void reset(size_t m) { used = m; }
+};
+
+B2_HD inline int b2_get_pac(const uint8_t* pac, int64_t l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }
+
+B2_HD inline int64_t b2_depos(int64_t l_pac, int64_t pos, int* is_rev) {
+  return (*is_rev = (pos >= l_pac)) ? (l_pac << 1) - 1 - pos : pos;
+}
+
+B2_HD inline int b2_pos2rid(const B2Index& ix, int64_t pos_f) {
+  if (pos_f >= ix.l_pac) return -1;
+  int left = 0, mid = 0, right = ix.n_seqs;
+  while (left < right) {
+    mid = (left + right) >> 1;
+    if (pos_f >= ix.anns[mid].offset) {
+      if (mid == ix.n_seqs - 1) break;
+      if (pos_f < ix.anns[mid + 1].offset) break;
+      left = mid + 1;
+    } else right = mid;
+  }
+  return mid;
+}
+
+B2_HD inline int b2_intv2rid(const B2Index& ix, int64_t rb, int64_t re) {
+  int is_rev;
+  if (rb < ix.l_pac && re > ix.l_pac) return -2;
+  int rid_b = b2_pos2rid(ix, b2_depos(ix.l_pac, rb, &is_rev));
+  int rid_e = rb < re ? b2_pos2rid(ix, b2_depos(ix.l_pac, re - 1, &is_rev)) : rid_b;
+  return rid_b == rid_e ? rid_b : -1;
+}
+
+// writes end-beg codes (after clamping) to seq; returns the length, 0 when bridging the strands
+B2_HD inline int64_t b2_get_seq(int64_t l_pac, const uint8_t* pac, int64_t beg, int64_t end, uint8_t* seq) {
+  if (end < beg) { int64_t t = beg; beg = end; end = t; }
+  if (end > l_pac << 1) end = l_pac << 1;
+  if (beg < 0) beg = 0;
+  if (beg >= l_pac || end <= l_pac) {
+    int64_t l = 0;
+    if (beg >= l_pac) {
+      int64_t beg_f = (l_pac << 1) - 1 - end, end_f = (l_pac << 1) - 1 - beg;
+      for (int64_t k = end_f; k > beg_f; --k) seq[l++] = 3 - b2_get_pac(pac, k);
+    } else {
+      for (int64_t k = beg; k < end; ++k) seq[l++] = b2_get_pac(pac, k);
+    }
+    return end - beg;
+  }
+  return 0;
+}
+
+// clamp [*beg,*end) to the contig/strand holding mid; returns rid
+B2_HD inline int b2_fetch_bounds(const B2Index& ix, int64_t* beg, int64_t mid, int64_t* end) {
+  int is_rev;
+  if (*end < *beg) { int64_t t = *beg; *beg = *end; *end = t; }
+  int rid = b2_pos2rid(ix, b2_depos(ix.l_pac, mid, &is_rev));
+  int64_t far_beg = ix.anns[rid].offset, far_end = far_beg + ix.anns[rid].len;
+  if (is_rev) {
+    int64_t tmp = far_beg;
+    far_beg = (ix.l_pac << 1) - far_end;
+    far_end = (ix.l_pac << 1) - tmp;
+  }
+  *beg = *beg > far_beg ? *beg : far_beg;
+  *end = *end < far_end ? *end : far_end;
+  return rid;
+}
+
+B2_HD inline int b2_cal_max_gap(const B2Opt& opt, int qlen) {
+  int l_del = (int)((double)(qlen * opt.a - opt.o_del) / opt.e_del + 1.);
+  int l_ins = (int)((double)(qlen * opt.a - opt.o_ins) / opt.e_ins + 1.);
+  int l = l_del > l_ins ? l_del : l_ins;
+  l = l > 1 ? l : 1;
+  return l < opt.w << 1 ? l : opt.w << 1;
+}
+
+struct B2U64Lt { B2_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
+
+// Extend every seed of one chain (longest first) and append regions to av[*n_av] (capacity cap_av).
+// srt: c.n u64 scratch.
+B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query, const uint8_t* query,
+                               const B2Chain& c, const B2Seed* seeds, B2Reg* av, int* n_av, int cap_av,
+                               uint64_t* srt, B2Scratch& sc) {
+  if (c.n == 0) return;
+  const int64_t l_pac = ix.l_pac;
+  int64_t rmax[2], max = 0;
+  int max_off[2], aw[2];
+  rmax[0] = l_pac << 1; rmax[1] = 0;
+  for (int i = 0; i < c.n; ++i) {
+    const B2Seed& t = seeds[i];
+    int64_t b = t.rbeg - (t.qbeg + b2_cal_max_gap(opt, t.qbeg));
+    int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + b2_cal_max_gap(opt, l_query - t.qbeg - t.len));
+    rmax[0] = rmax[0] < b ? rmax[0] : b;
+    rmax[1] = rmax[1] > e ? rmax[1] : e;
+    if (t.len > max) max = t.len;
+  }
+  rmax[0] = rmax[0] > 0 ? rmax[0] : 0;
+  rmax[1] = rmax[1] < l_pac << 1 ? rmax[1] : l_pac << 1;
+  if (rmax[0] < l_pac && l_pac < rmax[1]) {
+    if (seeds[0].rbeg < l_pac) rmax[1] = l_pac; else rmax[0] = l_pac;
+  }
+  b2_fetch_bounds(ix, &rmax[0], seeds[0].rbeg, &rmax[1]);
+  const size_t mk = sc.mark();
+  const int64_t rlen = rmax[1] - rmax[0];
+  uint8_t* rseq = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
+  uint8_t* qs = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
+  uint8_t* rs = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
+  B2EH* eh = (B2EH*)sc.alloc(sizeof(B2EH) * (size_t)(l_query + 2), 8);
+  if (sc.overflow) { sc.reset(mk); return; }
+  b2_get_seq(l_pac, ix.pac, rmax[0], rmax[1], rseq);
+
+  for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)seeds[i].score << 32 | (uint32_t)i;
+  b2_introsort(srt, (long)c.n, B2U64Lt());
+
+  for (int k = c.n - 1; k >= 0; --k) {
+    const B2Seed& s = seeds[(uint32_t)srt[k]];
+    int i;
+    for (i = 0; i < *n_av; ++i) {  // was this seed already covered by an earlier extension?
+      const B2Reg& p = av[i];
+      int64_t rd;
+      int qd, w, max_gap;
+      if (s.rbeg < p.rb || s.rbeg + s.len > p.re || s.qbeg < p.qb || s.qbeg + s.len > p.qe) continue;
+      if (s.len - p.seedlen0 > .1 * l_query) continue;
+      qd = s.qbeg - p.qb; rd = s.rbeg - p.rb;
+      max_gap = b2_cal_max_gap(opt, qd < rd ? qd : (int)rd);
+      w = max_gap < p.w ? max_gap : p.w;
+      if (qd - rd < w && rd - qd < w) break;
+      qd = p.qe - (s.qbeg + s.len); rd = p.re - (s.rbeg + s.len);
+      max_gap = b2_cal_max_gap(opt, qd < rd ? qd : (int)rd);
+      w = max_gap < p.w ? max_gap : p.w;
+      if (qd - rd < w && rd - qd < w) break;
+    }
+    if (i < *n_av) {
+      for (i = k + 1; i < c.n; ++i) {  // does an overlapping, off-diagonal seed in this chain disagree?
+        if (srt[i] == 0) continue;
+        const B2Seed& t = seeds[(uint32_t)srt[i]];
+        if (t.len < s.len * .95) continue;
+        if (s.qbeg <= t.qbeg && s.qbeg + s.len - t.qbeg >= s.len >> 2 && t.qbeg - s.qbeg != t.rbeg - s.rbeg) break;
+        if (t.qbeg <= s.qbeg && t.qbeg + t.len - s.qbeg >= s.len >> 2 && s.qbeg - t.qbeg != s.rbeg - t.rbeg) break;
+      }
+      if (i == c.n) { srt[k] = 0; continue; }
+    }
+    if (*n_av >= cap_av) { sc.overflow = 1; break; }
+    B2Reg& a = av[(*n_av)++];
+    {
+      B2Reg z = B2Reg();
+      a = z;
+    }
+    a.w = aw[0] = aw[1] = opt.w;
+    a.score = a.truesc = -1;
+    a.rid = c.rid;
+    if (s.qbeg) {  // left extension on reversed prefixes
+      int qle, tle, gtle, gscore;
+      int64_t tmp = s.rbeg - rmax[0];
+      for (i = 0; i < s.qbeg; ++i) qs[i] = query[s.qbeg - 1 - i];
+      for (int64_t j = 0; j < tmp; ++j) rs[j] = rseq[tmp - 1 - j];
+      for (i = 0; i < 2; ++i) {
+        int prev = a.score;
+        aw[0] = opt.w << i;
+        a.score = b2_extend2(s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
+                             opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], eh);
+        if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
+      }
+      if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) {
+        a.qb = s.qbeg - qle; a.rb = s.rbeg - tle;
+        a.truesc = a.score;
+      } else {
+        a.qb = 0; a.rb = s.rbeg - gtle;
+        a.truesc = gscore;
+      }
+    } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+
+    if (s.qbeg + s.len != l_query) {  // right extension
+      int qle, tle, qe, re, gtle, gscore, sc0 = a.score;
+      qe = s.qbeg + s.len;
+      re = (int)(s.rbeg + s.len - rmax[0]);
+      for (i = 0; i < 2; ++i) {
+        int prev = a.score;
+        aw[1] = opt.w << i;
+        a.score = b2_extend2(l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), rseq + re, opt.mat, opt.o_del,
+                             opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
+                             &gscore, &max_off[1], eh);
+        if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
+      }
+      if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) {
+        a.qe = qe + qle; a.re = rmax[0] + re + tle;
+        a.truesc += a.score - sc0;
+      } else {
+        a.qe = l_query; a.re = rmax[0] + re + gtle;
+        a.truesc += gscore - sc0;
+      }
+    } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+
+    a.seedcov = 0;
+    for (i = 0; i < c.n; ++i) {
+      const B2Seed& t = seeds[i];
+      if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+    }
+    a.w = aw[0] > aw[1] ? aw[0] : aw[1];
+    a.seedlen0 = s.len;
+    a.frac_rep = c.frac_rep;
+  }
+  sc.reset(mk);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Output of the end-point-constrained global alignment.
+struct B2Cigar {
+  uint32_t* cigar;  // capacity cap
+  int cap;
+  char* md;         // capacity md_cap
+  int md_cap;
+  int n_cigar, NM, l_md;
+};
+
+B2_HD inline int b2_put_int(char* s, int l, int cap, long c) {
+  char buf[24];
+  int n = 0;
+  if (c == 0) { if (l < cap) s[l] = '0'; return l + 1; }
+  unsigned long x = c < 0 ? (unsigned long)(-c) : (unsigned long)c;
+  for (; x > 0; x /= 10) buf[n++] = (char)('0' + x % 10);
+  if (c < 0) buf[n++] = '-';
+  for (int i = n - 1; i >= 0; --i, ++l) if (l < cap) s[l] = buf[i];
+  return l;
+}
+
+// want_cigar == 0: score only.  Returns 0 when the reference would have returned a null cigar
+// without touching *score (reject conditions), 1 otherwise.
+B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int l_query, uint8_t* query, int64_t rb,
+                               int64_t re, int* score, B2Cigar* out, B2Scratch& sc) {
+  const int64_t l_pac = ix.l_pac;
+  const int8_t* mat = opt.mat;
+  if (out) { out->n_cigar = 0; out->NM = -1; out->l_md = 0; if (out->md_cap > 0) out->md[0] = 0; }
+  if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return 0;
+  const size_t mk = sc.mark();
+  uint8_t* rseq = (uint8_t*)sc.alloc((size_t)(re - rb) + 1, 1);
+  if (sc.overflow) { sc.reset(mk); return 0; }
+  int64_t rlen = b2_get_seq(l_pac, ix.pac, rb, re, rseq);
+  if (re - rb != rlen) { sc.reset(mk); return 0; }
+  if (rb >= l_pac) {  // reverse both so that indels are placed leftmost on the forward strand
+    b2_revseq(l_query, query);
+    b2_revseq((int)rlen, rseq);
+  }
+  if (l_query == re - rb && w_ == 0) {
+    if (out) { out->cigar[0] = (uint32_t)l_query << 4 | 0; out->n_cigar = 1; }
+    int s = 0;
+    for (int i = 0; i < l_query; ++i) s += mat[rseq[i] * 5 + query[i]];
+    *score = s;
+  } else {
+    int w, max_gap, max_ins, max_del, min_w;
+    max_ins = (int)((double)(((l_query + 1) >> 1) * mat[0] - opt.o_ins) / opt.e_ins + 1.);
+    max_del = (int)((double)(((l_query + 1) >> 1) * mat[0] - opt.o_del) / opt.e_del + 1.);
+    max_gap = max_ins > max_del ? max_ins : max_del;
+    max_gap = max_gap > 1 ? max_gap : 1;
+    int dl = (int)(rlen - l_query); dl = dl < 0 ? -dl : dl;
+    w = (max_gap + dl + 1) >> 1;
+    w = w < w_ ? w : w_;
+    min_w = dl + 3;
+    w = w > min_w ? w : min_w;
+    B2EH* eh = (B2EH*)sc.alloc(sizeof(B2EH) * (size_t)(l_query + 2), 8);
+    uint8_t* z = 0;
+    if (out) {
+      int n_col = l_query < 2 * w + 1 ? l_query : 2 * w + 1;
+      z = (uint8_t*)sc.alloc((size_t)n_col * (size_t)rlen, 1);
+    }
+    if (sc.overflow) {
+      if (rb >= l_pac) b2_revseq(l_query, query);
+      sc.reset(mk);
+      return 0;
+    }
+    int nc = 0;
+    *score = b2_global2(l_query, query, (int)rlen, rseq, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, eh, z,
+                        out ? &nc : 0, out ? out->cigar : 0, out ? out->cap : 0);
+    if (out) {
+      if (nc < 0) { sc.overflow = 1; nc = 0; }
+      out->n_cigar = nc;
+    }
+  }
+  if (out) {  // NM and MD
+    int k, x, y, u, n_mm = 0, n_gap = 0, l = 0;
+    const char* int2base = rb < l_pac ? "ACGTN" : "TGCAN";
+    char* md = out->md;
+    const int cap = out->md_cap - 1;
+    for (k = 0, x = y = u = 0; k < out->n_cigar; ++k) {
+      int op = out->cigar[k] & 0xf, len = (int)(out->cigar[k] >> 4);
+      if (op == 0) {
+        for (int i = 0; i < len; ++i) {
+          if (query[x + i] != rseq[y + i]) {
+            l = b2_put_int(md, l, cap, u);
+            if (l < cap) md[l] = int2base[rseq[y + i]];
+            ++l; ++n_mm; u = 0;
+          } else ++u;
+        }
+        x += len; y += len;
+      } else if (op == 2) {
+        if (k > 0 && k < out->n_cigar - 1) {
+          l = b2_put_int(md, l, cap, u);
+          if (l < cap) md[l] = '^';
+          ++l;
+          for (int i = 0; i < len; ++i) { if (l < cap) md[l] = int2base[rseq[y + i]]; ++l; }
+          u = 0; n_gap += len;
+        }
+        y += len;
+      } else if (op == 1) { x += len; n_gap += len; }
+    }
+    l = b2_put_int(md, l, cap, u);
+    if (l > cap) { sc.overflow = 1; l = cap; }
+    md[l] = 0;
+    out->l_md = l;
+    out->NM = n_mm + n_gap;
+  }
+  if (rb >= l_pac) b2_revseq(l_query, query);
+  sc.reset(mk);
+  return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+#define B2_PATCH_MAX_R_BW 0.05f
+#define B2_PATCH_MIN_SC_RATIO 0.90f
+
+// have_ref == 0 mirrors the calls that pass bns == pac == query == 0 (mate rescue), which never patch.
+B2_HD inline int b2_patch_reg(const B2Opt& opt, const B2Index& ix, int have_ref, uint8_t* query, const B2Reg* a,
+                              const B2Reg* b, int* _w, B2Scratch& sc) {
+  int w, score = 0, q_s, r_s;
+  double r;
+  if (!have_ref || query == 0) return 0;
+  if (a->rb < ix.l_pac && b->rb >= ix.l_pac) return 0;
+  if (a->qb >= b->qb || a->qe >= b->qe || a->re >= b->re) return 0;
+  w = (int)((a->re - b->rb) - (a->qe - b->qb));
+  w = w > 0 ? w : -w;
+  r = (double)(a->re - b->rb) / (b->re - a->rb) - (double)(a->qe - b->qb) / (b->qe - a->qb);
+  r = r > 0. ? r : -r;
+  if (a->re < b->rb || a->qe < b->qb) {
+    if (w > opt.w << 1 || r >= B2_PATCH_MAX_R_BW) return 0;
+  } else if (w > opt.w << 2 || r >= B2_PATCH_MAX_R_BW * 2) return 0;
+  w += a->w + b->w;
+  w = w < opt.w << 2 ? w : opt.w << 2;
+  b2_gen_cigar2(opt, ix, w, b->qe - a->qb, query + a->qb, a->rb, b->re, &score, 0, sc);
+  q_s = (int)((double)(b->qe - a->qb) / ((b->qe - b->qb) + (a->qe - a->qb)) * (b->score + a->score) + .499);
+  r_s = (int)((double)(b->re - a->rb) / ((b->re - b->rb) + (a->re - a->rb)) * (b->score + a->score) + .499);
+  if ((double)score / (q_s > r_s ? q_s : r_s) < B2_PATCH_MIN_SC_RATIO) return 0;
+  *_w = w;
+  return score;
+}
+
+struct B2RegReLt { B2_HD bool operator()(const B2Reg& a, const B2Reg& b) const { return a.re < b.re; } };
+struct B2RegScLt {
+  B2_HD bool operator()(const B2Reg& a, const B2Reg& b) const {
+    return a.score > b.score || (a.score == b.score && (a.rb < b.rb || (a.rb == b.rb && a.qb < b.qb)));
+  }
+};
+
+B2_HD inline int b2_sort_dedup_patch(const B2Opt& opt, const B2Index& ix, int have_ref, uint8_t* query, int n,
+                                     B2Reg* a, B2Scratch& sc) {
+  int m, i, j;
+  if (n <= 1) return n;
+  b2_introsort(a, (long)n, B2RegReLt());
+  for (i = 0; i < n; ++i) a[i].n_comp = 1;
+  for (i = 1; i < n; ++i) {
+    B2Reg* p = &a[i];
+    if (p->rid != a[i - 1].rid || p->rb >= a[i - 1].re + opt.max_chain_gap) continue;
+    for (j = i - 1; j >= 0 && p->rid == a[j].rid && p->rb < a[j].re + opt.max_chain_gap; --j) {
+      B2Reg* q = &a[j];
+      int64_t orr, oq, mr, mq;
+      int score, w;
+      if (q->qe == q->qb) continue;
+      orr = q->re - p->rb;
+      oq = q->qb < p->qb ? q->qe - p->qb : p->qe - q->qb;
+      mr = q->re - q->rb < p->re - p->rb ? q->re - q->rb : p->re - p->rb;
+      mq = q->qe - q->qb < p->qe - p->qb ? q->qe - q->qb : p->qe - p->qb;
+      if (orr > opt.mask_level_redun * mr && oq > opt.mask_level_redun * mq) {
+        if (p->score < q->score) { p->qe = p->qb; break; }
+        else q->qe = q->qb;
+      } else if (q->rb < p->rb && (score = b2_patch_reg(opt, ix, have_ref, query, q, p, &w, sc)) > 0) {
+        p->n_comp += q->n_comp + 1;
+        p->seedcov = p->seedcov > q->seedcov ? p->seedcov : q->seedcov;
+        p->sub = p->sub > q->sub ? p->sub : q->sub;
+        p->csub = p->csub > q->csub ? p->csub : q->csub;
+        p->qb = q->qb; p->rb = q->rb;
+        p->truesc = p->score = score;
+        p->w = w;
+        q->qb = q->qe;
+      }
+    }
+  }
+  for (i = 0, m = 0; i < n; ++i)
+    if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+  n = m;
+  b2_introsort(a, (long)n, B2RegScLt());
+  for (i = 1; i < n; ++i)
+    if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
+  for (i = 1, m = 1; i < n; ++i)
+    if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
+  return m;
+}

@@ -1,0 +1,52 @@
+// Launch/memory shim.  The product build (nvcc, sm_100a) maps these onto the CUDA runtime.
+// Defining B2_HOSTSIM (done ONLY by tests/hostsim, never by the shipped library) turns a launch into
+// a serial loop over the same kernel bodies so the control logic can be checked on a machine
+// without a GPU; it is test scaffolding, not a fallback, and libbwa.so does not contain it.
+#pragma once
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#if defined(B2_HOSTSIM)
+struct B2Dim { int grid, block, tid; };
+extern thread_local B2Dim b2_dim;
+#define B2_KERNEL static void
+#define B2_GTID() (b2_dim.tid)
+#define B2_GSIZE() (b2_dim.grid * b2_dim.block)
+#define B2_LAUNCH(kern, _g, _b, stream, ...)                             \
+  do {                                                                   \
+    b2_dim.grid = (_g); b2_dim.block = (_b);                             \
+    for (int _t = 0; _t < (_g) * (_b); ++_t) { b2_dim.tid = _t; kern(__VA_ARGS__); } \
+  } while (0)
+typedef int b2_stream_t;
+inline int b2_dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+inline void b2_dev_free(void* p) { free(p); }
+inline int b2_h2d(void* d, const void* h, size_t n, b2_stream_t) { memcpy(d, h, n); return 0; }
+inline int b2_d2h(void* h, const void* d, size_t n, b2_stream_t) { memcpy(h, d, n); return 0; }
+inline int b2_dev_memset(void* d, int v, size_t n, b2_stream_t) { memset(d, v, n); return 0; }
+inline int b2_sync(b2_stream_t) { return 0; }
+inline int b2_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
+inline void b2_host_free(void* p) { free(p); }
+#define B2_ATOMIC_OR(p, v) (*(p) |= (v))
+#define B2_ATOMIC_ADD(p, v) (*(p) += (v))
+#define B2_LANE_GROUP 1
+#else
+#include <cuda_runtime.h>
+#define B2_KERNEL static __global__ void
+#define B2_GTID() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
+#define B2_GSIZE() ((int)(gridDim.x * blockDim.x))
+#define B2_LAUNCH(kern, _g, _b, stream, ...) kern<<<(_g), (_b), 0, (stream)>>>(__VA_ARGS__)
+typedef cudaStream_t b2_stream_t;
+inline int b2_dev_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
+inline void b2_dev_free(void* p) { if (p) cudaFree(p); }
+inline int b2_h2d(void* d, const void* h, size_t n, b2_stream_t s) { return cudaMemcpyAsync(d, h, n, cudaMemcpyHostToDevice, s) != cudaSuccess; }
+inline int b2_d2h(void* h, const void* d, size_t n, b2_stream_t s) { return cudaMemcpyAsync(h, d, n, cudaMemcpyDeviceToHost, s) != cudaSuccess; }
+inline int b2_dev_memset(void* d, int v, size_t n, b2_stream_t s) { return cudaMemsetAsync(d, v, n, s) != cudaSuccess; }
+inline int b2_sync(b2_stream_t s) { return cudaStreamSynchronize(s) != cudaSuccess; }
+inline int b2_host_alloc(void** p, size_t n) { return cudaMallocHost(p, n ? n : 1) != cudaSuccess; }
+inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
+#define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
+#define B2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define B2_LANE_GROUP B2_SEED_LANES
+#endif

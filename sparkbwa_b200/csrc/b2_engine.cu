@@ -1,0 +1,536 @@
+// GPU batch engine: owns the device-resident index image and per-worker stream/buffer sets, and
+// stages one -K batch through the kernels of b2_kernels.cuh (the unit the reference computes in
+// mem_process_seqs, bwa/bwamem.c:1172-1201).  Capacity overflows reported by a stage are answered
+// by re-running that (idempotent) stage with larger buffers; anything else fails loudly.
+#include <math.h>
+#include <algorithm>
+#include <string>
+#include <vector>
+#include "b2_engine.h"
+#include "b2_kernels.cuh"
+
+#if defined(B2_HOSTSIM)
+thread_local B2Dim b2_dim;
+#endif
+
+namespace {
+
+template <class T>
+struct DBuf {
+  T* p = nullptr;
+  size_t cap = 0;
+  int ensure(size_t n) {
+    if (n <= cap) return 0;
+    size_t want = n + n / 4 + 16;
+    b2_dev_free(p);
+    p = nullptr; cap = 0;
+    void* q = nullptr;
+    if (b2_dev_malloc(&q, want * sizeof(T))) return 1;
+    p = (T*)q; cap = want;
+    return 0;
+  }
+  void release() { b2_dev_free(p); p = nullptr; cap = 0; }
+};
+
+struct Timer {
+#if !defined(B2_HOSTSIM)
+  cudaEvent_t e[16];
+  int n = 0;
+  cudaStream_t s;
+  void init(cudaStream_t st) { s = st; for (auto& x : e) cudaEventCreate(&x); }
+  void destroy() { for (auto& x : e) cudaEventDestroy(x); }
+  void reset() { n = 0; }
+  int mark() { cudaEventRecord(e[n], s); return n++; }
+  float ms(int a, int b) { float t = 0; cudaEventElapsedTime(&t, e[a], e[b]); return t; }
+#else
+  void init(int) {}
+  void destroy() {}
+  void reset() {}
+  int mark() { return 0; }
+  float ms(int, int) { return 0.f; }
+#endif
+};
+
+struct Worker {
+  b2_stream_t stream{};
+  Timer timer;
+  // batch
+  DBuf<uint8_t> seq; DBuf<char> qual; DBuf<uint8_t> has_qual; DBuf<char> names, comments;
+  DBuf<int64_t> seq_off, name_off, com_off; DBuf<int32_t> l_seq, l_name, l_com;
+  // stages
+  DBuf<B2Intv> intv, seed_scratch; DBuf<int32_t> n_intv, n_tasks; DBuf<int64_t> seed_off;
+  DBuf<B2Seed> raw, cseeds; DBuf<int32_t> raw_rid; DBuf<B2Chain> chains; DBuf<int32_t> n_chain, reg_cap;
+  DBuf<int64_t> reg_off; DBuf<B2Reg> regs; DBuf<int32_t> n_regs;
+  DBuf<uint8_t> scratch; DBuf<int8_t> pe_dir; DBuf<int64_t> pe_is; DBuf<double> pairtab;
+  DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
+  DBuf<int> flags;
+  size_t scratch_per_lane = 0;
+  int cap_intv = 0, slot_size = 0;
+  // resident batch metadata
+  int n_reads = 0, max_len = 0;
+  int64_t n_processed = 0;
+  bool resident = false;
+  B2StageTimes times;
+  std::vector<int8_t> h_dir; std::vector<int64_t> h_is; std::vector<char> h_sam;
+  void* pin_sam = nullptr; size_t pin_sam_cap = 0;
+};
+
+}  // namespace
+
+class B2EngineImpl {
+ public:
+  B2EngineConfig cfg;
+  B2Opt opt;
+  B2Index ix{};  // device pointers
+  DBuf<uint32_t> d_bwt; DBuf<uint64_t> d_sa; DBuf<uint8_t> d_pac; DBuf<B2Ann> d_anns; DBuf<char> d_names;
+  DBuf<double> d_logtab; DBuf<char> d_rg;
+  bool owns_index = true;
+  size_t bwt_bytes = 0, sa_bytes = 0, pac_bytes = 0;
+  int n_log = 1 << 16;
+  B2Fmt fmt{};
+  std::vector<Worker> workers;
+  std::string err;
+
+  int fail(const std::string& m) { err = m; if (cfg.verbose >= 1) fprintf(stderr, "[E::b200bwa] %s\n", m.c_str()); return 1; }
+
+  int common_init(const B2IndexHost& h, const B2Opt& o, const char* rg_id, const B2EngineConfig& c) {
+    cfg = c; opt = o;
+#if !defined(B2_HOSTSIM)
+    if (cudaSetDevice(cfg.device) != cudaSuccess) return fail("cudaSetDevice failed (no usable CUDA device)");
+#endif
+    ix.primary = h.primary; ix.seq_len = h.seq_len;
+    for (int i = 0; i < 5; ++i) ix.L2[i] = h.L2[i];
+    ix.bwt_size = h.bwt_words ? h.bwt_words : h.bwt.size(); ix.n_sa = h.n_sa ? h.n_sa : h.sa.size();
+    ix.sa_intv = h.sa_intv;
+    ix.sa_shift = 0; while ((1 << ix.sa_shift) < h.sa_intv) ++ix.sa_shift;
+    ix.l_pac = h.l_pac; ix.n_seqs = h.n_seqs;
+    ix.max_name_len = 0;
+    for (auto& a : h.anns) ix.max_name_len = std::max(ix.max_name_len, a.name_len);
+    if (d_anns.ensure(h.anns.size()) || d_names.ensure(h.names.size() + 1)) return fail("device allocation failed (contig table)");
+    b2_h2d(d_anns.p, h.anns.data(), h.anns.size() * sizeof(B2Ann), 0);
+    b2_h2d(d_names.p, h.names.data(), h.names.size(), 0);
+    ix.anns = d_anns.p; ix.names = d_names.p;
+    std::vector<double> lt(n_log);
+    lt[0] = log(0.0);
+    for (int i = 1; i < n_log; ++i) lt[i] = log((double)i);
+    if (d_logtab.ensure(n_log)) return fail("device allocation failed (log table)");
+    b2_h2d(d_logtab.p, lt.data(), n_log * sizeof(double), 0);
+    if (set_rg(rg_id)) return 1;
+    b2_sync(0);
+    workers.resize(3);
+    for (auto& w : workers) {
+#if !defined(B2_HOSTSIM)
+      if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
+#endif
+      w.timer.init(w.stream);
+      w.scratch_per_lane = cfg.scratch_per_lane;
+      w.cap_intv = cfg.cap_intv;
+      if (w.flags.ensure(4)) return fail("device allocation failed");
+    }
+    return 0;
+  }
+
+  int set_rg(const char* rg_id) {
+    size_t l_rg = rg_id ? strlen(rg_id) : 0;
+    if (d_rg.ensure(l_rg + 1)) return fail("device allocation failed");
+    if (l_rg) b2_h2d(d_rg.p, rg_id, l_rg, 0);
+    b2_sync(0);
+    fmt.rg_id = d_rg.p; fmt.l_rg = (int)l_rg;
+    return 0;
+  }
+
+  int init(const B2IndexHost& h, const B2Opt& o, const char* rg_id, const B2EngineConfig& c) {
+    cfg = c;
+#if !defined(B2_HOSTSIM)
+    if (cudaSetDevice(c.device) != cudaSuccess) return fail("cudaSetDevice failed (no usable CUDA device)");
+#endif
+    bwt_bytes = h.bwt.size() * 4; sa_bytes = h.sa.size() * 8; pac_bytes = h.pac.size();
+    if (d_bwt.ensure(h.bwt.size() + 16) || d_sa.ensure(h.sa.size()) || d_pac.ensure(h.pac.size() + 8))
+      return fail("device allocation failed (index image)");
+    b2_h2d(d_bwt.p, h.bwt.data(), bwt_bytes, 0);
+    b2_h2d(d_sa.p, h.sa.data(), sa_bytes, 0);
+    b2_h2d(d_pac.p, h.pac.data(), pac_bytes, 0);
+    ix.bwt = d_bwt.p; ix.sa = d_sa.p; ix.pac = d_pac.p;
+    return common_init(h, o, rg_id, c);
+  }
+
+  int init_device(const B2IndexHost& h, const void* bwt, const void* sa, const void* pac, const B2Opt& o,
+                  const char* rg_id, const B2EngineConfig& c) {
+    owns_index = false;
+    ix.bwt = (const uint32_t*)bwt; ix.sa = (const uint64_t*)sa; ix.pac = (const uint8_t*)pac;
+    return common_init(h, o, rg_id, c);
+  }
+
+  ~B2EngineImpl() {
+    for (auto& w : workers) {
+      w.timer.destroy();
+      for (DBuf<uint8_t>* b : {&w.seq, &w.has_qual, &w.scratch}) b->release();
+      w.qual.release(); w.names.release(); w.comments.release(); w.seq_off.release(); w.name_off.release();
+      w.com_off.release(); w.l_seq.release(); w.l_name.release(); w.l_com.release(); w.intv.release();
+      w.seed_scratch.release(); w.n_intv.release(); w.n_tasks.release(); w.seed_off.release(); w.raw.release();
+      w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
+      w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
+      w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
+      w.flags.release();
+      if (w.pin_sam) b2_host_free(w.pin_sam);
+#if !defined(B2_HOSTSIM)
+      if (w.stream) cudaStreamDestroy(w.stream);
+#endif
+    }
+    if (owns_index) { d_bwt.release(); d_sa.release(); d_pac.release(); }
+    d_anns.release(); d_names.release(); d_logtab.release(); d_rg.release();
+  }
+
+  int check_cuda(const char* where) {
+#if !defined(B2_HOSTSIM)
+    cudaError_t e = cudaGetLastError();
+    if (e != cudaSuccess) return fail(std::string(where) + ": " + cudaGetErrorString(e));
+#endif
+    (void)where;
+    return 0;
+  }
+
+  int upload(Worker& w, const B2HostBatch& b) {
+    const int n = b.n_reads;
+    w.timer.reset();
+    w.times = B2StageTimes();
+    int t0 = w.timer.mark();
+    if (w.seq.ensure(b.seq.size() + 8) || w.qual.ensure(b.seq.size() + 8) || w.has_qual.ensure(n + 1) ||
+        w.names.ensure(b.names.size() + 8) || w.comments.ensure(b.comments.size() + 8) || w.seq_off.ensure(n + 1) ||
+        w.name_off.ensure(n + 1) || w.com_off.ensure(n + 1) || w.l_seq.ensure(n + 1) || w.l_name.ensure(n + 1) ||
+        w.l_com.ensure(n + 1))
+      return fail("device allocation failed (read batch)");
+    b2_h2d(w.seq.p, b.seq.data(), b.seq.size(), w.stream);
+    if (!b.qual.empty()) b2_h2d(w.qual.p, b.qual.data(), b.qual.size(), w.stream);
+    b2_h2d(w.has_qual.p, b.has_qual.data(), n, w.stream);
+    b2_h2d(w.names.p, b.names.data(), b.names.size(), w.stream);
+    if (!b.comments.empty()) b2_h2d(w.comments.p, b.comments.data(), b.comments.size(), w.stream);
+    b2_h2d(w.seq_off.p, b.seq_off.data(), n * sizeof(int64_t), w.stream);
+    b2_h2d(w.name_off.p, b.name_off.data(), n * sizeof(int64_t), w.stream);
+    b2_h2d(w.com_off.p, b.com_off.data(), n * sizeof(int64_t), w.stream);
+    b2_h2d(w.l_seq.p, b.l_seq.data(), n * sizeof(int32_t), w.stream);
+    b2_h2d(w.l_name.p, b.l_name.data(), n * sizeof(int32_t), w.stream);
+    b2_h2d(w.l_com.p, b.l_com.data(), n * sizeof(int32_t), w.stream);
+    int t1 = w.timer.mark();
+    b2_sync(w.stream);
+    w.times.h2d = w.timer.ms(t0, t1);
+    w.n_reads = n; w.max_len = b.max_len; w.n_processed = b.n_processed;
+    w.resident = true;
+    return check_cuda("upload");
+  }
+
+  int read_flags(Worker& w, int* f) {
+    b2_d2h(f, w.flags.p, sizeof(int), w.stream);
+    if (b2_sync(w.stream)) return fail("device synchronisation failed (kernel fault?)");
+    return check_cuda("kernel");
+  }
+
+  int run(Worker& w, const B2Pes* pes0, std::string* sam) {
+    if (!w.resident) return fail("no resident batch");
+    const int n = w.n_reads;
+    const bool pe = (opt.flag & B2_F_PE) != 0;
+    if (pe && (n & 1)) return fail("paired-end batch with an odd number of reads");
+    if (opt.flag & B2_F_SMARTPE) return fail("smart pairing (-p) is not supported by this build");
+    w.timer.reset();
+    float t_h2d = w.times.h2d;
+    w.times = B2StageTimes();
+    w.times.h2d = t_h2d;
+    if (n == 0) return 0;
+    B2Ctx c;
+    memset(&c, 0, sizeof(c));
+    c.opt = opt; c.ix = ix; c.fmt = fmt;
+    c.tb.logtab = d_logtab.p; c.tb.n_log = n_log;
+    c.n_processed = w.n_processed; c.max_len = w.max_len;
+    c.b.n_reads = n; c.b.seq = w.seq.p; c.b.qual = w.qual.p; c.b.has_qual = w.has_qual.p; c.b.names = w.names.p;
+    c.b.comments = w.comments.p; c.b.seq_off = w.seq_off.p; c.b.l_seq = w.l_seq.p; c.b.name_off = w.name_off.p;
+    c.b.l_name = w.l_name.p; c.b.com_off = w.com_off.p; c.b.l_com = w.l_com.p;
+    c.flags = w.flags.p;
+    const int lanes = cfg.lane_grid * cfg.lane_block;
+    int flags = 0;
+    int ev_begin = w.timer.mark();
+
+    // ---- seeding ----
+    const int seed_groups = cfg.seed_grid * cfg.seed_block / B2_LANE_GROUP;
+    if (w.n_intv.ensure(n + 1) || w.n_tasks.ensure(n + 1) || w.seed_off.ensure(n + 2) ||
+        w.seed_scratch.ensure((size_t)seed_groups * 3 * (size_t)(w.max_len + 1)))
+      return fail("device allocation failed (seeding)");
+    for (;;) {
+      if (w.intv.ensure((size_t)n * w.cap_intv)) return fail("device allocation failed (intervals)");
+      c.intv = w.intv.p; c.cap_intv = w.cap_intv; c.n_intv = w.n_intv.p; c.n_tasks = w.n_tasks.p;
+      c.seed_scratch = w.seed_scratch.p;
+      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      B2_LAUNCH(k_seed, cfg.seed_grid, cfg.seed_block, w.stream, c);
+      ++w.times.launches;
+      if (read_flags(w, &flags)) return 1;
+      if (!(flags & B2_FLAG_OVF_INTV)) break;
+      if (w.cap_intv >= 8192) return fail("seed interval capacity exceeded");
+      w.cap_intv *= 2;
+    }
+    int ev_seed = w.timer.mark();
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.n_tasks.p, w.seed_off.p, n);
+    ++w.times.launches;
+    int64_t S = 0;
+    b2_d2h(&S, w.seed_off.p + n, sizeof(int64_t), w.stream);
+    if (b2_sync(w.stream)) return fail("device synchronisation failed");
+    c.seed_off = w.seed_off.p; c.n_seed_tasks = S;
+    w.times.n_seed_tasks = S;
+
+    // ---- SA lookup ----
+    if (w.raw.ensure(S + 1) || w.raw_rid.ensure(S + 1) || w.chains.ensure(S + 1) || w.cseeds.ensure(S + 1) ||
+        w.n_chain.ensure(n + 1) || w.reg_cap.ensure(n + 1) || w.reg_off.ensure(n + 2) || w.n_regs.ensure(n + 1))
+      return fail("device allocation failed (seeds)");
+    c.raw = w.raw.p; c.raw_rid = w.raw_rid.p; c.chains = w.chains.p; c.cseeds = w.cseeds.p;
+    c.n_chain = w.n_chain.p; c.reg_cap = w.reg_cap.p; c.n_regs = w.n_regs.p;
+    if (S > 0) {
+      int grid = (int)std::min<int64_t>((S + 127) / 128, 148 * 16);
+      B2_LAUNCH(k_sa, grid, 128, w.stream, c);
+      ++w.times.launches;
+    }
+    int ev_sa = w.timer.mark();
+
+    // ---- lane-per-read stages with retry on scratch overflow ----
+    auto ensure_scratch = [&]() -> int {
+      if ((size_t)lanes * w.scratch_per_lane > cfg.max_scratch_bytes) return fail("per-lane scratch limit exceeded");
+      if (w.scratch.ensure((size_t)lanes * w.scratch_per_lane)) return fail("device allocation failed (scratch)");
+      c.scratch = w.scratch.p; c.scratch_per_lane = w.scratch_per_lane;
+      return 0;
+    };
+    for (;;) {
+      if (ensure_scratch()) return 1;
+      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      B2_LAUNCH(k_chain, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      ++w.times.launches;
+      if (read_flags(w, &flags)) return 1;
+      if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
+      w.scratch_per_lane *= 2;
+    }
+    int ev_chain = w.timer.mark();
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.reg_cap.p, w.reg_off.p, n);
+    ++w.times.launches;
+    int64_t R = 0;
+    b2_d2h(&R, w.reg_off.p + n, sizeof(int64_t), w.stream);
+    if (b2_sync(w.stream)) return fail("device synchronisation failed");
+    if (w.regs.ensure(R + 1)) return fail("device allocation failed (regions)");
+    c.reg_off = w.reg_off.p; c.regs = w.regs.p;
+    w.times.n_regs = R;
+    for (;;) {
+      if (ensure_scratch()) return 1;
+      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      B2_LAUNCH(k_extend, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      ++w.times.launches;
+      if (read_flags(w, &flags)) return 1;
+      if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
+      w.scratch_per_lane *= 2;
+    }
+    int ev_ext = w.timer.mark();
+
+    // ---- insert-size statistics (batch-wide barrier) ----
+    const int n_items = pe ? n >> 1 : n;
+    if (pe) {
+      if (pes0) memcpy(c.pes, pes0, sizeof(B2Pes) * 4);
+      else {
+        if (w.pe_dir.ensure(n_items + 1) || w.pe_is.ensure(n_items + 1)) return fail("device allocation failed");
+        c.pe_dir = w.pe_dir.p; c.pe_is = w.pe_is.p;
+        B2_LAUNCH(k_pestat, (n_items + 127) / 128, 128, w.stream, c);
+        ++w.times.launches;
+        w.h_dir.resize(n_items); w.h_is.resize(n_items);
+        b2_d2h(w.h_dir.data(), w.pe_dir.p, n_items, w.stream);
+        b2_d2h(w.h_is.data(), w.pe_is.p, n_items * sizeof(int64_t), w.stream);
+        if (b2_sync(w.stream)) return fail("device synchronisation failed");
+        b2_pestat_host(opt, n_items, w.h_dir.data(), w.h_is.data(), c.pes, cfg.verbose);
+      }
+      // pairing table: .721*log(2*erfc(|ns|/sqrt2))*a for every admissible insert size
+      std::vector<double> tab;
+      size_t offs[4] = {0, 0, 0, 0};
+      for (int d = 0; d < 4; ++d) {
+        c.tb.pair_n[d] = 0;
+        if (c.pes[d].failed || c.pes[d].high < c.pes[d].low) continue;
+        offs[d] = tab.size();
+        long cnt = (long)c.pes[d].high - c.pes[d].low + 1;
+        if (cnt > (1 << 24)) return fail("insert-size range too wide for the pairing table");
+        c.tb.pair_n[d] = (int)cnt;
+        for (long k = 0; k < cnt; ++k) {
+          int64_t dist = (int64_t)c.pes[d].low + k;
+          double ns = (dist - c.pes[d].avg) / c.pes[d].std;
+          tab.push_back(.721 * log(2. * erfc(fabs(ns) * M_SQRT1_2)) * opt.a);
+        }
+      }
+      if (w.pairtab.ensure(tab.size() + 1)) return fail("device allocation failed");
+      if (!tab.empty()) b2_h2d(w.pairtab.p, tab.data(), tab.size() * sizeof(double), w.stream);
+      for (int d = 0; d < 4; ++d) c.tb.pairtab[d] = w.pairtab.p + offs[d];
+      b2_sync(w.stream);
+    }
+    int ev_pes = w.timer.mark();
+
+    // ---- finalisation + SAM text ----
+    if (w.sam_len.ensure(n_items + 1) || w.sam_off.ensure(n_items + 2)) return fail("device allocation failed");
+    c.sam_len = w.sam_len.p;
+    if (w.slot_size == 0) {
+      int per_read = cfg.slot_per_read ? cfg.slot_per_read : 3 * w.max_len + 384;
+      w.slot_size = pe ? 2 * per_read : per_read;
+    }
+    for (;;) {
+      if (ensure_scratch()) return 1;
+      if (w.slots.ensure((size_t)n_items * w.slot_size)) return fail("device allocation failed (SAM slots)");
+      c.slots = w.slots.p; c.slot_size = w.slot_size;
+      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      if (pe) B2_LAUNCH(k_final_pe, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      else B2_LAUNCH(k_final_se, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      ++w.times.launches;
+      if (read_flags(w, &flags)) return 1;
+      if (flags & B2_FLAG_ERR_TABLE) return fail("log/pairing table index out of range");
+      if (!(flags & (B2_FLAG_OVF_SCRATCH | B2_FLAG_OVF_SLOT))) break;
+      if (flags & B2_FLAG_OVF_SCRATCH) w.scratch_per_lane *= 2;
+      if (flags & B2_FLAG_OVF_SLOT) {
+        if (w.slot_size > (1 << 24)) return fail("SAM slot limit exceeded");
+        w.slot_size *= 2;
+      }
+    }
+    int ev_fin = w.timer.mark();
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.sam_len.p, w.sam_off.p, n_items);
+    ++w.times.launches;
+    int64_t total = 0;
+    b2_d2h(&total, w.sam_off.p + n_items, sizeof(int64_t), w.stream);
+    if (b2_sync(w.stream)) return fail("device synchronisation failed");
+    if (w.sam_out.ensure(total + 16)) return fail("device allocation failed (SAM out)");
+    c.sam_off = w.sam_off.p; c.sam_out = w.sam_out.p;
+    {
+      int64_t work = (int64_t)n_items * ((w.slot_size + 15) / 16);
+      int grid = (int)std::min<int64_t>((work + 255) / 256, 148 * 32);
+      B2_LAUNCH(k_gather, grid, 256, w.stream, c, n_items);
+      ++w.times.launches;
+    }
+    int ev_gat = w.timer.mark();
+    w.times.sam_bytes = total;
+    int ev_d2h = ev_gat;
+    if (sam) {
+      if ((size_t)total > w.pin_sam_cap) {
+        if (w.pin_sam) b2_host_free(w.pin_sam);
+        w.pin_sam_cap = (size_t)total + (size_t)total / 4 + 4096;
+        if (b2_host_alloc(&w.pin_sam, w.pin_sam_cap)) return fail("pinned host allocation failed");
+      }
+      b2_d2h(w.pin_sam, w.sam_out.p, (size_t)total, w.stream);
+      ev_d2h = w.timer.mark();
+      if (b2_sync(w.stream)) return fail("device synchronisation failed");
+      sam->append((const char*)w.pin_sam, (size_t)total);
+    } else {
+      if (b2_sync(w.stream)) return fail("device synchronisation failed");
+    }
+    if (check_cuda("pipeline")) return 1;
+    w.times.seed = w.timer.ms(ev_begin, ev_seed);
+    w.times.sa = w.timer.ms(ev_seed, ev_sa);
+    w.times.chain = w.timer.ms(ev_sa, ev_chain);
+    w.times.extend = w.timer.ms(ev_chain, ev_ext);
+    w.times.pestat = w.timer.ms(ev_ext, ev_pes);
+    w.times.final_ = w.timer.ms(ev_pes, ev_fin);
+    w.times.gather = w.timer.ms(ev_fin, ev_gat);
+    w.times.d2h = w.timer.ms(ev_gat, ev_d2h);
+    w.times.total = w.timer.ms(ev_begin, ev_d2h);
+    return 0;
+  }
+};
+
+// ---------------------------------------------------------------------------------------------
+void b2_pestat_host(const B2Opt& opt, int n_pairs, const int8_t* dir, const int64_t* is, B2Pes pes[4], int verbose) {
+  std::vector<uint64_t> isize[4];
+  memset(pes, 0, 4 * sizeof(B2Pes));
+  (void)opt;
+  for (int i = 0; i < n_pairs; ++i)
+    if (dir[i] >= 0) isize[dir[i]].push_back((uint64_t)is[i]);
+  if (verbose >= 3)
+    fprintf(stderr, "[M::mem_pestat] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n",
+            (long)isize[0].size(), (long)isize[1].size(), (long)isize[2].size(), (long)isize[3].size());
+  for (int d = 0; d < 4; ++d) {
+    B2Pes* r = &pes[d];
+    std::vector<uint64_t>& q = isize[d];
+    int p25, p50, p75, x;
+    if (q.size() < 10) {
+      if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] skip orientation %c%c as there are not enough pairs\n", "FR"[d >> 1 & 1], "FR"[d & 1]);
+      r->failed = 1;
+      continue;
+    } else if (verbose >= 3)
+      fprintf(stderr, "[M::mem_pestat] analyzing insert size distribution for orientation %c%c...\n", "FR"[d >> 1 & 1], "FR"[d & 1]);
+    std::sort(q.begin(), q.end());
+    p25 = (int)q[(int)(.25 * q.size() + .499)];
+    p50 = (int)q[(int)(.50 * q.size() + .499)];
+    p75 = (int)q[(int)(.75 * q.size() + .499)];
+    r->low = (int)(p25 - 2.0 * (p75 - p25) + .499);
+    if (r->low < 1) r->low = 1;
+    r->high = (int)(p75 + 2.0 * (p75 - p25) + .499);
+    if (verbose >= 3) {
+      fprintf(stderr, "[M::mem_pestat] (25, 50, 75) percentile: (%d, %d, %d)\n", p25, p50, p75);
+      fprintf(stderr, "[M::mem_pestat] low and high boundaries for computing mean and std.dev: (%d, %d)\n", r->low, r->high);
+    }
+    size_t i;
+    for (i = 0, x = 0, r->avg = 0; i < q.size(); ++i)
+      if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) { r->avg += q[i]; ++x; }
+    r->avg /= x;
+    for (i = 0, r->std = 0; i < q.size(); ++i)
+      if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) r->std += (q[i] - r->avg) * (q[i] - r->avg);
+    r->std = sqrt(r->std / x);
+    if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] mean and std.dev: (%.2f, %.2f)\n", r->avg, r->std);
+    r->low = (int)(p25 - 3.0 * (p75 - p25) + .499);
+    r->high = (int)(p75 + 3.0 * (p75 - p25) + .499);
+    if (r->low > r->avg - 4.0 * r->std) r->low = (int)(r->avg - 4.0 * r->std + .499);
+    if (r->high < r->avg + 4.0 * r->std) r->high = (int)(r->avg + 4.0 * r->std + .499);
+    if (r->low < 1) r->low = 1;
+    if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] low and high boundaries for proper pairs: (%d, %d)\n", r->low, r->high);
+  }
+  size_t max = 0;
+  for (int d = 0; d < 4; ++d) max = std::max(max, isize[d].size());
+  for (int d = 0; d < 4; ++d)
+    if (pes[d].failed == 0 && isize[d].size() < max * 0.05) {
+      pes[d].failed = 1;
+      if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] skip orientation %c%c\n", "FR"[d >> 1 & 1], "FR"[d & 1]);
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
+B2Engine::B2Engine() : impl_(new B2EngineImpl) {}
+B2Engine::~B2Engine() { delete impl_; }
+int B2Engine::init(const B2IndexHost& idx, const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg) {
+  return impl_->init(idx, opt, rg_id, cfg);
+}
+int B2Engine::init_device_index(const B2IndexHost& meta, const void* d_bwt, const void* d_sa, const void* d_pac,
+                                const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg) {
+  return impl_->init_device(meta, d_bwt, d_sa, d_pac, opt, rg_id, cfg);
+}
+int B2Engine::process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam, int worker) {
+  Worker& w = impl_->workers[worker];
+  if (impl_->upload(w, b)) return 1;
+  return impl_->run(w, pes0, &sam);
+}
+int B2Engine::upload(const B2HostBatch& b, int worker) { return impl_->upload(impl_->workers[worker], b); }
+int B2Engine::run_resident(const B2Pes* pes0, std::string* sam, int worker) {
+  return impl_->run(impl_->workers[worker], pes0, sam);
+}
+void B2Engine::set_options(const B2Opt& opt, const char* rg_id, int verbose) {
+  impl_->opt = opt; impl_->cfg.verbose = verbose; impl_->set_rg(rg_id);
+}
+const B2Opt& B2Engine::options() const { return impl_->opt; }
+const B2StageTimes& B2Engine::times(int worker) const { return impl_->workers[worker].times; }
+const char* B2Engine::last_error() const { return impl_->err.c_str(); }
+int B2Engine::n_workers() const { return (int)impl_->workers.size(); }
+void B2Engine::index_device_ptrs(void** bwt, size_t* bb, void** sa, size_t* sb, void** pac, size_t* pb) {
+  *bwt = (void*)impl_->ix.bwt; *bb = impl_->bwt_bytes; *sa = (void*)impl_->ix.sa; *sb = impl_->sa_bytes;
+  *pac = (void*)impl_->ix.pac; *pb = impl_->pac_bytes;
+}
+int B2Engine::dump_intervals(int worker, std::vector<int32_t>& n_intv, std::vector<B2Intv>& intv) {
+  Worker& w = impl_->workers[worker];
+  n_intv.resize(w.n_reads); intv.resize((size_t)w.n_reads * w.cap_intv);
+  b2_d2h(n_intv.data(), w.n_intv.p, w.n_reads * sizeof(int32_t), w.stream);
+  b2_d2h(intv.data(), w.intv.p, intv.size() * sizeof(B2Intv), w.stream);
+  b2_sync(w.stream);
+  return w.cap_intv;
+}
+int B2Engine::dump_regs(int worker, std::vector<int32_t>& n_regs, std::vector<int64_t>& reg_off, std::vector<B2Reg>& regs) {
+  Worker& w = impl_->workers[worker];
+  n_regs.resize(w.n_reads); reg_off.resize(w.n_reads + 1);
+  b2_d2h(n_regs.data(), w.n_regs.p, w.n_reads * sizeof(int32_t), w.stream);
+  b2_d2h(reg_off.data(), w.reg_off.p, (w.n_reads + 1) * sizeof(int64_t), w.stream);
+  b2_sync(w.stream);
+  regs.resize(reg_off[w.n_reads]);
+  b2_d2h(regs.data(), w.regs.p, regs.size() * sizeof(B2Reg), w.stream);
+  b2_sync(w.stream);
+  return 0;
+}

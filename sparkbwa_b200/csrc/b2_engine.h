@@ -1,0 +1,93 @@
+// Host-side interface of the GPU batch engine (C++; the C-ABI in include/b200bwa.h sits on top).
+#pragma once
+#include <stdint.h>
+#include <stddef.h>
+#include <string>
+#include <vector>
+#include "b2_types.h"
+
+// Host copy of one index (files <prefix>.bwt/.sa/.pac/.ann/.amb[/.alt], bwa/bwa.c:252-279).
+struct B2IndexHost {
+  std::vector<uint32_t> bwt;   // payload after the 40-byte header
+  std::vector<uint64_t> sa;    // sa[0] = -1
+  std::vector<uint8_t> pac;
+  std::vector<B2Ann> anns;
+  std::string names;           // name/anno blob
+  std::vector<std::string> ann_names;
+  uint64_t primary, L2[5], seq_len;
+  size_t bwt_words = 0, n_sa = 0;  // sizes of the device images (valid even when the vectors are released)
+  int sa_intv;
+  int64_t l_pac;
+  int n_seqs, n_holes;
+};
+
+// One -K batch as cut by the reader (bseq_read, bwa/bwa.c:42-75).
+struct B2HostBatch {
+  int n_reads = 0, max_len = 0;
+  int64_t n_bases = 0;
+  int64_t n_processed = 0;       // absolute index of the first read (hash tie-breaks depend on it)
+  std::vector<uint8_t> seq;      // base codes 0..4
+  std::vector<char> qual;
+  std::vector<uint8_t> has_qual;
+  std::vector<char> names, comments;
+  std::vector<int64_t> seq_off, name_off, com_off;
+  std::vector<int32_t> l_seq, l_name, l_com;
+  void clear() {
+    n_reads = max_len = 0; n_bases = 0;
+    seq.clear(); qual.clear(); has_qual.clear(); names.clear(); comments.clear();
+    seq_off.clear(); name_off.clear(); com_off.clear(); l_seq.clear(); l_name.clear(); l_com.clear();
+  }
+};
+
+struct B2EngineConfig {
+  int device = 0;
+  int lane_grid = 148 * 4, lane_block = 128;   // lane-per-read kernels (persistent, grid-stride)
+  int seed_grid = 148 * 8, seed_block = 128;   // seeding groups of B2_SEED_LANES lanes
+  size_t scratch_per_lane = 48 << 10;
+  size_t max_scratch_bytes = (size_t)64 << 30;
+  int cap_intv = 64;
+  int slot_per_read = 0;                       // 0: derived from the longest read of the batch
+  int verbose = 3;
+};
+
+struct B2StageTimes {  // milliseconds, device time (CUDA events) of the last batch
+  float h2d = 0, seed = 0, sa = 0, chain = 0, extend = 0, pestat = 0, final_ = 0, gather = 0, d2h = 0, total = 0;
+  int launches = 0;
+  int64_t n_seed_tasks = 0, n_regs = 0, sam_bytes = 0;
+};
+
+class B2EngineImpl;
+
+class B2Engine {
+ public:
+  B2Engine();
+  ~B2Engine();
+  // uploads the index; returns 0 on success
+  int init(const B2IndexHost& idx, const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg);
+  // adopt an index image that already lives in device memory (NCCL-broadcast by the caller)
+  int init_device_index(const B2IndexHost& meta, const void* d_bwt, const void* d_sa, const void* d_pac,
+                        const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg);
+  // Aligns one batch and appends its SAM text to `sam`.  PE iff opt.flag & B2_F_PE.  pes0: user-supplied
+  // insert-size distribution (-I) or null.  `worker` selects one of the independent stream/buffer sets.
+  int process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam, int worker = 0);
+  // device-resident variant used by the benchmark: upload once, run the kernels many times
+  int upload(const B2HostBatch& b, int worker = 0);
+  int run_resident(const B2Pes* pes0, std::string* sam, int worker = 0);
+  // per-call options (a cached index serves successive calls with different bwa-mem options)
+  void set_options(const B2Opt& opt, const char* rg_id, int verbose);
+  const B2Opt& options() const;
+  const B2StageTimes& times(int worker = 0) const;
+  const char* last_error() const;
+  int n_workers() const;
+  // raw device pointers of the index image (for broadcasting it to peer GPUs)
+  void index_device_ptrs(void** bwt, size_t* bwt_bytes, void** sa, size_t* sa_bytes, void** pac, size_t* pac_bytes);
+  // stage dumps for the parity tests (valid after process/run_resident on that worker)
+  int dump_intervals(int worker, std::vector<int32_t>& n_intv, std::vector<B2Intv>& intv);
+  int dump_regs(int worker, std::vector<int32_t>& n_regs, std::vector<int64_t>& reg_off, std::vector<B2Reg>& regs);
+
+ private:
+  B2EngineImpl* impl_;
+};
+
+// mem_pestat second half (bwa/bwamem_pair.c:66-108) on the host: candidates -> pes[4]
+void b2_pestat_host(const B2Opt& opt, int n_pairs, const int8_t* dir, const int64_t* is, B2Pes pes[4], int verbose);

@@ -1,0 +1,783 @@
+// Finalisation: primary marking, mapping quality, CIGAR/NM/MD, XA, mate rescue, pairing and SAM
+// text, one read (SE) or one pair (PE) per task.
+//
+// Restates bwa/bwamem.c:493-558 (mem_mark_primary_se), :945-969 (mem_approx_mapq_se), :792-799
+// (infer_bw), :1057-1127 (mem_reg2aln), :801-939 (get_rlen, mem_aln2sam), :972-1017 (mem_reg2sam);
+// bwa/bwamem_extra.c:90-140 (mem_gen_alt); bwa/bwamem_pair.c:23-44 (mem_infer_dir, cal_sub),
+// :111-180 (mem_matesw), :182-243 (mem_pair), :249-388 (mem_sam_pe); utils.h:98-109 (hash_64).
+// log() is only ever taken of integers: the host uploads a table computed with the same libm
+// (SURVEY.md H8).  log(2*erfc(|ns|/sqrt2)) depends on the integer insert size and the batch's
+// insert-size statistics: the host uploads one table per orientation and batch.
+#pragma once
+#include "b2_types.h"
+#include "b2_align.cuh"
+
+struct B2Tables {
+  const double* logtab;   // logtab[i] = log((double)i), i < n_log
+  int n_log;
+  const double* pairtab[4];  // pairtab[d][dist - pes[d].low] = .721 * log(2 * erfc(|ns| * M_SQRT1_2)) * a
+  int pair_n[4];
+};
+
+struct B2Read {
+  const uint8_t* seq;   // codes 0..4
+  const char* qual;     // null if FASTA
+  const char* name;
+  const char* comment;  // null unless -C and present
+  int l_seq, l_name, l_comment;
+};
+
+struct B2Fmt {
+  const char* rg_id;  // device copy of bwa_rg_id (may be empty)
+  int l_rg;
+};
+
+struct B2Out {
+  char* p;
+  long cap, len;
+  B2_HD inline void putc_(int c) { if (len < cap) p[len] = (char)c; ++len; }
+  B2_HD inline void putsn(const char* s, int l) { for (int i = 0; i < l; ++i) putc_(s[i]); }
+  B2_HD inline void puts_(const char* s) { for (; *s; ++s) putc_(*s); }
+  B2_HD inline void putl(long c) {
+    char buf[24];
+    int n = 0;
+    if (c == 0) { putc_('0'); return; }
+    unsigned long x = c < 0 ? (unsigned long)(-c) : (unsigned long)c;
+    for (; x > 0; x /= 10) buf[n++] = (char)('0' + x % 10);
+    if (c < 0) buf[n++] = '-';
+    for (int i = n - 1; i >= 0; --i) putc_(buf[i]);
+  }
+};
+
+B2_HD inline uint64_t b2_hash64(uint64_t key) {
+  key += ~(key << 32); key ^= (key >> 22);
+  key += ~(key << 13); key ^= (key >> 8);
+  key += (key << 3);   key ^= (key >> 15);
+  key += ~(key << 27); key ^= (key >> 31);
+  return key;
+}
+
+B2_HD inline double b2_log_int(const B2Tables& tb, long v, int* err) {
+  if (v < 0 || v >= tb.n_log) { *err = 1; return 0.; }
+  return tb.logtab[v];
+}
+
+// ---------------------------------------------------------------------------------------------
+struct B2RegHashLt {
+  B2_HD bool operator()(const B2Reg& a, const B2Reg& b) const {
+    return a.score > b.score || (a.score == b.score && (a.is_alt < b.is_alt || (a.is_alt == b.is_alt && a.hash < b.hash)));
+  }
+};
+struct B2RegHash2Lt {
+  B2_HD bool operator()(const B2Reg& a, const B2Reg& b) const {
+    return a.is_alt < b.is_alt || (a.is_alt == b.is_alt && (a.score > b.score || (a.score == b.score && a.hash < b.hash)));
+  }
+};
+
+// z: int scratch of n entries
+B2_HD inline void b2_mark_primary_core(const B2Opt& opt, int n, B2Reg* a, int* z) {
+  int tmp = opt.a + opt.b, nz = 0;
+  tmp = opt.o_del + opt.e_del > tmp ? opt.o_del + opt.e_del : tmp;
+  tmp = opt.o_ins + opt.e_ins > tmp ? opt.o_ins + opt.e_ins : tmp;
+  z[nz++] = 0;
+  for (int i = 1; i < n; ++i) {
+    int k;
+    for (k = 0; k < nz; ++k) {
+      int j = z[k];
+      int b_max = a[j].qb > a[i].qb ? a[j].qb : a[i].qb;
+      int e_min = a[j].qe < a[i].qe ? a[j].qe : a[i].qe;
+      if (e_min > b_max) {
+        int min_l = a[i].qe - a[i].qb < a[j].qe - a[j].qb ? a[i].qe - a[i].qb : a[j].qe - a[j].qb;
+        if (e_min - b_max >= min_l * opt.mask_level) {
+          if (a[j].sub == 0) a[j].sub = a[i].score;
+          if (a[j].score - a[i].score <= tmp && (a[j].is_alt || !a[i].is_alt)) ++a[j].sub_n;
+          break;
+        }
+      }
+    }
+    if (k == nz) z[nz++] = i;
+    else a[i].secondary = z[k];
+  }
+}
+
+B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* a, int64_t id, int* z) {
+  int i, n_pri;
+  if (n == 0) return 0;
+  for (i = n_pri = 0; i < n; ++i) {
+    a[i].sub = a[i].alt_sc = 0; a[i].secondary = a[i].secondary_all = -1;
+    a[i].hash = b2_hash64((uint64_t)(id + i));
+    if (!a[i].is_alt) ++n_pri;
+  }
+  b2_introsort(a, (long)n, B2RegHashLt());
+  b2_mark_primary_core(opt, n, a, z);
+  for (i = 0; i < n; ++i) {
+    B2Reg* p = &a[i];
+    p->secondary_all = i;
+    if (!p->is_alt && p->secondary >= 0 && a[p->secondary].is_alt) p->alt_sc = a[p->secondary].score;
+  }
+  if (n_pri >= 0 && n_pri < n) {
+    if (n_pri > 0) b2_introsort(a, (long)n, B2RegHash2Lt());
+    for (i = 0; i < n; ++i) z[a[i].secondary_all] = i;
+    for (i = 0; i < n; ++i) {
+      if (a[i].secondary >= 0) {
+        a[i].secondary_all = z[a[i].secondary];
+        if (a[i].is_alt) a[i].secondary = 0x7fffffff;
+      } else a[i].secondary_all = -1;
+    }
+    if (n_pri > 0) {
+      for (i = 0; i < n_pri; ++i) { a[i].sub = 0; a[i].secondary = -1; }
+      b2_mark_primary_core(opt, n_pri, a, z);
+    }
+  } else {
+    for (i = 0; i < n; ++i) a[i].secondary_all = a[i].secondary;
+  }
+  return n_pri;
+}
+
+B2_HD inline int b2_approx_mapq_se(const B2Opt& opt, const B2Tables& tb, const B2Reg* a, int* err) {
+  int mapq, l, sub = a->sub ? a->sub : opt.min_seed_len * opt.a;
+  double identity;
+  sub = a->csub > sub ? a->csub : sub;
+  if (sub >= a->score) return 0;
+  l = a->qe - a->qb > a->re - a->rb ? a->qe - a->qb : (int)(a->re - a->rb);
+  identity = 1. - (double)(l * opt.a - a->score) / (opt.a + opt.b) / l;
+  if (a->score == 0) {
+    mapq = 0;
+  } else if (opt.mapQ_coef_len > 0) {
+    double tmp;
+    tmp = l < opt.mapQ_coef_len ? 1. : opt.mapQ_coef_fac / b2_log_int(tb, l, err);
+    tmp *= identity * identity;
+    mapq = (int)(6.02 * (a->score - sub) / opt.a * tmp * tmp + .499);
+  } else {
+    mapq = (int)(30.0 * (1. - (double)sub / a->score) * b2_log_int(tb, a->seedcov, err) + .499);
+    mapq = identity < 0.95 ? (int)(mapq * identity * identity + .499) : mapq;
+  }
+  if (a->sub_n > 0) mapq -= (int)(4.343 * b2_log_int(tb, a->sub_n + 1, err) + .499);
+  if (mapq > 60) mapq = 60;
+  if (mapq < 0) mapq = 0;
+  mapq = (int)(mapq * (1. - a->frac_rep) + .499);
+  return mapq;
+}
+
+B2_HD inline int b2_infer_bw(int l1, int l2, int score, int a, int q, int r) {
+  int w;
+  if (l1 == l2 && l1 * a - score < (q + r - a) << 1) return 0;
+  w = (int)((double)((l1 < l2 ? l1 : l2) * a - score - q) / r + 2.);
+  int d = l1 - l2; d = d < 0 ? -d : d;
+  if (w < d) w = d;
+  return w;
+}
+
+B2_HD inline int b2_get_rlen(int n_cigar, const uint32_t* cigar) {
+  int l = 0;
+  for (int k = 0; k < n_cigar; ++k) { int op = cigar[k] & 0xf; if (op == 0 || op == 2) l += cigar[k] >> 4; }
+  return l;
+}
+
+// ar == null: unmapped record.  qwork: l_query bytes of scratch holding a private copy of the read.
+// The cigar/MD of the result live in `sc` (not released here).
+B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, int l_query,
+                              const uint8_t* query_, const B2Reg* ar, B2Scratch& sc, int* err) {
+  B2Aln a;
+  a.pos = 0; a.rid = 0; a.flag = 0; a.is_rev = a.is_alt = a.mapq = a.NM = 0; a.n_cigar = 0;
+  a.cigar = 0; a.md = 0; a.XA = 0; a.score = a.sub = a.alt_sc = 0;
+  if (ar == 0 || ar->rb < 0 || ar->re < 0) { a.rid = -1; a.pos = -1; a.flag |= 0x4; return a; }
+  int i, w2, tmp, qb = ar->qb, qe = ar->qe, score = 0, is_rev, last_sc = -(1 << 30);
+  int64_t pos, rb = ar->rb, re = ar->re;
+  a.mapq = (uint32_t)(ar->secondary < 0 ? b2_approx_mapq_se(opt, tb, ar, err) : 0) & 0xff;
+  if (ar->secondary >= 0) a.flag |= 0x100;
+  tmp = b2_infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_del, opt.e_del);
+  w2 = b2_infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_ins, opt.e_ins);
+  w2 = w2 > tmp ? w2 : tmp;
+  if (w2 > opt.w) w2 = w2 < ar->w ? w2 : ar->w;
+  B2Cigar cg;
+  cg.cap = (qe - qb) + (int)(re - rb) + 4;
+  cg.cigar = (uint32_t*)sc.alloc(sizeof(uint32_t) * (size_t)cg.cap, 4);
+  cg.md_cap = 2 * (int)(re - rb) + (qe - qb) + 32;
+  cg.md = (char*)sc.alloc((size_t)cg.md_cap, 1);
+  uint8_t* query = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
+  if (sc.overflow) { a.rid = -1; a.pos = -1; a.flag |= 0x4; return a; }
+  for (i = 0; i < l_query; ++i) query[i] = query_[i];
+  cg.n_cigar = 0; cg.NM = -1; cg.l_md = 0; cg.md[0] = 0;
+  i = 0;
+  do {
+    w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
+    b2_gen_cigar2(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cg, sc);
+    if (score == last_sc || w2 == opt.w << 2) break;
+    last_sc = score;
+    w2 <<= 1;
+  } while (++i < 3 && score < ar->truesc - opt.a);
+  a.NM = (uint32_t)cg.NM & 0x3fffff;
+  a.n_cigar = cg.n_cigar;
+  a.cigar = cg.cigar;
+  a.md = cg.md;
+  pos = b2_depos(ix.l_pac, rb < ix.l_pac ? rb : re - 1, &is_rev);
+  a.is_rev = (uint32_t)is_rev;
+  if (a.n_cigar > 0) {  // squeeze out a leading or trailing deletion
+    if ((a.cigar[0] & 0xf) == 2) {
+      pos += a.cigar[0] >> 4;
+      --a.n_cigar;
+      for (i = 0; i < a.n_cigar; ++i) a.cigar[i] = a.cigar[i + 1];
+    } else if ((a.cigar[a.n_cigar - 1] & 0xf) == 2) {
+      --a.n_cigar;
+    }
+  }
+  if (qb != 0 || qe != l_query) {  // clipping
+    int clip5 = is_rev ? l_query - qe : qb, clip3 = is_rev ? qb : l_query - qe;
+    if (clip5) {
+      for (i = a.n_cigar; i > 0; --i) a.cigar[i] = a.cigar[i - 1];
+      a.cigar[0] = (uint32_t)clip5 << 4 | 3;
+      ++a.n_cigar;
+    }
+    if (clip3) a.cigar[a.n_cigar++] = (uint32_t)clip3 << 4 | 3;
+  }
+  a.rid = b2_pos2rid(ix, pos);
+  a.pos = pos - ix.anns[a.rid].offset;
+  a.score = ar->score; a.sub = ar->sub > ar->csub ? ar->sub : ar->csub;
+  a.is_alt = (uint32_t)ar->is_alt & 1; a.alt_sc = ar->alt_sc;
+  return a;
+}
+
+// ---------------------------------------------------------------------------------------------
+// XA strings: XA[k] (k < n) -> NUL-terminated string in `sc` or null.
+B2_HD inline int b2_pri_idx(double XA_drop_ratio, const B2Reg* a, int i) {
+  int k = a[i].secondary_all;
+  if (k >= 0 && a[i].score >= a[k].score * XA_drop_ratio) return k;
+  return -1;
+}
+
+B2_HD inline char** b2_gen_alt(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, int n, const B2Reg* a,
+                               int l_query, const uint8_t* query, B2Scratch& sc, int* err) {
+  if (n == 0) return 0;
+  int* cnt = (int*)sc.alloc(sizeof(int) * (size_t)n, 4);
+  char* has_alt = (char*)sc.alloc((size_t)n, 1);
+  if (sc.overflow) return 0;
+  int i, r, tot = 0;
+  for (i = 0; i < n; ++i) { cnt[i] = 0; has_alt[i] = 0; }
+  for (i = 0; i < n; ++i) {
+    r = b2_pri_idx(opt.XA_drop_ratio, a, i);
+    if (r >= 0) { ++cnt[r]; ++tot; if (a[i].is_alt) has_alt[r] = 1; }
+  }
+  if (tot == 0) return 0;
+  char** XA = (char**)sc.alloc(sizeof(char*) * (size_t)n, 8);
+  int* xlen = (int*)sc.alloc(sizeof(int) * (size_t)n, 4);
+  if (sc.overflow) return 0;
+  for (i = 0; i < n; ++i) { XA[i] = 0; xlen[i] = 0; }
+  // two passes per primary would need the lengths first; instead each listed hit is formatted once
+  // into a temporary and appended to its primary's growing buffer, which is sized by cnt[r].
+  const int per_hit = 96 + 3 * l_query + ix.max_name_len;  // bound on one "name,+pos,cigar,NM;" entry (checked below)
+  for (i = 0; i < n; ++i)
+    if (cnt[i] > 0 && !(cnt[i] > opt.max_XA_hits_alt || (!has_alt[i] && cnt[i] > opt.max_XA_hits))) {
+      XA[i] = (char*)sc.alloc((size_t)cnt[i] * per_hit + 1, 1);
+      if (sc.overflow) return 0;
+      XA[i][0] = 0;
+    }
+  for (i = 0; i < n; ++i) {
+    if ((r = b2_pri_idx(opt.XA_drop_ratio, a, i)) < 0) continue;
+    if (cnt[r] > opt.max_XA_hits_alt || (!has_alt[r] && cnt[r] > opt.max_XA_hits)) continue;
+    const size_t mk = sc.mark();
+    B2Aln t = b2_reg2aln(opt, ix, tb, l_query, query, &a[i], sc, err);
+    B2Out o; o.p = XA[r] + xlen[r]; o.cap = (long)cnt[r] * per_hit - xlen[r]; o.len = 0;
+    const B2Ann& an = ix.anns[t.rid];
+    o.putsn(ix.names + an.name_off, an.name_len);
+    o.putc_(','); o.putc_("+-"[t.is_rev]); o.putl(t.pos + 1);
+    o.putc_(',');
+    for (int k = 0; k < t.n_cigar; ++k) { o.putl(t.cigar[k] >> 4); o.putc_("MIDSHN"[t.cigar[k] & 0xf]); }
+    o.putc_(','); o.putl((int)t.NM);
+    o.putc_(';');
+    if (o.len > o.cap) { sc.overflow = 1; sc.reset(mk); return 0; }
+    xlen[r] += (int)o.len;
+    XA[r][xlen[r]] = 0;
+    sc.reset(mk);
+  }
+  return XA;
+}
+
+// ---------------------------------------------------------------------------------------------
+// "%.3f" of score/alt_sc, rounding the exact binary value half-to-even like printf
+B2_HD inline void b2_put_f3(B2Out& o, double x) {
+  if (x < 0) { o.putc_('-'); x = -x; }
+  union { double d; uint64_t u; } cv; cv.d = x;
+  int e = (int)(cv.u >> 52 & 0x7ff);
+  uint64_t m = cv.u & ((1ull << 52) - 1);
+  if (e) m |= 1ull << 52; else e = 1;
+  e -= 1075;  // x = m * 2^e
+  unsigned long long q;  // round(x * 1000)
+  if (e >= 0) q = (m << e) * 1000ull;   // only small magnitudes occur (a ratio of two alignment scores)
+  else if (-e >= 64 + 10) q = 0;
+  else {
+    // m*1000 < 2^63; shift right by s = -e with round-half-even
+    unsigned long long v = m * 1000ull;
+    int s = -e;
+    if (s >= 64) q = 0;
+    else {
+      q = v >> s;
+      unsigned long long rem = v & ((1ull << s) - 1), half = 1ull << (s - 1);
+      if (rem > half || (rem == half && (q & 1))) ++q;
+    }
+  }
+  o.putl((long)(q / 1000));
+  o.putc_('.');
+  int f = (int)(q % 1000);
+  o.putc_('0' + f / 100); o.putc_('0' + f / 10 % 10); o.putc_('0' + f % 10);
+}
+
+B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, const B2Fmt& fmt, B2Out& str, const B2Read& s, int n,
+                             const B2Aln* list, int which, const B2Aln* m_) {
+  B2Aln ptmp = list[which], *p = &ptmp, mtmp, *m = 0;
+  int i;
+  if (m_) { mtmp = *m_; m = &mtmp; }
+  p->flag |= m ? 0x1 : 0;
+  p->flag |= p->rid < 0 ? 0x4 : 0;
+  p->flag |= m && m->rid < 0 ? 0x8 : 0;
+  if (p->rid < 0 && m && m->rid >= 0) { p->rid = m->rid; p->pos = m->pos; p->is_rev = m->is_rev; p->n_cigar = 0; }
+  if (m && m->rid < 0 && p->rid >= 0) { m->rid = p->rid; m->pos = p->pos; m->is_rev = p->is_rev; m->n_cigar = 0; }
+  p->flag |= p->is_rev ? 0x10 : 0;
+  p->flag |= m && m->is_rev ? 0x20 : 0;
+
+  str.putsn(s.name, s.l_name); str.putc_('\t');
+  str.putl((p->flag & 0xffff) | (p->flag & 0x10000 ? 0x100 : 0)); str.putc_('\t');
+  if (p->rid >= 0) {
+    const B2Ann& an = ix.anns[p->rid];
+    str.putsn(ix.names + an.name_off, an.name_len); str.putc_('\t');
+    str.putl(p->pos + 1); str.putc_('\t');
+    str.putl((int)p->mapq); str.putc_('\t');
+    if (p->n_cigar) {
+      for (i = 0; i < p->n_cigar; ++i) {
+        int c = p->cigar[i] & 0xf;
+        if (!(opt.flag & B2_F_SOFTCLIP) && !p->is_alt && (c == 3 || c == 4)) c = which ? 4 : 3;
+        str.putl(p->cigar[i] >> 4); str.putc_("MIDSH"[c]);
+      }
+    } else str.putc_('*');
+  } else str.putsn("*\t0\t0\t*", 7);
+  str.putc_('\t');
+
+  if (m && m->rid >= 0) {
+    if (p->rid == m->rid) str.putc_('=');
+    else { const B2Ann& an = ix.anns[m->rid]; str.putsn(ix.names + an.name_off, an.name_len); }
+    str.putc_('\t');
+    str.putl(m->pos + 1); str.putc_('\t');
+    if (p->rid == m->rid) {
+      int64_t p0 = p->pos + (p->is_rev ? b2_get_rlen(p->n_cigar, p->cigar) - 1 : 0);
+      int64_t p1 = m->pos + (m->is_rev ? b2_get_rlen(m->n_cigar, m->cigar) - 1 : 0);
+      if (m->n_cigar == 0 || p->n_cigar == 0) str.putc_('0');
+      else str.putl(-(p0 - p1 + (p0 > p1 ? 1 : p0 < p1 ? -1 : 0)));
+    } else str.putc_('0');
+  } else str.putsn("*\t0\t0", 5);
+  str.putc_('\t');
+
+  if (p->flag & 0x100) {
+    str.putsn("*\t*", 3);
+  } else if (!p->is_rev) {
+    int qb = 0, qe = s.l_seq;
+    if (p->n_cigar && which && !(opt.flag & B2_F_SOFTCLIP) && !p->is_alt) {
+      if ((p->cigar[0] & 0xf) == 4 || (p->cigar[0] & 0xf) == 3) qb += p->cigar[0] >> 4;
+      if ((p->cigar[p->n_cigar - 1] & 0xf) == 4 || (p->cigar[p->n_cigar - 1] & 0xf) == 3) qe -= p->cigar[p->n_cigar - 1] >> 4;
+    }
+    for (i = qb; i < qe; ++i) str.putc_("ACGTN"[s.seq[i]]);
+    str.putc_('\t');
+    if (s.qual) { for (i = qb; i < qe; ++i) str.putc_(s.qual[i]); }
+    else str.putc_('*');
+  } else {
+    int qb = 0, qe = s.l_seq;
+    if (p->n_cigar && which && !(opt.flag & B2_F_SOFTCLIP) && !p->is_alt) {
+      if ((p->cigar[0] & 0xf) == 4 || (p->cigar[0] & 0xf) == 3) qe -= p->cigar[0] >> 4;
+      if ((p->cigar[p->n_cigar - 1] & 0xf) == 4 || (p->cigar[p->n_cigar - 1] & 0xf) == 3) qb += p->cigar[p->n_cigar - 1] >> 4;
+    }
+    for (i = qe - 1; i >= qb; --i) str.putc_("TGCAN"[s.seq[i]]);
+    str.putc_('\t');
+    if (s.qual) { for (i = qe - 1; i >= qb; --i) str.putc_(s.qual[i]); }
+    else str.putc_('*');
+  }
+
+  if (p->n_cigar) {
+    str.putsn("\tNM:i:", 6); str.putl((int)p->NM);
+    str.putsn("\tMD:Z:", 6); str.puts_(p->md);
+  }
+  if (p->score >= 0) { str.putsn("\tAS:i:", 6); str.putl(p->score); }
+  if (p->sub >= 0) { str.putsn("\tXS:i:", 6); str.putl(p->sub); }
+  if (fmt.l_rg) { str.putsn("\tRG:Z:", 6); str.putsn(fmt.rg_id, fmt.l_rg); }
+  if (!(p->flag & 0x100)) {
+    for (i = 0; i < n; ++i)
+      if (i != which && !(list[i].flag & 0x100)) break;
+    if (i < n) {
+      str.putsn("\tSA:Z:", 6);
+      for (i = 0; i < n; ++i) {
+        const B2Aln* r = &list[i];
+        if (i == which || (r->flag & 0x100)) continue;
+        const B2Ann& an = ix.anns[r->rid];
+        str.putsn(ix.names + an.name_off, an.name_len); str.putc_(',');
+        str.putl(r->pos + 1); str.putc_(',');
+        str.putc_("+-"[r->is_rev]); str.putc_(',');
+        for (int k = 0; k < r->n_cigar; ++k) { str.putl(r->cigar[k] >> 4); str.putc_("MIDSH"[r->cigar[k] & 0xf]); }
+        str.putc_(','); str.putl((int)r->mapq);
+        str.putc_(','); str.putl((int)r->NM);
+        str.putc_(';');
+      }
+    }
+    if (p->alt_sc > 0) { str.putsn("\tpa:f:", 6); b2_put_f3(str, (double)p->score / p->alt_sc); }
+  }
+  if (p->XA) { str.putsn("\tXA:Z:", 6); str.puts_(p->XA); }
+  if (s.comment) { str.putc_('\t'); str.putsn(s.comment, s.l_comment); }
+  if ((opt.flag & B2_F_REF_HDR) && p->rid >= 0 && ix.anns[p->rid].anno_len > 0) {
+    const B2Ann& an = ix.anns[p->rid];
+    str.putsn("\tXR:Z:", 6);
+    for (i = 0; i < an.anno_len; ++i) { char c = ix.names[an.anno_off + i]; str.putc_(c == '\t' ? ' ' : c); }
+  }
+  str.putc_('\n');
+}
+
+// SE record set of one read (also the unpaired branch of PE).
+B2_HD inline void b2_reg2sam(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Fmt& fmt, B2Out& str,
+                             const B2Read& s, int n, B2Reg* a, int extra_flag, const B2Aln* m, B2Scratch& sc, int* err) {
+  const size_t mk = sc.mark();
+  char** XA = 0;
+  if (!(opt.flag & B2_F_ALL)) XA = b2_gen_alt(opt, ix, tb, n, a, s.l_seq, s.seq, sc, err);
+  B2Aln* aa = (B2Aln*)sc.alloc(sizeof(B2Aln) * (size_t)(n > 0 ? n : 1), 8);
+  if (sc.overflow) { sc.reset(mk); return; }
+  int n_aa = 0, k, l;
+  for (k = l = 0; k < n; ++k) {
+    B2Reg* p = &a[k];
+    if (p->score < opt.T) continue;
+    if (p->secondary >= 0 && (p->is_alt || !(opt.flag & B2_F_ALL))) continue;
+    if (p->secondary >= 0 && p->secondary < 0x7fffffff && p->score < a[p->secondary].score * opt.drop_ratio) continue;
+    B2Aln* q = &aa[n_aa++];
+    *q = b2_reg2aln(opt, ix, tb, s.l_seq, s.seq, p, sc, err);
+    q->XA = XA ? XA[k] : 0;
+    q->flag |= extra_flag;
+    if (p->secondary >= 0) q->sub = -1;
+    if (l && p->secondary < 0) q->flag |= (opt.flag & B2_F_NO_MULTI) ? 0x10000 : 0x800;
+    if (l && !p->is_alt && q->mapq > aa[0].mapq) q->mapq = aa[0].mapq;
+    ++l;
+  }
+  if (n_aa == 0) {
+    B2Aln t = b2_reg2aln(opt, ix, tb, s.l_seq, s.seq, 0, sc, err);
+    t.flag |= extra_flag;
+    b2_aln2sam(opt, ix, fmt, str, s, 1, &t, 0, m);
+  } else {
+    for (k = 0; k < n_aa; ++k) b2_aln2sam(opt, ix, fmt, str, s, n_aa, aa, k, m);
+  }
+  sc.reset(mk);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Paired-end
+B2_HD inline int b2_infer_dir(int64_t l_pac, int64_t b1, int64_t b2, int64_t* dist) {
+  int r1 = (b1 >= l_pac), r2 = (b2 >= l_pac);
+  int64_t p2 = r1 == r2 ? b2 : (l_pac << 1) - 1 - b2;
+  *dist = p2 > b1 ? p2 - b1 : b1 - p2;
+  return (r1 == r2 ? 0 : 1) ^ (p2 > b1 ? 0 : 3);
+}
+
+B2_HD inline int b2_cal_sub(const B2Opt& opt, int n, const B2Reg* a) {
+  int j;
+  for (j = 1; j < n; ++j) {
+    int b_max = a[j].qb > a[0].qb ? a[j].qb : a[0].qb;
+    int e_min = a[j].qe < a[0].qe ? a[j].qe : a[0].qe;
+    if (e_min > b_max) {
+      int min_l = a[j].qe - a[j].qb < a[0].qe - a[0].qb ? a[j].qe - a[j].qb : a[0].qe - a[0].qb;
+      if (e_min - b_max >= min_l * opt.mask_level) break;
+    }
+  }
+  return j < n ? a[j].score : opt.min_seed_len * opt.a;
+}
+
+// Insert-size candidate of one pair for mem_pestat (bwamem_pair.c:52-64).  Returns dir (0..3) or -1.
+B2_HD inline int b2_pestat_candidate(const B2Opt& opt, int64_t l_pac, int n0, const B2Reg* r0, int n1, const B2Reg* r1,
+                                     int64_t* is) {
+  if (n0 == 0 || n1 == 0) return -1;
+  if (b2_cal_sub(opt, n0, r0) > 0.8 * r0[0].score) return -1;
+  if (b2_cal_sub(opt, n1, r1) > 0.8 * r1[0].score) return -1;
+  if (r0[0].rid != r1[0].rid) return -1;
+  int dir = b2_infer_dir(l_pac, r0[0].rb, r1[0].rb, is);
+  if (*is && *is <= opt.max_ins) return dir;
+  return -1;
+}
+
+// Mate rescue.  ma[*n_ma] may grow up to cap_ma.
+B2_HD inline int b2_matesw(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const B2Reg* a, int l_ms,
+                           const uint8_t* ms, B2Reg* ma, int* n_ma, int cap_ma, B2Scratch& sc) {
+  const int64_t l_pac = ix.l_pac;
+  int i, r, skip[4], n = 0;
+  for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+  for (i = 0; i < *n_ma; ++i) {
+    int64_t dist;
+    r = b2_infer_dir(l_pac, a->rb, ma[i].rb, &dist);
+    if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
+  }
+  if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
+  for (r = 0; r < 4; ++r) {
+    if (skip[r]) continue;
+    const size_t mk = sc.mark();
+    int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+    int64_t rb, re;
+    int rid = -1, have_ref = 0;
+    uint8_t* seq = (uint8_t*)sc.alloc((size_t)l_ms + 1, 1);
+    if (sc.overflow) { sc.reset(mk); return n; }
+    if (is_rev) { for (i = 0; i < l_ms; ++i) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; }
+    else { for (i = 0; i < l_ms; ++i) seq[i] = ms[i]; }
+    if (!is_rev) {
+      rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
+      re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
+    } else {
+      rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
+      re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
+    }
+    if (rb < 0) rb = 0;
+    if (re > l_pac << 1) re = l_pac << 1;
+    uint8_t* ref = 0;
+    if (rb < re) {
+      rid = b2_fetch_bounds(ix, &rb, (rb + re) >> 1, &re);
+      ref = (uint8_t*)sc.alloc((size_t)(re - rb) + 1, 1);
+      if (sc.overflow) { sc.reset(mk); return n; }
+      b2_get_seq(l_pac, ix.pac, rb, re, ref);
+      have_ref = 1;
+    }
+    // (when rb >= re the reference reads an uninitialised rid; such windows never pass the test below
+    //  unless a stale value happens to match -- treated as "no window")
+    if (have_ref && a->rid == rid && re - rb >= opt.min_seed_len) {
+      int xtra = B2_KSW_XSUBO | B2_KSW_XSTART | (l_ms * opt.a < 250 ? B2_KSW_XBYTE : 0) | (opt.min_seed_len * opt.a);
+      int tl = (int)(re - rb);
+      int lanes = (xtra & B2_KSW_XBYTE) ? 16 : 8;
+      int npad = ((l_ms + lanes - 1) / lanes) * lanes;
+      int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
+      uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
+      if (sc.overflow) { sc.reset(mk); return n; }
+      B2Kswr aln = b2_align2(l_ms, seq, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, work, bbuf);
+      if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
+        B2Reg b = B2Reg();
+        b.rid = a->rid;
+        b.is_alt = a->is_alt;
+        b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+        b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+        b.rb = is_rev ? (l_pac << 1) - (rb + aln.te + 1) : rb + aln.tb;
+        b.re = is_rev ? (l_pac << 1) - (rb + aln.tb) : rb + aln.te + 1;
+        b.score = aln.score;
+        b.csub = aln.score2;
+        b.secondary = -1;
+        b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+        if (*n_ma >= cap_ma) { sc.overflow = 1; sc.reset(mk); return n; }
+        ++*n_ma;
+        for (i = 0; i < *n_ma - 1; ++i)
+          if (ma[i].score < b.score) break;
+        int tmp = i;
+        for (i = *n_ma - 1; i > tmp; --i) ma[i] = ma[i - 1];
+        ma[i] = b;
+      }
+      ++n;
+    }
+    if (n) *n_ma = b2_sort_dedup_patch(opt, ix, 0, 0, *n_ma, ma, sc);
+    sc.reset(mk);
+  }
+  return n;
+}
+
+struct B2Pair64 { uint64_t x, y; };
+struct B2Pair64Lt {
+  B2_HD bool operator()(const B2Pair64& a, const B2Pair64& b) const { return a.x < b.x || (a.x == b.x && a.y < b.y); }
+};
+
+// Best proper pair.  `id` is deliberately an int and `id<<8` wraps in 32 bits like the reference.
+B2_HD inline int b2_pair(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Pes pes[4], const B2Reg* a0,
+                         const B2Reg* a1, int id, int* sub, int* n_sub, int z[2], const int n_pri[2], B2Scratch& sc,
+                         int* err) {
+  const int64_t l_pac = ix.l_pac;
+  const size_t mk = sc.mark();
+  const int nv = n_pri[0] + n_pri[1];
+  B2Pair64* v = (B2Pair64*)sc.alloc(sizeof(B2Pair64) * (size_t)(nv > 0 ? nv : 1), 8);
+  if (sc.overflow) { sc.reset(mk); *sub = 0; *n_sub = 0; return 0; }
+  int r, i, k, y[4], n = 0;
+  for (r = 0; r < 2; ++r) {
+    const B2Reg* a = r ? a1 : a0;
+    for (i = 0; i < n_pri[r]; ++i) {
+      const B2Reg* e = &a[i];
+      B2Pair64 key;
+      key.x = (uint64_t)(e->rb < l_pac ? e->rb : (l_pac << 1) - 1 - e->rb);
+      key.x = (uint64_t)e->rid << 32 | (key.x - (uint64_t)ix.anns[e->rid].offset);
+      key.y = (uint64_t)e->score << 32 | (uint64_t)(i << 2) | (uint64_t)((e->rb >= l_pac) << 1) | (uint64_t)r;
+      v[n++] = key;
+    }
+  }
+  b2_introsort(v, (long)n, B2Pair64Lt());
+  // the reference materialises every candidate pair in u[], sorts it and reads the top two; the order is
+  // total, so the maximum, the runner-up and the count near the runner-up are tracked in two sweeps instead.
+  B2Pair64 best, second;
+  best.x = best.y = second.x = second.y = 0;
+  long n_u = 0;
+  const uint32_t id8 = (uint32_t)id << 8;
+  const uint64_t idx = (uint64_t)(int64_t)(int32_t)id8;  // sign-extended like `id<<8` promoted to uint64
+  int tmp = opt.a + opt.b;
+  tmp = tmp > opt.o_del + opt.e_del ? tmp : opt.o_del + opt.e_del;
+  tmp = tmp > opt.o_ins + opt.e_ins ? tmp : opt.o_ins + opt.e_ins;
+  int subv = 0, cnt = 0;
+  for (int pass = 0; pass < 2; ++pass) {
+    y[0] = y[1] = y[2] = y[3] = -1;
+    for (i = 0; i < n; ++i) {
+      for (r = 0; r < 2; ++r) {
+        int dir = r << 1 | (int)(v[i].y >> 1 & 1), which;
+        if (pes[dir].failed) continue;
+        which = r << 1 | (int)((v[i].y & 1) ^ 1);
+        if (y[which] < 0) continue;
+        for (k = y[which]; k >= 0; --k) {
+          int64_t dist;
+          int q;
+          if ((int)(v[k].y & 3) != which) continue;
+          dist = (int64_t)v[i].x - (int64_t)v[k].x;
+          if (dist > pes[dir].high) break;
+          if (dist < pes[dir].low) continue;
+          long ti = (long)(dist - pes[dir].low);
+          double term;
+          if (ti < 0 || ti >= tb.pair_n[dir]) { *err = 1; term = 0.; } else term = tb.pairtab[dir][ti];
+          q = (int)((double)((v[i].y >> 32) + (v[k].y >> 32)) + term + .499);
+          if (q < 0) q = 0;
+          B2Pair64 p;
+          p.y = (uint64_t)k << 32 | (uint64_t)i;
+          p.x = (uint64_t)q << 32 | (b2_hash64(p.y ^ idx) & 0xffffffffU);
+          if (pass == 0) {
+            if (n_u == 0) best = p;
+            else if (B2Pair64Lt()(best, p)) { second = best; best = p; }
+            else if (n_u == 1 || B2Pair64Lt()(second, p)) second = p;
+            ++n_u;
+          } else {
+            if (!(p.x == best.x && p.y == best.y) && subv - (int)(p.x >> 32) <= tmp) ++cnt;
+          }
+        }
+      }
+      y[v[i].y & 3] = i;
+    }
+    if (pass == 0) {
+      if (n_u == 0) break;
+      subv = n_u > 1 ? (int)(second.x >> 32) : 0;
+    }
+  }
+  int ret;
+  if (n_u) {
+    i = (int)(best.y >> 32); k = (int)(best.y << 32 >> 32);
+    z[v[i].y & 1] = (int)(v[i].y << 32 >> 34);
+    z[v[k].y & 1] = (int)(v[k].y << 32 >> 34);
+    ret = (int)(best.x >> 32);
+    *sub = subv;
+    *n_sub = n_u > 1 ? cnt : 0;
+  } else { ret = 0; *sub = 0; *n_sub = 0; }
+  sc.reset(mk);
+  return ret;
+}
+
+B2_HD inline int b2_raw_mapq(int diff, int a) { return (int)(6.02 * diff / a + .499); }
+
+// One read pair: rescue, primary marking, pairing, SAM text for both mates.
+// a[i] has capacity cap[i] and n[i] entries; id = global pair index.
+B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Fmt& fmt,
+                            const B2Pes pes[4], uint64_t id, const B2Read s[2], B2Reg* a[2], int n[2], const int cap[2],
+                            B2Out& out, B2Scratch& sc, int* err) {
+  int i, j, z[2] = {0, 0}, o, subo = 0, n_sub = 0, extra_flag = 1, n_pri[2];
+  B2Aln h[2];
+  const size_t mk0 = sc.mark();
+  if (!(opt.flag & B2_F_NO_RESCUE)) {
+    B2Reg* b[2];
+    int nb[2] = {0, 0};
+    for (i = 0; i < 2; ++i) {
+      b[i] = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)(n[i] > 0 ? n[i] : 1), 8);
+      if (sc.overflow) { sc.reset(mk0); return; }
+      for (j = 0; j < n[i]; ++j)
+        if (a[i][j].score >= a[i][0].score - opt.pen_unpaired) b[i][nb[i]++] = a[i][j];
+    }
+    for (i = 0; i < 2; ++i)
+      for (j = 0; j < nb[i] && j < opt.max_matesw; ++j)
+        b2_matesw(opt, ix, pes, &b[i][j], s[!i].l_seq, s[!i].seq, a[!i], &n[!i], cap[!i], sc);
+    sc.reset(mk0);
+  }
+  int zn = (n[0] > n[1] ? n[0] : n[1]) + 1;
+  int* zbuf = (int*)sc.alloc(sizeof(int) * (size_t)zn, 4);
+  if (sc.overflow) { sc.reset(mk0); return; }
+  n_pri[0] = b2_mark_primary_se(opt, n[0], a[0], (int64_t)(id << 1 | 0), zbuf);
+  n_pri[1] = b2_mark_primary_se(opt, n[1], a[1], (int64_t)(id << 1 | 1), zbuf);
+  int no_pairing = 0;
+  if (opt.flag & B2_F_NOPAIRING) no_pairing = 1;
+  if (!no_pairing && n_pri[0] && n_pri[1] &&
+      (o = b2_pair(opt, ix, tb, pes, a[0], a[1], (int)id, &subo, &n_sub, z, n_pri, sc, err)) > 0) {
+    int is_multi[2], q_pe, score_un, q_se[2];
+    for (i = 0; i < 2; ++i) {
+      for (j = 1; j < n_pri[i]; ++j)
+        if (a[i][j].secondary < 0 && a[i][j].score >= opt.T) break;
+      is_multi[i] = j < n_pri[i] ? 1 : 0;
+    }
+    if (is_multi[0] || is_multi[1]) no_pairing = 1;
+    if (!no_pairing) {
+      score_un = a[0][0].score + a[1][0].score - opt.pen_unpaired;
+      subo = subo > score_un ? subo : score_un;
+      q_pe = b2_raw_mapq(o - subo, opt.a);
+      if (n_sub > 0) q_pe -= (int)(4.343 * b2_log_int(tb, n_sub + 1, err) + .499);
+      if (q_pe < 0) q_pe = 0;
+      if (q_pe > 60) q_pe = 60;
+      q_pe = (int)(q_pe * (1. - .5 * (a[0][0].frac_rep + a[1][0].frac_rep)) + .499);
+      if (o > score_un) {
+        B2Reg* c[2];
+        c[0] = &a[0][z[0]]; c[1] = &a[1][z[1]];
+        for (i = 0; i < 2; ++i) {
+          if (c[i]->secondary >= 0) { c[i]->sub = a[i][c[i]->secondary].score; c[i]->secondary = -2; }
+          q_se[i] = b2_approx_mapq_se(opt, tb, c[i], err);
+        }
+        q_se[0] = q_se[0] > q_pe ? q_se[0] : q_pe < q_se[0] + 40 ? q_pe : q_se[0] + 40;
+        q_se[1] = q_se[1] > q_pe ? q_se[1] : q_pe < q_se[1] + 40 ? q_pe : q_se[1] + 40;
+        extra_flag |= 2;
+        q_se[0] = q_se[0] < b2_raw_mapq(c[0]->score - c[0]->csub, opt.a) ? q_se[0] : b2_raw_mapq(c[0]->score - c[0]->csub, opt.a);
+        q_se[1] = q_se[1] < b2_raw_mapq(c[1]->score - c[1]->csub, opt.a) ? q_se[1] : b2_raw_mapq(c[1]->score - c[1]->csub, opt.a);
+      } else {
+        z[0] = z[1] = 0;
+        q_se[0] = b2_approx_mapq_se(opt, tb, &a[0][0], err);
+        q_se[1] = b2_approx_mapq_se(opt, tb, &a[1][0], err);
+      }
+      for (i = 0; i < 2; ++i) {
+        int k = a[i][z[i]].secondary_all;
+        if (k >= 0 && k < n_pri[i]) {
+          for (j = 0; j < n[i]; ++j)
+            if (a[i][j].secondary_all == k || j == k) a[i][j].secondary_all = z[i];
+          a[i][z[i]].secondary_all = -1;
+        }
+      }
+      char** XA[2] = {0, 0};
+      if (!(opt.flag & B2_F_ALL))
+        for (i = 0; i < 2; ++i) XA[i] = b2_gen_alt(opt, ix, tb, n[i], a[i], s[i].l_seq, s[i].seq, sc, err);
+      B2Aln g[2], aa[2][2];
+      int n_aa[2] = {0, 0};
+      for (i = 0; i < 2; ++i) {
+        h[i] = b2_reg2aln(opt, ix, tb, s[i].l_seq, s[i].seq, &a[i][z[i]], sc, err);
+        h[i].mapq = (uint32_t)q_se[i] & 0xff;
+        h[i].flag |= 0x40 << i | extra_flag;
+        h[i].XA = XA[i] ? XA[i][z[i]] : 0;
+        aa[i][n_aa[i]++] = h[i];
+        if (n_pri[i] < n[i]) {
+          B2Reg* p = &a[i][n_pri[i]];
+          if (p->score < opt.T || p->secondary >= 0 || !p->is_alt) continue;
+          g[i] = b2_reg2aln(opt, ix, tb, s[i].l_seq, s[i].seq, p, sc, err);
+          g[i].flag |= 0x800 | 0x40 << i | extra_flag;
+          g[i].XA = XA[i] ? XA[i][n_pri[i]] : 0;
+          aa[i][n_aa[i]++] = g[i];
+        }
+      }
+      for (i = 0; i < n_aa[0]; ++i) b2_aln2sam(opt, ix, fmt, out, s[0], n_aa[0], aa[0], i, &h[1]);
+      for (i = 0; i < n_aa[1]; ++i) b2_aln2sam(opt, ix, fmt, out, s[1], n_aa[1], aa[1], i, &h[0]);
+      sc.reset(mk0);
+      return;
+    }
+  }
+  // no_pairing
+  for (i = 0; i < 2; ++i) {
+    int which = -1;
+    if (n[i]) {
+      if (a[i][0].score >= opt.T) which = 0;
+      else if (n_pri[i] < n[i] && a[i][n_pri[i]].score >= opt.T) which = n_pri[i];
+    }
+    if (which >= 0) h[i] = b2_reg2aln(opt, ix, tb, s[i].l_seq, s[i].seq, &a[i][which], sc, err);
+    else h[i] = b2_reg2aln(opt, ix, tb, s[i].l_seq, s[i].seq, 0, sc, err);
+  }
+  if (!(opt.flag & B2_F_NOPAIRING) && h[0].rid == h[1].rid && h[0].rid >= 0) {
+    int64_t dist;
+    int d = b2_infer_dir(ix.l_pac, a[0][0].rb, a[1][0].rb, &dist);
+    if (!pes[d].failed && dist >= pes[d].low && dist <= pes[d].high) extra_flag |= 2;
+  }
+  b2_reg2sam(opt, ix, tb, fmt, out, s[0], n[0], a[0], 0x41 | extra_flag, &h[1], sc, err);
+  b2_reg2sam(opt, ix, tb, fmt, out, s[1], n[1], a[1], 0x81 | extra_flag, &h[0], sc, err);
+  sc.reset(mk0);
+}

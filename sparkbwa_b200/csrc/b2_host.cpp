@@ -1,0 +1,830 @@
+// Host driver: option parsing, index loading, FASTA/Q batching, SAM header and the batch pipeline
+// around the GPU engine.  Mirrors the behaviour (not the code) of bwa/fastmap.c:115-364 (main_mem),
+// :38-97 (process), bwa/bwa.c:42-75 (bseq_read), :252-284 (index load), :370-450 (SAM header, -R/-H),
+// bwa/bntseq.c:98-206 (bns_restore) and bwa/kseq.h:175-215 (kseq_read).
+#include "b2_host.h"
+
+#include <ctype.h>
+#include <errno.h>
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+#include <sys/resource.h>
+#include <sys/time.h>
+#include <zlib.h>
+
+#include <condition_variable>
+#include <deque>
+#include <map>
+#include <memory>
+#include <mutex>
+#include <thread>
+
+thread_local std::string b2_tls_error;
+
+static int set_err(const char* fmt, ...) {
+  char buf[2048];
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(buf, sizeof(buf), fmt, ap);
+  va_end(ap);
+  b2_tls_error = buf;
+  return 1;
+}
+
+static double b2_realtime() {
+  struct timeval tp;
+  gettimeofday(&tp, 0);
+  return tp.tv_sec + tp.tv_usec * 1e-6;
+}
+static double b2_cputime() {
+  struct rusage r;
+  getrusage(RUSAGE_SELF, &r);
+  return r.ru_utime.tv_sec + r.ru_stime.tv_sec + 1e-6 * (r.ru_utime.tv_usec + r.ru_stime.tv_usec);
+}
+
+// ---------------------------------------------------------------------------------------------
+// Options
+void b2_opt_init(B2Opt* o) {
+  memset(o, 0, sizeof(*o));
+  o->a = 1; o->b = 4;
+  o->o_del = o->o_ins = 6;
+  o->e_del = o->e_ins = 1;
+  o->w = 100; o->T = 30; o->zdrop = 100;
+  o->pen_unpaired = 17;
+  o->pen_clip5 = o->pen_clip3 = 5;
+  o->max_mem_intv = 20;
+  o->min_seed_len = 19; o->split_width = 10; o->max_occ = 500;
+  o->max_chain_gap = 10000; o->max_ins = 10000;
+  o->mask_level = 0.50f; o->drop_ratio = 0.50f; o->XA_drop_ratio = 0.80f;
+  o->split_factor = 1.5f;
+  o->chunk_size = 10000000; o->n_threads = 1;
+  o->max_XA_hits = 5; o->max_XA_hits_alt = 200;
+  o->max_matesw = 50;
+  o->mask_level_redun = 0.95f;
+  o->min_chain_weight = 0;
+  o->max_chain_extend = 1 << 30;
+  o->mapQ_coef_len = 50;
+  o->mapQ_coef_fac = (int)log(o->mapQ_coef_len);
+  b2_fill_scmat(o->a, o->b, o->mat);
+}
+
+void b2_fill_scmat(int a, int b, int8_t mat[25]) {
+  int i, j, k;
+  for (i = k = 0; i < 4; ++i) {
+    for (j = 0; j < 4; ++j) mat[k++] = i == j ? a : -b;
+    mat[k++] = -1;
+  }
+  for (j = 0; j < 5; ++j) mat[k++] = -1;
+}
+
+static void unescape(std::string& s) {  // bwa_escape: \t \n \r \\ (unknown escapes vanish)
+  std::string o;
+  for (size_t i = 0; i < s.size(); ++i) {
+    if (s[i] == '\\') {
+      ++i;
+      if (i >= s.size()) break;
+      if (s[i] == 't') o += '\t';
+      else if (s[i] == 'n') o += '\n';
+      else if (s[i] == 'r') o += '\r';
+      else if (s[i] == '\\') o += '\\';
+    } else o += s[i];
+  }
+  s.swap(o);
+}
+
+static void insert_header(const std::string& s, std::string& hdr) {
+  if (s.empty() || s[0] != '@') return;
+  std::string t = s;
+  unescape(t);
+  if (!hdr.empty()) hdr += '\n';
+  hdr += t;
+}
+
+// Re-entrant scanner over the bwa-mem option string; options may follow positionals (glibc permutes).
+int b2_parse_mem_args(int argc, char** argv, B2MemArgs* m) {
+  static const char* spec = "1paMCSPVYjk:c:v:s:r:t:R:A:B:O:E:U:w:L:d:T:Q:D:m:I:N:W:x:G:h:y:K:X:H:";
+  B2Opt* opt = &m->opt;
+  B2Opt opt0;
+  b2_opt_init(opt);
+  memset(&opt0, 0, sizeof(opt0));
+  m->verbose = 3; m->copy_comment = 0; m->fixed_chunk_size = -1; m->ignore_alt = 0; m->has_pes0 = 0;
+  m->rg_id.clear(); m->hdr_line.clear(); m->positional.clear();
+  memset(m->pes0, 0, sizeof(m->pes0));
+  for (int i = 0; i < 4; ++i) m->pes0[i].failed = 1;
+  std::string mode, rg_line;
+  char* p;
+  bool opts_done = false;
+  for (int ai = 1; ai < argc; ++ai) {
+    const char* arg = argv[ai];
+    if (opts_done || arg[0] != '-' || arg[1] == 0) { m->positional.push_back(arg); continue; }
+    if (arg[1] == '-' && arg[2] == 0) { opts_done = true; continue; }
+    for (int ci = 1; arg[ci]; ++ci) {
+      const int c = arg[ci];
+      const char* sp = strchr(spec, c);
+      if (!sp || c == ':') { fprintf(stderr, "%s: invalid option -- '%c'\n", argv[0], c); return 1; }
+      const char* optarg = 0;
+      if (sp[1] == ':') {
+        if (arg[ci + 1]) optarg = arg + ci + 1;
+        else if (ai + 1 < argc) optarg = argv[++ai];
+        else { fprintf(stderr, "%s: option requires an argument -- '%c'\n", argv[0], c); return 1; }
+      }
+      if (c == 'k') opt->min_seed_len = atoi(optarg), opt0.min_seed_len = 1;
+      else if (c == '1') {}
+      else if (c == 'x') mode = optarg;
+      else if (c == 'w') opt->w = atoi(optarg), opt0.w = 1;
+      else if (c == 'A') opt->a = atoi(optarg), opt0.a = 1;
+      else if (c == 'B') opt->b = atoi(optarg), opt0.b = 1;
+      else if (c == 'T') opt->T = atoi(optarg), opt0.T = 1;
+      else if (c == 'U') opt->pen_unpaired = atoi(optarg), opt0.pen_unpaired = 1;
+      else if (c == 't') opt->n_threads = atoi(optarg), opt->n_threads = opt->n_threads > 1 ? opt->n_threads : 1;
+      else if (c == 'P') opt->flag |= B2_F_NOPAIRING;
+      else if (c == 'a') opt->flag |= B2_F_ALL;
+      else if (c == 'p') opt->flag |= B2_F_PE | B2_F_SMARTPE;
+      else if (c == 'M') opt->flag |= B2_F_NO_MULTI;
+      else if (c == 'S') opt->flag |= B2_F_NO_RESCUE;
+      else if (c == 'Y') opt->flag |= B2_F_SOFTCLIP;
+      else if (c == 'V') opt->flag |= B2_F_REF_HDR;
+      else if (c == 'c') opt->max_occ = atoi(optarg), opt0.max_occ = 1;
+      else if (c == 'd') opt->zdrop = atoi(optarg), opt0.zdrop = 1;
+      else if (c == 'v') m->verbose = atoi(optarg);
+      else if (c == 'j') m->ignore_alt = 1;
+      else if (c == 'r') opt->split_factor = atof(optarg), opt0.split_factor = 1.;
+      else if (c == 'D') opt->drop_ratio = atof(optarg), opt0.drop_ratio = 1.;
+      else if (c == 'm') opt->max_matesw = atoi(optarg), opt0.max_matesw = 1;
+      else if (c == 's') opt->split_width = atoi(optarg), opt0.split_width = 1;
+      else if (c == 'G') opt->max_chain_gap = atoi(optarg), opt0.max_chain_gap = 1;
+      else if (c == 'N') opt->max_chain_extend = atoi(optarg), opt0.max_chain_extend = 1;
+      else if (c == 'W') opt->min_chain_weight = atoi(optarg), opt0.min_chain_weight = 1;
+      else if (c == 'y') opt->max_mem_intv = atol(optarg), opt0.max_mem_intv = 1;
+      else if (c == 'C') m->copy_comment = 1;
+      else if (c == 'K') m->fixed_chunk_size = atoi(optarg);
+      else if (c == 'X') opt->mask_level = atof(optarg);
+      else if (c == 'h') {
+        opt0.max_XA_hits = opt0.max_XA_hits_alt = 1;
+        opt->max_XA_hits = opt->max_XA_hits_alt = strtol(optarg, &p, 10);
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) opt->max_XA_hits_alt = strtol(p + 1, &p, 10);
+      } else if (c == 'Q') {
+        opt0.mapQ_coef_len = 1;
+        opt->mapQ_coef_len = atoi(optarg);
+        opt->mapQ_coef_fac = opt->mapQ_coef_len > 0 ? log(opt->mapQ_coef_len) : 0;
+      } else if (c == 'O') {
+        opt0.o_del = opt0.o_ins = 1;
+        opt->o_del = opt->o_ins = strtol(optarg, &p, 10);
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) opt->o_ins = strtol(p + 1, &p, 10);
+      } else if (c == 'E') {
+        opt0.e_del = opt0.e_ins = 1;
+        opt->e_del = opt->e_ins = strtol(optarg, &p, 10);
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) opt->e_ins = strtol(p + 1, &p, 10);
+      } else if (c == 'L') {
+        opt0.pen_clip5 = opt0.pen_clip3 = 1;
+        opt->pen_clip5 = opt->pen_clip3 = strtol(optarg, &p, 10);
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) opt->pen_clip3 = strtol(p + 1, &p, 10);
+      } else if (c == 'R') {
+        std::string s = optarg;
+        if (s.compare(0, 3, "@RG") != 0) {
+          if (m->verbose >= 1) fprintf(stderr, "[E::bwa_set_rg] the read group line is not started with @RG\n");
+          return 1;
+        }
+        unescape(s);
+        size_t pid = s.find("\tID:");
+        if (pid == std::string::npos) {
+          if (m->verbose >= 1) fprintf(stderr, "[E::bwa_set_rg] no ID at the read group line\n");
+          return 1;
+        }
+        pid += 4;
+        size_t q = pid;
+        while (q < s.size() && s[q] != '\t' && s[q] != '\n') ++q;
+        if (q - pid + 1 > 256) {
+          if (m->verbose >= 1) fprintf(stderr, "[E::bwa_set_rg] @RG:ID is longer than 255 characters\n");
+          return 1;
+        }
+        m->rg_id = s.substr(pid, q - pid);
+        rg_line = s;
+      } else if (c == 'H') {
+        if (optarg[0] != '@') {
+          FILE* fp = fopen(optarg, "r");
+          if (fp) {
+            std::vector<char> buf(0x10000);
+            while (fgets(buf.data(), 0xffff, fp)) {
+              size_t l = strlen(buf.data());
+              if (l && buf[l - 1] == '\n') buf[l - 1] = 0;
+              insert_header(buf.data(), m->hdr_line);
+            }
+            fclose(fp);
+          }
+        } else insert_header(optarg, m->hdr_line);
+      } else if (c == 'I') {
+        B2Pes* pes = m->pes0;
+        m->has_pes0 = 1;
+        pes[1].failed = 0;
+        pes[1].avg = strtod(optarg, &p);
+        pes[1].std = pes[1].avg * .1;
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) pes[1].std = strtod(p + 1, &p);
+        pes[1].high = (int)(pes[1].avg + 4. * pes[1].std + .499);
+        pes[1].low = (int)(pes[1].avg - 4. * pes[1].std + .499);
+        if (pes[1].low < 1) pes[1].low = 1;
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) pes[1].high = (int)(strtod(p + 1, &p) + .499);
+        if (*p != 0 && ispunct(*p) && isdigit(p[1])) pes[1].low = (int)(strtod(p + 1, &p) + .499);
+        if (m->verbose >= 3)
+          fprintf(stderr, "[M::main_mem] mean insert size: %.3f, stddev: %.3f, max: %d, min: %d\n", pes[1].avg,
+                  pes[1].std, pes[1].high, pes[1].low);
+      }
+      if (sp[1] == ':') break;  // the rest of this token was the argument
+    }
+  }
+  if (!rg_line.empty()) {  // already unescaped
+    if (!m->hdr_line.empty()) m->hdr_line += '\n';
+    m->hdr_line += rg_line;
+  }
+  if (opt->n_threads < 1) opt->n_threads = 1;
+  if (!mode.empty()) {
+    if (mode == "intractg") {
+      if (!opt0.o_del) opt->o_del = 16;
+      if (!opt0.o_ins) opt->o_ins = 16;
+      if (!opt0.b) opt->b = 9;
+      if (!opt0.pen_clip5) opt->pen_clip5 = 5;
+      if (!opt0.pen_clip3) opt->pen_clip3 = 5;
+    } else if (mode == "pacbio" || mode == "pbref" || mode == "ont2d") {
+      if (!opt0.o_del) opt->o_del = 1;
+      if (!opt0.e_del) opt->e_del = 1;
+      if (!opt0.o_ins) opt->o_ins = 1;
+      if (!opt0.e_ins) opt->e_ins = 1;
+      if (!opt0.b) opt->b = 1;
+      if (opt0.split_factor == 0.) opt->split_factor = 10.;
+      if (mode == "ont2d") {
+        if (!opt0.min_chain_weight) opt->min_chain_weight = 20;
+        if (!opt0.min_seed_len) opt->min_seed_len = 14;
+      } else {
+        if (!opt0.min_chain_weight) opt->min_chain_weight = 40;
+        if (!opt0.min_seed_len) opt->min_seed_len = 17;
+      }
+      if (!opt0.pen_clip5) opt->pen_clip5 = 0;
+      if (!opt0.pen_clip3) opt->pen_clip3 = 0;
+    } else {
+      fprintf(stderr, "[E::main_mem] unknown read type '%s'\n", mode.c_str());
+      return 1;
+    }
+  } else if (opt0.a) {  // update_a: -A rescales the penalties the user did not set
+    if (!opt0.b) opt->b *= opt->a;
+    if (!opt0.T) opt->T *= opt->a;
+    if (!opt0.o_del) opt->o_del *= opt->a;
+    if (!opt0.e_del) opt->e_del *= opt->a;
+    if (!opt0.o_ins) opt->o_ins *= opt->a;
+    if (!opt0.e_ins) opt->e_ins *= opt->a;
+    if (!opt0.zdrop) opt->zdrop *= opt->a;
+    if (!opt0.pen_clip5) opt->pen_clip5 *= opt->a;
+    if (!opt0.pen_clip3) opt->pen_clip3 *= opt->a;
+    if (!opt0.pen_unpaired) opt->pen_unpaired *= opt->a;
+  }
+  b2_fill_scmat(opt->a, opt->b, opt->mat);
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Index files
+static int read_file(const std::string& fn, std::vector<char>& buf) {
+  FILE* fp = fopen(fn.c_str(), "rb");
+  if (!fp) return 1;
+  fseek(fp, 0, SEEK_END);
+  long n = ftell(fp);
+  fseek(fp, 0, SEEK_SET);
+  buf.resize(n);
+  size_t got = n ? fread(buf.data(), 1, n, fp) : 0;
+  fclose(fp);
+  return got != (size_t)n;
+}
+
+static std::string infer_prefix(const std::string& hint) {
+  FILE* fp;
+  if ((fp = fopen((hint + ".64.bwt").c_str(), "rb")) != 0) { fclose(fp); return hint + ".64"; }
+  if ((fp = fopen((hint + ".bwt").c_str(), "rb")) != 0) { fclose(fp); return hint; }
+  return std::string();
+}
+
+int b2_load_index(const char* hint, B2IndexHost* ix, int verbose, int meta_only) {
+  std::string prefix = infer_prefix(hint);
+  if (prefix.empty()) {
+    if (verbose >= 1) fprintf(stderr, "[E::bwa_idx_load_from_disk] fail to locate the index files\n");
+    return set_err("fail to locate the index files for '%s'", hint);
+  }
+  {  // .bwt
+    FILE* fp = fopen((prefix + ".bwt").c_str(), "rb");
+    if (!fp) return set_err("cannot open %s.bwt", prefix.c_str());
+    fseek(fp, 0, SEEK_END);
+    long sz = ftell(fp);
+    fseek(fp, 0, SEEK_SET);
+    uint64_t hdr[5];
+    if (sz < 40 || fread(hdr, 8, 5, fp) != 5) { fclose(fp); return set_err("truncated %s.bwt", prefix.c_str()); }
+    ix->primary = hdr[0];
+    ix->L2[0] = 0;
+    for (int i = 0; i < 4; ++i) ix->L2[i + 1] = hdr[i + 1];
+    ix->seq_len = ix->L2[4];
+    size_t words = (size_t)(sz - 40) >> 2;
+    ix->bwt.resize(meta_only ? 0 : words);
+    if (!meta_only && fread(ix->bwt.data(), 4, words, fp) != words) { fclose(fp); return set_err("truncated %s.bwt", prefix.c_str()); }
+    ix->bwt_words = words;
+    fclose(fp);
+  }
+  {  // .sa
+    FILE* fp = fopen((prefix + ".sa").c_str(), "rb");
+    if (!fp) return set_err("cannot open %s.sa", prefix.c_str());
+    uint64_t hdr[7];
+    if (fread(hdr, 8, 7, fp) != 7) { fclose(fp); return set_err("truncated %s.sa", prefix.c_str()); }
+    if (hdr[0] != ix->primary) { fclose(fp); return set_err("SA-BWT inconsistency: primary is not the same."); }
+    ix->sa_intv = (int)hdr[5];
+    if (hdr[6] != ix->seq_len) { fclose(fp); return set_err("SA-BWT inconsistency: seq_len is not the same."); }
+    size_t n_sa = (ix->seq_len + ix->sa_intv) / ix->sa_intv;
+    ix->n_sa = n_sa;
+    ix->sa.resize(meta_only ? 0 : n_sa);
+    if (!meta_only) {
+      ix->sa[0] = (uint64_t)-1;
+      if (fread(ix->sa.data() + 1, 8, n_sa - 1, fp) != n_sa - 1) { fclose(fp); return set_err("truncated %s.sa", prefix.c_str()); }
+    }
+    fclose(fp);
+  }
+  {  // .ann
+    FILE* fp = fopen((prefix + ".ann").c_str(), "r");
+    if (!fp) return set_err("cannot open %s.ann", prefix.c_str());
+    long long xx;
+    unsigned seed;
+    char str[8192];
+    if (fscanf(fp, "%lld%d%u", &xx, &ix->n_seqs, &seed) != 3) { fclose(fp); return set_err("Parse error reading %s.ann", prefix.c_str()); }
+    ix->l_pac = xx;
+    ix->anns.resize(ix->n_seqs);
+    ix->ann_names.resize(ix->n_seqs);
+    ix->names.clear();
+    for (int i = 0; i < ix->n_seqs; ++i) {
+      B2Ann& p = ix->anns[i];
+      unsigned gi;
+      char* q = str;
+      int c;
+      if (fscanf(fp, "%u%8191s", &gi, str) != 2) { fclose(fp); return set_err("Parse error reading %s.ann", prefix.c_str()); }
+      ix->ann_names[i] = str;
+      p.name_off = (int32_t)ix->names.size(); p.name_len = (int32_t)strlen(str);
+      ix->names += str;
+      while (q - str < (long)sizeof(str) - 1 && (c = fgetc(fp)) != '\n' && c != EOF) *q++ = c;
+      while (c != '\n' && c != EOF) c = fgetc(fp);
+      if (c == EOF) { fclose(fp); return set_err("Unexpected end of file reading %s.ann", prefix.c_str()); }
+      *q = 0;
+      std::string anno;
+      if (q - str > 1 && strcmp(str, " (null)") != 0) anno = str + 1;
+      p.anno_off = (int32_t)ix->names.size(); p.anno_len = (int32_t)anno.size();
+      ix->names += anno;
+      int n_ambs;
+      if (fscanf(fp, "%lld%d%d", &xx, &p.len, &n_ambs) != 3) { fclose(fp); return set_err("Parse error reading %s.ann", prefix.c_str()); }
+      p.offset = xx;
+      p.is_alt = 0;
+    }
+    fclose(fp);
+  }
+  {  // .amb: only consistency-checked (holes are not needed on the mem path)
+    FILE* fp = fopen((prefix + ".amb").c_str(), "r");
+    if (!fp) return set_err("cannot open %s.amb", prefix.c_str());
+    long long xx;
+    int n_seqs;
+    if (fscanf(fp, "%lld%d%d", &xx, &n_seqs, &ix->n_holes) != 3) { fclose(fp); return set_err("Parse error reading %s.amb", prefix.c_str()); }
+    fclose(fp);
+    if (xx != ix->l_pac || n_seqs != ix->n_seqs) return set_err("inconsistent .ann and .amb files.");
+  }
+  if (!meta_only) {  // .pac
+    FILE* fp = fopen((prefix + ".pac").c_str(), "rb");
+    if (!fp) return set_err("cannot open %s.pac", prefix.c_str());
+    ix->pac.resize(ix->l_pac / 4 + 1);
+    if (fread(ix->pac.data(), 1, ix->pac.size(), fp) != ix->pac.size()) { fclose(fp); return set_err("truncated %s.pac", prefix.c_str()); }
+    fclose(fp);
+  }
+  {  // .alt (optional)
+    FILE* fp = fopen((prefix + ".alt").c_str(), "r");
+    if (fp) {
+      std::map<std::string, int> h;
+      for (int i = 0; i < ix->n_seqs; ++i) h.insert(std::make_pair(ix->ann_names[i], i));  // first name wins (kh_put keeps the old key)
+      // note: the reference overwrites the value on duplicates (kh_val(h,k) = i): last index wins
+      for (int i = 0; i < ix->n_seqs; ++i) h[ix->ann_names[i]] = i;
+      std::string str;
+      int c;
+      while ((c = fgetc(fp)) != EOF) {
+        if (c == '\t' || c == '\n' || c == '\r') {
+          if (!str.empty() && str[0] != '@') {
+            std::map<std::string, int>::iterator it = h.find(str);
+            if (it != h.end()) ix->anns[it->second].is_alt = 1;
+          }
+          while (c != '\n' && c != EOF) c = fgetc(fp);
+          str.clear();
+        } else str += (char)c;
+      }
+      fclose(fp);
+    }
+  }
+  int c = 0;
+  for (int i = 0; i < ix->n_seqs; ++i) if (ix->anns[i].is_alt) ++c;
+  if (verbose >= 3) fprintf(stderr, "[M::bwa_idx_load_from_disk] read %d ALT contigs\n", c);
+  return 0;
+}
+
+std::string b2_sam_header(const B2IndexHost& ix, const std::string& hdr_line, const std::string& pg) {
+  std::string out;
+  int n_SQ = 0;
+  if (!hdr_line.empty()) {
+    size_t p = 0;
+    while ((p = hdr_line.find("@SQ\t", p)) != std::string::npos) {
+      if (p == 0 || hdr_line[p - 1] == '\n') ++n_SQ;
+      p += 4;
+    }
+  }
+  if (n_SQ == 0) {
+    char buf[64];
+    for (int i = 0; i < ix.n_seqs; ++i) {
+      out += "@SQ\tSN:"; out += ix.ann_names[i];
+      snprintf(buf, sizeof(buf), "\tLN:%d", ix.anns[i].len);
+      out += buf;
+      out += ix.anns[i].is_alt ? "\tAH:*\n" : "\n";
+    }
+  } else if (n_SQ != ix.n_seqs)
+    fprintf(stderr, "[W::bwa_print_sam_hdr] %d @SQ lines provided with -H; %d sequences in the index. Continue anyway.\n", n_SQ, ix.n_seqs);
+  if (!hdr_line.empty()) { out += hdr_line; out += '\n'; }
+  if (!pg.empty()) { out += pg; out += '\n'; }
+  return out;
+}
+
+// ---------------------------------------------------------------------------------------------
+// FASTA/FASTQ reader with kseq semantics
+static const unsigned char nt4_table[256] = {
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 0, 4, 1, 4, 4, 4, 2, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 3, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4,
+    4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4, 4};
+
+const unsigned char* b2_nt4_table() { return nt4_table; }
+
+struct B2SeqReader::Impl {
+  gzFile fp = 0;
+  std::vector<unsigned char> buf;
+  size_t begin = 0, end = 0;
+  bool is_eof = false;
+  int last_char = 0;
+  std::string name, comment, seq, qual;
+  int getc_() {
+    if (is_eof && begin >= end) return -1;
+    if (begin >= end) {
+      begin = 0;
+      int n = gzread(fp, buf.data(), (unsigned)buf.size());
+      end = n > 0 ? (size_t)n : 0;
+      if (end == 0) { is_eof = true; return -1; }
+    }
+    return buf[begin++];
+  }
+  // delimiter: 0 = any whitespace, 2 = newline.  Returns length or -1 at EOF without data.
+  int getuntil(int delim, std::string& str, int* dret, bool append) {
+    bool gotany = false;
+    if (dret) *dret = 0;
+    if (!append) str.clear();
+    for (;;) {
+      if (begin >= end) {
+        if (!is_eof) {
+          begin = 0;
+          int n = gzread(fp, buf.data(), (unsigned)buf.size());
+          end = n > 0 ? (size_t)n : 0;
+          if (end == 0) { is_eof = true; break; }
+        } else break;
+      }
+      size_t i;
+      if (delim == 2) {
+        const unsigned char* q = (const unsigned char*)memchr(buf.data() + begin, '\n', end - begin);
+        i = q ? (size_t)(q - buf.data()) : end;
+      } else {
+        for (i = begin; i < end; ++i) if (isspace(buf[i])) break;
+      }
+      gotany = true;
+      str.append((const char*)buf.data() + begin, i - begin);
+      begin = i + 1;
+      if (i < end) { if (dret) *dret = buf[i]; break; }
+    }
+    if (!gotany && is_eof && begin >= end) return -1;
+    if (delim == 2 && str.size() > 1 && str[str.size() - 1] == '\r') str.resize(str.size() - 1);
+    return (int)str.size();
+  }
+  int read() {
+    int c;
+    if (last_char == 0) {
+      while ((c = getc_()) != -1 && c != '>' && c != '@') {}
+      if (c == -1) return -1;
+      last_char = c;
+    }
+    comment.clear(); seq.clear(); qual.clear();
+    if (getuntil(0, name, &c, false) < 0) return -1;
+    if (c != '\n') getuntil(2, comment, 0, false);
+    while ((c = getc_()) != -1 && c != '>' && c != '+' && c != '@') {
+      if (c == '\n') continue;
+      seq += (char)c;
+      getuntil(2, seq, 0, true);
+    }
+    if (c == '>' || c == '@') last_char = c;
+    if (c != '+') return (int)seq.size();
+    while ((c = getc_()) != -1 && c != '\n') {}
+    if (c == -1) return -2;
+    while (getuntil(2, qual, 0, true) >= 0 && qual.size() < seq.size()) {}
+    last_char = 0;
+    if (seq.size() != qual.size()) return -2;
+    return (int)seq.size();
+  }
+};
+
+B2SeqReader::B2SeqReader() : impl_(new Impl) {}
+B2SeqReader::~B2SeqReader() { close(); delete impl_; }
+int B2SeqReader::open(const char* fn) {
+  impl_->fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(0, "r");
+  if (!impl_->fp) return 1;
+  gzbuffer(impl_->fp, 1 << 20);
+  impl_->buf.resize(1 << 20);
+  return 0;
+}
+void B2SeqReader::close() { if (impl_->fp) { gzclose(impl_->fp); impl_->fp = 0; } }
+int B2SeqReader::next() { return impl_->read(); }
+const std::string& B2SeqReader::name() const { return impl_->name; }
+const std::string& B2SeqReader::comment() const { return impl_->comment; }
+const std::string& B2SeqReader::seq() const { return impl_->seq; }
+const std::string& B2SeqReader::qual() const { return impl_->qual; }
+
+static void append_read(B2HostBatch* b, B2SeqReader* ks, int copy_comment) {
+  std::string name = ks->name();
+  // strlen semantics of the reference's strdup'ed strings: cut at an embedded NUL
+  size_t z = name.find('\0');
+  if (z != std::string::npos) name.resize(z);
+  size_t l = name.size();
+  if (l > 2 && name[l - 2] == '/' && isdigit((unsigned char)name[l - 1])) name.resize(l - 2);  // trim_readno
+  const std::string& s = ks->seq();
+  size_t ls = s.size();
+  z = s.find('\0');
+  if (z != std::string::npos) ls = z;
+  b->seq_off.push_back((int64_t)b->seq.size());
+  b->l_seq.push_back((int32_t)ls);
+  size_t o = b->seq.size();
+  b->seq.resize(o + ls);
+  for (size_t i = 0; i < ls; ++i) { unsigned char c = nt4_table[(unsigned char)s[i]]; b->seq[o + i] = c; }
+  b->qual.resize(o + ls);
+  if (!ks->qual().empty()) {
+    memcpy(b->qual.data() + o, ks->qual().data(), ls);
+    b->has_qual.push_back(1);
+  } else {
+    memset(b->qual.data() + o, 0, ls);
+    b->has_qual.push_back(0);
+  }
+  b->name_off.push_back((int64_t)b->names.size());
+  b->l_name.push_back((int32_t)name.size());
+  b->names.insert(b->names.end(), name.begin(), name.end());
+  if (copy_comment && !ks->comment().empty()) {
+    b->com_off.push_back((int64_t)b->comments.size());
+    b->l_com.push_back((int32_t)ks->comment().size());
+    b->comments.insert(b->comments.end(), ks->comment().begin(), ks->comment().end());
+  } else {
+    b->com_off.push_back(0);
+    b->l_com.push_back(-1);
+  }
+  ++b->n_reads;
+  b->n_bases += (int64_t)ls;
+  if ((int)ls > b->max_len) b->max_len = (int)ls;
+}
+
+// one batch exactly as bseq_read cuts it; returns the number of reads
+int b2_read_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, int copy_comment, B2HostBatch* b) {
+  b->clear();
+  int size = 0;
+  while (ks->next() >= 0) {
+    if (ks2 && ks2->next() < 0) {
+      fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n");
+      break;
+    }
+    append_read(b, ks, copy_comment);
+    size += b->l_seq.back();
+    if (ks2) {
+      append_read(b, ks2, copy_comment);
+      size += b->l_seq.back();
+    }
+    if (size >= chunk_size && (b->n_reads & 1) == 0) break;
+  }
+  if (size == 0) {
+    if (ks2 && ks2->next() >= 0) fprintf(stderr, "[W::bseq_read] the 1st file has fewer sequences.\n");
+  }
+  return b->n_reads;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Index cache: like `bwa shm` keeps the index in host shared memory (bwa/bwashm.c:87-118), the
+// device image stays resident across calls in one executor process, keyed by prefix.
+struct CachedIndex {
+  std::string prefix;
+  int device;
+  std::unique_ptr<B2IndexHost> host;
+  std::unique_ptr<B2Engine> engine;
+  bool ignore_alt;
+};
+static std::mutex g_cache_mu;
+static std::vector<std::unique_ptr<CachedIndex>> g_cache;
+static std::mutex g_run_mu;  // one aligning call at a time per process (the reference is not re-entrant either)
+
+B2Engine* b2_get_engine(const char* prefix, int device, int ignore_alt, const B2Opt& opt, const char* rg_id, int verbose,
+                        B2IndexHost** host_out) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  for (auto& c : g_cache)
+    if (c->prefix == prefix && c->device == device && c->ignore_alt == (ignore_alt != 0)) {
+      c->engine->set_options(opt, rg_id, verbose);
+      if (host_out) *host_out = c->host.get();
+      return c->engine.get();
+    }
+  std::unique_ptr<CachedIndex> c(new CachedIndex);
+  c->prefix = prefix; c->device = device; c->ignore_alt = ignore_alt != 0;
+  c->host.reset(new B2IndexHost);
+  if (b2_load_index(prefix, c->host.get(), verbose, 0)) return 0;
+  if (ignore_alt) for (auto& a : c->host->anns) a.is_alt = 0;
+  c->engine.reset(new B2Engine);
+  B2EngineConfig cfg;
+  cfg.device = device;
+  cfg.verbose = verbose;
+  b2_engine_config_from_env(&cfg);
+  if (c->engine->init(*c->host, opt, rg_id, cfg)) { set_err("%s", c->engine->last_error()); return 0; }
+  // the host copies of the big arrays are no longer needed once they are in HBM
+  std::vector<uint32_t>().swap(c->host->bwt);
+  std::vector<uint64_t>().swap(c->host->sa);
+  std::vector<uint8_t>().swap(c->host->pac);
+  if (host_out) *host_out = c->host.get();
+  B2Engine* e = c->engine.get();
+  g_cache.push_back(std::move(c));
+  return e;
+}
+
+void b2_engine_config_from_env(B2EngineConfig* cfg) {
+  const char* s;
+  if ((s = getenv("B200BWA_LANE_GRID"))) cfg->lane_grid = atoi(s);
+  if ((s = getenv("B200BWA_LANE_BLOCK"))) cfg->lane_block = atoi(s);
+  if ((s = getenv("B200BWA_SEED_GRID"))) cfg->seed_grid = atoi(s);
+  if ((s = getenv("B200BWA_SEED_BLOCK"))) cfg->seed_block = atoi(s);
+  if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
+  if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
+}
+
+// ---------------------------------------------------------------------------------------------
+// main_mem
+namespace {
+struct Job {
+  std::unique_ptr<B2HostBatch> batch;
+  std::string sam;
+  int rc = 0;
+  bool done = false;
+};
+}  // namespace
+
+int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdline) {
+  B2MemArgs m;
+  double t_real = b2_realtime();
+  if (b2_parse_mem_args(argc, argv, &m)) return 1;
+  if (m.positional.size() < 2 || m.positional.size() > 3) {
+    fprintf(stderr, "\nUsage: bwa mem [options] <idxbase> <in1.fq> [in2.fq]\n\n");
+    fprintf(stderr, "b200bwa accepts the option set of bwa-0.7.15 `mem` (see bwa.1); -p is not supported.\n\n");
+    return 1;
+  }
+  std::lock_guard<std::mutex> run_lock(g_run_mu);
+  B2Opt opt = m.opt;
+  B2SeqReader ks, ks2;
+  bool have2 = false;
+  // index first (same order of failure modes as the reference: index, then reads)
+  B2IndexHost* host = 0;
+  int device = 0;
+  if (getenv("B200BWA_DEVICE")) device = atoi(getenv("B200BWA_DEVICE"));
+  if (ks.open(m.positional[1].c_str())) {
+    // the reference loads the index before opening the reads; keep its message and code
+    B2Engine* probe = b2_get_engine(m.positional[0].c_str(), device, m.ignore_alt, opt, m.rg_id.c_str(), m.verbose, &host);
+    if (!probe) return 1;
+    if (m.verbose >= 1) fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", m.positional[1].c_str());
+    return set_err("fail to open file `%s'", m.positional[1].c_str());
+  }
+  if (m.positional.size() == 3) {
+    if (opt.flag & B2_F_PE) {
+      if (m.verbose >= 2) fprintf(stderr, "[W::main_mem] when '-p' is in use, the second query file is ignored.\n");
+    } else {
+      if (ks2.open(m.positional[2].c_str())) {
+        if (m.verbose >= 1) fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", m.positional[2].c_str());
+        return set_err("fail to open file `%s'", m.positional[2].c_str());
+      }
+      have2 = true;
+      opt.flag |= B2_F_PE;
+    }
+  }
+  if (opt.flag & B2_F_SMARTPE) {
+    fprintf(stderr, "[E::main_mem] smart pairing (-p) is not supported by b200bwa\n");
+    return set_err("smart pairing (-p) is not supported");
+  }
+  B2Engine* eng = b2_get_engine(m.positional[0].c_str(), device, m.ignore_alt, opt, m.rg_id.c_str(), m.verbose, &host);
+  if (!eng) return 1;
+
+  FILE* out = stdout;
+  if (out_path) {
+    out = fopen(out_path, "wb");
+    if (!out) { fprintf(stderr, "[E::main_mem] fail to open output `%s'.\n", out_path); return set_err("fail to open output `%s'", out_path); }
+    setvbuf(out, 0, _IOFBF, 1 << 22);
+  }
+  std::string hdr = b2_sam_header(*host, m.hdr_line, pg_cmdline ? pg_cmdline : "");
+  fwrite(hdr.data(), 1, hdr.size(), out);
+
+  const int chunk = m.fixed_chunk_size > 0 ? m.fixed_chunk_size : opt.chunk_size * opt.n_threads;
+  const B2Pes* pes0 = m.has_pes0 ? m.pes0 : 0;
+  const int n_workers = eng->n_workers();
+
+  // Pipeline (kt_pipeline's three ordered steps): reader thread -> GPU workers -> ordered writer (this thread).
+  std::mutex mu;
+  std::condition_variable cv;
+  std::deque<std::shared_ptr<Job>> todo, inorder;
+  bool read_done = false, failed = false;
+  const size_t max_inflight = (size_t)n_workers + 2;
+
+  std::thread reader([&]() {
+    int64_t n_processed = 0;
+    for (;;) {
+      std::shared_ptr<Job> j(new Job);
+      j->batch.reset(new B2HostBatch);
+      int n = b2_read_batch(chunk, &ks, have2 ? &ks2 : 0, m.copy_comment, j->batch.get());
+      if (n == 0) break;
+      j->batch->n_processed = n_processed;
+      n_processed += n;
+      if (m.verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)j->batch->n_bases);
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
+      if (failed) break;
+      todo.push_back(j);
+      inorder.push_back(j);
+      cv.notify_all();
+    }
+    std::lock_guard<std::mutex> lk(mu);
+    read_done = true;
+    cv.notify_all();
+  });
+
+  std::vector<std::thread> gpu;
+  for (int wi = 0; wi < n_workers; ++wi)
+    gpu.emplace_back([&, wi]() {
+      for (;;) {
+        std::shared_ptr<Job> j;
+        {
+          std::unique_lock<std::mutex> lk(mu);
+          cv.wait(lk, [&] { return !todo.empty() || read_done || failed; });
+          if (failed || (todo.empty() && read_done)) return;
+          j = todo.front();
+          todo.pop_front();
+        }
+        double ct = b2_cputime(), rt = b2_realtime();
+        int rc = eng->process(*j->batch, pes0, j->sam, wi);
+        if (m.verbose >= 3 && !rc)
+          fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", j->batch->n_reads,
+                  b2_cputime() - ct, b2_realtime() - rt);
+        j->batch.reset();
+        std::lock_guard<std::mutex> lk(mu);
+        j->rc = rc; j->done = true;
+        if (rc) { failed = true; b2_tls_error = eng->last_error(); }
+        cv.notify_all();
+      }
+    });
+
+  int rc = 0;
+  std::string errmsg;
+  for (;;) {
+    std::shared_ptr<Job> j;
+    {
+      std::unique_lock<std::mutex> lk(mu);
+      cv.wait(lk, [&] { return failed || (!inorder.empty() && inorder.front()->done) || (inorder.empty() && read_done); });
+      if (failed) { rc = 1; break; }
+      if (inorder.empty()) break;
+      j = inorder.front();
+      inorder.pop_front();
+      cv.notify_all();
+    }
+    if (fwrite(j->sam.data(), 1, j->sam.size(), out) != j->sam.size()) {
+      std::lock_guard<std::mutex> lk(mu);
+      failed = true; rc = 1; errmsg = "write error on SAM output";
+      cv.notify_all();
+      break;
+    }
+  }
+  {
+    std::lock_guard<std::mutex> lk(mu);
+    if (rc) failed = true;
+    cv.notify_all();
+  }
+  reader.join();
+  for (auto& t : gpu) t.join();
+  if (rc) set_err("%s", errmsg.empty() ? eng->last_error() : errmsg.c_str());
+  if (out_path) { if (fclose(out) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }
+  else fflush(out);
+  if (rc == 0 && m.verbose >= 3) {
+    fprintf(stderr, "[main] Version: %s\n", B200BWA_VERSION);
+    fprintf(stderr, "[main] CMD:");
+    if (pg_cmdline) { const char* p = strstr(pg_cmdline, "CL:"); fprintf(stderr, " %s", p ? p + 3 : ""); }
+    fprintf(stderr, "\n[main] Real time: %.3f sec; CPU: %.3f sec\n", b2_realtime() - t_real, b2_cputime());
+  }
+  return rc;
+}

@@ -1,0 +1,300 @@
+// Kernel bodies of the batch pipeline (mem_process_seqs, bwa/bwamem.c:1172-1201, re-staged for a GPU):
+//   k_seed    SMEM seeding, one B2_SEED_LANES-lane group per read           (mem_collect_intv)
+//   k_sa      one task per sampled suffix-array position                     (bwt_sa + bns_intv2rid)
+//   k_chain   chaining + chain filter, one read per lane                     (mem_chain, mem_chain_flt)
+//   k_extend  seed extension + de-dup, one read per lane                     (mem_chain2aln, mem_sort_dedup_patch)
+//   k_pestat  insert-size candidates, one pair per lane                      (mem_pestat, first loop)
+//   k_final_* primary marking, rescue, pairing, CIGAR, SAM text              (worker2)
+//   k_scan / k_gather  ordered compaction of the per-read SAM slots
+// Every kernel is idempotent (inputs are never modified) so the host can re-run a stage with larger
+// scratch when a capacity flag is raised.
+#pragma once
+#include "b2_backend.h"
+#include "b2_types.h"
+#include "b2_bwt.cuh"
+#include "b2_chain.cuh"
+#include "b2_align.cuh"
+#include "b2_final.cuh"
+
+#define B2_FLAG_OVF_INTV 1
+#define B2_FLAG_OVF_SCRATCH 2
+#define B2_FLAG_OVF_SLOT 4
+#define B2_FLAG_ERR_TABLE 8
+#define B2_FLAG_OVF_REG 16
+
+struct B2Batch {  // device-resident read batch
+  int n_reads;
+  const uint8_t* seq;       // base codes 0..4, concatenated
+  const char* qual;         // same offsets as seq
+  const uint8_t* has_qual;  // per read
+  const char* names;
+  const char* comments;
+  const int64_t* seq_off;
+  const int32_t* l_seq;
+  const int64_t* name_off;
+  const int32_t* l_name;
+  const int64_t* com_off;
+  const int32_t* l_com;     // -1: no comment
+};
+
+struct B2Ctx {
+  B2Opt opt;
+  B2Index ix;
+  B2Batch b;
+  B2Tables tb;
+  B2Fmt fmt;
+  B2Pes pes[4];
+  int64_t n_processed;
+  int max_len;            // longest read in the batch
+  int* flags;
+  // seeding
+  B2Intv* intv; int cap_intv; int32_t* n_intv; int32_t* n_tasks;
+  B2Intv* seed_scratch;   // per group: 3*(max_len+1)
+  // SA / chaining
+  const int64_t* seed_off; int64_t n_seed_tasks;
+  B2Seed* raw; int32_t* raw_rid;
+  B2Chain* chains; B2Seed* cseeds; int32_t* n_chain; int32_t* reg_cap;
+  // extension
+  const int64_t* reg_off; B2Reg* regs; int32_t* n_regs;
+  // per-lane scratch for the lane-per-read kernels
+  uint8_t* scratch; size_t scratch_per_lane;
+  // pestat
+  int8_t* pe_dir; int64_t* pe_is;
+  // SAM
+  char* slots; int slot_size; int32_t* sam_len; const int64_t* sam_off; char* sam_out;
+};
+
+B2_HD inline B2Read b2_make_read(const B2Batch& b, int r, int copy_comment) {
+  B2Read s;
+  s.seq = b.seq + b.seq_off[r];
+  s.qual = b.has_qual[r] ? b.qual + b.seq_off[r] : 0;
+  s.name = b.names + b.name_off[r];
+  s.l_seq = b.l_seq[r]; s.l_name = b.l_name[r];
+  if (copy_comment && b.l_com[r] >= 0) { s.comment = b.comments + b.com_off[r]; s.l_comment = b.l_com[r]; }
+  else { s.comment = 0; s.l_comment = 0; }
+  return s;
+}
+
+B2_KERNEL k_seed(B2Ctx c) {
+  const int gid = B2_GTID() / B2_LANE_GROUP, n_groups = B2_GSIZE() / B2_LANE_GROUP;
+#if defined(B2_HOSTSIM)
+  B2OccScalar occ;
+#else
+  B2OccCoop occ;
+  occ.g = threadIdx.x & (B2_SEED_LANES - 1);
+  occ.mask = ((1u << B2_SEED_LANES) - 1) << ((threadIdx.x & 31) & ~(B2_SEED_LANES - 1));
+#endif
+  B2Intv* scratch = c.seed_scratch + (size_t)gid * 3 * (size_t)(c.max_len + 1);
+  for (int r = gid; r < c.b.n_reads; r += n_groups) {
+    const int len = c.b.l_seq[r];
+    int n = 0;
+    long tasks = 0;
+    B2Intv* out = c.intv + (size_t)r * c.cap_intv;
+    if (len >= c.opt.min_seed_len) {
+      n = b2_collect_intv(c.opt, c.ix, occ, len, c.b.seq + c.b.seq_off[r], out, c.cap_intv, scratch);
+      if (n > c.cap_intv) { if (occ.leader()) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_INTV); n = c.cap_intv; }
+      for (int i = 0; i < n; ++i) tasks += out[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)out[i].x[2];
+    }
+    if (occ.leader()) { c.n_intv[r] = n; c.n_tasks[r] = (int32_t)tasks; }
+  }
+}
+
+B2_KERNEL k_sa(B2Ctx c) {
+  for (int64_t t = B2_GTID(); t < c.n_seed_tasks; t += B2_GSIZE()) {
+    int lo = 0, hi = c.b.n_reads;  // last r with seed_off[r] <= t
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.seed_off[mid] <= t) lo = mid; else hi = mid; }
+    const int r = lo;
+    long idx = (long)(t - c.seed_off[r]);
+    const B2Intv* iv = c.intv + (size_t)r * c.cap_intv;
+    const int n = c.n_intv[r];
+    int i = 0;
+    for (; i < n; ++i) {
+      long cnt = iv[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)iv[i].x[2];
+      if (idx < cnt) break;
+      idx -= cnt;
+    }
+    const B2Intv& p = iv[i];
+    const long step = p.x[2] > (uint64_t)c.opt.max_occ ? (long)(p.x[2] / c.opt.max_occ) : 1;
+    const int slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
+    B2Seed s;
+    s.rbeg = (int64_t)b2_sa(c.ix, p.x[0] + (uint64_t)(idx * step));
+    s.qbeg = (int32_t)(p.info >> 32);
+    s.len = s.score = slen;
+    s.next = -1;
+    c.raw[t] = s;
+    c.raw_rid[t] = b2_intv2rid(c.ix, s.rbeg, s.rbeg + s.len);
+  }
+}
+
+B2_HD inline B2Scratch b2_lane_scratch(const B2Ctx& c, int lane) {
+  B2Scratch sc;
+  sc.base = c.scratch + (size_t)lane * c.scratch_per_lane;
+  sc.cap = c.scratch_per_lane; sc.used = 0; sc.overflow = 0;
+  return sc;
+}
+
+B2_KERNEL k_chain(B2Ctx c) {
+  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
+  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+    const int64_t off = c.seed_off[r];
+    const int n_raw = (int)(c.seed_off[r + 1] - off);
+    int kept = 0, cap = 0;
+    if (n_raw > 0) {
+      sc.reset(0);
+      const int node_cap = n_raw / 3 + 4;
+      B2Seed* raw = (B2Seed*)sc.alloc(sizeof(B2Seed) * (size_t)n_raw, 8);
+      B2Chain* tree_ch = (B2Chain*)sc.alloc(sizeof(B2Chain) * (size_t)n_raw, 8);
+      int* order = (int*)sc.alloc(sizeof(int) * (size_t)n_raw, 4);
+      B2BtNode* nodes = (B2BtNode*)sc.alloc(sizeof(B2BtNode) * (size_t)node_cap, 4);
+      if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+      else {
+        for (int i = 0; i < n_raw; ++i) { raw[i] = c.raw[off + i]; raw[i].next = c.raw_rid[off + i]; }
+        int ovf = 0;
+        kept = b2_chain_read(c.opt, c.ix.l_pac, c.ix.anns, c.b.l_seq[r], c.intv + (size_t)r * c.cap_intv, c.n_intv[r],
+                             raw, n_raw, tree_ch, c.chains + off, c.cseeds + off, order, nodes, node_cap, &ovf);
+        if (ovf) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH);
+        for (int i = 0; i < kept; ++i) cap += c.chains[off + i].n;
+      }
+    }
+    c.n_chain[r] = kept;
+    c.reg_cap[r] = cap;
+  }
+}
+
+B2_KERNEL k_extend(B2Ctx c) {
+  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
+  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+    const int64_t off = c.seed_off[r];
+    const int nch = c.n_chain[r];
+    const int l_seq = c.b.l_seq[r];
+    B2Reg* av = c.regs + c.reg_off[r];
+    const int cap = (int)(c.reg_off[r + 1] - c.reg_off[r]);
+    int n_av = 0;
+    sc.reset(0);
+    if (nch > 0) {
+      int max_n = 0;
+      for (int i = 0; i < nch; ++i) max_n = max_n > c.chains[off + i].n ? max_n : c.chains[off + i].n;
+      uint64_t* srt = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)max_n, 8);
+      uint8_t* query = (uint8_t*)sc.alloc((size_t)l_seq + 1, 1);
+      if (!sc.overflow) {
+        const uint8_t* q0 = c.b.seq + c.b.seq_off[r];
+        for (int i = 0; i < l_seq; ++i) query[i] = q0[i];
+        for (int i = 0; i < nch && !sc.overflow; ++i) {
+          const B2Chain& ch = c.chains[off + i];
+          b2_chain2aln(c.opt, c.ix, l_seq, query, ch, c.cseeds + off + ch.seed_head, av, &n_av, cap, srt, sc);
+        }
+        if (!sc.overflow) n_av = b2_sort_dedup_patch(c.opt, c.ix, 1, query, n_av, av, sc);
+        for (int i = 0; i < n_av; ++i)
+          if (av[i].rid >= 0 && c.ix.anns[av[i].rid].is_alt) av[i].is_alt = 1;
+      }
+      if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; n_av = 0; }
+    }
+    c.n_regs[r] = n_av;
+  }
+}
+
+B2_KERNEL k_pestat(B2Ctx c) {
+  const int n_pairs = c.b.n_reads >> 1;
+  for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
+    int64_t is = 0;
+    int d = b2_pestat_candidate(c.opt, c.ix.l_pac, c.n_regs[2 * i], c.regs + c.reg_off[2 * i], c.n_regs[2 * i + 1],
+                                c.regs + c.reg_off[2 * i + 1], &is);
+    c.pe_dir[i] = (int8_t)d;
+    c.pe_is[i] = is;
+  }
+}
+
+B2_KERNEL k_final_se(B2Ctx c) {
+  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
+  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+    sc.reset(0);
+    int err = 0;
+    const int n = c.n_regs[r];
+    B2Reg* a = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)(n > 0 ? n : 1), 8);
+    int* z = (int*)sc.alloc(sizeof(int) * (size_t)(n + 1), 4);
+    B2Out out; out.p = c.slots + (size_t)r * c.slot_size; out.cap = c.slot_size; out.len = 0;
+    if (!sc.overflow) {
+      for (int i = 0; i < n; ++i) a[i] = c.regs[c.reg_off[r] + i];
+      B2Read s = b2_make_read(c.b, r, 1);
+      b2_mark_primary_se(c.opt, n, a, c.n_processed + r, z);
+      b2_reg2sam(c.opt, c.ix, c.tb, c.fmt, out, s, n, a, 0, 0, sc, &err);
+    }
+    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+    if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE);
+    if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
+    c.sam_len[r] = (int32_t)out.len;
+  }
+}
+
+B2_KERNEL k_final_pe(B2Ctx c) {
+  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
+  const int n_pairs = c.b.n_reads >> 1;
+  for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
+    sc.reset(0);
+    int err = 0;
+    int n[2], cap[2];
+    B2Reg* a[2];
+    B2Read s[2];
+    n[0] = c.n_regs[2 * i]; n[1] = c.n_regs[2 * i + 1];
+    for (int k = 0; k < 2; ++k) {
+      int other = n[!k] < c.opt.max_matesw ? n[!k] : c.opt.max_matesw;
+      cap[k] = n[k] + ((c.opt.flag & B2_F_NO_RESCUE) ? 0 : 4 * other) + 1;
+      a[k] = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)cap[k], 8);
+      s[k] = b2_make_read(c.b, 2 * i + k, 1);
+    }
+    B2Out out; out.p = c.slots + (size_t)i * c.slot_size; out.cap = c.slot_size; out.len = 0;
+    if (!sc.overflow) {
+      for (int k = 0; k < 2; ++k)
+        for (int j = 0; j < n[k]; ++j) a[k][j] = c.regs[c.reg_off[2 * i + k] + j];
+      b2_sam_pe(c.opt, c.ix, c.tb, c.fmt, c.pes, (uint64_t)((c.n_processed >> 1) + i), s, a, n, cap, out, sc, &err);
+    }
+    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+    if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE);
+    if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
+    c.sam_len[i] = (int32_t)out.len;
+  }
+}
+
+// exclusive scan int32 -> int64, out[n] = total.  One block.
+B2_KERNEL k_scan(const int32_t* in, int64_t* out, int n) {
+#if defined(B2_HOSTSIM)
+  if (B2_GTID() != 0) return;
+  int64_t s = 0;
+  for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
+  out[n] = s;
+#else
+  __shared__ int64_t part[1024];
+  const int t = threadIdx.x, T = blockDim.x;
+  const int chunk = (n + T - 1) / T;
+  const int b = t * chunk, e = b + chunk < n ? b + chunk : n;
+  int64_t s = 0;
+  for (int i = b; i < e; ++i) s += in[i];
+  part[t] = s;
+  __syncthreads();
+  for (int d = 1; d < T; d <<= 1) {
+    int64_t v = t >= d ? part[t - d] : 0;
+    __syncthreads();
+    part[t] += v;
+    __syncthreads();
+  }
+  int64_t base = t ? part[t - 1] : 0;
+  for (int i = b; i < e; ++i) { out[i] = base; base += in[i]; }
+  if (t == T - 1) out[n] = part[T - 1];
+#endif
+}
+
+// ordered compaction of SAM slots: 16-byte pieces, one per lane
+B2_KERNEL k_gather(B2Ctx c, int n_items) {
+  const int pieces = (c.slot_size + 15) / 16;
+  const int64_t total = (int64_t)n_items * pieces;
+  for (int64_t t = B2_GTID(); t < total; t += B2_GSIZE()) {
+    const int item = (int)(t / pieces), pc = (int)(t % pieces);
+    const int len = c.sam_len[item];
+    const int b = pc * 16;
+    if (b >= len) continue;
+    const int e = b + 16 < len ? b + 16 : len;
+    const char* src = c.slots + (size_t)item * c.slot_size;
+    char* dst = c.sam_out + c.sam_off[item];
+    for (int k = b; k < e; ++k) dst[k] = src[k];
+  }
+}

@@ -1,0 +1,152 @@
+"""Seeded synthetic references and wgsim-style reads.
+
+The reference ships no data, tests or read simulator, so every workload of BASELINE.json is
+regenerated from a seed: an i.i.d. uniform ACGT reference with planted dispersed repeats (so that
+`max_occ`, B-tree splits and mate rescue are exercised) and no `N` (keeps `.pac` independent of
+`lrand48`, bntseq.c:290), and reads with substitutions, geometric indels, constant quality,
+FR paired ends with N(mean, sd) outer distance and `/1` `/2` name suffixes (trimmed by the
+reader exactly like bwa.c:27-31).
+"""
+from __future__ import annotations
+
+import numpy as np
+
+_BASES = np.frombuffer(b"ACGT", dtype=np.uint8)
+_COMP = np.array([3, 2, 1, 0, 4], dtype=np.uint8)
+
+
+def make_reference(total_len: int, n_contigs: int = 1, seed: int = 1, repeat_frac: float = 0.02,
+                   rep_len=(300, 5000), rep_copies=(2, 50), rep_div=0.03):
+    """Return a list of (name, codes uint8[0..3]) contigs."""
+    rng = np.random.default_rng(seed)
+    codes = rng.integers(0, 4, size=total_len, dtype=np.uint8)
+    planted = 0
+    budget = int(total_len * repeat_frac)
+    while planted < budget and total_len > 4 * rep_len[0]:
+        L = int(rng.integers(rep_len[0], min(rep_len[1], max(rep_len[0] + 1, total_len // 8)) + 1))
+        ncopy = int(rng.integers(rep_copies[0], rep_copies[1] + 1))
+        src = int(rng.integers(0, total_len - L))
+        fam = codes[src:src + L].copy()
+        div = float(rng.uniform(0, rep_div))
+        for _ in range(ncopy):
+            cp = fam.copy()
+            nmut = rng.binomial(L, div)
+            if nmut:
+                pos = rng.integers(0, L, size=nmut)
+                cp[pos] = (cp[pos] + rng.integers(1, 4, size=nmut, dtype=np.uint8)) & 3
+            if rng.random() < 0.5:
+                cp = (3 - cp[::-1]).astype(np.uint8)
+            dst = int(rng.integers(0, total_len - L))
+            codes[dst:dst + L] = cp
+            planted += L
+            if planted >= budget:
+                break
+    # cut into contigs of slightly unequal length
+    bounds = [0]
+    base = total_len // n_contigs
+    for i in range(1, n_contigs):
+        bounds.append(i * base + int(rng.integers(-base // 8, base // 8 + 1)))
+    bounds.append(total_len)
+    return [(f"chr{i + 1}", codes[bounds[i]:bounds[i + 1]]) for i in range(n_contigs)]
+
+
+def write_fasta(path: str, contigs, width: int = 60):
+    with open(path, "wb") as f:
+        for name, codes in contigs:
+            f.write(b">" + name.encode() + b"\n")
+            s = _BASES[codes]
+            n = len(s)
+            full = (n // width) * width
+            if full:
+                body = np.empty((full // width, width + 1), dtype=np.uint8)
+                body[:, :width] = s[:full].reshape(-1, width)
+                body[:, width] = 10
+                f.write(body.tobytes())
+            if n > full:
+                f.write(s[full:].tobytes() + b"\n")
+
+
+def _mutate(rng, frag, sub, indel, ext=0.3):
+    """Apply substitutions and geometric indels; returns codes (may change length)."""
+    L = len(frag)
+    out = frag.copy()
+    if sub > 0:
+        m = rng.random(L) < sub
+        k = int(m.sum())
+        if k:
+            out[m] = (out[m] + rng.integers(1, 4, size=k, dtype=np.uint8)) & 3
+    if indel > 0:
+        n_ev = rng.binomial(L, indel)
+        if n_ev:
+            pieces = []
+            pos = np.sort(rng.integers(1, L - 1, size=n_ev))
+            last = 0
+            for p in pos:
+                if p < last:
+                    continue
+                glen = int(rng.geometric(1 - ext))
+                pieces.append(out[last:p])
+                if rng.random() < 0.5:  # insertion
+                    pieces.append(rng.integers(0, 4, size=glen, dtype=np.uint8))
+                    last = p
+                else:  # deletion
+                    last = min(L, p + glen)
+            pieces.append(out[last:])
+            out = np.concatenate(pieces)
+    return out
+
+
+def simulate_reads(contigs, n: int, read_len: int, paired: bool, seed: int = 7, sub: float = 0.01,
+                   indel: float = 0.001, ins_mean: float = 400.0, ins_sd: float = 40.0,
+                   n_frac: float = 0.0, mate2_sub: float | None = None, junk_frac: float = 0.0):
+    """Return (reads1, reads2|None); each a list of (name bytes, seq bytes, qual bytes)."""
+    rng = np.random.default_rng(seed)
+    lens = np.array([len(c[1]) for c in contigs], dtype=np.int64)
+    prob = lens / lens.sum()
+    r1, r2 = [], []
+    slack = 64
+    for i in range(n):
+        ci = int(rng.choice(len(contigs), p=prob))
+        ref = contigs[ci][1]
+        if paired:
+            isz = int(max(read_len + 10, rng.normal(ins_mean, ins_sd)))
+        else:
+            isz = read_len
+        isz = min(isz, len(ref) - slack - 1)
+        st = int(rng.integers(0, len(ref) - isz - slack))
+        frag = ref[st:st + isz + slack]
+        flip = rng.random() < 0.5
+        name = f"r{i}".encode()
+        if rng.random() < junk_frac:
+            a = rng.integers(0, 4, size=read_len, dtype=np.uint8)
+            b = rng.integers(0, 4, size=read_len, dtype=np.uint8)
+        else:
+            left = _mutate(rng, frag[:read_len + slack // 2], sub, indel)[:read_len]
+            if paired:
+                rgt_src = (3 - frag[:isz][::-1]).astype(np.uint8)
+                right = _mutate(rng, rgt_src[:read_len + slack // 2] if len(rgt_src) >= read_len + slack // 2
+                                else rgt_src, sub if mate2_sub is None else mate2_sub, indel)[:read_len]
+            else:
+                right = None
+            if flip:
+                if paired:
+                    a, b = right, left
+                else:
+                    a, b = (3 - left[::-1]).astype(np.uint8), None
+            else:
+                a, b = left, right
+        for seqc, dst, sfx in ((a, r1, b"/1"), (b, r2, b"/2")):
+            if seqc is None:
+                continue
+            s = _BASES[seqc].copy()
+            if n_frac > 0:
+                m = rng.random(len(s)) < n_frac
+                s[m] = ord("N")
+            dst.append((name + (sfx if paired else b""), s.tobytes(), b"I" * len(s)))
+    return r1, (r2 if paired else None)
+
+
+def write_fastq(path: str, reads):
+    with open(path, "wb") as f:
+        for name, seq, qual in reads:
+            f.write(b"@" + name + b"\n" + seq + b"\n+\n" + qual + b"\n")
