@@ -1,0 +1,126 @@
+"""Shared helpers of the parity tests: seeded workloads, the oracle binary, SAM comparison.
+
+The oracle (`oracle/_ref/bwa`, the unmodified reference compiled by oracle/Makefile) is test
+infrastructure only: it builds the index files and produces the SAM the engine must reproduce.
+"""
+from __future__ import annotations
+
+import hashlib
+import os
+import subprocess
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+from sparkbwa_b200 import synth  # noqa: E402
+
+ORACLE = os.path.join(ROOT, "oracle", "_ref", "bwa")
+CLI = os.path.join(ROOT, "sparkbwa_b200", "b200bwa")
+HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "_build", "b200bwa_hostsim")
+
+# name -> (reference kwargs, reads kwargs, extra bwa-mem options)
+CASES = {
+    # config 1 shape (scaled): single-end 100 bp, 2 % error
+    "se100": (dict(total_len=1_000_000, n_contigs=3, seed=1, repeat_frac=0.05),
+              dict(n=2000, read_len=100, paired=False, seed=3, sub=0.02, indel=0.002, n_frac=0.002, junk_frac=0.01), []),
+    # config 2 shape (scaled): paired-end 2x150 bp, 1 % error, several -K batches
+    "pe150": (dict(total_len=1_000_000, n_contigs=3, seed=1, repeat_frac=0.05),
+              dict(n=3000, read_len=150, paired=True, seed=5, sub=0.01, indel=0.001, junk_frac=0.01), ["-K", "300000"]),
+    # config 4 shape: single-end 250 bp, 3.5 % substitutions + 1.5 % indels (wide bands)
+    "se250": (dict(total_len=600_000, n_contigs=2, seed=2, repeat_frac=0.03),
+              dict(n=800, read_len=250, paired=False, seed=9, sub=0.035, indel=0.015), []),
+    # noisy mate 2: forces mate rescue (ksw_u8 path)
+    "pe_rescue": (dict(total_len=500_000, n_contigs=2, seed=4, repeat_frac=0.03),
+                  dict(n=1500, read_len=150, paired=True, seed=11, sub=0.01, indel=0.001, mate2_sub=0.10), []),
+    # repeat-rich reference: deep B-trees, max_occ sampling, many rescues, XA tags
+    "pe_repeat": (dict(total_len=300_000, n_contigs=2, seed=6, repeat_frac=0.60, rep_len=(300, 3000), rep_copies=(5, 60), rep_div=0.04),
+                  dict(n=1200, read_len=150, paired=True, seed=13, sub=0.01, indel=0.001), []),
+    # 250 bp pairs -> 16-bit local SW in mate rescue
+    "pe250": (dict(total_len=400_000, n_contigs=1, seed=8, repeat_frac=0.10),
+              dict(n=600, read_len=250, paired=True, seed=15, sub=0.02, indel=0.004, mate2_sub=0.08, ins_mean=600.0, ins_sd=60.0), []),
+}
+
+
+def have_oracle() -> bool:
+    return os.access(ORACLE, os.X_OK)
+
+
+def run(cmd, **kw):
+    return subprocess.run(cmd, check=True, stdout=subprocess.PIPE, stderr=subprocess.PIPE, **kw)
+
+
+def make_case(workdir: str, name: str):
+    """Generate reference + reads + index (+ oracle SAM).  Returns dict of paths and options."""
+    ref_kw, reads_kw, opts = CASES[name]
+    d = os.path.join(workdir, name)
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, "ref.fa")
+    out = {"dir": d, "ref": fa, "opts": list(opts), "paired": reads_kw["paired"]}
+    ctg = None
+    if not os.path.exists(fa + ".bwt"):
+        ctg = synth.make_reference(**ref_kw)
+        synth.write_fasta(fa, ctg)
+        run([ORACLE, "index", fa])
+    fq1 = os.path.join(d, "r_1.fq")
+    fq2 = os.path.join(d, "r_2.fq")
+    if not os.path.exists(fq1):
+        if ctg is None:
+            ctg = synth.make_reference(**ref_kw)
+        r1, r2 = synth.simulate_reads(ctg, **reads_kw)
+        synth.write_fastq(fq1, r1)
+        if r2 is not None:
+            synth.write_fastq(fq2, r2)
+    out["fq"] = [fq1] + ([fq2] if reads_kw["paired"] else [])
+    return out
+
+
+def oracle_sam(case, extra=()):
+    p = os.path.join(case["dir"], "oracle.sam")
+    cmd = [ORACLE, "mem"] + case["opts"] + list(extra) + [case["ref"]] + case["fq"]
+    with open(p, "wb") as f:
+        subprocess.run(cmd, check=True, stdout=f, stderr=subprocess.DEVNULL)
+    return p
+
+
+def engine_sam(case, binary, extra=(), env=None, via_f=True):
+    p = os.path.join(case["dir"], "engine.sam")
+    cmd = [binary, "mem"] + case["opts"] + list(extra) + (["-f", p] if via_f else []) + [case["ref"]] + case["fq"]
+    e = dict(os.environ)
+    if env:
+        e.update(env)
+    r = subprocess.run(cmd, stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=e)
+    if r.returncode != 0:
+        raise RuntimeError(f"engine failed rc={r.returncode}: {r.stderr.decode()[-2000:]}")
+    if not via_f:
+        with open(p, "wb") as f:
+            f.write(r.stdout)
+    return p
+
+
+def sam_body(path):
+    with open(path, "rb") as f:
+        return [l for l in f if not l.startswith(b"@PG")]
+
+
+def sam_digest(path):
+    h = hashlib.md5()
+    for l in sam_body(path):
+        h.update(l)
+    return h.hexdigest()
+
+
+def first_diff(a, b, limit=3):
+    la, lb = sam_body(a), sam_body(b)
+    out = []
+    for i, (x, y) in enumerate(zip(la, lb)):
+        if x != y:
+            out.append((i, x.decode(errors="replace")[:300], y.decode(errors="replace")[:300]))
+            if len(out) >= limit:
+                break
+    if len(la) != len(lb):
+        out.append((min(len(la), len(lb)), f"len {len(la)}", f"len {len(lb)}"))
+    return out
+
+
+HOSTSIM_ENV = {"B200BWA_LANE_GRID": "1", "B200BWA_LANE_BLOCK": "1", "B200BWA_SEED_GRID": "1",
+               "B200BWA_SEED_BLOCK": "1", "B200BWA_SCRATCH": str(4 << 20)}
