@@ -98,7 +98,8 @@ def _mutate(rng, frag, sub, indel, ext=0.3):
 
 def simulate_reads(contigs, n: int, read_len: int, paired: bool, seed: int = 7, sub: float = 0.01,
                    indel: float = 0.001, ins_mean: float = 400.0, ins_sd: float = 40.0,
-                   n_frac: float = 0.0, mate2_sub: float | None = None, junk_frac: float = 0.0):
+                   n_frac: float = 0.0, mate2_sub: float | None = None, junk_frac: float = 0.0,
+                   chimeric_frac: float = 0.0, ragged: bool = False):
     """Return (reads1, reads2|None); each a list of (name bytes, seq bytes, qual bytes)."""
     rng = np.random.default_rng(seed)
     lens = np.array([len(c[1]) for c in contigs], dtype=np.int64)
@@ -135,6 +136,17 @@ def simulate_reads(contigs, n: int, read_len: int, paired: bool, seed: int = 7, 
                     a, b = (3 - left[::-1]).astype(np.uint8), None
             else:
                 a, b = left, right
+        if chimeric_frac > 0 and rng.random() < chimeric_frac:  # splice in a segment from elsewhere
+            cj = int(rng.choice(len(contigs), p=prob))
+            other = contigs[cj][1]
+            cut = int(rng.integers(30, read_len - 30))
+            st2 = int(rng.integers(0, len(other) - read_len))
+            seg = other[st2:st2 + read_len - cut]
+            if rng.random() < 0.5:
+                seg = (3 - seg[::-1]).astype(np.uint8)
+            a = np.concatenate([a[:cut], seg])
+        if ragged:
+            a = a[:int(rng.integers(1, read_len + 1))]
         for seqc, dst, sfx in ((a, r1, b"/1"), (b, r2, b"/2")):
             if seqc is None:
                 continue

@@ -38,6 +38,14 @@ CASES = {
     # 250 bp pairs -> 16-bit local SW in mate rescue
     "pe250": (dict(total_len=400_000, n_contigs=1, seed=8, repeat_frac=0.10),
               dict(n=600, read_len=250, paired=True, seed=15, sub=0.02, indel=0.004, mate2_sub=0.08, ins_mean=600.0, ins_sd=60.0), []),
+    # chimeric reads -> supplementary alignments (SA tag, 0x800, hard clips)
+    "pe_chimeric": (dict(total_len=400_000, n_contigs=3, seed=31, repeat_frac=0.04),
+                    dict(n=800, read_len=150, paired=True, seed=33, sub=0.01, indel=0.001, chimeric_frac=0.25), []),
+    # short and ragged reads: below min_seed_len, empty alignments, length 1
+    "se_short": (dict(total_len=200_000, n_contigs=1, seed=35, repeat_frac=0.02),
+                 dict(n=600, read_len=60, paired=False, seed=37, sub=0.03, indel=0.003, n_frac=0.02, ragged=True), []),
+    "pe_small": (dict(total_len=200_000, n_contigs=2, seed=41, repeat_frac=0.20, rep_len=(200, 1500), rep_copies=(2, 12)),
+                 dict(n=400, read_len=125, paired=True, seed=43, sub=0.015, indel=0.002, mate2_sub=0.05, chimeric_frac=0.05), []),
 }
 
 

@@ -1,0 +1,143 @@
+"""CPU-side tests (no GPU): oracle pinned to the golden vectors, host logic, ABI surface.
+
+The kernel bodies are additionally compiled for the host by tests/hostsim (test scaffolding, never
+part of libbwa.so) and must reproduce the reference SAM bit for bit; this checks the control logic
+here, the `-m gpu` tests check the CUDA build on a B200.
+"""
+import ctypes
+import os
+import re
+import subprocess
+
+import pytest
+
+import parity_util as pu
+
+ROOT = pu.ROOT
+GOLD = os.path.join(ROOT, "tests", "golden", "tiny")
+LIB = os.path.join(ROOT, "sparkbwa_b200", "libbwa.so")
+
+
+@pytest.fixture(scope="session")
+def hostsim():
+    d = os.path.join(ROOT, "tests", "hostsim")
+    subprocess.run(["make", "-C", d, "-j4"], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    return pu.HOSTSIM
+
+
+# ---- the oracle is pinned to the committed golden vectors -------------------------------------
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("args,gold", [
+    (["ref.fa", "se.fq"], "se.sam"),
+    (["-K", "20000", "ref.fa", "pe_1.fq", "pe_2.fq"], "pe.sam"),
+])
+def test_oracle_reproduces_golden(tmp_path, args, gold):
+    r = subprocess.run([pu.ORACLE, "mem"] + args, cwd=GOLD, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+    body = [l for l in r.stdout.splitlines(True) if not l.startswith(b"@PG")]
+    assert body == pu.sam_body(os.path.join(GOLD, gold))
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_oracle_thread_independence(tmp_path):
+    """Output depends on -K but not on -t: the property multi-GPU sharding relies on."""
+    outs = []
+    for t in ("1", "3"):
+        r = subprocess.run([pu.ORACLE, "mem", "-t", t, "-K", "20000", "ref.fa", "pe_1.fq", "pe_2.fq"], cwd=GOLD,
+                           stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+        outs.append([l for l in r.stdout.splitlines(True) if not l.startswith(b"@PG")])
+    assert outs[0] == outs[1]
+
+
+# ---- kernel bodies on the host vs golden / oracle ---------------------------------------------
+@pytest.mark.parametrize("args,gold", [
+    (["ref.fa", "se.fq"], "se.sam"),
+    (["-K", "20000", "ref.fa", "pe_1.fq", "pe_2.fq"], "pe.sam"),
+    (["-K", "20000", "-M", "-Y", "-R", r"@RG\tID:g1\tSM:s1", "-C", "ref.fa", "pe_1.fq", "pe_2.fq"], "pe_opts.sam"),
+])
+def test_hostsim_matches_golden(hostsim, tmp_path, args, gold):
+    out = str(tmp_path / "o.sam")
+    r = subprocess.run([hostsim, "mem"] + args, cwd=GOLD, stdout=open(out, "wb"), stderr=subprocess.PIPE,
+                       env=dict(os.environ, **pu.HOSTSIM_ENV))
+    assert r.returncode == 0, r.stderr.decode()[-1000:]
+    assert pu.sam_body(out) == pu.sam_body(os.path.join(GOLD, gold))
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["se100", "pe150", "se250", "pe_rescue", "pe_repeat", "pe250", "pe_chimeric", "se_short"])
+def test_hostsim_matches_oracle(hostsim, workdir, name):
+    c = pu.make_case(workdir, name)
+    ref = pu.oracle_sam(c)
+    our = pu.engine_sam(c, hostsim, env=pu.HOSTSIM_ENV)
+    assert not pu.first_diff(ref, our)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("extra", [["-a"], ["-k", "15", "-w", "40", "-T", "20"], ["-A", "2"], ["-S"], ["-P"],
+                                   ["-I", "400,40"], ["-U", "9", "-L", "3,7"], ["-O", "4,8", "-E", "2,1"],
+                                   ["-c", "20", "-y", "8"], ["-m", "3", "-D", "0.3"], ["-M", "-h", "3"]])
+def test_hostsim_option_surface(hostsim, workdir, extra):
+    c = pu.make_case(workdir, "pe_small")
+    ref = pu.oracle_sam(c, extra=extra)
+    our = pu.engine_sam(c, hostsim, extra=extra, env=pu.HOSTSIM_ENV)
+    assert not pu.first_diff(ref, our)
+
+
+# ---- ABI surface -------------------------------------------------------------------------------
+def _declared_symbols():
+    txt = open(os.path.join(ROOT, "include", "b200bwa.h")).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(b200bwa_[a-z_]+)\s*\(", txt)))
+
+
+def test_library_exports_declared_symbols():
+    assert os.path.exists(LIB), "libbwa.so not built (python -c 'import __graft_entry__ as g; g.build()')"
+    lib = ctypes.CDLL(LIB)
+    syms = _declared_symbols()
+    assert len(syms) >= 14
+    for s in syms:
+        assert hasattr(lib, s), s
+    assert hasattr(lib, "Java_com_github_sparkbwa_BwaJni_bwa_1jni")
+
+
+def test_error_behaviour_without_exit(tmp_path):
+    """Nothing may exit the process (a JVM in production): failures come back as return codes."""
+    lib = ctypes.CDLL(LIB)
+    lib.b200bwa_main_to.restype = ctypes.c_int
+    lib.b200bwa_last_error.restype = ctypes.c_char_p
+
+    def call(args, out=None):
+        arr = (ctypes.c_char_p * len(args))(*[a.encode() for a in args])
+        return lib.b200bwa_main_to(len(args), arr, out.encode() if out else None)
+
+    assert call(["bwa"]) == 1
+    assert call(["bwa", "index", "x.fa"]) == 1                      # only `mem` is provided
+    assert b"unrecognized command" in lib.b200bwa_last_error()
+    assert call(["bwa", "mem"]) == 1                                 # usage
+    assert call(["bwa", "mem", "-Z", "a", "b"]) == 1                 # unknown option
+    assert call(["bwa", "mem", "-R", "RG\\tID:x", "a", "b"]) == 1    # bad read group
+    assert call(["bwa", "mem", "/nonexistent/idx", os.path.join(GOLD, "se.fq")], str(tmp_path / "o.sam")) == 1
+    assert b"index" in lib.b200bwa_last_error()
+
+
+def test_no_cpu_fallback_without_cuda(tmp_path):
+    """With no CUDA device the aligning call must fail loudly instead of computing on the CPU."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    out = str(tmp_path / "o.sam")
+    r = subprocess.run([pu.CLI, "mem", "-f", out, os.path.join(GOLD, "ref.fa"), os.path.join(GOLD, "se.fq")],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode != 0
+    assert b"CUDA" in r.stderr or b"cuda" in r.stderr
+
+
+def test_jni_symbol_through_fake_env(tmp_path):
+    exe = str(tmp_path / "jni_fake")
+    subprocess.run(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "jni_fake.c"), "-ldl"], check=True)
+    r = subprocess.run([exe, LIB, "bwa", "index", "x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert b"rc=1 released=3" in r.stdout, (r.stdout, r.stderr)
+    # "-f <out>" is consumed by the glue and not passed on as an aligner option
+    r = subprocess.run([exe, LIB, "bwa", "mem", "-f", str(tmp_path / "x.sam"), "/nonexistent/idx", "r.fq"],
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert b"rc=1 released=6" in r.stdout, (r.stdout, r.stderr)
+    assert b"invalid option" not in r.stderr

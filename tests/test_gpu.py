@@ -1,0 +1,150 @@
+"""GPU parity tests (run on the B200 box): the CUDA build, called through the C-ABI / CLI twin,
+must reproduce the reference's SAM bit for bit (the @PG line excluded)."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+import parity_util as pu
+
+pytestmark = pytest.mark.gpu
+ROOT = pu.ROOT
+GOLD = os.path.join(ROOT, "tests", "golden", "tiny")
+LIB = os.path.join(ROOT, "sparkbwa_b200", "libbwa.so")
+
+
+def _lib():
+    lib = ctypes.CDLL(LIB)
+    lib.b200bwa_main_to.restype = ctypes.c_int
+    lib.b200bwa_last_error.restype = ctypes.c_char_p
+    lib.b200bwa_index_load.restype = ctypes.c_void_p
+    lib.b200bwa_index_load.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.b200bwa_index_free.argtypes = [ctypes.c_void_p]
+    lib.b200bwa_set_options.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.b200bwa_align_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p,
+                                        ctypes.c_char_p, ctypes.c_int64, ctypes.c_int, ctypes.POINTER(ctypes.c_void_p),
+                                        ctypes.POINTER(ctypes.c_size_t)]
+    lib.b200bwa_free.argtypes = [ctypes.c_void_p]
+    return lib
+
+
+def _main_to(lib, args, out):
+    arr = (ctypes.c_char_p * len(args))(*[a.encode() for a in args])
+    return lib.b200bwa_main_to(len(args), arr, out.encode())
+
+
+@pytest.mark.parametrize("args,gold", [
+    (["ref.fa", "se.fq"], "se.sam"),
+    (["-K", "20000", "ref.fa", "pe_1.fq", "pe_2.fq"], "pe.sam"),
+    (["-K", "20000", "-M", "-Y", "-R", r"@RG\tID:g1\tSM:s1", "-C", "ref.fa", "pe_1.fq", "pe_2.fq"], "pe_opts.sam"),
+])
+def test_cabi_matches_golden(tmp_path, args, gold):
+    """In-process call through the C-ABI (what the JNI symbol forwards to) against committed vectors."""
+    lib = _lib()
+    out = str(tmp_path / "o.sam")
+    full = ["bwa", "mem"] + [os.path.join(GOLD, a) if a.endswith((".fa", ".fq")) else a for a in args]
+    rc = _main_to(lib, full, out)
+    assert rc == 0, lib.b200bwa_last_error()
+    assert pu.sam_body(out) == pu.sam_body(os.path.join(GOLD, gold))
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", list(pu.CASES))
+def test_cli_matches_oracle(workdir, name):
+    c = pu.make_case(workdir, name)
+    ref = pu.oracle_sam(c)
+    our = pu.engine_sam(c, pu.CLI)
+    assert not pu.first_diff(ref, our)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("extra", [["-a"], ["-k", "15", "-w", "40", "-T", "20"], ["-A", "2"], ["-S"], ["-P"],
+                                   ["-I", "400,40"], ["-O", "4,8", "-E", "2,1"], ["-c", "20", "-y", "8"], ["-M", "-h", "3"]])
+def test_cli_option_surface(workdir, extra):
+    c = pu.make_case(workdir, "pe_small")
+    ref = pu.oracle_sam(c, extra=extra)
+    our = pu.engine_sam(c, pu.CLI, extra=extra)
+    assert not pu.first_diff(ref, our)
+
+
+def test_jni_symbol_end_to_end(tmp_path):
+    """The exact SparkBWA argv (Bwa.java:289-390): bwa mem <-w tokens> -f <out> <idx> <fq1> <fq2>."""
+    exe = str(tmp_path / "jni_fake")
+    subprocess.run(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "jni_fake.c"), "-ldl"], check=True)
+    out = str(tmp_path / "part0.sam")
+    r = subprocess.run([exe, LIB, "bwa", "mem", "-K", "20000", "-f", out, os.path.join(GOLD, "ref.fa"),
+                        os.path.join(GOLD, "pe_1.fq"), os.path.join(GOLD, "pe_2.fq")], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert b"rc=0" in r.stdout, r.stderr[-2000:]
+    assert pu.sam_body(out) == pu.sam_body(os.path.join(GOLD, "pe.sam"))
+
+
+def _load_fastq(path):
+    names, seqs, quals = [], [], []
+    with open(path, "rb") as f:
+        lines = f.read().split(b"\n")
+    for i in range(0, len(lines) - 3, 4):
+        n = lines[i][1:]
+        if len(n) > 2 and n[-2:-1] == b"/" and n[-1:].isdigit():
+            n = n[:-2]
+        names.append(n); seqs.append(lines[i + 1]); quals.append(lines[i + 3])
+    return names, seqs, quals
+
+
+def test_library_batch_api_host_buffers(tmp_path):
+    """b200bwa_align_batch with reads in host memory == the file path, batch for batch."""
+    lib = _lib()
+    ix = lib.b200bwa_index_load(os.path.join(GOLD, "ref.fa").encode(), 0)
+    assert ix, lib.b200bwa_last_error()
+    assert lib.b200bwa_set_options(ix, b"") == 0
+    n1, s1, q1 = _load_fastq(os.path.join(GOLD, "pe_1.fq"))
+    n2, s2, q2 = _load_fastq(os.path.join(GOLD, "pe_2.fq"))
+    names, seqs, quals = [], [], []
+    for a, b, c, d, e, f in zip(n1, s1, q1, n2, s2, q2):
+        names += [a, d]; seqs += [b, e]; quals += [c, f]
+    # cut batches the way bseq_read does for -K 20000
+    out = b""
+    i = 0
+    n_processed = 0
+    while i < len(seqs):
+        size = 0
+        j = i
+        while j < len(seqs):
+            size += len(seqs[j]) + len(seqs[j + 1]); j += 2
+            if size >= 20000:
+                break
+        off = np.zeros(j - i + 1, dtype=np.int64)
+        off[1:] = np.cumsum([len(s) for s in seqs[i:j]])
+        sam = ctypes.c_void_p(); ln = ctypes.c_size_t()
+        rc = lib.b200bwa_align_batch(ix, j - i, b"".join(seqs[i:j]), b"".join(quals[i:j]), off.ctypes.data,
+                                     b"\0".join(names[i:j]) + b"\0", n_processed, 1, ctypes.byref(sam), ctypes.byref(ln))
+        assert rc == 0, lib.b200bwa_last_error()
+        out += ctypes.string_at(sam.value, ln.value)
+        lib.b200bwa_free(sam)
+        n_processed += j - i
+        i = j
+    lib.b200bwa_index_free(ix)
+    gold = b"".join(l for l in pu.sam_body(os.path.join(GOLD, "pe.sam")) if not l.startswith(b"@"))
+    assert out == gold
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_batch_size_independence_of_se(workdir):
+    """Size-independent property: single-end output does not depend on -K (no batch-wide statistics)."""
+    c = pu.make_case(workdir, "se100")
+    a = pu.sam_digest(pu.engine_sam(c, pu.CLI, extra=["-K", "30000"]))
+    b = pu.sam_digest(pu.engine_sam(c, pu.CLI, extra=["-K", "100000000"]))
+    assert a == b
+
+
+def test_repeat_call_same_process(tmp_path):
+    """Two JNI-style calls in one process reuse the HBM-resident index and stay deterministic."""
+    lib = _lib()
+    outs = []
+    for k in range(2):
+        out = str(tmp_path / f"o{k}.sam")
+        rc = _main_to(lib, ["bwa", "mem", os.path.join(GOLD, "ref.fa"), os.path.join(GOLD, "se.fq")], out)
+        assert rc == 0
+        outs.append(pu.sam_digest(out))
+    assert outs[0] == outs[1]
