@@ -1,0 +1,437 @@
+#!/usr/bin/env python
+"""Benchmark of the BWA-MEM hot path (BASELINE.json metric: reads/s, 2x150 bp paired end).
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--pairs P] [--ref-len L]
+
+One "step" is one pass of the device pipeline over the whole synthetic job (P read pairs cut into
+-K 10,000,000-base batches exactly as bseq_read does).  Workload at N=1: BASELINE.json configs[1]
+(1 M x 2x150 bp pairs vs a 100 Mbp synthetic reference; both scale down with --pairs/--ref-len).
+Reported on one JSON line:
+  value      reads/s with the reads already resident in HBM (kernels + the small per-batch
+             host<->device control traffic; SAM text stays on the device)
+  e2e        reads/s through the reference-facing call b200bwa_main_to (FASTQ files -> SAM file, the
+             argv SparkBWA builds), host parsing, H2D, kernels, D2H and file write inside the timed region
+  roofline   seeding kernel: algorithmic bytes (64 B per occ-block touch, counted by the kernel the way
+             SURVEY.md 8(d) defines them) / its CUDA-event duration, against the measured HBM peak
+  sw         DP work: cells of ksw_extend2 + ksw_global2 + local SW over the DP stages' device time
+  cpu_baseline  the reference's own `bwa mem -t <host cores>` (oracle/_ref) on a bounded sample
+Multi-GPU (torchrun): read batches are sharded over ranks (weak scaling: P pairs per rank), the index
+image is broadcast once over NCCL, no collective on the data path.
+"""
+import argparse
+import ctypes
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+LIB = os.path.join(ROOT, "sparkbwa_b200", "libbwa.so")
+ORACLE = os.path.join(ROOT, "oracle", "_ref", "bwa")
+
+
+class Times(ctypes.Structure):
+    _fields_ = [(n, ctypes.c_float) for n in ("h2d", "seed", "sa", "chain", "extend", "pestat", "finalize", "gather", "d2h", "total")] + \
+               [("launches", ctypes.c_int), ("n_seed_tasks", ctypes.c_int64), ("n_regs", ctypes.c_int64), ("sam_bytes", ctypes.c_int64)]
+
+
+def load_lib():
+    lib = ctypes.CDLL(LIB)
+    lib.b200bwa_last_error.restype = ctypes.c_char_p
+    lib.b200bwa_index_load.restype = ctypes.c_void_p
+    lib.b200bwa_index_load.argtypes = [ctypes.c_char_p, ctypes.c_int]
+    lib.b200bwa_index_adopt.restype = ctypes.c_void_p
+    lib.b200bwa_index_adopt.argtypes = [ctypes.c_char_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_void_p]
+    lib.b200bwa_set_options.argtypes = [ctypes.c_void_p, ctypes.c_char_p]
+    lib.b200bwa_set_paired.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.b200bwa_upload_batch.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_char_p, ctypes.c_char_p, ctypes.c_void_p,
+                                         ctypes.c_char_p, ctypes.c_int64]
+    lib.b200bwa_run_resident_range.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_int, ctypes.c_int,
+                                               ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p, ctypes.POINTER(Times)]
+    lib.b200bwa_counters.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_void_p, ctypes.c_int]
+    lib.b200bwa_process_counters.argtypes = [ctypes.c_void_p, ctypes.c_int]
+    lib.b200bwa_main_to.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_char_p]
+    lib.b200bwa_index_free.argtypes = [ctypes.c_void_p]
+    return lib
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks/throttle reasons during the timed region (B200_PROFILING.md)."""
+
+    def __init__(self, gpu):
+        super().__init__(daemon=True)
+        self.gpu, self.rows, self.stop_ev = gpu, [], threading.Event()
+
+    def run(self):
+        q = "clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
+            "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        while not self.stop_ev.is_set():
+            try:
+                r = subprocess.run(["nvidia-smi", "-i", str(self.gpu), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, timeout=5)
+                self.rows.append([x.strip() for x in r.stdout.decode().strip().split(",")])
+            except Exception:
+                pass
+            self.stop_ev.wait(0.2)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if len(r) >= 6 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 6 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 6:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[2:6]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def workdir(args):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
+    d = os.path.join(base, f"b2bench_L{args.ref_len}_P{args.pairs}_s{args.seed}")
+    os.makedirs(d, exist_ok=True)
+    return d
+
+
+def prepare_reference(args, d, rank):
+    """Reference FASTA-less: contigs in memory -> index files written by sparkbwa_b200.index (rank 0)."""
+    from sparkbwa_b200 import synth, index
+    prefix = os.path.join(d, "ref")
+    n_ctg = 4 if args.ref_len >= 20_000_000 else 2
+    ctg = synth.make_reference(args.ref_len, n_contigs=n_ctg, seed=args.seed, repeat_frac=0.02)
+    if rank == 0 and not os.path.exists(prefix + ".sa"):
+        t = time.time()
+        index.build_index(ctg, prefix + ".tmp")
+        for e in ("pac", "ann", "amb", "bwt", "sa"):
+            os.replace(prefix + ".tmp." + e, prefix + "." + e)
+        sys.stderr.write(f"[bench] index built in {time.time() - t:.1f}s\n")
+    return ctg, prefix
+
+
+def prepare_reads(args, d, ctg, rank):
+    from sparkbwa_b200 import synth
+    f1 = os.path.join(d, f"r{rank}_1.fq")
+    f2 = os.path.join(d, f"r{rank}_2.fq")
+    s1, s2 = [], []
+    t = time.time()
+    for a, b in synth.simulate_pairs_fast(ctg, args.pairs, 150, seed=args.seed * 1000 + 17 + rank, sub=0.01, indel=0.001):
+        s1.append(a); s2.append(b)
+    if not os.path.exists(f2):
+        synth.write_fastq_fixed(f1 + ".tmp", s1, 0, b"/1"); os.replace(f1 + ".tmp", f1)
+        synth.write_fastq_fixed(f2 + ".tmp", s2, 0, b"/2"); os.replace(f2 + ".tmp", f2)
+    sys.stderr.write(f"[bench] rank {rank}: {args.pairs} pairs simulated in {time.time() - t:.1f}s\n")
+    return np.concatenate(s1), np.concatenate(s2), f1, f2
+
+
+def cut_batches(n_reads, read_len, chunk):
+    """bseq_read (bwa.c:42-75): a batch ends once its bases reach `chunk` and the read count is even."""
+    out, first = [], 0
+    per = read_len
+    while first < n_reads:
+        n = 0
+        size = 0
+        while first + n < n_reads:
+            n += 2; size += 2 * per
+            if size >= chunk:
+                break
+        out.append((first, n))
+        first += n
+    return out
+
+
+def cpu_reference(args, prefix, f1, f2, sample_pairs, threads):
+    """Times the reference's own bwa mem on the host cores over the first `sample_pairs` pairs."""
+    d = os.path.dirname(f1)
+    h1, h2 = os.path.join(d, "cpu_1.fq"), os.path.join(d, "cpu_2.fq")
+    rec = 4  # lines per record
+    for src, dst in ((f1, h1), (f2, h2)):
+        with open(src, "rb") as fi, open(dst, "wb") as fo:
+            first = fi.readline()
+            fi.seek(0)
+            # fixed-width records: size of one record = 4 lines
+            l2 = len(first) + 150 + 1 + 2 + 150 + 1
+            fo.write(fi.read(l2 * sample_pairs))
+    # index load warm-up is part of the reference run (as it is for a SparkBWA task); report wall time of the whole call
+    t = time.time()
+    r = subprocess.run([ORACLE, "mem", "-t", str(threads), "-K", str(args.K), prefix, h1, h2], stdout=subprocess.DEVNULL,
+                       stderr=subprocess.PIPE)
+    dt = time.time() - t
+    if r.returncode != 0:
+        raise RuntimeError("oracle bwa failed: " + r.stderr.decode()[-500:])
+    # subtract nothing: honest wall clock; parse bwa's own per-batch times for the note
+    proc = [float(l.split(" in ")[1].split(" CPU")[0]) for l in r.stderr.decode().splitlines() if "Processed" in l]
+    return 2 * sample_pairs / dt, dt, sum(proc)
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="engine")
+    ap.add_argument("--pairs", type=int, default=1_000_000)
+    ap.add_argument("--ref-len", type=int, default=100_000_000)
+    ap.add_argument("--K", type=int, default=10_000_000)
+    ap.add_argument("--seed", type=int, default=1)
+    ap.add_argument("--workers", type=int, default=3)
+    ap.add_argument("--cpu-sample-pairs", type=int, default=200_000)
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    host_cores = os.cpu_count() or 1
+    workload = f"BWA-MEM paired-end {args.pairs} x 2x150bp vs {args.ref_len} bp synthetic reference (2% planted repeats), -K {args.K}"
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        d = workdir(args)
+        try:  # data preparation only (outside the timed path): the GPU index builder writes files byte-identical to `bwa index`
+            import torch
+            have_cuda = torch.cuda.is_available()
+        except Exception:
+            have_cuda = False
+        ctg, prefix = prepare_reference(args, d, 0) if have_cuda else prepare_reference_cpu_only(args, d)
+        s1, s2, f1, f2 = prepare_reads(args, d, ctg, 0)
+        sample = min(args.pairs, args.cpu_sample_pairs)
+        vals = []
+        for i in range(args.warmup + args.steps):
+            v, dt, _ = cpu_reference(args, prefix, f1, f2, sample, host_cores)
+            if i >= args.warmup:
+                vals.append((v, dt))
+        v = float(np.mean([x[0] for x in vals]))
+        ms = float(np.mean([x[1] for x in vals])) * 1e3
+        print(json.dumps({
+            "impl": "reference", "metric": "BWA-MEM reads/sec 2x150bp PE", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "int32", "data": "synthetic",
+            "config": {"workload": workload, "timing": "wall clock of `bwa mem` incl. index load from page cache"},
+            "cpu_baseline": {"value": v, "unit": "reads/s", "cores": host_cores, "kind": "reference",
+                             "sample": f"first {sample} pairs of the workload, bwa mem -t {host_cores} -K {args.K}"},
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: the engine has no CPU path")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = load_lib()
+    d = workdir(args)
+    ctg, prefix = prepare_reference(args, d, rank)
+    if world > 1:
+        dist.barrier()
+    s1, s2, f1, f2 = prepare_reads(args, d, ctg, rank)
+    del ctg
+
+    # ---- index image: read by rank 0, broadcast over NCCL, adopted in place by every rank ----------
+    def file_tensor(path, skip, pad):
+        a = np.fromfile(path, dtype=np.uint8)[skip:]
+        t = torch.zeros(a.size + pad, dtype=torch.uint8, device="cuda")
+        if rank == 0:
+            t[: a.size] = torch.from_numpy(a).cuda()
+        return t
+    bwt_t = file_tensor(prefix + ".bwt", 40, 256)
+    sa_raw = np.fromfile(prefix + ".sa", dtype=np.uint8)[56 - 8:].copy()  # keep one slot for sa[0] = -1
+    sa_raw[:8] = 255
+    sa_t = torch.zeros(sa_raw.size + 64, dtype=torch.uint8, device="cuda")
+    if rank == 0:
+        sa_t[: sa_raw.size] = torch.from_numpy(sa_raw).cuda()
+    pac_t = file_tensor(prefix + ".pac", 0, 64)
+    if world > 1:
+        for t in (bwt_t, sa_t, pac_t):
+            dist.broadcast(t, src=0)
+    torch.cuda.synchronize()
+    ix = lib.b200bwa_index_adopt(prefix.encode(), local, bwt_t.data_ptr(), sa_t.data_ptr(), pac_t.data_ptr())
+    if not ix:
+        raise SystemExit("index adopt failed: " + lib.b200bwa_last_error().decode())
+    assert lib.b200bwa_set_options(ix, f"-K {args.K}".encode()) == 0
+    lib.b200bwa_set_paired(ix, 1)
+
+    # ---- resident job ------------------------------------------------------------------------------
+    n_reads = 2 * args.pairs
+    inter = np.empty((n_reads, 150), dtype=np.uint8)
+    inter[0::2] = s1; inter[1::2] = s2
+    del s1, s2
+    seq = inter.tobytes()
+    qual = b"I" * len(seq)
+    off = (np.arange(n_reads + 1, dtype=np.int64) * 150)
+    names = b"".join(b"r%09d\0r%09d\0" % (i, i) for i in range(args.pairs))
+    if lib.b200bwa_upload_batch(ix, n_reads, seq, qual, off.ctypes.data, names, 0) != 0:
+        raise SystemExit("upload failed: " + lib.b200bwa_last_error().decode())
+    del inter
+    batches = cut_batches(n_reads, 150, args.K)
+    n_workers = max(1, min(args.workers, 3))
+
+    def one_pass(collect=None):
+        lock = threading.Lock()
+        nxt = [0]
+        err = []
+
+        def work(wi):
+            t = Times()
+            while True:
+                with lock:
+                    b = nxt[0]; nxt[0] += 1
+                if b >= len(batches) or err:
+                    return
+                first, cnt = batches[b]
+                rc = lib.b200bwa_run_resident_range(ix, wi, first, cnt, 1, 0, None, None, ctypes.byref(t))
+                if rc != 0:
+                    err.append(lib.b200bwa_last_error().decode()); return
+                if collect is not None:
+                    collect.append({k: getattr(t, k) for k, _ in Times._fields_})
+        th = [threading.Thread(target=work, args=(w,)) for w in range(n_workers)]
+        [x.start() for x in th]; [x.join() for x in th]
+        if err:
+            raise SystemExit("pipeline failed: " + err[0])
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        one_pass()
+    cnt0 = (ctypes.c_ulonglong * 16)()
+    for w in range(3):
+        lib.b200bwa_counters(ix, w, cnt0, 1)
+    pc = (ctypes.c_ulonglong * 3)()
+    lib.b200bwa_process_counters(pc, 1)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        one_pass()
+    torch.cuda.synchronize()
+    e1.record(); e1.synchronize()
+    ms_total = e0.elapsed_time(e1)
+    sampler.stop_ev.set(); sampler.join()
+    lib.b200bwa_process_counters(pc, 0)
+    launches = int(pc[2])
+    tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+    ms_total = float(tt.item())
+    ms_step = ms_total / args.steps
+    value = world * n_reads / (ms_step / 1e3)
+
+    # ---- single-stream pass for clean per-kernel CUDA-event durations + algorithmic counters ------
+    for w in range(3):
+        lib.b200bwa_counters(ix, w, cnt0, 1)
+    n_workers_saved, n_workers = n_workers, 1
+    stage = []
+    one_pass(stage)
+    n_workers = n_workers_saved
+    cnt = (ctypes.c_ulonglong * 16)()
+    lib.b200bwa_counters(ix, 0, cnt, 1)
+    tot = {k: float(sum(s[k] for s in stage)) for k in ("seed", "sa", "chain", "extend", "pestat", "finalize", "gather", "total")}
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    seed_bytes = 64.0 * cnt[0]
+    seed_gbs = seed_bytes / (tot["seed"] / 1e3) / 1e9 if tot["seed"] > 0 else 0.0
+    sa_bytes = 64.0 * cnt[2] + 8.0 * cnt[1]
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "seed_traffic.json"))).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {"kernel": "k_seed", "bound": "hbm", "achieved": seed_gbs, "peak": peak, "unit": "GB/s",
+                "frac": seed_gbs / peak, "traffic": traffic,
+                "peak_source": "measured (MEASURED_PEAKS.json)" if peaks else "fallback",
+                "algorithmic_bytes_per_read": seed_bytes / n_reads, "launches": len(batches),
+                "ms_per_launch": tot["seed"] / len(batches),
+                "sa_kernel": {"bytes_per_read": sa_bytes / n_reads, "GB/s": sa_bytes / (tot["sa"] / 1e3) / 1e9 if tot["sa"] > 0 else 0.0}}
+    cells = float(cnt[3] + cnt[5] + cnt[7])
+    dp_ms = tot["extend"] + tot["finalize"]
+    sw = {"cells_per_read": {"extend": cnt[3] / n_reads, "global": cnt[5] / n_reads, "local": cnt[7] / n_reads},
+          "GCUPS_stage": cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else 0.0,
+          "GCUPS_extend_stage": cnt[3] / (tot["extend"] / 1e3) / 1e9 if tot["extend"] > 0 else 0.0}
+
+    out = {"metric": "BWA-MEM reads/sec 2x150bp PE", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+           "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+           "dtype": "int32", "data": "synthetic",
+           "config": {"workload": workload, "batches_per_step": len(batches), "streams": n_workers,
+                      "l2": "inputs (index + reads, > 800 MB) larger than the 126 MB L2", "parallelism": f"read-batch sharding x{world}"},
+           "gpu_launches": launches, "roofline": roofline, "sw": sw,
+           "stage_ms_per_step": {k: v for k, v in tot.items()}, "clocks": sampler.summary()}
+
+    if rank == 0 and not args.no_cpu and os.access(ORACLE, os.X_OK) and world == 1:
+        sample = min(args.pairs, args.cpu_sample_pairs)
+        v, dt, cpu_s = cpu_reference(args, prefix, f1, f2, sample, host_cores)
+        out["cpu_baseline"] = {"value": v, "unit": "reads/s", "cores": host_cores, "kind": "reference",
+                               "sample": f"first {sample} pairs, oracle/_ref/bwa mem -t {host_cores} -K {args.K}, wall {dt:.1f}s"}
+
+    if not args.no_e2e:
+        # ---- end to end through the reference-facing entry point (what the JNI symbol forwards to) ----
+        sam = os.path.join(d, f"e2e_{rank}.sam")
+        argv = ["bwa", "mem", "-v", "1", "-K", str(args.K), prefix, f1, f2]
+        arr = (ctypes.c_char_p * len(argv))(*[a.encode() for a in argv])
+        os.environ["B200BWA_DEVICE"] = str(local)
+        e2e_pairs = args.pairs
+        if lib.b200bwa_main_to(len(argv), arr, sam.encode()) != 0:  # warm-up: loads + caches the index in HBM
+            raise SystemExit("e2e failed: " + lib.b200bwa_last_error().decode())
+        lib.b200bwa_process_counters(pc, 1)
+        barrier()
+        t0 = time.time()
+        n_e2e = max(1, min(2, args.steps))
+        for _ in range(n_e2e):
+            if lib.b200bwa_main_to(len(argv), arr, sam.encode()) != 0:
+                raise SystemExit("e2e failed: " + lib.b200bwa_last_error().decode())
+        torch.cuda.synchronize()
+        dt = (time.time() - t0) / n_e2e
+        tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        lib.b200bwa_process_counters(pc, 0)
+        out["e2e"] = {"value": world * 2 * e2e_pairs / dt, "unit": "reads/s", "h2d_bytes_per_step": int(pc[0] // n_e2e),
+                      "d2h_bytes_per_step": int(pc[1] // n_e2e), "path": "b200bwa_main_to: FASTQ files (tmpfs) -> SAM file (tmpfs)",
+                      "sam_bytes": os.path.getsize(sam), "seconds_per_step": dt}
+        try:
+            os.remove(sam)
+        except OSError:
+            pass
+    if rank == 0:
+        print(json.dumps(out))
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def prepare_reference_cpu_only(args, d):
+    """--impl reference on a box where the engine arm has not run yet: the index is built by the
+    reference's own `bwa index` (this arm is the reference; it may use its own tools)."""
+    from sparkbwa_b200 import synth
+    prefix = os.path.join(d, "ref")
+    n_ctg = 4 if args.ref_len >= 20_000_000 else 2
+    ctg = synth.make_reference(args.ref_len, n_contigs=n_ctg, seed=args.seed, repeat_frac=0.02)
+    if not os.path.exists(prefix + ".sa"):
+        fa = os.path.join(d, "ref.fa")
+        synth.write_fasta(fa, ctg)
+        t = time.time()
+        subprocess.run([ORACLE, "index", "-p", prefix + ".tmp", fa], check=True, stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        for e in ("pac", "ann", "amb", "bwt", "sa"):
+            os.replace(prefix + ".tmp." + e, prefix + "." + e)
+        sys.stderr.write(f"[bench] reference index built by bwa index in {time.time() - t:.1f}s\n")
+    return ctg, prefix
+
+
+if __name__ == "__main__":
+    main()

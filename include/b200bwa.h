@@ -83,6 +83,20 @@ int b200bwa_upload_batch(b200bwa_index_t* idx, int n_reads, const char* seq, con
                          const int64_t* seq_off, const char* names, int64_t n_processed);
 int b200bwa_run_resident(b200bwa_index_t* idx, int paired, int want_sam, char** sam_out, size_t* sam_len);
 
+/* Runs reads [first, first+count) of the batch uploaded by b200bwa_upload_batch on stream/buffer set
+ * `worker` (0..2; sets may run concurrently from different host threads).  Pairing mode comes from
+ * b200bwa_set_paired.  `t` (may be NULL) receives the device stage times of this call. */
+int b200bwa_run_resident_range(b200bwa_index_t* idx, int worker, int first, int count, int paired, int want_sam,
+                               char** sam_out, size_t* sam_len, b200bwa_times_t* t);
+int b200bwa_set_paired(b200bwa_index_t* idx, int paired);
+
+/* Algorithmic-work counters accumulated by the kernels of one worker: [0] 64-byte occ-block touches of
+ * SMEM seeding, [1] SA lookups, [2] SA walk steps, [3] ksw_extend2 cells, [4] calls, [5] ksw_global2
+ * cells, [6] calls, [7] local-SW cells, [8] calls (definitions: SURVEY.md 8(d)). */
+int b200bwa_counters(b200bwa_index_t* idx, int worker, unsigned long long out[16], int reset);
+/* Process-wide totals: [0] host->device bytes, [1] device->host bytes, [2] kernel launches. */
+int b200bwa_process_counters(unsigned long long out[3], int reset);
+
 /* Multi-GPU plumbing: device pointers/sizes of the index image, and adoption of an image that a
  * peer already placed in this GPU's memory (e.g. by ncclBroadcast). */
 int b200bwa_index_device_image(b200bwa_index_t* idx, void** bwt, size_t* bwt_bytes, void** sa, size_t* sa_bytes,

@@ -14,6 +14,9 @@ struct B2Scratch {
   uint8_t* base;
   size_t cap, used;
   int overflow;
+  // algorithmic DP work of this lane: cells = sum over rows of the band actually computed
+  unsigned long long ext_cells = 0, glob_cells = 0, sw_cells = 0;
+  unsigned ext_calls = 0, glob_calls = 0, sw_calls = 0;
   B2_HD inline void* alloc(size_t bytes, size_t align = 8) {
     size_t o = (used + align - 1) & ~(align - 1);
     if (o + bytes > cap) { overflow = 1; o = 0; if (bytes > cap) return base; }
@@ -178,7 +181,8 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
         int prev = a.score;
         aw[0] = opt.w << i;
         a.score = b2_extend2(s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
-                             opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], eh);
+                             opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], eh, &sc.ext_cells);
+        ++sc.ext_calls;
         if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
       }
       if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) {
@@ -199,7 +203,8 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
         aw[1] = opt.w << i;
         a.score = b2_extend2(l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), rseq + re, opt.mat, opt.o_del,
                              opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
-                             &gscore, &max_off[1], eh);
+                             &gscore, &max_off[1], eh, &sc.ext_cells);
+        ++sc.ext_calls;
         if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
       }
       if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) {
@@ -290,7 +295,8 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
     }
     int nc = 0;
     *score = b2_global2(l_query, query, (int)rlen, rseq, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, eh, z,
-                        out ? &nc : 0, out ? out->cigar : 0, out ? out->cap : 0);
+                        out ? &nc : 0, out ? out->cigar : 0, out ? out->cap : 0, &sc.glob_cells);
+    ++sc.glob_calls;
     if (out) {
       if (nc < 0) { sc.overflow = 1; nc = 0; }
       out->n_cigar = nc;

@@ -83,16 +83,28 @@ B2_HD inline uint64_t b2_inv_psi(const B2Index& ix, uint64_t k) {
   return ix.L2[c] + b2_occ1(ix, k, c);
 }
 
-B2_HD inline uint64_t b2_sa(const B2Index& ix, uint64_t k) {
+B2_HD inline uint64_t b2_sa(const B2Index& ix, uint64_t k, unsigned* n_steps = 0) {
   uint64_t steps = 0, mask = (uint64_t)ix.sa_intv - 1;
   while (k & mask) { ++steps; k = b2_inv_psi(ix, k); }
+  if (n_steps) *n_steps = (unsigned)steps;
   return steps + ix.sa[k >> ix.sa_shift];
 }
 
 // ---------------------------------------------------------------------------------------------
 // Rank pair provider: scalar (host checker builds / single-lane device code) or group-cooperative.
+// 64-byte block touches counted the way SURVEY.md 8(d) defines the algorithmic seeding bytes: one per
+// bwt_occ4 call with k != -1, one for the same-block path of bwt_2occ4 (bwa/bwt.c:177,200).
+B2_HD inline unsigned b2_pair_blocks(const B2Index& ix, uint64_t k, uint64_t l) {
+  const bool kv = (k != (uint64_t)-1), lv = (l != (uint64_t)-1);
+  uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
+  if (kv && lv && (kk >> 7) == (ll >> 7)) return 1;
+  return (unsigned)kv + (unsigned)lv;
+}
+
 struct B2OccScalar {
+  mutable unsigned long long n_blk = 0;
   B2_HD inline void pair(const B2Index& ix, uint64_t k, uint64_t l, uint64_t tk[4], uint64_t tl[4]) const {
+    n_blk += b2_pair_blocks(ix, k, l);
     b2_occ4(ix, k, tk);
     b2_occ4(ix, l, tl);
   }
@@ -103,8 +115,10 @@ struct B2OccScalar {
 struct B2OccCoop {
   unsigned mask;  // lanes of this group inside the warp
   int g;          // lane index inside the group (0..B2_SEED_LANES-1)
+  mutable unsigned long long n_blk = 0;
   __device__ inline bool leader() const { return g == 0; }
   __device__ inline void pair(const B2Index& ix, uint64_t k, uint64_t l, uint64_t tk[4], uint64_t tl[4]) const {
+    n_blk += b2_pair_blocks(ix, k, l);
     const bool kv = (k != (uint64_t)-1), lv = (l != (uint64_t)-1);
     uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
     uint4 vk = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);

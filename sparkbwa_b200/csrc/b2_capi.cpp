@@ -7,6 +7,7 @@
 #include <string>
 #include <vector>
 #include <memory>
+#include <atomic>
 #include "../../include/b200bwa.h"
 #include "b2_host.h"
 
@@ -264,6 +265,47 @@ int b200bwa_run_resident(b200bwa_index_t* ix, int paired, int want_sam, char** s
     if (want_sam && sam_out) { *sam_out = dup_out(sam, sam_len); return *sam_out ? 0 : 1; }
     return 0;
   } catch (const std::exception& e) { b2_tls_error = e.what(); return 1; }
+}
+
+int b200bwa_run_resident_range(b200bwa_index_t* ix, int worker, int first, int count, int paired, int want_sam,
+                               char** sam_out, size_t* sam_len, b200bwa_times_t* t) {
+  try {
+    if (!ix) return 1;
+    // options are set once by the caller (b200bwa_set_options / b200bwa_set_paired); concurrent workers share them
+    std::string sam;
+    if (ix->engine->run_resident_range(ix->args.has_pes0 ? ix->args.pes0 : 0, want_sam ? &sam : 0, worker, 0, first, count)) {
+      b2_tls_error = ix->engine->last_error();
+      return 1;
+    }
+    if (t) {
+      const B2StageTimes& s = ix->engine->times(worker);
+      t->h2d = s.h2d; t->seed = s.seed; t->sa = s.sa; t->chain = s.chain; t->extend = s.extend; t->pestat = s.pestat;
+      t->finalize = s.final_; t->gather = s.gather; t->d2h = s.d2h; t->total = s.total; t->launches = s.launches;
+      t->n_seed_tasks = s.n_seed_tasks; t->n_regs = s.n_regs; t->sam_bytes = s.sam_bytes;
+    }
+    (void)paired;
+    if (want_sam && sam_out) { *sam_out = dup_out(sam, sam_len); return *sam_out ? 0 : 1; }
+    return 0;
+  } catch (const std::exception& e) { b2_tls_error = e.what(); return 1; }
+}
+
+int b200bwa_set_paired(b200bwa_index_t* ix, int paired) {
+  if (!ix) return 1;
+  if (paired) ix->args.opt.flag |= B2_F_PE; else ix->args.opt.flag &= ~B2_F_PE;
+  ix->engine->set_options(ix->args.opt, ix->args.rg_id.c_str(), ix->args.verbose);
+  return 0;
+}
+
+int b200bwa_counters(b200bwa_index_t* ix, int worker, unsigned long long out[16], int reset) {
+  if (!ix) return 1;
+  return ix->engine->counters(worker, out, 0, 0, reset);
+}
+
+extern std::atomic<unsigned long long> b2_g_h2d_bytes, b2_g_d2h_bytes, b2_g_launches;
+int b200bwa_process_counters(unsigned long long out[3], int reset) {
+  out[0] = b2_g_h2d_bytes.load(); out[1] = b2_g_d2h_bytes.load(); out[2] = b2_g_launches.load();
+  if (reset) { b2_g_h2d_bytes = 0; b2_g_d2h_bytes = 0; b2_g_launches = 0; }
+  return 0;
 }
 
 int b200bwa_index_device_image(b200bwa_index_t* ix, void** bwt, size_t* bwt_bytes, void** sa, size_t* sa_bytes, void** pac,

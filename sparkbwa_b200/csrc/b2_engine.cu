@@ -13,6 +13,9 @@
 thread_local B2Dim b2_dim;
 #endif
 
+#include <atomic>
+std::atomic<unsigned long long> b2_g_h2d_bytes{0}, b2_g_d2h_bytes{0}, b2_g_launches{0};
+
 namespace {
 
 template <class T>
@@ -64,12 +67,16 @@ struct Worker {
   DBuf<uint8_t> scratch; DBuf<int8_t> pe_dir; DBuf<int64_t> pe_is; DBuf<double> pairtab;
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
+  DBuf<unsigned long long> counters;
+  unsigned long long h_counters[16] = {0};
+  unsigned long long h2d_bytes = 0, d2h_bytes = 0;
   size_t scratch_per_lane = 0;
   int cap_intv = 0, slot_size = 0;
   // resident batch metadata
   int n_reads = 0, max_len = 0;
   int64_t n_processed = 0;
   bool resident = false;
+  int n_reads_run = 0;
   B2StageTimes times;
   std::vector<int8_t> h_dir; std::vector<int64_t> h_is; std::vector<char> h_sam;
   void* pin_sam = nullptr; size_t pin_sam_cap = 0;
@@ -125,7 +132,8 @@ class B2EngineImpl {
       w.timer.init(w.stream);
       w.scratch_per_lane = cfg.scratch_per_lane;
       w.cap_intv = cfg.cap_intv;
-      if (w.flags.ensure(4)) return fail("device allocation failed");
+      if (w.flags.ensure(4) || w.counters.ensure(16)) return fail("device allocation failed");
+      b2_dev_memset(w.counters.p, 0, 16 * sizeof(unsigned long long), w.stream);
     }
     return 0;
   }
@@ -171,7 +179,7 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release();
+      w.flags.release(); w.counters.release();
       if (w.pin_sam) b2_host_free(w.pin_sam);
 #if !defined(B2_HOSTSIM)
       if (w.stream) cudaStreamDestroy(w.stream);
@@ -211,6 +219,8 @@ class B2EngineImpl {
     b2_h2d(w.l_seq.p, b.l_seq.data(), n * sizeof(int32_t), w.stream);
     b2_h2d(w.l_name.p, b.l_name.data(), n * sizeof(int32_t), w.stream);
     b2_h2d(w.l_com.p, b.l_com.data(), n * sizeof(int32_t), w.stream);
+    b2_g_h2d_bytes += b.seq.size() + b.qual.size() + n + b.names.size() + b.comments.size() + (size_t)n * (3 * 8 + 3 * 4);
+    w.h2d_bytes += b.seq.size() + b.qual.size() + n + b.names.size() + b.comments.size() + (size_t)n * (3 * 8 + 3 * 4);
     int t1 = w.timer.mark();
     b2_sync(w.stream);
     w.times.h2d = w.timer.ms(t0, t1);
@@ -225,9 +235,14 @@ class B2EngineImpl {
     return check_cuda("kernel");
   }
 
-  int run(Worker& w, const B2Pes* pes0, std::string* sam) {
-    if (!w.resident) return fail("no resident batch");
-    const int n = w.n_reads;
+  // Runs the pipeline over reads [first, first+count) of the batch resident on `src` using the stream and
+  // buffers of `w` (src == w for the ordinary one-batch call).
+  int run(Worker& w, const B2Pes* pes0, std::string* sam, Worker* srcp = nullptr, int first = 0, int count = -1) {
+    Worker& src = srcp ? *srcp : w;
+    if (!src.resident) return fail("no resident batch");
+    if (count < 0) count = src.n_reads - first;
+    if (first < 0 || first + count > src.n_reads) return fail("resident range out of bounds");
+    const int n = count;
     const bool pe = (opt.flag & B2_F_PE) != 0;
     if (pe && (n & 1)) return fail("paired-end batch with an odd number of reads");
     if (opt.flag & B2_F_SMARTPE) return fail("smart pairing (-p) is not supported by this build");
@@ -240,11 +255,15 @@ class B2EngineImpl {
     memset(&c, 0, sizeof(c));
     c.opt = opt; c.ix = ix; c.fmt = fmt;
     c.tb.logtab = d_logtab.p; c.tb.n_log = n_log;
-    c.n_processed = w.n_processed; c.max_len = w.max_len;
-    c.b.n_reads = n; c.b.seq = w.seq.p; c.b.qual = w.qual.p; c.b.has_qual = w.has_qual.p; c.b.names = w.names.p;
-    c.b.comments = w.comments.p; c.b.seq_off = w.seq_off.p; c.b.l_seq = w.l_seq.p; c.b.name_off = w.name_off.p;
-    c.b.l_name = w.l_name.p; c.b.com_off = w.com_off.p; c.b.l_com = w.l_com.p;
+    c.n_processed = src.n_processed + first; c.max_len = src.max_len;
+    w.max_len = src.max_len;
+    c.b.n_reads = n; c.b.seq = src.seq.p; c.b.qual = src.qual.p; c.b.has_qual = src.has_qual.p + first; c.b.names = src.names.p;
+    c.b.comments = src.comments.p; c.b.seq_off = src.seq_off.p + first; c.b.l_seq = src.l_seq.p + first;
+    c.b.name_off = src.name_off.p + first; c.b.l_name = src.l_name.p + first; c.b.com_off = src.com_off.p + first;
+    c.b.l_com = src.l_com.p + first;
+    w.n_reads_run = n;
     c.flags = w.flags.p;
+    c.counters = w.counters.p;
     const int lanes = cfg.lane_grid * cfg.lane_block;
     int flags = 0;
     int ev_begin = w.timer.mark();
@@ -410,6 +429,8 @@ class B2EngineImpl {
         if (b2_host_alloc(&w.pin_sam, w.pin_sam_cap)) return fail("pinned host allocation failed");
       }
       b2_d2h(w.pin_sam, w.sam_out.p, (size_t)total, w.stream);
+      w.d2h_bytes += (size_t)total;
+      b2_g_d2h_bytes += (size_t)total;
       ev_d2h = w.timer.mark();
       if (b2_sync(w.stream)) return fail("device synchronisation failed");
       sam->append((const char*)w.pin_sam, (size_t)total);
@@ -417,6 +438,7 @@ class B2EngineImpl {
       if (b2_sync(w.stream)) return fail("device synchronisation failed");
     }
     if (check_cuda("pipeline")) return 1;
+    b2_g_launches += (unsigned long long)w.times.launches;
     w.times.seed = w.timer.ms(ev_begin, ev_seed);
     w.times.sa = w.timer.ms(ev_seed, ev_sa);
     w.times.chain = w.timer.ms(ev_sa, ev_chain);
@@ -504,11 +526,27 @@ int B2Engine::upload(const B2HostBatch& b, int worker) { return impl_->upload(im
 int B2Engine::run_resident(const B2Pes* pes0, std::string* sam, int worker) {
   return impl_->run(impl_->workers[worker], pes0, sam);
 }
+int B2Engine::run_resident_range(const B2Pes* pes0, std::string* sam, int worker, int src_worker, int first, int count) {
+  return impl_->run(impl_->workers[worker], pes0, sam, &impl_->workers[src_worker], first, count);
+}
 void B2Engine::set_options(const B2Opt& opt, const char* rg_id, int verbose) {
   impl_->opt = opt; impl_->cfg.verbose = verbose; impl_->set_rg(rg_id);
 }
 const B2Opt& B2Engine::options() const { return impl_->opt; }
 const B2StageTimes& B2Engine::times(int worker) const { return impl_->workers[worker].times; }
+int B2Engine::counters(int worker, unsigned long long out[16], unsigned long long* h2d, unsigned long long* d2h, int reset) {
+  Worker& w = impl_->workers[worker];
+  b2_d2h(out, w.counters.p, 16 * sizeof(unsigned long long), w.stream);
+  b2_sync(w.stream);
+  if (h2d) *h2d = w.h2d_bytes;
+  if (d2h) *d2h = w.d2h_bytes;
+  if (reset) {
+    b2_dev_memset(w.counters.p, 0, 16 * sizeof(unsigned long long), w.stream);
+    b2_sync(w.stream);
+    w.h2d_bytes = w.d2h_bytes = 0;
+  }
+  return 0;
+}
 const char* B2Engine::last_error() const { return impl_->err.c_str(); }
 int B2Engine::n_workers() const { return (int)impl_->workers.size(); }
 void B2Engine::index_device_ptrs(void** bwt, size_t* bb, void** sa, size_t* sb, void** pac, size_t* pb) {

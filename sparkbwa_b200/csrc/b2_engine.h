@@ -73,10 +73,14 @@ class B2Engine {
   // device-resident variant used by the benchmark: upload once, run the kernels many times
   int upload(const B2HostBatch& b, int worker = 0);
   int run_resident(const B2Pes* pes0, std::string* sam, int worker = 0);
+  // reads [first, first+count) of the batch resident on src_worker, run on `worker`'s stream/buffers
+  int run_resident_range(const B2Pes* pes0, std::string* sam, int worker, int src_worker, int first, int count);
   // per-call options (a cached index serves successive calls with different bwa-mem options)
   void set_options(const B2Opt& opt, const char* rg_id, int verbose);
   const B2Opt& options() const;
   const B2StageTimes& times(int worker = 0) const;
+  // cumulative algorithmic-work counters of a worker (see B2_CNT_* in b2_kernels.cuh) plus copied bytes
+  int counters(int worker, unsigned long long out[16], unsigned long long* h2d_bytes, unsigned long long* d2h_bytes, int reset);
   const char* last_error() const;
   int n_workers() const;
   // raw device pointers of the index image (for broadcasting it to peer GPUs)

@@ -22,6 +22,9 @@
 #define B2_FLAG_ERR_TABLE 8
 #define B2_FLAG_OVF_REG 16
 
+enum { B2_CNT_OCC_BLOCKS = 0, B2_CNT_SA_CALLS, B2_CNT_SA_STEPS, B2_CNT_EXT_CELLS, B2_CNT_EXT_CALLS, B2_CNT_GLOB_CELLS,
+       B2_CNT_GLOB_CALLS, B2_CNT_SW_CELLS, B2_CNT_SW_CALLS, B2_CNT_N };
+
 struct B2Batch {  // device-resident read batch
   int n_reads;
   const uint8_t* seq;       // base codes 0..4, concatenated
@@ -47,6 +50,7 @@ struct B2Ctx {
   int64_t n_processed;
   int max_len;            // longest read in the batch
   int* flags;
+  unsigned long long* counters;  // [B2_CNT_*], algorithmic work
   // seeding
   B2Intv* intv; int cap_intv; int32_t* n_intv; int32_t* n_tasks;
   B2Intv* seed_scratch;   // per group: 3*(max_len+1)
@@ -97,9 +101,11 @@ B2_KERNEL k_seed(B2Ctx c) {
     }
     if (occ.leader()) { c.n_intv[r] = n; c.n_tasks[r] = (int32_t)tasks; }
   }
+  if (occ.leader() && occ.n_blk) B2_ATOMIC_ADD(&c.counters[B2_CNT_OCC_BLOCKS], occ.n_blk);
 }
 
 B2_KERNEL k_sa(B2Ctx c) {
+  unsigned long long steps_total = 0, calls = 0;
   for (int64_t t = B2_GTID(); t < c.n_seed_tasks; t += B2_GSIZE()) {
     int lo = 0, hi = c.b.n_reads;  // last r with seed_off[r] <= t
     while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.seed_off[mid] <= t) lo = mid; else hi = mid; }
@@ -117,13 +123,16 @@ B2_KERNEL k_sa(B2Ctx c) {
     const long step = p.x[2] > (uint64_t)c.opt.max_occ ? (long)(p.x[2] / c.opt.max_occ) : 1;
     const int slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
     B2Seed s;
-    s.rbeg = (int64_t)b2_sa(c.ix, p.x[0] + (uint64_t)(idx * step));
+    unsigned n_steps = 0;
+    s.rbeg = (int64_t)b2_sa(c.ix, p.x[0] + (uint64_t)(idx * step), &n_steps);
+    steps_total += n_steps; ++calls;
     s.qbeg = (int32_t)(p.info >> 32);
     s.len = s.score = slen;
     s.next = -1;
     c.raw[t] = s;
     c.raw_rid[t] = b2_intv2rid(c.ix, s.rbeg, s.rbeg + s.len);
   }
+  if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_CALLS], calls); B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_STEPS], steps_total); }
 }
 
 B2_HD inline B2Scratch b2_lane_scratch(const B2Ctx& c, int lane) {
@@ -131,6 +140,12 @@ B2_HD inline B2Scratch b2_lane_scratch(const B2Ctx& c, int lane) {
   sc.base = c.scratch + (size_t)lane * c.scratch_per_lane;
   sc.cap = c.scratch_per_lane; sc.used = 0; sc.overflow = 0;
   return sc;
+}
+
+B2_D inline void b2_flush_counters(const B2Ctx& c, const B2Scratch& sc) {
+  if (sc.ext_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], sc.ext_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], (unsigned long long)sc.ext_calls); }
+  if (sc.glob_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CELLS], sc.glob_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CALLS], (unsigned long long)sc.glob_calls); }
+  if (sc.sw_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_SW_CELLS], sc.sw_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_SW_CALLS], (unsigned long long)sc.sw_calls); }
 }
 
 B2_KERNEL k_chain(B2Ctx c) {
@@ -191,6 +206,7 @@ B2_KERNEL k_extend(B2Ctx c) {
     }
     c.n_regs[r] = n_av;
   }
+  b2_flush_counters(c, sc);
 }
 
 B2_KERNEL k_pestat(B2Ctx c) {
@@ -224,6 +240,7 @@ B2_KERNEL k_final_se(B2Ctx c) {
     if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
     c.sam_len[r] = (int32_t)out.len;
   }
+  b2_flush_counters(c, sc);
 }
 
 B2_KERNEL k_final_pe(B2Ctx c) {
@@ -253,6 +270,7 @@ B2_KERNEL k_final_pe(B2Ctx c) {
     if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
     c.sam_len[i] = (int32_t)out.len;
   }
+  b2_flush_counters(c, sc);
 }
 
 // exclusive scan int32 -> int64, out[n] = total.  One block.

@@ -17,7 +17,8 @@ struct B2EH { int32_t h, e; };
 // query/target: codes 0..4; eh: qlen+1 entries of scratch.  Returns the best extension score.
 B2_HD inline int b2_extend2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat,
                             int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
-                            int* _qle, int* _tle, int* _gtle, int* _gscore, int* _max_off, B2EH* eh) {
+                            int* _qle, int* _tle, int* _gtle, int* _gscore, int* _max_off, B2EH* eh,
+                            unsigned long long* cells = 0) {
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
   int i, j, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
   for (j = 0; j <= qlen; ++j) eh[j].h = eh[j].e = 0;
@@ -40,6 +41,7 @@ B2_HD inline int b2_extend2(int qlen, const uint8_t* query, int tlen, const uint
     if (beg < i - w) beg = i - w;
     if (end > i + w + 1) end = i + w + 1;
     if (end > qlen) end = qlen;
+    if (cells) *cells += (unsigned long long)(end > beg ? end - beg : 0);
     if (beg == 0) {
       h1 = h0 - (o_del + e_del * (i + 1));
       if (h1 < 0) h1 = 0;
@@ -102,7 +104,7 @@ B2_HD inline int b2_push_cigar(uint32_t* cigar, int n, int op, int len) {
 // cigar (capacity cigar_cap) receives the operations; *n_cigar < 0 signals capacity overflow.
 B2_HD inline int b2_global2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat,
                             int o_del, int e_del, int o_ins, int e_ins, int w, B2EH* eh, uint8_t* z,
-                            int* n_cigar_, uint32_t* cigar, int cigar_cap) {
+                            int* n_cigar_, uint32_t* cigar, int cigar_cap, unsigned long long* cells = 0) {
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
   int i, j, n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
   if (n_cigar_) *n_cigar_ = 0;
@@ -115,6 +117,7 @@ B2_HD inline int b2_global2(int qlen, const uint8_t* query, int tlen, const uint
     beg = i > w ? i - w : 0;
     end = i + w + 1 < qlen ? i + w + 1 : qlen;
     h1 = beg == 0 ? -(o_del + e_del * (i + 1)) : B2_MINUS_INF;
+    if (cells) *cells += (unsigned long long)(end > beg ? end - beg : 0);
     uint8_t* zi = z ? z + (long)i * n_col : 0;
     for (j = beg; j < end; ++j) {
       B2EH* p = &eh[j];
@@ -174,7 +177,7 @@ struct B2Kswr { int score, te, qe, score2, te2, tb, qb; };
 // sub-optimal list (bounded by tlen because consecutive rows are merged).
 B2_HD inline B2Kswr b2_sw_local(int size, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                 const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra,
-                                int16_t* work, uint64_t* bbuf) {
+                                int16_t* work, uint64_t* bbuf, unsigned long long* cells = 0) {
   const int lanes = size == 1 ? 16 : 8;
   const int slen = (qlen + lanes - 1) / lanes;
   const int n = slen * lanes;
@@ -197,6 +200,7 @@ B2_HD inline B2Kswr b2_sw_local(int size, int qlen, const uint8_t* query, int tl
   for (int i = 0; i < tlen; ++i) {
     const int8_t* srow = mat + target[i] * 5;
     int imax;
+    if (cells) *cells += (unsigned long long)qlen;
     for (int l = 0; l < lanes; ++l) { fv[l] = 0; mxv[l] = 0; }
     for (int l = lanes - 1; l > 0; --l) hv[l] = H0[(slen - 1) * lanes + l - 1];
     hv[0] = 0;
@@ -286,13 +290,14 @@ B2_HD inline void b2_revseq(int l, uint8_t* s) {
 
 // query/target are modified in place and restored (as the reference does).
 B2_HD inline B2Kswr b2_align2(int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat, int o_del,
-                              int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf) {
+                              int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf,
+                              unsigned long long* cells = 0) {
   const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;
-  B2Kswr r = b2_sw_local(size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf);
+  B2Kswr r = b2_sw_local(size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, cells);
   if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
   b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target);
   B2Kswr rr = b2_sw_local(size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
-                          B2_KSW_XSTOP | r.score, work, bbuf);
+                          B2_KSW_XSTOP | r.score, work, bbuf, cells);
   b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target);
   if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
   return r;

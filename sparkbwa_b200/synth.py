@@ -162,3 +162,77 @@ def write_fastq(path: str, reads):
     with open(path, "wb") as f:
         for name, seq, qual in reads:
             f.write(b"@" + name + b"\n" + seq + b"\n+\n" + qual + b"\n")
+
+
+def simulate_pairs_fast(contigs, n_pairs: int, read_len: int = 150, seed: int = 7, sub: float = 0.01,
+                        indel: float = 0.001, ins_mean: float = 400.0, ins_sd: float = 40.0, chunk: int = 200_000):
+    """Vectorised paired-end simulator for the benchmark workloads (millions of pairs).
+
+    Same model as simulate_reads (uniform start, 50/50 strand, per-base substitutions, FR pairs with
+    N(ins_mean, ins_sd) outer distance) with at most one single-base indel per read.  Yields chunks
+    (seq1, seq2) of ASCII uint8 arrays shaped (m, read_len); names are r%09d by global pair index.
+    """
+    rng = np.random.default_rng(seed)
+    ref = np.concatenate([c for _, c in contigs]).astype(np.uint8)
+    lens = np.array([len(c) for _, c in contigs], dtype=np.int64)
+    offs = np.concatenate([[0], np.cumsum(lens)[:-1]])
+    prob = lens / lens.sum()
+    L = read_len
+    cols = np.arange(L, dtype=np.int64)
+    done = 0
+    while done < n_pairs:
+        m = min(chunk, n_pairs - done)
+        ci = rng.choice(len(contigs), size=m, p=prob)
+        isz = np.maximum(L + 10, rng.normal(ins_mean, ins_sd, size=m)).astype(np.int64)
+        isz = np.minimum(isz, lens[ci] - 4)
+        st = offs[ci] + (rng.random(m) * (lens[ci] - isz - 2)).astype(np.int64)
+        out = []
+        for which in range(2):
+            if which == 0:
+                idx = st[:, None] + cols[None, :]
+            else:
+                idx = (st + isz - 1)[:, None] - cols[None, :]
+            # one optional single-base indel per read: shift the source index after position p
+            ev = rng.random(m) < indel * L
+            p = rng.integers(10, L - 10, size=m)
+            is_del = rng.random(m) < 0.5
+            shift = (cols[None, :] >= p[:, None]) & ev[:, None]
+            step = np.where(is_del, 1, -1)[:, None] * (1 if which == 0 else -1)
+            idx = idx + shift * step
+            r = ref[idx]
+            if which == 1:
+                r = 3 - r
+            ins = ev & ~is_del
+            if ins.any():  # the inserted base itself is random
+                rows = np.nonzero(ins)[0]
+                r[rows, p[rows]] = rng.integers(0, 4, size=rows.size, dtype=np.uint8)
+            if sub > 0:
+                msk = rng.random((m, L)) < sub
+                k = int(msk.sum())
+                r[msk] = (r[msk] + rng.integers(1, 4, size=k, dtype=np.uint8)) & 3
+            out.append(r.astype(np.uint8))
+        flip = rng.random(m) < 0.5
+        a = np.where(flip[:, None], out[1], out[0])
+        b = np.where(flip[:, None], out[0], out[1])
+        yield _BASES[a], _BASES[b]
+        done += m
+
+
+def write_fastq_fixed(path: str, seq_chunks, first_index: int = 0, suffix: bytes = b"/1"):
+    """Write fixed-width FASTQ records from (m, L) ASCII arrays; returns the number of reads."""
+    n = 0
+    with open(path, "wb") as f:
+        for s in seq_chunks:
+            m, L = s.shape
+            ids = np.arange(first_index + n, first_index + n + m)
+            name = np.char.zfill(ids.astype(str), 9).astype("S9").view(np.uint8).reshape(m, 9)
+            head = np.empty((m, 1 + 1 + 9 + len(suffix) + 1), dtype=np.uint8)
+            head[:, 0] = ord("@"); head[:, 1] = ord("r"); head[:, 2:11] = name
+            head[:, 11:11 + len(suffix)] = np.frombuffer(suffix, dtype=np.uint8)
+            head[:, -1] = 10
+            mid = np.frombuffer(b"\n+\n", dtype=np.uint8)
+            rec = np.concatenate([head, s, np.broadcast_to(mid, (m, 3)), np.full((m, L), ord("I"), dtype=np.uint8),
+                                  np.full((m, 1), 10, dtype=np.uint8)], axis=1)
+            f.write(rec.tobytes())
+            n += m
+    return n
