@@ -8,6 +8,7 @@
 #include "b2_types.h"
 #include "b2_sort.cuh"
 #include "b2_ksw.cuh"
+#include "b2_coop.cuh"
 
 // Per-task bump scratch (stack discipline via mark/reset).
 struct B2Scratch {
@@ -17,6 +18,14 @@ struct B2Scratch {
   // algorithmic DP work of this lane: cells = sum over rows of the band actually computed
   unsigned long long ext_cells = 0, glob_cells = 0, sw_cells = 0;
   unsigned ext_calls = 0, glob_calls = 0, sw_calls = 0;
+  // lane group serving this task (device: B2_TASK_LANES lanes running the same control flow)
+  int lane = 0, gsize = 1;
+  unsigned gmask = 0;
+  B2_HD inline void gsync() const {
+#if defined(__CUDA_ARCH__)
+    if (gsize > 1) __syncwarp(gmask);
+#endif
+  }
   B2_HD inline void* alloc(size_t bytes, size_t align = 8) {
     size_t o = (used + align - 1) & ~(align - 1);
     if (o + bytes > cap) { overflow = 1; o = 0; if (bytes > cap) return base; }
@@ -26,6 +35,44 @@ struct B2Scratch {
   B2_HD inline size_t mark() const { return used; }
   B2_HD inline void reset(size_t m) { used = m; }
 };
+
+B2_HD inline int b2_extend2_any(B2Scratch& sc, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
+                                int zdrop, int h0, int* qle, int* tle, int* gtle, int* gscore, int* max_off, B2EH* eh) {
+  ++sc.ext_calls;
+#if defined(__CUDA_ARCH__)
+  if (sc.gsize > 1) {
+    B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
+    return b2_extend2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle,
+                           gtle, gscore, max_off, eh, &sc.ext_cells);
+  }
+#endif
+  return b2_extend2(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle, gtle,
+                    gscore, max_off, eh, &sc.ext_cells);
+}
+
+B2_HD inline B2Kswr b2_align2_any(B2Scratch& sc, int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat,
+                                  int o_del, int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf) {
+  ++sc.sw_calls;
+#if defined(__CUDA_ARCH__)
+  if (sc.gsize >= 16) {
+    B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
+    const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;
+    B2Kswr r = b2_sw_local_coop(g, size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
+    if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
+    // all lanes reverse the same private-to-the-group buffers: do it once
+    if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
+    g.sync();
+    B2Kswr rr = b2_sw_local_coop(g, size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
+                                 B2_KSW_XSTOP | r.score, work, bbuf, &sc.sw_cells);
+    if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
+    g.sync();
+    if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+    return r;
+  }
+#endif
+  return b2_align2(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
+}
 
 B2_HD inline int b2_get_pac(const uint8_t* pac, int64_t l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }
 
@@ -180,9 +227,8 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
       for (i = 0; i < 2; ++i) {
         int prev = a.score;
         aw[0] = opt.w << i;
-        a.score = b2_extend2(s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
-                             opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], eh, &sc.ext_cells);
-        ++sc.ext_calls;
+        a.score = b2_extend2_any(sc, s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
+                                 opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], eh);
         if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
       }
       if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) {
@@ -201,10 +247,9 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
       for (i = 0; i < 2; ++i) {
         int prev = a.score;
         aw[1] = opt.w << i;
-        a.score = b2_extend2(l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), rseq + re, opt.mat, opt.o_del,
-                             opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
-                             &gscore, &max_off[1], eh, &sc.ext_cells);
-        ++sc.ext_calls;
+        a.score = b2_extend2_any(sc, l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), rseq + re, opt.mat, opt.o_del,
+                                 opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
+                                 &gscore, &max_off[1], eh);
         if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
       }
       if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) {
@@ -263,8 +308,9 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
   int64_t rlen = b2_get_seq(l_pac, ix.pac, rb, re, rseq);
   if (re - rb != rlen) { sc.reset(mk); return 0; }
   if (rb >= l_pac) {  // reverse both so that indels are placed leftmost on the forward strand
-    b2_revseq(l_query, query);
-    b2_revseq((int)rlen, rseq);
+    sc.gsync();
+    if (sc.lane == 0) { b2_revseq(l_query, query); b2_revseq((int)rlen, rseq); }
+    sc.gsync();
   }
   if (l_query == re - rb && w_ == 0) {
     if (out) { out->cigar[0] = (uint32_t)l_query << 4 | 0; out->n_cigar = 1; }
@@ -289,7 +335,7 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
       z = (uint8_t*)sc.alloc((size_t)n_col * (size_t)rlen, 1);
     }
     if (sc.overflow) {
-      if (rb >= l_pac) b2_revseq(l_query, query);
+      if (rb >= l_pac) { sc.gsync(); if (sc.lane == 0) b2_revseq(l_query, query); sc.gsync(); }
       sc.reset(mk);
       return 0;
     }
@@ -335,7 +381,7 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
     out->l_md = l;
     out->NM = n_mm + n_gap;
   }
-  if (rb >= l_pac) b2_revseq(l_query, query);
+  if (rb >= l_pac) { sc.gsync(); if (sc.lane == 0) b2_revseq(l_query, query); sc.gsync(); }
   sc.reset(mk);
   return 1;
 }

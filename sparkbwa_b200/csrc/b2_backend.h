@@ -31,6 +31,7 @@ inline void b2_host_free(void* p) { free(p); }
 #define B2_ATOMIC_OR(p, v) (*(p) |= (v))
 #define B2_ATOMIC_ADD(p, v) (*(p) += (v))
 #define B2_LANE_GROUP 1
+#define B2_TASK_GROUP 1
 #else
 #include <cuda_runtime.h>
 #define B2_KERNEL static __global__ void
@@ -49,4 +50,5 @@ inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2_LANE_GROUP B2_SEED_LANES
+#define B2_TASK_GROUP B2_TASK_LANES
 #endif

@@ -1,0 +1,278 @@
+// Group-cooperative (sub-warp) forms of the DP kernels, device only.
+//
+// A "task group" of B2_TASK_LANES lanes serves one read (extension stage) or one read pair
+// (finalisation stage).  All lanes run the same control flow on the same data; inside the DP
+// routines below the lanes split the cells of a row and exchange partial results with warp
+// shuffles, so the per-read critical path shrinks by about the group width while the results stay
+// bit-identical to the scalar forms in b2_ksw.cuh (which the host checker build keeps using):
+//
+//   b2_extend2_coop   row-parallel ksw_extend2 (bwa/ksw.c:380-479).  Within a row E depends only on
+//                     the previous row and F is a max-plus prefix scan of M:
+//                       F[j] = max_{beg<=k<j}( max(0, M[k]-oe_ins) + k*e_ins ) - (j-1)*e_ins
+//                     each lane owns a contiguous chunk of the band, one exclusive prefix-max scan
+//                     over the lanes links the chunks, and the row reductions (max with last-index
+//                     tie rule, first/last non-zero cell for the band trimming) are butterflies.
+//   b2_sw_local_coop  ksw_u8/ksw_i16 (bwa/ksw.c:111-334) with one GPU lane per SSE lane: the striped
+//                     layout, the byte/word saturation, the lane shifts (_mm_slli_si128) and the
+//                     lazy-F loop with its early exit map one to one.
+#pragma once
+#include "b2_ksw.cuh"
+
+#define B2_TASK_LANES 16
+
+#if defined(__CUDACC__)
+
+struct B2G {
+  unsigned mask;  // lanes of this group inside the warp
+  int lane;       // 0..size-1
+  int size;       // power of two
+  __device__ inline int shfl(int v, int src) const { return __shfl_sync(mask, v, src, size); }
+  __device__ inline int shfl_up(int v, int d) const { return __shfl_up_sync(mask, v, d, size); }
+  __device__ inline int shfl_xor(int v, int m) const { return __shfl_xor_sync(mask, v, m, size); }
+  __device__ inline long long shfl_xor64(long long v, int m) const { return __shfl_xor_sync(mask, v, m, size); }
+  __device__ inline void sync() const { __syncwarp(mask); }
+  __device__ inline int max_all(int v) const { for (int d = size >> 1; d; d >>= 1) { int o = shfl_xor(v, d); v = v > o ? v : o; } return v; }
+  __device__ inline int min_all(int v) const { for (int d = size >> 1; d; d >>= 1) { int o = shfl_xor(v, d); v = v < o ? v : o; } return v; }
+  __device__ inline long long max_all64(long long v) const { for (int d = size >> 1; d; d >>= 1) { long long o = shfl_xor64(v, d); v = v > o ? v : o; } return v; }
+};
+
+__device__ inline int b2_extend2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                      const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
+                                      int zdrop, int h0, int* _qle, int* _tle, int* _gtle, int* _gscore, int* _max_off,
+                                      B2EH* eh, unsigned long long* cells) {
+  const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+  const int G = g.size;
+  int i, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
+  {  // first row (closed form of the reference's serial initialisation)
+    const int a1 = h0 > oe_ins ? h0 - oe_ins : 0;
+    for (int j = g.lane; j <= qlen; j += G) {
+      int h = 0;
+      if (j == 0) h = h0;
+      else { h = a1 - (j - 1) * e_ins; h = h > 0 ? h : 0; }
+      eh[j].h = h; eh[j].e = 0;
+    }
+  }
+  g.sync();
+  max = 0;
+  for (i = 0; i < 25; ++i) max = max > mat[i] ? max : mat[i];
+  max_ins = (int)((double)(qlen * max + end_bonus - o_ins) / e_ins + 1.);
+  max_ins = max_ins > 1 ? max_ins : 1;
+  w = w < max_ins ? w : max_ins;
+  max_del = (int)((double)(qlen * max + end_bonus - o_del) / e_del + 1.);
+  max_del = max_del > 1 ? max_del : 1;
+  w = w < max_del ? w : max_del;
+  max = h0; max_i = max_j = -1; max_ie = -1; gscore = -1; max_off = 0;
+  beg = 0; end = qlen;
+  const int NEG = -(1 << 29);
+  for (i = 0; i < tlen; ++i) {
+    const int8_t* q = mat + target[i] * 5;
+    if (beg < i - w) beg = i - w;
+    if (end > i + w + 1) end = i + w + 1;
+    if (end > qlen) end = qlen;
+    const int n = end - beg;
+    int h1init;
+    if (beg == 0) { h1init = h0 - (o_del + e_del * (i + 1)); if (h1init < 0) h1init = 0; } else h1init = 0;
+    if (n <= 0) {  // empty band: the reference's inner loop does not run, m stays 0
+      if (end == qlen) { max_ie = gscore > h1init ? max_ie : i; gscore = gscore > h1init ? gscore : h1init; }
+      break;
+    }
+    if (cells && g.lane == 0) *cells += (unsigned long long)n;
+    const int C = (n + G - 1) / G;
+    const int mb = beg + g.lane * C;
+    int me = mb + C; me = me < end ? me : end;
+    // pass A: chunk-local maximum of V[k] = max(0, M[k]-oe_ins) + k*e_ins
+    int vloc = NEG;
+    for (int j = mb; j < me; ++j) {
+      int M = eh[j].h;
+      M = M ? M + q[query[j]] : 0;
+      int t = M - oe_ins; t = t > 0 ? t : 0;
+      t += j * e_ins;
+      vloc = vloc > t ? vloc : t;
+    }
+    // exclusive prefix maximum over the lanes
+    int incl = vloc;
+    for (int d = 1; d < G; d <<= 1) { int o = g.shfl_up(incl, d); if (g.lane >= d) incl = incl > o ? incl : o; }
+    int pre = g.shfl_up(incl, 1);
+    if (g.lane == 0) pre = NEG;
+    // pass B: cells of this lane, left to right
+    long long key = -1;            // (H << 32 | j): row maximum, ties to the larger j
+    int first_nz = 1 << 30, last_nz = -1;
+    int lastH = 0, prevH = 0, pend_e = 0;
+    for (int j = mb; j < me; ++j) {
+      int M = eh[j].h, e = eh[j].e;
+      M = M ? M + q[query[j]] : 0;
+      int f = (j == beg) ? 0 : pre - (j - 1) * e_ins;
+      int h = M > e ? M : e;
+      h = h > f ? h : f;
+      long long k = ((long long)h << 32) | (unsigned)j;
+      key = key > k ? key : k;
+      int t = M - oe_del; t = t > 0 ? t : 0;
+      e -= e_del; e = e > t ? e : t;
+      eh[j].e = e;
+      if (j == mb) pend_e = e;  // its .h needs the left neighbour lane's last H
+      else {
+        eh[j].h = prevH;
+        if (prevH | e) { first_nz = first_nz < j ? first_nz : j; last_nz = j; }
+      }
+      t = M - oe_ins; t = t > 0 ? t : 0;
+      t += j * e_ins;
+      pre = pre > t ? pre : t;
+      prevH = h;
+      lastH = h;
+    }
+    int inH = g.shfl_up(lastH, 1);
+    if (mb < me) {
+      int hh = (mb == beg) ? h1init : inH;
+      eh[mb].h = hh;
+      if (hh | pend_e) { first_nz = first_nz < mb ? first_nz : mb; last_nz = last_nz > mb ? last_nz : mb; }
+    }
+    const int last_lane = (n - 1) / C;
+    const int h1 = g.shfl(lastH, last_lane);
+    if (g.lane == last_lane) { eh[end].h = h1; eh[end].e = 0; }
+    if (h1) last_nz = end;  // eh[end] = {h1, 0}
+    key = g.max_all64(key);
+    first_nz = g.min_all(first_nz);
+    last_nz = g.max_all(last_nz);
+    g.sync();
+    const int m = (int)(key >> 32), mj = (int)(key & 0xffffffff);
+    if (end == qlen) { max_ie = gscore > h1 ? max_ie : i; gscore = gscore > h1 ? gscore : h1; }
+    if (m == 0) break;
+    if (m > max) {
+      max = m; max_i = i; max_j = mj;
+      int off = mj - i; off = off < 0 ? -off : off;
+      max_off = max_off > off ? max_off : off;
+    } else if (zdrop > 0) {
+      if (i - max_i > mj - max_j) {
+        if (max - m - ((i - max_i) - (mj - max_j)) * e_del > zdrop) break;
+      } else {
+        if (max - m - ((mj - max_j) - (i - max_i)) * e_ins > zdrop) break;
+      }
+    }
+    // band trimming: first non-zero cell of the new row, last non-zero cell (eh[end] included) + 2
+    int nb = first_nz < end ? first_nz : end;          // no non-zero cell in [beg,end): beg = end
+    int jl = last_nz >= nb ? last_nz : nb - 1;          // scanning down from `end` stops at nb-1
+    beg = nb;
+    end = jl + 2 < qlen ? jl + 2 : qlen;
+  }
+  if (_qle) *_qle = max_j + 1;
+  if (_tle) *_tle = max_i + 1;
+  if (_gtle) *_gtle = max_ie + 1;
+  if (_gscore) *_gscore = gscore;
+  if (_max_off) *_max_off = max_off;
+  return max;
+}
+
+// One GPU lane per SSE lane.  Lanes >= `lanes` of the group idle (16-bit mode uses 8 of 16).
+__device__ inline B2Kswr b2_sw_local_coop(const B2G& g, int size, int qlen, const uint8_t* query, int tlen,
+                                          const uint8_t* target, const int8_t* mat, int o_del, int e_del, int o_ins,
+                                          int e_ins, int xtra, int16_t* work, uint64_t* bbuf, unsigned long long* cells) {
+  const int lanes = size == 1 ? 16 : 8;
+  const int slen = (qlen + lanes - 1) / lanes;
+  const int n = slen * lanes;
+  int shift = 127, mx = 0;
+  for (int a = 0; a < 25; ++a) {
+    if (mat[a] < (int8_t)shift) shift = mat[a];
+    if (mat[a] > (int8_t)mx) mx = mat[a];
+  }
+  shift = (256 - shift) & 0xff;
+  const int oe_d = o_del + e_del, oe_i = o_ins + e_ins;
+  int16_t *H0 = work, *H1 = work + n, *E = work + 2 * n, *Hmax = work + 3 * n;
+  B2Kswr r; r.score = 0; r.te = r.qe = r.score2 = r.te2 = r.tb = r.qb = -1;
+  const int minsc = (xtra & B2_KSW_XSUBO) ? xtra & 0xffff : 0x10000;
+  const int endsc = (xtra & B2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
+  int n_b = 0, te = -1, gmax = 0;
+  const int l = g.lane;
+  const bool act = l < lanes;
+  // sub-group of the active lanes (a contiguous, aligned block of `lanes` lanes inside the group)
+  const unsigned amask = lanes == g.size ? g.mask : (g.mask & (((1u << lanes) - 1) << (__ffs(g.mask) - 1)));
+  for (int i = l; i < n; i += g.size) { H0[i] = 0; E[i] = 0; Hmax[i] = 0; }
+  g.sync();
+  int broke = 0;
+  for (int i = 0; i < tlen && !broke; ++i) {
+    int imax = 0;
+    if (act) {
+      const int8_t* srow = mat + target[i] * 5;
+      int f = 0, mxv = 0;
+      int h = H0[(slen - 1) * lanes + l];
+      h = __shfl_up_sync(amask, h, 1, lanes);
+      if (l == 0) h = 0;
+      for (int j = 0; j < slen; ++j) {
+        const int col = l * slen + j;
+        const int s = col < qlen ? srow[query[col]] : 0;
+        int e = E[j * lanes + l], t;
+        if (size == 1) {
+          h = h + (s + shift); if (h > 255) h = 255;
+          h = h - shift; if (h < 0) h = 0;
+        } else {
+          h = h + s; if (h > 32767) h = 32767; if (h < -32768) h = -32768;
+        }
+        h = h > e ? h : e;
+        h = h > f ? h : f;
+        mxv = mxv > h ? mxv : h;
+        H1[j * lanes + l] = (int16_t)h;
+        e = e - e_del; if (e < 0) e = 0;
+        t = h - oe_d; if (t < 0) t = 0;
+        e = e > t ? e : t;
+        E[j * lanes + l] = (int16_t)e;
+        f = f - e_ins; if (f < 0) f = 0;
+        t = h - oe_i; if (t < 0) t = 0;
+        f = f > t ? f : t;
+        h = H0[j * lanes + l];
+      }
+      // lazy-F
+      for (int k = 0, done = 0; k < 16 && !done; ++k) {
+        f = __shfl_up_sync(amask, f, 1, lanes);
+        if (l == 0) f = 0;
+        for (int j = 0; j < slen; ++j) {
+          int hh = H1[j * lanes + l];
+          hh = hh > f ? hh : f;
+          H1[j * lanes + l] = (int16_t)hh;
+          hh = hh - oe_i; if (hh < 0) hh = 0;
+          f = f - e_ins; if (f < 0) f = 0;
+          if (__all_sync(amask, !(f > hh))) { done = 1; break; }
+        }
+      }
+      imax = mxv;
+      for (int d = lanes >> 1; d; d >>= 1) { int o = __shfl_xor_sync(amask, imax, d, lanes); imax = imax > o ? imax : o; }
+    }
+    imax = g.shfl(imax, 0);
+    if (cells && l == 0) *cells += (unsigned long long)qlen;
+    if (imax >= minsc) {
+      if (n_b == 0 || (int32_t)bbuf[n_b - 1] + 1 != i) { if (l == 0) bbuf[n_b] = (uint64_t)imax << 32 | (uint32_t)i; ++n_b; }
+      else if ((int)(bbuf[n_b - 1] >> 32) < imax) { if (l == 0) bbuf[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i; }
+      g.sync();
+    }
+    if (imax > gmax) {
+      gmax = imax; te = i;
+      if (act) for (int j = 0; j < slen; ++j) Hmax[j * lanes + l] = H1[j * lanes + l];
+      if ((size == 1 && gmax + shift >= 255) || gmax >= endsc) broke = 1;
+    }
+    g.sync();
+    { int16_t* t = H1; H1 = H0; H0 = t; }
+  }
+  g.sync();
+  if (size == 1) r.score = gmax + shift < 255 ? gmax : 255; else r.score = gmax;
+  r.te = te;
+  if (size != 1 || r.score != 255) {
+    int max = -1;
+    if (size != 1) r.qe = -1;
+    for (int i = 0; i < n; ++i) {
+      int v = (size == 1) ? (Hmax[i] & 0xff) : (uint16_t)Hmax[i];
+      int col = i / lanes + i % lanes * slen;
+      if (v > max) { max = v; r.qe = col; }
+      else if (v == max && col < r.qe) r.qe = col;
+    }
+    if (n_b) {
+      int ii = (r.score + mx - 1) / mx;
+      int low = te - ii, high = te + ii;
+      for (int i = 0; i < n_b; ++i) {
+        int e = (int32_t)bbuf[i];
+        if ((e < low || e > high) && (int)(bbuf[i] >> 32) > r.score2) { r.score2 = (int)(bbuf[i] >> 32); r.te2 = e; }
+      }
+    }
+  }
+  g.sync();
+  return r;
+}
+
+#endif  // __CUDACC__

@@ -264,6 +264,8 @@ class B2EngineImpl {
     w.n_reads_run = n;
     c.flags = w.flags.p;
     c.counters = w.counters.p;
+    // k_chain uses one lane per read, k_extend/k_final one B2_TASK_GROUP-lane group per read/pair; the scratch
+    // region is indexed by lane resp. group, so size it for the larger count
     const int lanes = cfg.lane_grid * cfg.lane_block;
     int flags = 0;
     int ev_begin = w.timer.mark();

@@ -543,9 +543,8 @@ B2_HD inline int b2_matesw(const B2Opt& opt, const B2Index& ix, const B2Pes pes[
       int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
       uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
       if (sc.overflow) { sc.reset(mk); return n; }
-      B2Kswr aln = b2_align2(l_ms, seq, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, work, bbuf,
-                             &sc.sw_cells);
-      ++sc.sw_calls;
+      sc.gsync();
+      B2Kswr aln = b2_align2_any(sc, l_ms, seq, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, work, bbuf);
       if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
         B2Reg b = B2Reg();
         b.rid = a->rid;

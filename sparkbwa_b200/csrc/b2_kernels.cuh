@@ -142,7 +142,21 @@ B2_HD inline B2Scratch b2_lane_scratch(const B2Ctx& c, int lane) {
   return sc;
 }
 
+// scratch + lane-group identity of a task group (B2_TASK_GROUP lanes per read / pair)
+B2_HD inline B2Scratch b2_group_scratch(const B2Ctx& c, int* gid, int* n_groups) {
+  *gid = B2_GTID() / B2_TASK_GROUP;
+  *n_groups = B2_GSIZE() / B2_TASK_GROUP;
+  B2Scratch sc = b2_lane_scratch(c, *gid);
+#if defined(__CUDA_ARCH__)
+  sc.gsize = B2_TASK_GROUP;
+  sc.lane = threadIdx.x & (B2_TASK_GROUP - 1);
+  sc.gmask = (B2_TASK_GROUP == 32 ? 0xffffffffu : ((1u << B2_TASK_GROUP) - 1)) << ((threadIdx.x & 31) & ~(B2_TASK_GROUP - 1));
+#endif
+  return sc;
+}
+
 B2_D inline void b2_flush_counters(const B2Ctx& c, const B2Scratch& sc) {
+  if (sc.lane != 0) return;
   if (sc.ext_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], sc.ext_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], (unsigned long long)sc.ext_calls); }
   if (sc.glob_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CELLS], sc.glob_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CALLS], (unsigned long long)sc.glob_calls); }
   if (sc.sw_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_SW_CELLS], sc.sw_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_SW_CALLS], (unsigned long long)sc.sw_calls); }
@@ -177,8 +191,9 @@ B2_KERNEL k_chain(B2Ctx c) {
 }
 
 B2_KERNEL k_extend(B2Ctx c) {
-  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
-  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+  int gid, n_groups;
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  for (int r = gid; r < c.b.n_reads; r += n_groups) {
     const int64_t off = c.seed_off[r];
     const int nch = c.n_chain[r];
     const int l_seq = c.b.l_seq[r];
@@ -194,6 +209,7 @@ B2_KERNEL k_extend(B2Ctx c) {
       if (!sc.overflow) {
         const uint8_t* q0 = c.b.seq + c.b.seq_off[r];
         for (int i = 0; i < l_seq; ++i) query[i] = q0[i];
+        sc.gsync();
         for (int i = 0; i < nch && !sc.overflow; ++i) {
           const B2Chain& ch = c.chains[off + i];
           b2_chain2aln(c.opt, c.ix, l_seq, query, ch, c.cseeds + off + ch.seed_head, av, &n_av, cap, srt, sc);
@@ -204,6 +220,7 @@ B2_KERNEL k_extend(B2Ctx c) {
       }
       if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; n_av = 0; }
     }
+    sc.gsync();
     c.n_regs[r] = n_av;
   }
   b2_flush_counters(c, sc);
@@ -221,8 +238,10 @@ B2_KERNEL k_pestat(B2Ctx c) {
 }
 
 B2_KERNEL k_final_se(B2Ctx c) {
-  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
-  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+  int gid, n_groups;
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  for (int r = gid; r < c.b.n_reads; r += n_groups) {
+    sc.gsync();
     sc.reset(0);
     int err = 0;
     const int n = c.n_regs[r];
@@ -244,9 +263,11 @@ B2_KERNEL k_final_se(B2Ctx c) {
 }
 
 B2_KERNEL k_final_pe(B2Ctx c) {
-  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
+  int gid, n_groups;
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
   const int n_pairs = c.b.n_reads >> 1;
-  for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
+  for (int i = gid; i < n_pairs; i += n_groups) {
+    sc.gsync();
     sc.reset(0);
     int err = 0;
     int n[2], cap[2];
