@@ -51,6 +51,21 @@ B2_HD inline int b2_extend2_any(B2Scratch& sc, int qlen, const uint8_t* query, i
                     gscore, max_off, eh, &sc.ext_cells);
 }
 
+B2_HD inline int b2_global2_any(B2Scratch& sc, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, B2EH* eh, uint8_t* z,
+                                int* n_cigar_, uint32_t* cigar, int cigar_cap) {
+  ++sc.glob_calls;
+#if defined(__CUDA_ARCH__)
+  if (sc.gsize > 1) {
+    B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
+    return b2_global2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, eh, z, n_cigar_, cigar,
+                           cigar_cap, &sc.glob_cells);
+  }
+#endif
+  return b2_global2(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, eh, z, n_cigar_, cigar, cigar_cap,
+                    &sc.glob_cells);
+}
+
 B2_HD inline B2Kswr b2_align2_any(B2Scratch& sc, int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat,
                                   int o_del, int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf) {
   ++sc.sw_calls;
@@ -340,9 +355,9 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
       return 0;
     }
     int nc = 0;
-    *score = b2_global2(l_query, query, (int)rlen, rseq, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, eh, z,
-                        out ? &nc : 0, out ? out->cigar : 0, out ? out->cap : 0, &sc.glob_cells);
-    ++sc.glob_calls;
+    sc.gsync();
+    *score = b2_global2_any(sc, l_query, query, (int)rlen, rseq, mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, w, eh, z,
+                            out ? &nc : 0, out ? out->cigar : 0, out ? out->cap : 0);
     if (out) {
       if (nc < 0) { sc.overflow = 1; nc = 0; }
       out->n_cigar = nc;

@@ -162,6 +162,96 @@ __device__ inline int b2_extend2_coop(const B2G& g, int qlen, const uint8_t* que
   return max;
 }
 
+// Row-parallel ksw_global2 (bwa/ksw.c:504-606): the band [i-w, i+w] of row i is split over the lanes; F is the
+// max-plus scan  F[j] = max( MINUS_INF-(j-beg)*e_ins, max_{beg<=k<j}( M[k]-oe_ins-(j-1-k)*e_ins ) ), which is the
+// unrolled form of the reference's serial recurrence, so H, E, F and every direction bit (ties: m>=e, h>=f, e>t,
+// f>t) are the same integers.  The traceback (a few hundred dependent steps) stays serial.
+__device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                      const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, B2EH* eh,
+                                      uint8_t* z, int* n_cigar_, uint32_t* cigar, int cigar_cap, unsigned long long* cells) {
+  const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
+  const int G = g.size;
+  const int n_col = qlen < 2 * w + 1 ? qlen : 2 * w + 1;
+  if (n_cigar_) *n_cigar_ = 0;
+  for (int j = g.lane; j <= qlen; j += G) {
+    if (j == 0) { eh[0].h = 0; eh[0].e = B2_MINUS_INF; }
+    else if (j <= w) { eh[j].h = -(o_ins + e_ins * j); eh[j].e = B2_MINUS_INF; }
+    else { eh[j].h = B2_MINUS_INF; eh[j].e = B2_MINUS_INF; }
+  }
+  g.sync();
+  const long long NEG = -(1ll << 40);
+  for (int i = 0; i < tlen; ++i) {
+    const int8_t* q = mat + target[i] * 5;
+    const int beg = i > w ? i - w : 0;
+    const int end = i + w + 1 < qlen ? i + w + 1 : qlen;
+    const int h1init = beg == 0 ? -(o_del + e_del * (i + 1)) : B2_MINUS_INF;
+    const int n = end - beg;
+    if (n <= 0) { if (g.lane == 0) { eh[end].h = h1init; eh[end].e = B2_MINUS_INF; } g.sync(); continue; }
+    if (cells && g.lane == 0) *cells += (unsigned long long)n;
+    const int C = (n + G - 1) / G;
+    const int mb = beg + g.lane * C;
+    int me = mb + C; me = me < end ? me : end;
+    long long vloc = NEG;  // max over own cells of M[k] - oe_ins + k*e_ins
+    for (int j = mb; j < me; ++j) {
+      long long v = (long long)(eh[j].h + q[query[j]]) - oe_ins + (long long)j * e_ins;
+      vloc = vloc > v ? vloc : v;
+    }
+    long long incl = vloc;
+    for (int d = 1; d < G; d <<= 1) { long long o = __shfl_up_sync(g.mask, incl, d, G); if (g.lane >= d) incl = incl > o ? incl : o; }
+    long long pre = __shfl_up_sync(g.mask, incl, 1, G);
+    if (g.lane == 0) pre = NEG;
+    uint8_t* zi = z ? z + (long)i * n_col : 0;
+    int lastH = 0, prevH = 0;
+    for (int j = mb; j < me; ++j) {
+      int m = eh[j].h + q[query[j]], e = eh[j].e;
+      long long f0 = (long long)B2_MINUS_INF - (long long)(j - beg) * e_ins;  // the serial recurrence's start value
+      long long fs = pre - (long long)(j - 1) * e_ins;
+      int f = (int)(j == beg ? (long long)B2_MINUS_INF : (fs > f0 ? fs : f0));
+      uint8_t d = m >= e ? 0 : 1;
+      int h = m >= e ? m : e;
+      d = h >= f ? d : 2;
+      h = h >= f ? h : f;
+      int t = m - oe_del;
+      e -= e_del;
+      d |= e > t ? 1 << 2 : 0;
+      e = e > t ? e : t;
+      eh[j].e = e;
+      t = m - oe_ins;
+      d |= (f - e_ins) > t ? 2 << 4 : 0;
+      if (zi) zi[j - beg] = d;
+      if (j != mb) eh[j].h = prevH;
+      long long v = (long long)m - oe_ins + (long long)j * e_ins;
+      pre = pre > v ? pre : v;
+      prevH = h; lastH = h;
+    }
+    int inH = g.shfl_up(lastH, 1);
+    if (mb < me) eh[mb].h = (mb == beg) ? h1init : inH;
+    const int last_lane = (n - 1) / C;
+    const int h1 = g.shfl(lastH, last_lane);
+    if (g.lane == last_lane) { eh[end].h = h1; eh[end].e = B2_MINUS_INF; }
+    g.sync();
+  }
+  int score = eh[qlen].h;
+  if (z && n_cigar_) {
+    int n = 0, which = 0, k, i = tlen - 1;
+    k = (i + w + 1 < qlen ? i + w + 1 : qlen) - 1;
+    while (i >= 0 && k >= 0) {
+      if (n + 2 > cigar_cap) { *n_cigar_ = -1; g.sync(); return score; }
+      which = z[(long)i * n_col + (k - (i > w ? i - w : 0))] >> (which << 1) & 3;
+      if (which == 0) { n = b2_push_cigar(cigar, n, 0, 1); --i; --k; }
+      else if (which == 1) { n = b2_push_cigar(cigar, n, 2, 1); --i; }
+      else { n = b2_push_cigar(cigar, n, 1, 1); --k; }
+    }
+    if (n + 2 > cigar_cap) { *n_cigar_ = -1; g.sync(); return score; }
+    if (i >= 0) n = b2_push_cigar(cigar, n, 2, i + 1);
+    if (k >= 0) n = b2_push_cigar(cigar, n, 1, k + 1);
+    for (i = 0; i < n >> 1; ++i) { uint32_t tmp = cigar[i]; cigar[i] = cigar[n - 1 - i]; cigar[n - 1 - i] = tmp; }
+    *n_cigar_ = n;
+  }
+  g.sync();
+  return score;
+}
+
 // One GPU lane per SSE lane.  Lanes >= `lanes` of the group idle (16-bit mode uses 8 of 16).
 __device__ inline B2Kswr b2_sw_local_coop(const B2G& g, int size, int qlen, const uint8_t* query, int tlen,
                                           const uint8_t* target, const int8_t* mat, int o_del, int e_del, int o_ins,

@@ -264,6 +264,7 @@ class B2EngineImpl {
     w.n_reads_run = n;
     c.flags = w.flags.p;
     c.counters = w.counters.p;
+    c.work = w.flags.p + 1;
     // k_chain uses one lane per read, k_extend/k_final one B2_TASK_GROUP-lane group per read/pair; the scratch
     // region is indexed by lane resp. group, so size it for the larger count
     const int lanes = cfg.lane_grid * cfg.lane_block;
@@ -318,7 +319,7 @@ class B2EngineImpl {
     };
     for (;;) {
       if (ensure_scratch()) return 1;
-      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
       B2_LAUNCH(k_chain, cfg.lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
@@ -336,7 +337,7 @@ class B2EngineImpl {
     w.times.n_regs = R;
     for (;;) {
       if (ensure_scratch()) return 1;
-      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
       B2_LAUNCH(k_extend, cfg.lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
@@ -394,7 +395,7 @@ class B2EngineImpl {
       if (ensure_scratch()) return 1;
       if (w.slots.ensure((size_t)n_items * w.slot_size)) return fail("device allocation failed (SAM slots)");
       c.slots = w.slots.p; c.slot_size = w.slot_size;
-      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
+      b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
       if (pe) B2_LAUNCH(k_final_pe, cfg.lane_grid, cfg.lane_block, w.stream, c);
       else B2_LAUNCH(k_final_se, cfg.lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;

@@ -51,6 +51,7 @@ struct B2Ctx {
   int max_len;            // longest read in the batch
   int* flags;
   unsigned long long* counters;  // [B2_CNT_*], algorithmic work
+  int* work;                     // dynamic work-distribution cursor of the running stage
   // seeding
   B2Intv* intv; int cap_intv; int32_t* n_intv; int32_t* n_tasks;
   B2Intv* seed_scratch;   // per group: 3*(max_len+1)
@@ -155,6 +156,19 @@ B2_HD inline B2Scratch b2_group_scratch(const B2Ctx& c, int* gid, int* n_groups)
   return sc;
 }
 
+// Next task index for this group: groups pull reads/pairs from a shared cursor, so a group stuck on an
+// expensive read (repeats: hundreds of chains, dozens of rescue windows) does not also own a fixed share of the rest.
+B2_D inline int b2_next_task(const B2Ctx& c, const B2Scratch& sc) {
+#if defined(__CUDA_ARCH__)
+  int r = 0;
+  if (sc.lane == 0) r = atomicAdd(c.work, 1);
+  if (sc.gsize > 1) r = __shfl_sync(sc.gmask, r, 0, sc.gsize);
+  return r;
+#else
+  return (*c.work)++;
+#endif
+}
+
 B2_D inline void b2_flush_counters(const B2Ctx& c, const B2Scratch& sc) {
   if (sc.lane != 0) return;
   if (sc.ext_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], sc.ext_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], (unsigned long long)sc.ext_calls); }
@@ -164,7 +178,7 @@ B2_D inline void b2_flush_counters(const B2Ctx& c, const B2Scratch& sc) {
 
 B2_KERNEL k_chain(B2Ctx c) {
   B2Scratch sc = b2_lane_scratch(c, B2_GTID());
-  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+  for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     const int64_t off = c.seed_off[r];
     const int n_raw = (int)(c.seed_off[r + 1] - off);
     int kept = 0, cap = 0;
@@ -193,7 +207,7 @@ B2_KERNEL k_chain(B2Ctx c) {
 B2_KERNEL k_extend(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
-  for (int r = gid; r < c.b.n_reads; r += n_groups) {
+  for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     const int64_t off = c.seed_off[r];
     const int nch = c.n_chain[r];
     const int l_seq = c.b.l_seq[r];
@@ -240,7 +254,7 @@ B2_KERNEL k_pestat(B2Ctx c) {
 B2_KERNEL k_final_se(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
-  for (int r = gid; r < c.b.n_reads; r += n_groups) {
+  for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
     int err = 0;
@@ -266,7 +280,7 @@ B2_KERNEL k_final_pe(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
   const int n_pairs = c.b.n_reads >> 1;
-  for (int i = gid; i < n_pairs; i += n_groups) {
+  for (int i = b2_next_task(c, sc); i < n_pairs; i = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
     int err = 0;
