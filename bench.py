@@ -37,7 +37,8 @@ ORACLE = os.path.join(ROOT, "oracle", "_ref", "bwa")
 
 class Times(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("h2d", "seed", "sa", "chain", "extend", "pestat", "finalize", "gather", "d2h", "total")] + \
-               [("launches", ctypes.c_int), ("n_seed_tasks", ctypes.c_int64), ("n_regs", ctypes.c_int64), ("sam_bytes", ctypes.c_int64)]
+               [("launches", ctypes.c_int), ("n_seed_tasks", ctypes.c_int64), ("n_regs", ctypes.c_int64), ("sam_bytes", ctypes.c_int64),
+                ("rescue", ctypes.c_float), ("n_rescue_tasks", ctypes.c_int64)]
 
 
 def load_lib():
@@ -179,7 +180,7 @@ def main():
     ap.add_argument("--ref-len", type=int, default=100_000_000)
     ap.add_argument("--K", type=int, default=10_000_000)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--workers", type=int, default=3)
+    ap.add_argument("--workers", type=int, default=4)
     ap.add_argument("--cpu-sample-pairs", type=int, default=200_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -272,7 +273,7 @@ def main():
         raise SystemExit("upload failed: " + lib.b200bwa_last_error().decode())
     del inter
     batches = cut_batches(n_reads, 150, args.K)
-    n_workers = max(1, min(args.workers, 3))
+    n_workers = max(1, min(args.workers, int(os.environ.get("B200BWA_WORKERS", "4"))))
 
     def one_pass(collect=None):
         lock = threading.Lock()
@@ -305,7 +306,7 @@ def main():
     for _ in range(args.warmup):
         one_pass()
     cnt0 = (ctypes.c_ulonglong * 16)()
-    for w in range(3):
+    for w in range(n_workers):
         lib.b200bwa_counters(ix, w, cnt0, 1)
     pc = (ctypes.c_ulonglong * 3)()
     lib.b200bwa_process_counters(pc, 1)
@@ -329,7 +330,7 @@ def main():
     value = world * n_reads / (ms_step / 1e3)
 
     # ---- single-stream pass for clean per-kernel CUDA-event durations + algorithmic counters ------
-    for w in range(3):
+    for w in range(n_workers):
         lib.b200bwa_counters(ix, w, cnt0, 1)
     n_workers_saved, n_workers = n_workers, 1
     stage = []
@@ -337,7 +338,7 @@ def main():
     n_workers = n_workers_saved
     cnt = (ctypes.c_ulonglong * 16)()
     lib.b200bwa_counters(ix, 0, cnt, 1)
-    tot = {k: float(sum(s[k] for s in stage)) for k in ("seed", "sa", "chain", "extend", "pestat", "finalize", "gather", "total")}
+    tot = {k: float(sum(s[k] for s in stage)) for k in ("seed", "sa", "chain", "extend", "pestat", "rescue", "finalize", "gather", "total")}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -359,7 +360,7 @@ def main():
                 "ms_per_launch": tot["seed"] / len(batches),
                 "sa_kernel": {"bytes_per_read": sa_bytes / n_reads, "GB/s": sa_bytes / (tot["sa"] / 1e3) / 1e9 if tot["sa"] > 0 else 0.0}}
     cells = float(cnt[3] + cnt[5] + cnt[7])
-    dp_ms = tot["extend"] + tot["finalize"]
+    dp_ms = tot["extend"] + tot["rescue"] + tot["finalize"]
     sw = {"cells_per_read": {"extend": cnt[3] / n_reads, "global": cnt[5] / n_reads, "local": cnt[7] / n_reads},
           "GCUPS_stage": cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else 0.0,
           "GCUPS_extend_stage": cnt[3] / (tot["extend"] / 1e3) / 1e9 if tot["extend"] > 0 else 0.0}

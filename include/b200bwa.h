@@ -75,6 +75,8 @@ typedef struct {
   float h2d, seed, sa, chain, extend, pestat, finalize, gather, d2h, total;
   int launches;
   int64_t n_seed_tasks, n_regs, sam_bytes;
+  float rescue;   /* planned mate-rescue SW tasks (between pestat and finalize) */
+  int64_t n_rescue_tasks;
 } b200bwa_times_t;
 int b200bwa_last_times(b200bwa_index_t* idx, b200bwa_times_t* t);
 

@@ -73,13 +73,17 @@ B2_HD inline B2Kswr b2_align2_any(B2Scratch& sc, int qlen, uint8_t* query, int t
   if (sc.gsize >= 16) {
     B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
     const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;
-    B2Kswr r = b2_sw_local_coop(g, size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
+    const bool reg_ok = size == 1 && sc.gsize == 16 && qlen <= 16 * B2_SW_SLMAX && mat[24] == mat[4] && mat[9] == mat[4];
+    B2Kswr r = reg_ok ? b2_sw_local_u8_reg(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, bbuf, &sc.sw_cells)
+                      : b2_sw_local_coop(g, size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
     if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
     // all lanes reverse the same private-to-the-group buffers: do it once
     if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
     g.sync();
-    B2Kswr rr = b2_sw_local_coop(g, size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
-                                 B2_KSW_XSTOP | r.score, work, bbuf, &sc.sw_cells);
+    B2Kswr rr = reg_ok ? b2_sw_local_u8_reg(g, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
+                                            B2_KSW_XSTOP | r.score, bbuf, &sc.sw_cells)
+                       : b2_sw_local_coop(g, size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
+                                          B2_KSW_XSTOP | r.score, work, bbuf, &sc.sw_cells);
     if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
     g.sync();
     if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }

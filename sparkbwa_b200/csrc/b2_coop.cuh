@@ -252,6 +252,128 @@ __device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* que
   return score;
 }
 
+// Byte-mode striped SW with the whole DP state in registers: lane l owns query columns l*slen .. l*slen+slen-1
+// (slen <= B2_SW_SLMAX, i.e. reads up to 16*B2_SW_SLMAX bases) as H/E/Hmax register arrays, and the substitution
+// score comes from the base codes directly (the matrix is always bwa_fill_scmat's: a on the diagonal, -b off it,
+// -1 against N; bwa/bwa.c:99-108), so the inner loops touch no memory at all.  Same lane-for-lane arithmetic as
+// b2_sw_local_coop below (which remains the general path for word mode and longer reads).
+#define B2_SW_SLMAX 16
+__device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                            const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra,
+                                            uint64_t* bbuf, unsigned long long* cells) {
+  const int lanes = 16;
+  const int slen = (qlen + lanes - 1) / lanes;
+  const int sa = mat[0], sb = mat[1], sn = mat[4];  // match, mismatch, ambiguous
+  int shift = 127, mx = 0;
+  for (int a = 0; a < 25; ++a) {
+    if (mat[a] < (int8_t)shift) shift = mat[a];
+    if (mat[a] > (int8_t)mx) mx = mat[a];
+  }
+  shift = (256 - shift) & 0xff;
+  const int oe_d = o_del + e_del, oe_i = o_ins + e_ins;
+  B2Kswr r; r.score = 0; r.te = r.qe = r.score2 = r.te2 = r.tb = r.qb = -1;
+  const int minsc = (xtra & B2_KSW_XSUBO) ? xtra & 0xffff : 0x10000;
+  const int endsc = (xtra & B2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
+  int n_b = 0, te = -1, gmax = 0;
+  const int l = g.lane;
+  int H[B2_SW_SLMAX], E[B2_SW_SLMAX], Hm[B2_SW_SLMAX], H1[B2_SW_SLMAX], qc[B2_SW_SLMAX];
+#pragma unroll
+  for (int j = 0; j < B2_SW_SLMAX; ++j) {
+    H[j] = E[j] = Hm[j] = H1[j] = 0;
+    const int col = l * slen + j;
+    qc[j] = (j < slen && col < qlen) ? query[col] : 5;  // 5: pad column, score 0
+  }
+  int last_b_row = -2, last_b_sc = 0;  // mirror of bbuf[n_b-1] kept in registers
+  for (int i = 0; i < tlen; ++i) {
+    const int tb = target[i];
+    int f = 0, mxv = 0;
+    int h;
+    {  // H[slen-1] of the left lane (the byte shift of the last striped vector)
+      int hl = 0;
+#pragma unroll
+      for (int j = 0; j < B2_SW_SLMAX; ++j) if (j == slen - 1) hl = H[j];
+      h = g.shfl_up(hl, 1);
+      if (l == 0) h = 0;
+    }
+#pragma unroll
+    for (int j = 0; j < B2_SW_SLMAX; ++j) {
+      if (j < slen) {
+        const int q = qc[j];
+        const int s = q == 5 ? 0 : ((q | tb) >= 4 ? sn : (q == tb ? sa : sb));
+        int e = E[j], t;
+        h = h + (s + shift); if (h > 255) h = 255;
+        h = h - shift; if (h < 0) h = 0;
+        h = h > e ? h : e;
+        h = h > f ? h : f;
+        mxv = mxv > h ? mxv : h;
+        H1[j] = h;
+        e = e - e_del; if (e < 0) e = 0;
+        t = h - oe_d; if (t < 0) t = 0;
+        E[j] = e > t ? e : t;
+        f = f - e_ins; if (f < 0) f = 0;
+        t = h - oe_i; if (t < 0) t = 0;
+        f = f > t ? f : t;
+        h = H[j];
+      }
+    }
+    for (int k = 0, done = 0; k < 16 && !done; ++k) {  // lazy-F
+      f = g.shfl_up(f, 1);
+      if (l == 0) f = 0;
+#pragma unroll
+      for (int j = 0; j < B2_SW_SLMAX; ++j) {
+        if (j < slen && !done) {
+          int hh = H1[j];
+          hh = hh > f ? hh : f;
+          H1[j] = hh;
+          hh = hh - oe_i; if (hh < 0) hh = 0;
+          f = f - e_ins; if (f < 0) f = 0;
+          if (__all_sync(g.mask, !(f > hh))) done = 1;
+        }
+      }
+    }
+    const int imax = g.max_all(mxv);
+    if (imax >= minsc) {
+      if (n_b == 0 || last_b_row + 1 != i) { if (l == 0) bbuf[n_b] = (uint64_t)imax << 32 | (uint32_t)i; ++n_b; last_b_row = i; last_b_sc = imax; }
+      else if (last_b_sc < imax) { if (l == 0) bbuf[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i; last_b_row = i; last_b_sc = imax; }
+    }
+    int stop = 0;
+    if (imax > gmax) {
+      gmax = imax; te = i;
+#pragma unroll
+      for (int j = 0; j < B2_SW_SLMAX; ++j) Hm[j] = H1[j];
+      if (gmax + shift >= 255 || gmax >= endsc) stop = 1;
+    }
+#pragma unroll
+    for (int j = 0; j < B2_SW_SLMAX; ++j) H[j] = H1[j];
+    if (stop) break;
+  }
+  if (cells && l == 0) *cells += (unsigned long long)qlen * (unsigned long long)(te >= 0 && (gmax + shift >= 255 || gmax >= endsc) ? te + 1 : tlen);
+  g.sync();
+  r.score = gmax + shift < 255 ? gmax : 255;
+  r.te = te;
+  if (r.score != 255) {
+    // qe: smallest query column holding the maximum of the saved row
+    int best = -1, bcol = 1 << 30;
+#pragma unroll
+    for (int j = 0; j < B2_SW_SLMAX; ++j)
+      if (j < slen) { int v = Hm[j] & 0xff, col = l * slen + j; if (v > best) { best = v; bcol = col; } }
+    // reduce (max value, then min column)
+    long long key = ((long long)best << 32) | (unsigned)(0x7fffffff - bcol);
+    key = g.max_all64(key);
+    r.qe = 0x7fffffff - (int)(key & 0xffffffff);
+    if (n_b) {
+      int ii = (r.score + mx - 1) / mx;
+      int low = te - ii, high = te + ii;
+      for (int i = 0; i < n_b; ++i) {
+        int e = (int32_t)bbuf[i];
+        if ((e < low || e > high) && (int)(bbuf[i] >> 32) > r.score2) { r.score2 = (int)(bbuf[i] >> 32); r.te2 = e; }
+      }
+    }
+  }
+  g.sync();
+  return r;
+}
+
 // One GPU lane per SSE lane.  Lanes >= `lanes` of the group idle (16-bit mode uses 8 of 16).
 __device__ inline B2Kswr b2_sw_local_coop(const B2G& g, int size, int qlen, const uint8_t* query, int tlen,
                                           const uint8_t* target, const int8_t* mat, int o_del, int e_del, int o_ins,

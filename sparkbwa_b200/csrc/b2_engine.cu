@@ -67,6 +67,8 @@ struct Worker {
   DBuf<uint8_t> scratch; DBuf<int8_t> pe_dir; DBuf<int64_t> pe_is; DBuf<double> pairtab;
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
+  DBuf<long long> dbg;
+  DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
   DBuf<unsigned long long> counters;
   unsigned long long h_counters[16] = {0};
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;
@@ -124,7 +126,7 @@ class B2EngineImpl {
     b2_h2d(d_logtab.p, lt.data(), n_log * sizeof(double), 0);
     if (set_rg(rg_id)) return 1;
     b2_sync(0);
-    workers.resize(3);
+    workers.resize(cfg.n_workers < 1 ? 1 : (cfg.n_workers > 8 ? 8 : cfg.n_workers));
     for (auto& w : workers) {
 #if !defined(B2_HOSTSIM)
       if (cudaStreamCreateWithFlags(&w.stream, cudaStreamNonBlocking) != cudaSuccess) return fail("cudaStreamCreate failed");
@@ -179,7 +181,8 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release(); w.counters.release();
+      w.flags.release(); w.counters.release(); w.dbg.release();
+      w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       if (w.pin_sam) b2_host_free(w.pin_sam);
 #if !defined(B2_HOSTSIM)
       if (w.stream) cudaStreamDestroy(w.stream);
@@ -265,6 +268,7 @@ class B2EngineImpl {
     c.flags = w.flags.p;
     c.counters = w.counters.p;
     c.work = w.flags.p + 1;
+    c.dbg = nullptr;
     // k_chain uses one lane per read, k_extend/k_final one B2_TASK_GROUP-lane group per read/pair; the scratch
     // region is indexed by lane resp. group, so size it for the larger count
     const int lanes = cfg.lane_grid * cfg.lane_block;
@@ -382,6 +386,37 @@ class B2EngineImpl {
       for (int d = 0; d < 4; ++d) c.tb.pairtab[d] = w.pairtab.p + offs[d];
       b2_sync(w.stream);
     }
+    int ev_pes0 = w.timer.mark();
+    // ---- mate-rescue attempts as independent SW tasks ------------------------------------------------
+    c.resc_off = nullptr; c.n_resc = 0;
+    if (pe && !(opt.flag & B2_F_NO_RESCUE)) {
+      if (w.resc_cnt.ensure(n_items + 1) || w.resc_off.ensure(n_items + 2)) return fail("device allocation failed");
+      c.resc_cnt = w.resc_cnt.p;
+      B2_LAUNCH(k_resc_plan, (n_items + 127) / 128, 128, w.stream, c, 0);
+      B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.resc_cnt.p, w.resc_off.p, n_items);
+      w.times.launches += 2;
+      int64_t T = 0;
+      b2_d2h(&T, w.resc_off.p + n_items, sizeof(int64_t), w.stream);
+      if (b2_sync(w.stream)) return fail("device synchronisation failed");
+      if (w.resc_tasks.ensure(T + 1) || w.resc_res.ensure(T + 1)) return fail("device allocation failed (rescue tasks)");
+      c.resc_off = w.resc_off.p; c.resc_tasks = w.resc_tasks.p; c.resc_res = w.resc_res.p; c.n_resc = T;
+      w.times.n_resc = T;
+      if (T > 0) {
+        B2_LAUNCH(k_resc_plan, (n_items + 127) / 128, 128, w.stream, c, 1);
+        ++w.times.launches;
+        for (;;) {
+          if (ensure_scratch()) return 1;
+          b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+          const int64_t groups_needed = (T * B2_TASK_GROUP + cfg.lane_block - 1) / cfg.lane_block;
+          const int grid = (int)std::min<int64_t>(groups_needed, cfg.lane_grid);
+          B2_LAUNCH(k_resc_sw, grid, cfg.lane_block, w.stream, c);
+          ++w.times.launches;
+          if (read_flags(w, &flags)) return 1;
+          if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
+          w.scratch_per_lane *= 2;
+        }
+      }
+    }
     int ev_pes = w.timer.mark();
 
     // ---- finalisation + SAM text ----
@@ -395,6 +430,11 @@ class B2EngineImpl {
       if (ensure_scratch()) return 1;
       if (w.slots.ensure((size_t)n_items * w.slot_size)) return fail("device allocation failed (SAM slots)");
       c.slots = w.slots.p; c.slot_size = w.slot_size;
+      if (getenv("B200BWA_DEBUG_TIMES")) {
+        if (w.dbg.ensure((size_t)n_items * 4 + 4)) return fail("device allocation failed");
+        b2_dev_memset(w.dbg.p, 0, (size_t)n_items * 4 * sizeof(long long), w.stream);
+        c.dbg = w.dbg.p;
+      }
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
       if (pe) B2_LAUNCH(k_final_pe, cfg.lane_grid, cfg.lane_block, w.stream, c);
       else B2_LAUNCH(k_final_se, cfg.lane_grid, cfg.lane_block, w.stream, c);
@@ -409,6 +449,25 @@ class B2EngineImpl {
       }
     }
     int ev_fin = w.timer.mark();
+    if (c.dbg) {
+      std::vector<long long> h((size_t)n_items * 4);
+      b2_d2h(h.data(), w.dbg.p, h.size() * sizeof(long long), w.stream);
+      b2_sync(w.stream);
+      std::vector<int> ord(n_items);
+      for (int i = 0; i < n_items; ++i) ord[i] = i;
+      std::sort(ord.begin(), ord.end(), [&](int a, int b) { return h[4 * a] > h[4 * b]; });
+      long long tot = 0, totsw = 0, totgl = 0;
+      for (int i = 0; i < n_items; ++i) { tot += h[4 * i]; totsw += h[4 * i + 1]; totgl += h[4 * i + 2]; }
+      fprintf(stderr, "[D::final] items %d total cycles %lld sw_calls %lld glob_calls %lld; median cycles %lld\n", n_items, tot, totsw, totgl, h[4 * ord[n_items / 2]]);
+      for (int k = 0; k < 12 && k < n_items; ++k) {
+        int i = ord[k];
+        fprintf(stderr, "[D::final]  item %d cycles %lld sw %lld glob %lld regs %lld/%lld\n", i, h[4 * i], h[4 * i + 1], h[4 * i + 2], h[4 * i + 3] >> 32, h[4 * i + 3] & 0xffffffff);
+      }
+      // histogram by sw calls
+      long long cyc_by[4] = {0, 0, 0, 0}, cnt_by[4] = {0, 0, 0, 0};
+      for (int i = 0; i < n_items; ++i) { int b = h[4 * i + 1] == 0 ? 0 : h[4 * i + 1] <= 2 ? 1 : h[4 * i + 1] <= 8 ? 2 : 3; cyc_by[b] += h[4 * i]; ++cnt_by[b]; }
+      for (int b = 0; b < 4; ++b) fprintf(stderr, "[D::final]  sw-bin %d: items %lld cycles %lld (avg %lld)\n", b, cnt_by[b], cyc_by[b], cnt_by[b] ? cyc_by[b] / cnt_by[b] : 0);
+    }
     B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.sam_len.p, w.sam_off.p, n_items);
     ++w.times.launches;
     int64_t total = 0;
@@ -446,7 +505,8 @@ class B2EngineImpl {
     w.times.sa = w.timer.ms(ev_seed, ev_sa);
     w.times.chain = w.timer.ms(ev_sa, ev_chain);
     w.times.extend = w.timer.ms(ev_chain, ev_ext);
-    w.times.pestat = w.timer.ms(ev_ext, ev_pes);
+    w.times.pestat = w.timer.ms(ev_ext, ev_pes0);
+    w.times.rescue = w.timer.ms(ev_pes0, ev_pes);
     w.times.final_ = w.timer.ms(ev_pes, ev_fin);
     w.times.gather = w.timer.ms(ev_fin, ev_gat);
     w.times.d2h = w.timer.ms(ev_gat, ev_d2h);

@@ -45,15 +45,16 @@ struct B2EngineConfig {
   int seed_grid = 148 * 8, seed_block = 128;   // seeding groups of B2_SEED_LANES lanes
   size_t scratch_per_lane = 48 << 10;
   size_t max_scratch_bytes = (size_t)64 << 30;
+  int n_workers = 4;                           // independent stream/buffer sets (batches in flight)
   int cap_intv = 64;
   int slot_per_read = 0;                       // 0: derived from the longest read of the batch
   int verbose = 3;
 };
 
 struct B2StageTimes {  // milliseconds, device time (CUDA events) of the last batch
-  float h2d = 0, seed = 0, sa = 0, chain = 0, extend = 0, pestat = 0, final_ = 0, gather = 0, d2h = 0, total = 0;
+  float h2d = 0, seed = 0, sa = 0, chain = 0, extend = 0, pestat = 0, rescue = 0, final_ = 0, gather = 0, d2h = 0, total = 0;
   int launches = 0;
-  int64_t n_seed_tasks = 0, n_regs = 0, sam_bytes = 0;
+  int64_t n_seed_tasks = 0, n_regs = 0, sam_bytes = 0, n_resc = 0;
 };
 
 class B2EngineImpl;

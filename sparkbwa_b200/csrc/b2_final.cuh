@@ -494,57 +494,133 @@ B2_HD inline int b2_pestat_candidate(const B2Opt& opt, int64_t l_pac, int n0, co
   return -1;
 }
 
-// Mate rescue.  ma[*n_ma] may grow up to cap_ma.
-B2_HD inline int b2_matesw(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const B2Reg* a, int l_ms,
-                           const uint8_t* ms, B2Reg* ma, int* n_ma, int cap_ma, B2Scratch& sc) {
+// ---- mate-rescue windows ---------------------------------------------------------------------
+// The SW inputs of a rescue attempt (mate sequence, reference window) depend only on the anchor hit, the
+// orientation and the batch's insert-size statistics -- not on what earlier attempts found.  They are
+// therefore planned for every pair up front, computed as independent tasks by a separate kernel (one lane
+// group per task), and b2_matesw below looks the result up instead of running the SW inside the serial
+// per-pair control flow.  An attempt that was not planned (possible only when an earlier rescue changed the
+// mate's hit list in a way that un-skips an orientation) is still computed in place, so the outcome is the
+// reference's either way.
+struct B2RescTask {
+  int32_t item;      // pair index inside the batch
+  int16_t end_i, r;  // anchor read (0/1), orientation (0..3)
+  int32_t j;         // anchor rank in the filtered list b[i]
+  int32_t l_ms;
+  int64_t rb, re;    // reference window after clamping
+};
+struct B2RescCache { const B2RescTask* tasks; const B2Kswr* res; int n; };
+
+// Window of orientation r around anchor `a` (bwamem_pair.c:127-145).  Returns 1 iff the reference would run the SW.
+B2_HD inline int b2_matesw_window(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const B2Reg* a, int l_ms, int r,
+                                  int64_t* rb_, int64_t* re_, int* is_rev_) {
   const int64_t l_pac = ix.l_pac;
-  int i, r, skip[4], n = 0;
-  for (r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
-  for (i = 0; i < *n_ma; ++i) {
+  const int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+  int64_t rb, re;
+  if (!is_rev) {
+    rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
+    re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
+  } else {
+    rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
+    re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
+  }
+  if (rb < 0) rb = 0;
+  if (re > l_pac << 1) re = l_pac << 1;
+  *is_rev_ = is_rev;
+  *rb_ = rb; *re_ = re;
+  if (rb >= re) return 0;  // (the reference tests an uninitialised rid here; re - rb < min_seed_len rejects it anyway)
+  int rid = b2_fetch_bounds(ix, &rb, (rb + re) >> 1, &re);
+  *rb_ = rb; *re_ = re;
+  return a->rid == rid && re - rb >= opt.min_seed_len;
+}
+
+B2_HD inline void b2_matesw_skip(const B2Index& ix, const B2Pes pes[4], const B2Reg* a, const B2Reg* ma, int n_ma, int skip[4]) {
+  for (int r = 0; r < 4; ++r) skip[r] = pes[r].failed ? 1 : 0;
+  for (int i = 0; i < n_ma; ++i) {
     int64_t dist;
-    r = b2_infer_dir(l_pac, a->rb, ma[i].rb, &dist);
+    int r = b2_infer_dir(ix.l_pac, a->rb, ma[i].rb, &dist);
     if (dist >= pes[r].low && dist <= pes[r].high) skip[r] = 1;
   }
+}
+
+// Rescue attempts of one pair given the hit lists as they are before any rescue.  out == null: count only.
+B2_HD inline int b2_rescue_plan(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const int n[2], const B2Reg* const a[2],
+                                const int l_seq[2], int item, B2RescTask* out) {
+  if (opt.flag & B2_F_NO_RESCUE) return 0;
+  int cnt = 0;
+  for (int i = 0; i < 2; ++i) {
+    int nb = 0;
+    for (int j0 = 0; j0 < n[i] && nb < opt.max_matesw; ++j0) {
+      if (a[i][j0].score < a[i][0].score - opt.pen_unpaired) continue;
+      const int j = nb++;
+      int skip[4];
+      b2_matesw_skip(ix, pes, &a[i][j0], a[!i], n[!i], skip);
+      for (int r = 0; r < 4; ++r) {
+        if (skip[r]) continue;
+        int64_t rb, re;
+        int is_rev;
+        if (!b2_matesw_window(opt, ix, pes, &a[i][j0], l_seq[!i], r, &rb, &re, &is_rev)) continue;
+        if (out) {
+          B2RescTask t;
+          t.item = item; t.end_i = (int16_t)i; t.r = (int16_t)r; t.j = j; t.l_ms = l_seq[!i]; t.rb = rb; t.re = re;
+          out[cnt] = t;
+        }
+        ++cnt;
+      }
+    }
+  }
+  return cnt;
+}
+
+// The SW of one planned attempt.  ms: the mate's base codes.
+B2_HD inline B2Kswr b2_rescue_sw(const B2Opt& opt, const B2Index& ix, const B2RescTask& t, const uint8_t* ms, B2Scratch& sc) {
+  const size_t mk = sc.mark();
+  const int l_ms = t.l_ms;
+  const int is_rev = (t.r >> 1 != (t.r & 1));
+  const int tl = (int)(t.re - t.rb);
+  const int xtra = B2_KSW_XSUBO | B2_KSW_XSTART | (l_ms * opt.a < 250 ? B2_KSW_XBYTE : 0) | (opt.min_seed_len * opt.a);
+  const int lanes = (xtra & B2_KSW_XBYTE) ? 16 : 8;
+  const int npad = ((l_ms + lanes - 1) / lanes) * lanes;
+  uint8_t* seq = (uint8_t*)sc.alloc((size_t)l_ms + 1, 1);
+  uint8_t* ref = (uint8_t*)sc.alloc((size_t)tl + 1, 1);
+  int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
+  uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
+  B2Kswr aln; aln.score = 0; aln.te = aln.qe = aln.score2 = aln.te2 = aln.tb = aln.qb = -1;
+  if (sc.overflow) { sc.reset(mk); return aln; }
+  if (is_rev) { for (int i = 0; i < l_ms; ++i) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; }
+  else { for (int i = 0; i < l_ms; ++i) seq[i] = ms[i]; }
+  b2_get_seq(ix.l_pac, ix.pac, t.rb, t.re, ref);
+  sc.gsync();
+  aln = b2_align2_any(sc, l_ms, seq, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, work, bbuf);
+  sc.reset(mk);
+  return aln;
+}
+
+// Mate rescue.  ma[*n_ma] may grow up to cap_ma.
+B2_HD inline int b2_matesw(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const B2Reg* a, int l_ms,
+                           const uint8_t* ms, B2Reg* ma, int* n_ma, int cap_ma, B2Scratch& sc, int end_i, int anchor_j,
+                           const B2RescCache* cache) {
+  const int64_t l_pac = ix.l_pac;
+  int i, r, skip[4], n = 0;
+  b2_matesw_skip(ix, pes, a, ma, *n_ma, skip);
   if (skip[0] + skip[1] + skip[2] + skip[3] == 4) return 0;
   for (r = 0; r < 4; ++r) {
     if (skip[r]) continue;
     const size_t mk = sc.mark();
-    int is_rev = (r >> 1 != (r & 1)), is_larger = !(r >> 1);
+    int is_rev;
     int64_t rb, re;
-    int rid = -1, have_ref = 0;
-    uint8_t* seq = (uint8_t*)sc.alloc((size_t)l_ms + 1, 1);
-    if (sc.overflow) { sc.reset(mk); return n; }
-    if (is_rev) { for (i = 0; i < l_ms; ++i) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; }
-    else { for (i = 0; i < l_ms; ++i) seq[i] = ms[i]; }
-    if (!is_rev) {
-      rb = is_larger ? a->rb + pes[r].low : a->rb - pes[r].high;
-      re = (is_larger ? a->rb + pes[r].high : a->rb - pes[r].low) + l_ms;
-    } else {
-      rb = (is_larger ? a->rb + pes[r].low : a->rb - pes[r].high) - l_ms;
-      re = is_larger ? a->rb + pes[r].high : a->rb - pes[r].low;
-    }
-    if (rb < 0) rb = 0;
-    if (re > l_pac << 1) re = l_pac << 1;
-    uint8_t* ref = 0;
-    if (rb < re) {
-      rid = b2_fetch_bounds(ix, &rb, (rb + re) >> 1, &re);
-      ref = (uint8_t*)sc.alloc((size_t)(re - rb) + 1, 1);
-      if (sc.overflow) { sc.reset(mk); return n; }
-      b2_get_seq(l_pac, ix.pac, rb, re, ref);
-      have_ref = 1;
-    }
-    // (when rb >= re the reference reads an uninitialised rid; such windows never pass the test below
-    //  unless a stale value happens to match -- treated as "no window")
-    if (have_ref && a->rid == rid && re - rb >= opt.min_seed_len) {
-      int xtra = B2_KSW_XSUBO | B2_KSW_XSTART | (l_ms * opt.a < 250 ? B2_KSW_XBYTE : 0) | (opt.min_seed_len * opt.a);
-      int tl = (int)(re - rb);
-      int lanes = (xtra & B2_KSW_XBYTE) ? 16 : 8;
-      int npad = ((l_ms + lanes - 1) / lanes) * lanes;
-      int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
-      uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
-      if (sc.overflow) { sc.reset(mk); return n; }
-      sc.gsync();
-      B2Kswr aln = b2_align2_any(sc, l_ms, seq, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, work, bbuf);
+    if (b2_matesw_window(opt, ix, pes, a, l_ms, r, &rb, &re, &is_rev)) {
+      B2Kswr aln;
+      int hit = 0;
+      if (cache)
+        for (int t = 0; t < cache->n; ++t)
+          if (cache->tasks[t].end_i == end_i && cache->tasks[t].j == anchor_j && cache->tasks[t].r == r) { aln = cache->res[t]; hit = 1; break; }
+      if (!hit) {
+        B2RescTask t;
+        t.item = 0; t.end_i = (int16_t)end_i; t.r = (int16_t)r; t.j = anchor_j; t.l_ms = l_ms; t.rb = rb; t.re = re;
+        aln = b2_rescue_sw(opt, ix, t, ms, sc);
+        if (sc.overflow) { sc.reset(mk); return n; }
+      }
       if (aln.score >= opt.min_seed_len && aln.qb >= 0) {
         B2Reg b = B2Reg();
         b.rid = a->rid;
@@ -670,7 +746,7 @@ B2_HD inline int b2_raw_mapq(int diff, int a) { return (int)(6.02 * diff / a + .
 // a[i] has capacity cap[i] and n[i] entries; id = global pair index.
 B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Fmt& fmt,
                             const B2Pes pes[4], uint64_t id, const B2Read s[2], B2Reg* a[2], int n[2], const int cap[2],
-                            B2Out& out, B2Scratch& sc, int* err) {
+                            B2Out& out, B2Scratch& sc, int* err, const B2RescCache* cache = 0) {
   int i, j, z[2] = {0, 0}, o, subo = 0, n_sub = 0, extra_flag = 1, n_pri[2];
   B2Aln h[2];
   const size_t mk0 = sc.mark();
@@ -685,7 +761,7 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
     }
     for (i = 0; i < 2; ++i)
       for (j = 0; j < nb[i] && j < opt.max_matesw; ++j)
-        b2_matesw(opt, ix, pes, &b[i][j], s[!i].l_seq, s[!i].seq, a[!i], &n[!i], cap[!i], sc);
+        b2_matesw(opt, ix, pes, &b[i][j], s[!i].l_seq, s[!i].seq, a[!i], &n[!i], cap[!i], sc, i, j, cache);
     sc.reset(mk0);
   }
   int zn = (n[0] > n[1] ? n[0] : n[1]) + 1;

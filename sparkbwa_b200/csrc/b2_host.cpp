@@ -667,6 +667,7 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_SEED_BLOCK"))) cfg->seed_block = atoi(s);
   if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
   if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
+  if ((s = getenv("B200BWA_WORKERS"))) cfg->n_workers = atoi(s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -784,8 +785,8 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
                   b2_cputime() - ct, b2_realtime() - rt);
         if (getenv("B200BWA_TIMES") && !rc) {
           const B2StageTimes& t = eng->times(wi);
-          fprintf(stderr, "[T::b200bwa] worker %d reads %d: h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
-                  wi, j->batch->n_reads, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.final_, t.gather, t.d2h, t.total,
+          fprintf(stderr, "[T::b200bwa] worker %d reads %d: h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f rescue %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
+                  wi, j->batch->n_reads, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
                   t.launches, (long)t.n_seed_tasks, (long)t.n_regs, (long)t.sam_bytes);
         }
         j->batch.reset();

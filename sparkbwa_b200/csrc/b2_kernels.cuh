@@ -52,6 +52,7 @@ struct B2Ctx {
   int* flags;
   unsigned long long* counters;  // [B2_CNT_*], algorithmic work
   int* work;                     // dynamic work-distribution cursor of the running stage
+  long long* dbg;                // optional per-item profile: [4*i] = {cycles, sw calls, glob calls, n regs}
   // seeding
   B2Intv* intv; int cap_intv; int32_t* n_intv; int32_t* n_tasks;
   B2Intv* seed_scratch;   // per group: 3*(max_len+1)
@@ -65,6 +66,8 @@ struct B2Ctx {
   uint8_t* scratch; size_t scratch_per_lane;
   // pestat
   int8_t* pe_dir; int64_t* pe_is;
+  // planned mate-rescue attempts
+  int32_t* resc_cnt; const int64_t* resc_off; B2RescTask* resc_tasks; B2Kswr* resc_res; int64_t n_resc;
   // SAM
   char* slots; int slot_size; int32_t* sam_len; const int64_t* sam_off; char* sam_out;
 };
@@ -251,6 +254,38 @@ B2_KERNEL k_pestat(B2Ctx c) {
   }
 }
 
+// mode 0: count the planned rescue attempts of every pair; mode 1: write them at resc_off[pair]
+B2_KERNEL k_resc_plan(B2Ctx c, int mode) {
+  const int n_pairs = c.b.n_reads >> 1;
+  for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
+    int n[2], l_seq[2];
+    const B2Reg* a[2];
+    for (int k = 0; k < 2; ++k) {
+      n[k] = c.n_regs[2 * i + k];
+      a[k] = c.regs + c.reg_off[2 * i + k];
+      l_seq[k] = c.b.l_seq[2 * i + k];
+    }
+    int cnt = b2_rescue_plan(c.opt, c.ix, c.pes, n, a, l_seq, i, mode ? c.resc_tasks + c.resc_off[i] : 0);
+    if (!mode) c.resc_cnt[i] = cnt;
+  }
+}
+
+// one task group per planned attempt: local SW of the mate against the rescue window
+B2_KERNEL k_resc_sw(B2Ctx c) {
+  int gid, n_groups;
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  for (int t = b2_next_task(c, sc); t < c.n_resc; t = b2_next_task(c, sc)) {
+    sc.gsync();
+    sc.reset(0);
+    const B2RescTask task = c.resc_tasks[t];
+    const int mate = 2 * task.item + (task.end_i ? 0 : 1);
+    B2Kswr r = b2_rescue_sw(c.opt, c.ix, task, c.b.seq + c.b.seq_off[mate], sc);
+    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+    if (sc.lane == 0) c.resc_res[t] = r;
+  }
+  b2_flush_counters(c, sc);
+}
+
 B2_KERNEL k_final_se(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
@@ -283,6 +318,10 @@ B2_KERNEL k_final_pe(B2Ctx c) {
   for (int i = b2_next_task(c, sc); i < n_pairs; i = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
+#if defined(__CUDA_ARCH__)
+    const long long t0 = clock64();
+    const unsigned sw0 = sc.sw_calls, gl0 = sc.glob_calls;
+#endif
     int err = 0;
     int n[2], cap[2];
     B2Reg* a[2];
@@ -298,12 +337,25 @@ B2_KERNEL k_final_pe(B2Ctx c) {
     if (!sc.overflow) {
       for (int k = 0; k < 2; ++k)
         for (int j = 0; j < n[k]; ++j) a[k][j] = c.regs[c.reg_off[2 * i + k] + j];
-      b2_sam_pe(c.opt, c.ix, c.tb, c.fmt, c.pes, (uint64_t)((c.n_processed >> 1) + i), s, a, n, cap, out, sc, &err);
+      B2RescCache cache;
+      cache.n = 0; cache.tasks = 0; cache.res = 0;
+      if (c.resc_off) {
+        cache.n = (int)(c.resc_off[i + 1] - c.resc_off[i]);
+        cache.tasks = c.resc_tasks + c.resc_off[i];
+        cache.res = c.resc_res + c.resc_off[i];
+      }
+      b2_sam_pe(c.opt, c.ix, c.tb, c.fmt, c.pes, (uint64_t)((c.n_processed >> 1) + i), s, a, n, cap, out, sc, &err, &cache);
     }
     if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
     if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE);
     if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
     c.sam_len[i] = (int32_t)out.len;
+#if defined(__CUDA_ARCH__)
+    if (c.dbg && sc.lane == 0) {
+      c.dbg[4 * i] = clock64() - t0; c.dbg[4 * i + 1] = sc.sw_calls - sw0; c.dbg[4 * i + 2] = sc.glob_calls - gl0;
+      c.dbg[4 * i + 3] = (long long)n[0] << 32 | (unsigned)n[1];
+    }
+#endif
   }
   b2_flush_counters(c, sc);
 }
