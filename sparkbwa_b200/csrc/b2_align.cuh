@@ -165,15 +165,39 @@ B2_HD inline int b2_cal_max_gap(const B2Opt& opt, int qlen) {
 
 struct B2U64Lt { B2_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
 
-// Extend every seed of one chain (longest first) and append regions to av[*n_av] (capacity cap_av).
-// srt: c.n u64 scratch.
-B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query, const uint8_t* query,
-                               const B2Chain& c, const B2Seed* seeds, B2Reg* av, int* n_av, int cap_av,
-                               uint64_t* srt, B2Scratch& sc) {
-  if (c.n == 0) return;
+// lane-parallel variant of b2_get_seq for a task group (every lane ends up seeing the whole window)
+B2_HD inline int64_t b2_get_seq_g(B2Scratch& sc, int64_t l_pac, const uint8_t* pac, int64_t beg, int64_t end, uint8_t* seq) {
+  if (end < beg) { int64_t t = beg; beg = end; end = t; }
+  if (end > l_pac << 1) end = l_pac << 1;
+  if (beg < 0) beg = 0;
+  if (beg >= l_pac || end <= l_pac) {
+    const int64_t n = end - beg;
+    sc.gsync();
+    if (beg >= l_pac) {
+      const int64_t end_f = (l_pac << 1) - 1 - beg;
+      for (int64_t l = sc.lane; l < n; l += sc.gsize) seq[l] = 3 - b2_get_pac(pac, end_f - l);
+    } else {
+      for (int64_t l = sc.lane; l < n; l += sc.gsize) seq[l] = b2_get_pac(pac, beg + l);
+    }
+    sc.gsync();
+    return n;
+  }
+  return 0;
+}
+
+// Reference window and work buffers of one chain, set up on first use.
+struct B2ChainPrep {
+  int ready;
+  int64_t rmax[2];
+  uint8_t *rseq, *qs, *rs;
+  B2EH* eh;
+};
+
+B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, int l_query, const B2Chain& c, const B2Seed* seeds,
+                               B2ChainPrep& P, B2Scratch& sc) {
+  if (P.ready) return 1;
   const int64_t l_pac = ix.l_pac;
-  int64_t rmax[2], max = 0;
-  int max_off[2], aw[2];
+  int64_t* rmax = P.rmax;
   rmax[0] = l_pac << 1; rmax[1] = 0;
   for (int i = 0; i < c.n; ++i) {
     const B2Seed& t = seeds[i];
@@ -181,7 +205,6 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
     int64_t e = t.rbeg + t.len + ((l_query - t.qbeg - t.len) + b2_cal_max_gap(opt, l_query - t.qbeg - t.len));
     rmax[0] = rmax[0] < b ? rmax[0] : b;
     rmax[1] = rmax[1] > e ? rmax[1] : e;
-    if (t.len > max) max = t.len;
   }
   rmax[0] = rmax[0] > 0 ? rmax[0] : 0;
   rmax[1] = rmax[1] < l_pac << 1 ? rmax[1] : l_pac << 1;
@@ -189,20 +212,104 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
     if (seeds[0].rbeg < l_pac) rmax[1] = l_pac; else rmax[0] = l_pac;
   }
   b2_fetch_bounds(ix, &rmax[0], seeds[0].rbeg, &rmax[1]);
-  const size_t mk = sc.mark();
   const int64_t rlen = rmax[1] - rmax[0];
-  uint8_t* rseq = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
-  uint8_t* qs = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
-  uint8_t* rs = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
-  B2EH* eh = (B2EH*)sc.alloc(sizeof(B2EH) * (size_t)(l_query + 2), 8);
-  if (sc.overflow) { sc.reset(mk); return; }
-  b2_get_seq(l_pac, ix.pac, rmax[0], rmax[1], rseq);
+  P.rseq = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
+  P.qs = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
+  P.rs = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
+  P.eh = (B2EH*)sc.alloc(sizeof(B2EH) * (size_t)(l_query + 2), 8);
+  if (sc.overflow) return 0;
+  b2_get_seq_g(sc, l_pac, ix.pac, rmax[0], rmax[1], P.rseq);
+  P.ready = 1;
+  return 1;
+}
+
+// Left/right extension of one seed inside its chain's window -> the region it yields (bwamem.c:709-781).
+// Depends only on the seed, the chain and the read -- not on the regions found so far.
+B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, const uint8_t* query, const B2Chain& c, const B2Seed* seeds,
+                                 const B2Seed& s, const B2ChainPrep& P, B2Reg& a, B2Scratch& sc) {
+  const int64_t* rmax = P.rmax;
+  int max_off[2], aw[2], i;
+  { B2Reg z = B2Reg(); a = z; }
+  a.w = aw[0] = aw[1] = opt.w;
+  a.score = a.truesc = -1;
+  a.rid = c.rid;
+  if (s.qbeg) {  // left extension on reversed prefixes
+    int qle, tle, gtle, gscore;
+    const int64_t tmp = s.rbeg - rmax[0];
+    sc.gsync();
+    for (i = sc.lane; i < s.qbeg; i += sc.gsize) P.qs[i] = query[s.qbeg - 1 - i];
+    for (int64_t j = sc.lane; j < tmp; j += sc.gsize) P.rs[j] = P.rseq[tmp - 1 - j];
+    sc.gsync();
+    for (i = 0; i < 2; ++i) {
+      int prev = a.score;
+      aw[0] = opt.w << i;
+      a.score = b2_extend2_any(sc, s.qbeg, P.qs, (int)tmp, P.rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
+                               opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], P.eh);
+      if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
+    }
+    if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) {
+      a.qb = s.qbeg - qle; a.rb = s.rbeg - tle;
+      a.truesc = a.score;
+    } else {
+      a.qb = 0; a.rb = s.rbeg - gtle;
+      a.truesc = gscore;
+    }
+  } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
+
+  if (s.qbeg + s.len != l_query) {  // right extension
+    int qle, tle, qe, re, gtle, gscore, sc0 = a.score;
+    qe = s.qbeg + s.len;
+    re = (int)(s.rbeg + s.len - rmax[0]);
+    for (i = 0; i < 2; ++i) {
+      int prev = a.score;
+      aw[1] = opt.w << i;
+      a.score = b2_extend2_any(sc, l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), P.rseq + re, opt.mat, opt.o_del,
+                               opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
+                               &gscore, &max_off[1], P.eh);
+      if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
+    }
+    if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) {
+      a.qe = qe + qle; a.re = rmax[0] + re + tle;
+      a.truesc += a.score - sc0;
+    } else {
+      a.qe = l_query; a.re = rmax[0] + re + gtle;
+      a.truesc += gscore - sc0;
+    }
+  } else { a.qe = l_query; a.re = s.rbeg + s.len; }
+
+  a.seedcov = 0;
+  for (i = 0; i < c.n; ++i) {
+    const B2Seed& t = seeds[i];
+    if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
+  }
+  a.w = aw[0] > aw[1] ? aw[0] : aw[1];
+  a.seedlen0 = s.len;
+  a.frac_rep = c.frac_rep;
+}
+
+// Extend the seeds of one chain, longest first, skipping seeds already covered by a region in av[] (bwamem.c:632-786).
+//   mode 0  direct: av is the read's region list
+//   mode 1  produce: av is a chain-local list (starts empty); every region computed is also stored in cand[seed],
+//           cand_ok[seed] = 1 (per-chain tasks running ahead of the serial per-read pass)
+//   mode 2  consume: av is the read's region list; a seed that has to be extended takes cand[seed] when present
+//           and is computed in place otherwise
+// srt: c.n u64 scratch.
+B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query, const uint8_t* query,
+                               const B2Chain& c, const B2Seed* seeds, B2Reg* av, int* n_av, int cap_av,
+                               uint64_t* srt, B2Scratch& sc, int mode = 0, B2Reg* cand = 0, uint8_t* cand_ok = 0) {
+  if (c.n == 0) return;
+  const size_t mk = sc.mark();
+  B2ChainPrep P;
+  P.ready = 0;
+  if (mode != 2 && !b2_chain_prep(opt, ix, l_query, c, seeds, P, sc)) { sc.reset(mk); return; }
+  if (mode == 1) for (int i = sc.lane; i < c.n; i += sc.gsize) cand_ok[i] = 0;
 
   for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)seeds[i].score << 32 | (uint32_t)i;
   b2_introsort(srt, (long)c.n, B2U64Lt());
 
   for (int k = c.n - 1; k >= 0; --k) {
-    const B2Seed& s = seeds[(uint32_t)srt[k]];
+    const int si = (int)(uint32_t)srt[k];
+    const B2Seed& s = seeds[si];
     int i;
     for (i = 0; i < *n_av; ++i) {  // was this seed already covered by an earlier extension?
       const B2Reg& p = av[i];
@@ -231,64 +338,15 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
     }
     if (*n_av >= cap_av) { sc.overflow = 1; break; }
     B2Reg& a = av[(*n_av)++];
-    {
-      B2Reg z = B2Reg();
-      a = z;
+    if (mode == 2 && cand_ok[si]) { a = cand[si]; continue; }
+    if (!b2_chain_prep(opt, ix, l_query, c, seeds, P, sc)) break;
+    b2_extend_seed(opt, l_query, query, c, seeds, s, P, a, sc);
+    if (mode == 1) {
+      sc.gsync();
+      if (sc.lane == 0) { cand[si] = a; cand_ok[si] = 1; }
     }
-    a.w = aw[0] = aw[1] = opt.w;
-    a.score = a.truesc = -1;
-    a.rid = c.rid;
-    if (s.qbeg) {  // left extension on reversed prefixes
-      int qle, tle, gtle, gscore;
-      int64_t tmp = s.rbeg - rmax[0];
-      for (i = 0; i < s.qbeg; ++i) qs[i] = query[s.qbeg - 1 - i];
-      for (int64_t j = 0; j < tmp; ++j) rs[j] = rseq[tmp - 1 - j];
-      for (i = 0; i < 2; ++i) {
-        int prev = a.score;
-        aw[0] = opt.w << i;
-        a.score = b2_extend2_any(sc, s.qbeg, qs, (int)tmp, rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
-                                 opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], eh);
-        if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
-      }
-      if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) {
-        a.qb = s.qbeg - qle; a.rb = s.rbeg - tle;
-        a.truesc = a.score;
-      } else {
-        a.qb = 0; a.rb = s.rbeg - gtle;
-        a.truesc = gscore;
-      }
-    } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
-
-    if (s.qbeg + s.len != l_query) {  // right extension
-      int qle, tle, qe, re, gtle, gscore, sc0 = a.score;
-      qe = s.qbeg + s.len;
-      re = (int)(s.rbeg + s.len - rmax[0]);
-      for (i = 0; i < 2; ++i) {
-        int prev = a.score;
-        aw[1] = opt.w << i;
-        a.score = b2_extend2_any(sc, l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), rseq + re, opt.mat, opt.o_del,
-                                 opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
-                                 &gscore, &max_off[1], eh);
-        if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
-      }
-      if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) {
-        a.qe = qe + qle; a.re = rmax[0] + re + tle;
-        a.truesc += a.score - sc0;
-      } else {
-        a.qe = l_query; a.re = rmax[0] + re + gtle;
-        a.truesc += gscore - sc0;
-      }
-    } else { a.qe = l_query; a.re = s.rbeg + s.len; }
-
-    a.seedcov = 0;
-    for (i = 0; i < c.n; ++i) {
-      const B2Seed& t = seeds[i];
-      if (t.qbeg >= a.qb && t.qbeg + t.len <= a.qe && t.rbeg >= a.rb && t.rbeg + t.len <= a.re) a.seedcov += t.len;
-    }
-    a.w = aw[0] > aw[1] ? aw[0] : aw[1];
-    a.seedlen0 = s.len;
-    a.frac_rep = c.frac_rep;
   }
+  sc.gsync();
   sc.reset(mk);
 }
 

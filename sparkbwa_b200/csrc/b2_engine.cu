@@ -68,6 +68,7 @@ struct Worker {
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
   DBuf<long long> dbg;
+  DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
   DBuf<unsigned long long> counters;
   unsigned long long h_counters[16] = {0};
@@ -182,6 +183,7 @@ class B2EngineImpl {
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
       w.flags.release(); w.counters.release(); w.dbg.release();
+      w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       if (w.pin_sam) b2_host_free(w.pin_sam);
 #if !defined(B2_HOSTSIM)
@@ -339,8 +341,24 @@ class B2EngineImpl {
     if (w.regs.ensure(R + 1)) return fail("device allocation failed (regions)");
     c.reg_off = w.reg_off.p; c.regs = w.regs.p;
     w.times.n_regs = R;
+    // speculative per-chain extension tasks, then the serial per-read pass
+    if (w.chain_off.ensure(n + 2) || w.cand.ensure(S + 1) || w.cand_ok.ensure(S + 1)) return fail("device allocation failed (extension)");
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.n_chain.p, w.chain_off.p, n);
+    ++w.times.launches;
+    int64_t TC = 0;
+    b2_d2h(&TC, w.chain_off.p + n, sizeof(int64_t), w.stream);
+    if (b2_sync(w.stream)) return fail("device synchronisation failed");
+    c.chain_off = w.chain_off.p; c.n_chain_tasks = TC; c.cand = w.cand.p; c.cand_ok = w.cand_ok.p;
     for (;;) {
       if (ensure_scratch()) return 1;
+      if (TC > 0) {
+        b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+        const int64_t blocks_needed = (TC * B2_TASK_GROUP + cfg.lane_block - 1) / cfg.lane_block;
+        B2_LAUNCH(k_ext_chain, (int)std::min<int64_t>(blocks_needed, cfg.lane_grid), cfg.lane_block, w.stream, c);
+        ++w.times.launches;
+        if (read_flags(w, &flags)) return 1;
+        if (flags & B2_FLAG_OVF_SCRATCH) { w.scratch_per_lane *= 2; continue; }
+      }
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
       B2_LAUNCH(k_extend, cfg.lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;

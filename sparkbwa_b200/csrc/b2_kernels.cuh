@@ -62,6 +62,8 @@ struct B2Ctx {
   B2Chain* chains; B2Seed* cseeds; int32_t* n_chain; int32_t* reg_cap;
   // extension
   const int64_t* reg_off; B2Reg* regs; int32_t* n_regs;
+  const int64_t* chain_off; int64_t n_chain_tasks;   // (read, chain) tasks of the speculative extension kernel
+  B2Reg* cand; uint8_t* cand_ok;                     // per seed: region computed ahead of the serial pass
   // per-lane scratch for the lane-per-read kernels
   uint8_t* scratch; size_t scratch_per_lane;
   // pestat
@@ -207,9 +209,37 @@ B2_KERNEL k_chain(B2Ctx c) {
   }
 }
 
-B2_KERNEL k_extend(B2Ctx c) {
+// One task group per (read, kept chain): extends the chain's seeds against a chain-local region list and
+// leaves every region it computes in cand[] for the serial per-read pass below (mem_chain2aln's DP, hoisted
+// out of the per-read control flow so that a read with hundreds of chains is spread over as many groups).
+B2_KERNEL k_ext_chain(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  for (int64_t t = b2_next_task(c, sc); t < c.n_chain_tasks; t = b2_next_task(c, sc)) {
+    sc.gsync();
+    sc.reset(0);
+    int lo = 0, hi = c.b.n_reads;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.chain_off[mid] <= t) lo = mid; else hi = mid; }
+    const int r = lo;
+    const int64_t off = c.seed_off[r];
+    const B2Chain& ch = c.chains[off + (t - c.chain_off[r])];
+    const int l_seq = c.b.l_seq[r];
+    uint64_t* srt = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)ch.n, 8);
+    B2Reg* av = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)ch.n, 8);
+    if (!sc.overflow) {
+      int n_av = 0;
+      b2_chain2aln(c.opt, c.ix, l_seq, c.b.seq + c.b.seq_off[r], ch, c.cseeds + off + ch.seed_head, av, &n_av, ch.n, srt, sc, 1,
+                   c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head);
+    }
+    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+  }
+  b2_flush_counters(c, sc);
+}
+
+// Serial per-read pass of the extension stage (one lane per read): decides which seeds are extended in the
+// reference's order, taking the regions from cand[], then mem_sort_dedup_patch.
+B2_KERNEL k_extend(B2Ctx c) {
+  B2Scratch sc = b2_lane_scratch(c, B2_GTID());
   for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     const int64_t off = c.seed_off[r];
     const int nch = c.n_chain[r];
@@ -225,19 +255,20 @@ B2_KERNEL k_extend(B2Ctx c) {
       uint8_t* query = (uint8_t*)sc.alloc((size_t)l_seq + 1, 1);
       if (!sc.overflow) {
         const uint8_t* q0 = c.b.seq + c.b.seq_off[r];
-        for (int i = 0; i < l_seq; ++i) query[i] = q0[i];
-        sc.gsync();
         for (int i = 0; i < nch && !sc.overflow; ++i) {
           const B2Chain& ch = c.chains[off + i];
-          b2_chain2aln(c.opt, c.ix, l_seq, query, ch, c.cseeds + off + ch.seed_head, av, &n_av, cap, srt, sc);
+          b2_chain2aln(c.opt, c.ix, l_seq, q0, ch, c.cseeds + off + ch.seed_head, av, &n_av, cap, srt, sc, 2,
+                       c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head);
         }
-        if (!sc.overflow) n_av = b2_sort_dedup_patch(c.opt, c.ix, 1, query, n_av, av, sc);
+        if (!sc.overflow && n_av > 1) {
+          for (int i = 0; i < l_seq; ++i) query[i] = q0[i];  // patching may reverse the read in place
+          n_av = b2_sort_dedup_patch(c.opt, c.ix, 1, query, n_av, av, sc);
+        }
         for (int i = 0; i < n_av; ++i)
           if (av[i].rid >= 0 && c.ix.anns[av[i].rid].is_alt) av[i].is_alt = 1;
       }
       if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; n_av = 0; }
     }
-    sc.gsync();
     c.n_regs[r] = n_av;
   }
   b2_flush_counters(c, sc);
