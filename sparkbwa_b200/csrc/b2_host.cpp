@@ -668,12 +668,16 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
   if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
   if ((s = getenv("B200BWA_WORKERS"))) cfg->n_workers = atoi(s);
+  if ((s = getenv("B200BWA_CAP_INTV"))) cfg->cap_intv = atoi(s);
+  if ((s = getenv("B200BWA_SLOT"))) cfg->slot_per_read = atoi(s);
 }
 
 // ---------------------------------------------------------------------------------------------
 // main_mem
 namespace {
 struct Job {
+  int64_t index = 0;
+  int n_reads = 0;
   std::unique_ptr<B2HostBatch> batch;
   std::string sam;
   int rc = 0;
@@ -730,8 +734,20 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     if (!out) { fprintf(stderr, "[E::main_mem] fail to open output `%s'.\n", out_path); return set_err("fail to open output `%s'", out_path); }
     setvbuf(out, 0, _IOFBF, 1 << 22);
   }
+  // Multi-GPU sharding: B200BWA_SHARD=<rank>/<world> makes this call align only the -K batches
+  // b with b % world == rank (each still tagged with its absolute n_processed).  Rank 0 writes the header; every
+  // rank writes "<out>.batches" (batch index, reads, SAM bytes per line) so the pieces can be merged in order.
+  int shard_rank = 0, shard_world = 1;
+  if (const char* sh = getenv("B200BWA_SHARD")) {
+    if (sscanf(sh, "%d/%d", &shard_rank, &shard_world) != 2 || shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) {
+      if (out_path) fclose(out);
+      return set_err("bad B200BWA_SHARD '%s' (want rank/world)", sh);
+    }
+  }
+  FILE* fidx = 0;
+  if (shard_world > 1 && out_path) fidx = fopen((std::string(out_path) + ".batches").c_str(), "w");
   std::string hdr = b2_sam_header(*host, m.hdr_line, pg_cmdline ? pg_cmdline : "");
-  fwrite(hdr.data(), 1, hdr.size(), out);
+  if (shard_rank == 0) fwrite(hdr.data(), 1, hdr.size(), out);
 
   const int chunk = m.fixed_chunk_size > 0 ? m.fixed_chunk_size : opt.chunk_size * opt.n_threads;
   const B2Pes* pes0 = m.has_pes0 ? m.pes0 : 0;
@@ -746,13 +762,17 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
 
   std::thread reader([&]() {
     int64_t n_processed = 0;
+    int64_t batch_index = 0;
     for (;;) {
       std::shared_ptr<Job> j(new Job);
       j->batch.reset(new B2HostBatch);
       int n = b2_read_batch(chunk, &ks, have2 ? &ks2 : 0, m.copy_comment, j->batch.get());
       if (n == 0) break;
       j->batch->n_processed = n_processed;
+      j->index = batch_index;
+      j->n_reads = n;
       n_processed += n;
+      if (batch_index++ % shard_world != shard_rank) continue;
       if (m.verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)j->batch->n_bases);
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
@@ -810,6 +830,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       inorder.pop_front();
       cv.notify_all();
     }
+    if (fidx) fprintf(fidx, "%ld\t%d\t%zu\n", (long)j->index, j->n_reads, j->sam.size());
     if (fwrite(j->sam.data(), 1, j->sam.size(), out) != j->sam.size()) {
       std::lock_guard<std::mutex> lk(mu);
       failed = true; rc = 1; errmsg = "write error on SAM output";
@@ -825,6 +846,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   reader.join();
   for (auto& t : gpu) t.join();
   if (rc) set_err("%s", errmsg.empty() ? eng->last_error() : errmsg.c_str());
+  if (fidx) fclose(fidx);
   if (out_path) { if (fclose(out) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }
   else fflush(out);
   if (rc == 0 && m.verbose >= 3) {

@@ -141,3 +141,14 @@ def test_jni_symbol_through_fake_env(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert b"rc=1 released=6" in r.stdout, (r.stdout, r.stderr)
     assert b"invalid option" not in r.stderr
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_capacity_retry_paths(hostsim, workdir):
+    """Deliberately tiny interval / scratch / SAM-slot capacities: every stage must notice the overflow,
+    grow the buffer, re-run (the kernels are idempotent) and still produce the reference's SAM."""
+    c = pu.make_case(workdir, "pe_small")
+    ref = pu.oracle_sam(c)
+    env = dict(pu.HOSTSIM_ENV, B200BWA_SCRATCH="512", B200BWA_CAP_INTV="2", B200BWA_SLOT="64")
+    our = pu.engine_sam(c, hostsim, env=env)
+    assert not pu.first_diff(ref, our)
