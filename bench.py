@@ -171,6 +171,9 @@ def cpu_reference(args, prefix, f1, f2, sample_pairs, threads):
 
 
 def main():
+    # the driver reads ONE JSON line from stdout: keep everything else (NCCL banners, library chatter) on stderr
+    real_stdout = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=3)
@@ -211,14 +214,16 @@ def main():
                 vals.append((v, dt))
         v = float(np.mean([x[0] for x in vals]))
         ms = float(np.mean([x[1] for x in vals])) * 1e3
-        print(json.dumps({
+        print(file=real_stdout, end="")
+        real_stdout.write(json.dumps({
             "impl": "reference", "metric": "BWA-MEM reads/sec 2x150bp PE", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload, "timing": "wall clock of `bwa mem` incl. index load from page cache"},
             "cpu_baseline": {"value": v, "unit": "reads/s", "cores": host_cores, "kind": "reference",
                              "sample": f"first {sample} pairs of the workload, bwa mem -t {host_cores} -K {args.K}"},
-            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+            "e2e": {"value": v, "unit": "reads/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}) + "\n")
+        real_stdout.flush()
         return
 
     import torch
@@ -410,7 +415,8 @@ def main():
         except OSError:
             pass
     if rank == 0:
-        print(json.dumps(out))
+        real_stdout.write(json.dumps(out) + "\n")
+        real_stdout.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -194,6 +194,13 @@ class B2EngineImpl {
     d_anns.release(); d_names.release(); d_logtab.release(); d_rg.release();
   }
 
+  // the CUDA device is a per-thread setting: every entry point that may run on a caller's thread selects it
+  void bind_device() {
+#if !defined(B2_HOSTSIM)
+    cudaSetDevice(cfg.device);
+#endif
+  }
+
   int check_cuda(const char* where) {
 #if !defined(B2_HOSTSIM)
     cudaError_t e = cudaGetLastError();
@@ -204,6 +211,7 @@ class B2EngineImpl {
   }
 
   int upload(Worker& w, const B2HostBatch& b) {
+    bind_device();
     const int n = b.n_reads;
     w.timer.reset();
     w.times = B2StageTimes();
@@ -243,6 +251,7 @@ class B2EngineImpl {
   // Runs the pipeline over reads [first, first+count) of the batch resident on `src` using the stream and
   // buffers of `w` (src == w for the ordinary one-batch call).
   int run(Worker& w, const B2Pes* pes0, std::string* sam, Worker* srcp = nullptr, int first = 0, int count = -1) {
+    bind_device();
     Worker& src = srcp ? *srcp : w;
     if (!src.resident) return fail("no resident batch");
     if (count < 0) count = src.n_reads - first;
@@ -611,11 +620,13 @@ int B2Engine::run_resident_range(const B2Pes* pes0, std::string* sam, int worker
   return impl_->run(impl_->workers[worker], pes0, sam, &impl_->workers[src_worker], first, count);
 }
 void B2Engine::set_options(const B2Opt& opt, const char* rg_id, int verbose) {
+  impl_->bind_device();
   impl_->opt = opt; impl_->cfg.verbose = verbose; impl_->set_rg(rg_id);
 }
 const B2Opt& B2Engine::options() const { return impl_->opt; }
 const B2StageTimes& B2Engine::times(int worker) const { return impl_->workers[worker].times; }
 int B2Engine::counters(int worker, unsigned long long out[16], unsigned long long* h2d, unsigned long long* d2h, int reset) {
+  impl_->bind_device();
   Worker& w = impl_->workers[worker];
   b2_d2h(out, w.counters.p, 16 * sizeof(unsigned long long), w.stream);
   b2_sync(w.stream);
