@@ -26,6 +26,20 @@ struct B2Scratch {
     if (gsize > 1) __syncwarp(gmask);
 #endif
   }
+  // sum of v over the lanes of the group (every lane gets the total)
+  B2_HD inline int gsum(int v) const {
+#if defined(__CUDA_ARCH__)
+    for (int d = gsize >> 1; d; d >>= 1) v += __shfl_xor_sync(gmask, v, d, gsize);
+#endif
+    return v;
+  }
+  // bit i set iff lane i of the group passed a true predicate
+  B2_HD inline unsigned gballot(int pred) const {
+#if defined(__CUDA_ARCH__)
+    if (gsize > 1) return (__ballot_sync(gmask, pred) & gmask) >> (__ffs(gmask) - 1);
+#endif
+    return pred ? 1u : 0u;
+  }
   B2_HD inline void* alloc(size_t bytes, size_t align = 8) {
     size_t o = (used + align - 1) & ~(align - 1);
     if (o + bytes > cap) { overflow = 1; o = 0; if (bytes > cap) return base; }
@@ -382,7 +396,7 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
   const size_t mk = sc.mark();
   uint8_t* rseq = (uint8_t*)sc.alloc((size_t)(re - rb) + 1, 1);
   if (sc.overflow) { sc.reset(mk); return 0; }
-  int64_t rlen = b2_get_seq(l_pac, ix.pac, rb, re, rseq);
+  int64_t rlen = b2_get_seq_g(sc, l_pac, ix.pac, rb, re, rseq);
   if (re - rb != rlen) { sc.reset(mk); return 0; }
   if (rb >= l_pac) {  // reverse both so that indels are placed leftmost on the forward strand
     sc.gsync();
@@ -392,8 +406,8 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
   if (l_query == re - rb && w_ == 0) {
     if (out) { out->cigar[0] = (uint32_t)l_query << 4 | 0; out->n_cigar = 1; }
     int s = 0;
-    for (int i = 0; i < l_query; ++i) s += mat[rseq[i] * 5 + query[i]];
-    *score = s;
+    for (int i = sc.lane; i < l_query; i += sc.gsize) s += mat[rseq[i] * 5 + query[i]];
+    *score = sc.gsum(s);
   } else {
     int w, max_gap, max_ins, max_del, min_w;
     max_ins = (int)((double)(((l_query + 1) >> 1) * mat[0] - opt.o_ins) / opt.e_ins + 1.);
@@ -432,14 +446,24 @@ B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int 
     const int cap = out->md_cap - 1;
     for (k = 0, x = y = u = 0; k < out->n_cigar; ++k) {
       int op = out->cigar[k] & 0xf, len = (int)(out->cigar[k] >> 4);
-      if (op == 0) {
-        for (int i = 0; i < len; ++i) {
-          if (query[x + i] != rseq[y + i]) {
+      if (op == 0) {  // the lanes compare gsize positions at a time; mismatches are then emitted in order
+        int cur = 0;
+        for (int i0 = 0; i0 < len; i0 += sc.gsize) {
+          const int i = i0 + sc.lane;
+          unsigned bits = sc.gballot(i < len && query[x + i] != rseq[y + i]);
+          while (bits) {
+            int b = 0;
+            while (!(bits >> b & 1)) ++b;
+            bits &= bits - 1;
+            const int p = i0 + b;
+            u += p - cur;
             l = b2_put_int(md, l, cap, u);
-            if (l < cap) md[l] = int2base[rseq[y + i]];
+            if (l < cap) md[l] = int2base[rseq[y + p]];
             ++l; ++n_mm; u = 0;
-          } else ++u;
+            cur = p + 1;
+          }
         }
+        u += len - cur;
         x += len; y += len;
       } else if (op == 2) {
         if (k > 0 && k < out->n_cigar - 1) {

@@ -35,6 +35,16 @@ struct B2Fmt {
 struct B2Out {
   char* p;
   long cap, len;
+  int lane = 0, gsize = 1;  // task group writing this record: bulk fields are written lane-strided
+  // n characters tab[codes[i]] for i = from, from+step, ... (step = +1 or -1)
+  B2_HD inline void put_codes(const uint8_t* codes, int from, int step, int n, const char* tab) {
+    for (int i = lane; i < n; i += gsize) if (len + i < cap) p[len + i] = tab[codes[from + i * step]];
+    len += n;
+  }
+  B2_HD inline void put_chars(const char* s, int from, int step, int n) {
+    for (int i = lane; i < n; i += gsize) if (len + i < cap) p[len + i] = s[from + i * step];
+    len += n;
+  }
   B2_HD inline void putc_(int c) { if (len < cap) p[len] = (char)c; ++len; }
   B2_HD inline void putsn(const char* s, int l) { for (int i = 0; i < l; ++i) putc_(s[i]); }
   B2_HD inline void puts_(const char* s) { for (; *s; ++s) putc_(*s); }
@@ -197,7 +207,9 @@ B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, const B2Table
   cg.md = (char*)sc.alloc((size_t)cg.md_cap, 1);
   uint8_t* query = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
   if (sc.overflow) { a.rid = -1; a.pos = -1; a.flag |= 0x4; return a; }
-  for (i = 0; i < l_query; ++i) query[i] = query_[i];
+  sc.gsync();
+  for (i = sc.lane; i < l_query; i += sc.gsize) query[i] = query_[i];
+  sc.gsync();
   cg.n_cigar = 0; cg.NM = -1; cg.l_md = 0; cg.md[0] = 0;
   i = 0;
   do {
@@ -374,9 +386,9 @@ B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, const B2Fmt& f
       if ((p->cigar[0] & 0xf) == 4 || (p->cigar[0] & 0xf) == 3) qb += p->cigar[0] >> 4;
       if ((p->cigar[p->n_cigar - 1] & 0xf) == 4 || (p->cigar[p->n_cigar - 1] & 0xf) == 3) qe -= p->cigar[p->n_cigar - 1] >> 4;
     }
-    for (i = qb; i < qe; ++i) str.putc_("ACGTN"[s.seq[i]]);
+    str.put_codes(s.seq, qb, 1, qe - qb, "ACGTN");
     str.putc_('\t');
-    if (s.qual) { for (i = qb; i < qe; ++i) str.putc_(s.qual[i]); }
+    if (s.qual) str.put_chars(s.qual, qb, 1, qe - qb);
     else str.putc_('*');
   } else {
     int qb = 0, qe = s.l_seq;
@@ -384,9 +396,9 @@ B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, const B2Fmt& f
       if ((p->cigar[0] & 0xf) == 4 || (p->cigar[0] & 0xf) == 3) qe -= p->cigar[0] >> 4;
       if ((p->cigar[p->n_cigar - 1] & 0xf) == 4 || (p->cigar[p->n_cigar - 1] & 0xf) == 3) qb += p->cigar[p->n_cigar - 1] >> 4;
     }
-    for (i = qe - 1; i >= qb; --i) str.putc_("TGCAN"[s.seq[i]]);
+    str.put_codes(s.seq, qe - 1, -1, qe - qb, "TGCAN");
     str.putc_('\t');
-    if (s.qual) { for (i = qe - 1; i >= qb; --i) str.putc_(s.qual[i]); }
+    if (s.qual) str.put_chars(s.qual, qe - 1, -1, qe - qb);
     else str.putc_('*');
   }
 
@@ -587,9 +599,10 @@ B2_HD inline B2Kswr b2_rescue_sw(const B2Opt& opt, const B2Index& ix, const B2Re
   uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
   B2Kswr aln; aln.score = 0; aln.te = aln.qe = aln.score2 = aln.te2 = aln.tb = aln.qb = -1;
   if (sc.overflow) { sc.reset(mk); return aln; }
-  if (is_rev) { for (int i = 0; i < l_ms; ++i) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; }
-  else { for (int i = 0; i < l_ms; ++i) seq[i] = ms[i]; }
-  b2_get_seq(ix.l_pac, ix.pac, t.rb, t.re, ref);
+  sc.gsync();
+  if (is_rev) { for (int i = sc.lane; i < l_ms; i += sc.gsize) seq[l_ms - 1 - i] = ms[i] < 4 ? 3 - ms[i] : 4; }
+  else { for (int i = sc.lane; i < l_ms; i += sc.gsize) seq[i] = ms[i]; }
+  b2_get_seq_g(sc, ix.l_pac, ix.pac, t.rb, t.re, ref);
   sc.gsync();
   aln = b2_align2_any(sc, l_ms, seq, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, xtra, work, bbuf);
   sc.reset(mk);

@@ -328,6 +328,7 @@ B2_KERNEL k_final_se(B2Ctx c) {
     B2Reg* a = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)(n > 0 ? n : 1), 8);
     int* z = (int*)sc.alloc(sizeof(int) * (size_t)(n + 1), 4);
     B2Out out; out.p = c.slots + (size_t)r * c.slot_size; out.cap = c.slot_size; out.len = 0;
+    out.lane = sc.lane; out.gsize = sc.gsize;
     if (!sc.overflow) {
       for (int i = 0; i < n; ++i) a[i] = c.regs[c.reg_off[r] + i];
       B2Read s = b2_make_read(c.b, r, 1);
@@ -365,6 +366,7 @@ B2_KERNEL k_final_pe(B2Ctx c) {
       s[k] = b2_make_read(c.b, 2 * i + k, 1);
     }
     B2Out out; out.p = c.slots + (size_t)i * c.slot_size; out.cap = c.slot_size; out.len = 0;
+    out.lane = sc.lane; out.gsize = sc.gsize;
     if (!sc.overflow) {
       for (int k = 0; k < 2; ++k)
         for (int j = 0; j < n[k]; ++j) a[k][j] = c.regs[c.reg_off[2 * i + k] + j];
