@@ -101,76 +101,95 @@ B2_HD inline unsigned b2_pair_blocks(const B2Index& ix, uint64_t k, uint64_t l) 
   return (unsigned)kv + (unsigned)lv;
 }
 
+// packed counts (A | C<<8 | G<<16 | T<<24) of the top m (0..32) symbols of 32 symbols held MSB-first in a u64
+B2_HD inline uint32_t b2_cnt_dword(uint64_t w, int m) {
+  if (m <= 0) return 0;
+  const uint64_t vm = 0x5555555555555555ull & (m >= 32 ? ~0ull : (~0ull << (64 - 2 * m)));
+  const uint64_t hi = w >> 1, lo = w;
+#if defined(__CUDA_ARCH__)
+  uint32_t t = __popcll(hi & lo & vm), g = __popcll(hi & ~lo & vm), c = __popcll(~hi & lo & vm);
+#else
+  uint32_t t = __builtin_popcountll(hi & lo & vm), g = __builtin_popcountll(hi & ~lo & vm),
+           c = __builtin_popcountll(~hi & lo & vm);
+#endif
+  uint32_t a = (uint32_t)(m > 32 ? 32 : m) - t - g - c;
+  return a | c << 8 | g << 16 | t << 24;
+}
+
+// Child interval of `ik` for symbol c (one step of bwt_extend, bwa/bwt.c:262-275, keeping only ok[c]):
+//   ok[c].x[f]  = L2[c] + 1 + rank_c(k)            k = ik.x[f]-1, l = k + ik.x[2], f = !is_back
+//   ok[c].x[2]  = rank_c(l) - rank_c(k)
+//   ok[c].x[b]  = ik.x[b] + [$ inside ik] + sum_{j>c} ok[j].x[2]
 struct B2OccScalar {
   mutable unsigned long long n_blk = 0;
-  B2_HD inline void pair(const B2Index& ix, uint64_t k, uint64_t l, uint64_t tk[4], uint64_t tl[4]) const {
+  B2_HD inline bool leader() const { return true; }
+  B2_HD inline void child(const B2Index& ix, const B2Intv& ik, int c, int is_back, B2Intv& out) const {
+    const int f = !is_back;
+    uint64_t tk[4], tl[4];
+    const uint64_t k = ik.x[f] - 1, l = ik.x[f] - 1 + ik.x[2];
     n_blk += b2_pair_blocks(ix, k, l);
     b2_occ4(ix, k, tk);
     b2_occ4(ix, l, tl);
+    uint64_t xb = ik.x[is_back] + (ik.x[f] <= ix.primary && ik.x[f] + ik.x[2] - 1 >= ix.primary);
+    for (int j = 3; j > c; --j) xb += tl[j] - tk[j];
+    out.x[f] = ix.L2[c] + 1 + tk[c];
+    out.x[2] = tl[c] - tk[c];
+    out.x[is_back] = xb;
   }
-  B2_HD inline bool leader() const { return true; }
 };
 
 #if defined(__CUDACC__)
+// Group-cooperative form: lane g (0..3) of the group fetches, for each of the two blocks, the cumulative count of
+// symbol g (8 bytes) and BWT words 2g, 2g+1 (8 bytes = 32 symbols), popcounts its 32 symbols for all four
+// symbols, the packed partial counts are summed over the group with two butterfly steps, and lane g ends up
+// with rank_g(k), rank_g(l).  A suffix sum over the lanes gives x[b]; the child of symbol c is broadcast from lane c.
 struct B2OccCoop {
   unsigned mask;  // lanes of this group inside the warp
   int g;          // lane index inside the group (0..B2_SEED_LANES-1)
   mutable unsigned long long n_blk = 0;
   __device__ inline bool leader() const { return g == 0; }
-  __device__ inline void pair(const B2Index& ix, uint64_t k, uint64_t l, uint64_t tk[4], uint64_t tl[4]) const {
+  __device__ inline uint64_t bc64(uint64_t v, int src) const {
+    return (uint64_t)__shfl_sync(mask, (unsigned)v, src, B2_SEED_LANES) |
+           (uint64_t)__shfl_sync(mask, (unsigned)(v >> 32), src, B2_SEED_LANES) << 32;
+  }
+  __device__ inline void child(const B2Index& ix, const B2Intv& ik, int c, int is_back, B2Intv& out) const {
+    const int f = !is_back;
+    const uint64_t k = ik.x[f] - 1, l = ik.x[f] - 1 + ik.x[2];
     n_blk += b2_pair_blocks(ix, k, l);
     const bool kv = (k != (uint64_t)-1), lv = (l != (uint64_t)-1);
-    uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-    uint4 vk = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-    if (kv) vk = __ldg(reinterpret_cast<const uint4*>(ix.bwt + ((kk >> 7) << 4)) + g);
-    if (lv) vl = __ldg(reinterpret_cast<const uint4*>(ix.bwt + ((ll >> 7) << 4)) + g);
-    uint32_t pk = 0, pl = 0;
-    if (g >= 2) {
-      int base = (g - 2) * 64;
-      int nk = (int)(kk & 127) + 1 - base, nl = (int)(ll & 127) + 1 - base;
-      const uint32_t wk[4] = {vk.x, vk.y, vk.z, vk.w}, wl[4] = {vl.x, vl.y, vl.z, vl.w};
-#pragma unroll
-      for (int wi = 0; wi < 4; ++wi) {
-        int mk = nk - 16 * wi, ml = nl - 16 * wi;
-        pk += b2_cnt_word(wk[wi], mk > 16 ? 16 : mk);
-        pl += b2_cnt_word(wl[wi], ml > 16 ? 16 : ml);
-      }
+    const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
+    uint64_t ck = 0, cl = 0, wk = 0, wl = 0;
+    if (kv) {
+      const uint64_t* b = reinterpret_cast<const uint64_t*>(ix.bwt + ((kk >> 7) << 4));
+      ck = __ldg(b + g);
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(b + 4 + g));
+      wk = (uint64_t)w.x << 32 | w.y;
     }
-    pk = __shfl_sync(mask, pk, 2, B2_SEED_LANES) + __shfl_sync(mask, pk, 3, B2_SEED_LANES);
-    pl = __shfl_sync(mask, pl, 2, B2_SEED_LANES) + __shfl_sync(mask, pl, 3, B2_SEED_LANES);
-#define B2_BC64(v_lo, v_hi, src) \
-  ((uint64_t)__shfl_sync(mask, v_lo, src, B2_SEED_LANES) | (uint64_t)__shfl_sync(mask, v_hi, src, B2_SEED_LANES) << 32)
-    tk[0] = B2_BC64(vk.x, vk.y, 0) + (pk & 0xff);
-    tk[1] = B2_BC64(vk.z, vk.w, 0) + (pk >> 8 & 0xff);
-    tk[2] = B2_BC64(vk.x, vk.y, 1) + (pk >> 16 & 0xff);
-    tk[3] = B2_BC64(vk.z, vk.w, 1) + (pk >> 24);
-    tl[0] = B2_BC64(vl.x, vl.y, 0) + (pl & 0xff);
-    tl[1] = B2_BC64(vl.z, vl.w, 0) + (pl >> 8 & 0xff);
-    tl[2] = B2_BC64(vl.x, vl.y, 1) + (pl >> 16 & 0xff);
-    tl[3] = B2_BC64(vl.z, vl.w, 1) + (pl >> 24);
-#undef B2_BC64
-    if (!kv) tk[0] = tk[1] = tk[2] = tk[3] = 0;
-    if (!lv) tl[0] = tl[1] = tl[2] = tl[3] = 0;
+    if (lv) {
+      const uint64_t* b = reinterpret_cast<const uint64_t*>(ix.bwt + ((ll >> 7) << 4));
+      cl = __ldg(b + g);
+      const uint2 w = __ldg(reinterpret_cast<const uint2*>(b + 4 + g));
+      wl = (uint64_t)w.x << 32 | w.y;
+    }
+    uint32_t pk = kv ? b2_cnt_dword(wk, (int)(kk & 127) + 1 - 32 * g) : 0;
+    uint32_t pl = lv ? b2_cnt_dword(wl, (int)(ll & 127) + 1 - 32 * g) : 0;
+    pk += __shfl_xor_sync(mask, pk, 1, B2_SEED_LANES); pl += __shfl_xor_sync(mask, pl, 1, B2_SEED_LANES);
+    pk += __shfl_xor_sync(mask, pk, 2, B2_SEED_LANES); pl += __shfl_xor_sync(mask, pl, 2, B2_SEED_LANES);
+    const uint64_t tk = ck + (pk >> (8 * g) & 0xff), tl = cl + (pl >> (8 * g) & 0xff);  // ranks of symbol g
+    const uint64_t x2 = tl - tk;
+    // suffix sum of the child sizes over symbols > g
+    uint64_t suf = x2;
+    {
+      uint64_t o = bc64(suf, (g + 1) & 3); if (g + 1 < 4) suf += o;
+      o = bc64(suf, (g + 2) & 3); if (g + 2 < 4) suf += o;
+    }
+    const uint64_t xb = ik.x[is_back] + (ik.x[f] <= ix.primary && ik.x[f] + ik.x[2] - 1 >= ix.primary) + (suf - x2);
+    out.x[f] = bc64(ix.L2[g] + 1 + tk, c);
+    out.x[2] = bc64(x2, c);
+    out.x[is_back] = bc64(xb, c);
   }
 };
 #endif
-
-// One bidirectional extension step: children of `ik` for the four symbols.
-template <class Occ>
-B2_HD inline void b2_extend(const B2Index& ix, const Occ& occ, const B2Intv& ik, B2Intv ok[4], int is_back) {
-  uint64_t tk[4], tl[4];
-  const int f = !is_back;
-  occ.pair(ix, ik.x[f] - 1, ik.x[f] - 1 + ik.x[2], tk, tl);
-  for (int i = 0; i < 4; ++i) {
-    ok[i].x[f] = ix.L2[i] + 1 + tk[i];
-    ok[i].x[2] = tl[i] - tk[i];
-  }
-  // the '$' sentinel sorts before A in the complementary direction
-  ok[3].x[is_back] = ik.x[is_back] + (ik.x[f] <= ix.primary && ik.x[f] + ik.x[2] - 1 >= ix.primary);
-  ok[2].x[is_back] = ok[3].x[is_back] + ok[3].x[2];
-  ok[1].x[is_back] = ok[2].x[is_back] + ok[2].x[2];
-  ok[0].x[is_back] = ok[1].x[is_back] + ok[1].x[2];
-}
 
 B2_HD inline void b2_set_intv(const B2Index& ix, int c, B2Intv& ik) {
   ik.x[0] = ix.L2[c] + 1;
@@ -191,7 +210,8 @@ B2_HD inline int b2_smem1(const B2Index& ix, const Occ& occ, int len, const uint
   *n_mem = 0;
   if (q[x] > 3) return x + 1;
   if (min_intv < 1) min_intv = 1;
-  B2Intv ik, ok[4];
+  B2Intv ik, okc;
+  okc.x[0] = okc.x[1] = okc.x[2] = okc.info = 0;
   B2Intv *prev = ta, *curr = tb;
   int n_prev, n_curr = 0, i;
   b2_set_intv(ix, q[x], ik);
@@ -199,12 +219,12 @@ B2_HD inline int b2_smem1(const B2Index& ix, const Occ& occ, int len, const uint
   for (i = x + 1; i < len; ++i) {  // forward: longest match starting at x, recording size changes
     if (q[i] < 4) {
       int c = 3 - q[i];
-      b2_extend(ix, occ, ik, ok, 0);
-      if (ok[c].x[2] != ik.x[2]) {
+      occ.child(ix, ik, c, 0, okc);
+      if (okc.x[2] != ik.x[2]) {
         curr[n_curr++] = ik;
-        if (ok[c].x[2] < (uint64_t)min_intv) break;
+        if (okc.x[2] < (uint64_t)min_intv) break;
       }
-      ik = ok[c];
+      ik = okc;
       ik.info = (uint64_t)(i + 1);
     } else {
       curr[n_curr++] = ik;
@@ -222,8 +242,8 @@ B2_HD inline int b2_smem1(const B2Index& ix, const Occ& occ, int len, const uint
     n_curr = 0;
     for (int j = 0; j < n_prev; ++j) {
       const B2Intv& p = prev[j];
-      if (c >= 0) b2_extend(ix, occ, p, ok, 1);
-      if (c < 0 || ok[c].x[2] < (uint64_t)min_intv) {
+      if (c >= 0) occ.child(ix, p, c, 1, okc);
+      if (c < 0 || okc.x[2] < (uint64_t)min_intv) {
         if (n_curr == 0) {
           if (nm == 0 || (uint64_t)(i + 1) < (mem[nm - 1].info >> 32)) {
             ik = p;
@@ -231,9 +251,9 @@ B2_HD inline int b2_smem1(const B2Index& ix, const Occ& occ, int len, const uint
             mem[nm++] = ik;
           }
         }
-      } else if (n_curr == 0 || ok[c].x[2] != curr[n_curr - 1].x[2]) {
-        ok[c].info = p.info;
-        curr[n_curr++] = ok[c];
+      } else if (n_curr == 0 || okc.x[2] != curr[n_curr - 1].x[2]) {
+        okc.info = p.info;
+        curr[n_curr++] = okc;
       }
     }
     if (n_curr == 0) break;
@@ -250,18 +270,19 @@ B2_HD inline int b2_seed_strategy1(const B2Index& ix, const Occ& occ, int len, c
                                    int max_intv, B2Intv* m) {
   m->x[0] = m->x[1] = m->x[2] = m->info = 0;
   if (q[x] > 3) return x + 1;
-  B2Intv ik, ok[4];
+  B2Intv ik, okc;
+  okc.info = 0;
   b2_set_intv(ix, q[x], ik);
   for (int i = x + 1; i < len; ++i) {
     if (q[i] < 4) {
       int c = 3 - q[i];
-      b2_extend(ix, occ, ik, ok, 0);
-      if (ok[c].x[2] < (uint64_t)max_intv && i - x >= min_len) {
-        *m = ok[c];
+      occ.child(ix, ik, c, 0, okc);
+      if (okc.x[2] < (uint64_t)max_intv && i - x >= min_len) {
+        *m = okc;
         m->info = (uint64_t)x << 32 | (uint64_t)(i + 1);
         return i + 1;
       }
-      ik = ok[c];
+      ik = okc;
     } else return i + 1;
   }
   return len;
