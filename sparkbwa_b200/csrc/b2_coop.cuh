@@ -31,9 +31,17 @@ struct B2G {
   __device__ inline int shfl_xor(int v, int m) const { return __shfl_xor_sync(mask, v, m, size); }
   __device__ inline long long shfl_xor64(long long v, int m) const { return __shfl_xor_sync(mask, v, m, size); }
   __device__ inline void sync() const { __syncwarp(mask); }
-  __device__ inline int max_all(int v) const { for (int d = size >> 1; d; d >>= 1) { int o = shfl_xor(v, d); v = v > o ? v : o; } return v; }
-  __device__ inline int min_all(int v) const { for (int d = size >> 1; d; d >>= 1) { int o = shfl_xor(v, d); v = v < o ? v : o; } return v; }
-  __device__ inline long long max_all64(long long v) const { for (int d = size >> 1; d; d >>= 1) { long long o = shfl_xor64(v, d); v = v > o ? v : o; } return v; }
+  // redux.sync: one instruction per 32-bit reduction over the lanes named in the mask
+  __device__ inline int max_all(int v) const { return __reduce_max_sync(mask, v); }
+  __device__ inline int min_all(int v) const { return __reduce_min_sync(mask, v); }
+  // maximum of (hi, lo) pairs in lexicographic order, lo >= 0
+  __device__ inline long long max_all64(long long v) const {
+    const int hi = (int)(v >> 32);
+    const int mh = __reduce_max_sync(mask, hi);
+    const int lo = hi == mh ? (int)(v & 0x7fffffff) : -1;
+    const int ml = __reduce_max_sync(mask, lo);
+    return ((long long)mh << 32) | (unsigned)ml;
+  }
 };
 
 __device__ inline int b2_extend2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
@@ -179,7 +187,7 @@ __device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* que
     else { eh[j].h = B2_MINUS_INF; eh[j].e = B2_MINUS_INF; }
   }
   g.sync();
-  const long long NEG = -(1ll << 40);
+  const int NEG = -0x7f000000;  // below every value of the recurrence (MINUS_INF = -2^30 minus penalties)
   for (int i = 0; i < tlen; ++i) {
     const int8_t* q = mat + target[i] * 5;
     const int beg = i > w ? i - w : 0;
@@ -191,22 +199,22 @@ __device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* que
     const int C = (n + G - 1) / G;
     const int mb = beg + g.lane * C;
     int me = mb + C; me = me < end ? me : end;
-    long long vloc = NEG;  // max over own cells of M[k] - oe_ins + k*e_ins
+    int vloc = NEG;  // max over own cells of M[k] - oe_ins + k*e_ins
     for (int j = mb; j < me; ++j) {
-      long long v = (long long)(eh[j].h + q[query[j]]) - oe_ins + (long long)j * e_ins;
+      int v = (eh[j].h + q[query[j]]) - oe_ins + j * e_ins;
       vloc = vloc > v ? vloc : v;
     }
-    long long incl = vloc;
-    for (int d = 1; d < G; d <<= 1) { long long o = __shfl_up_sync(g.mask, incl, d, G); if (g.lane >= d) incl = incl > o ? incl : o; }
-    long long pre = __shfl_up_sync(g.mask, incl, 1, G);
+    int incl = vloc;
+    for (int d = 1; d < G; d <<= 1) { int o = g.shfl_up(incl, d); if (g.lane >= d) incl = incl > o ? incl : o; }
+    int pre = g.shfl_up(incl, 1);
     if (g.lane == 0) pre = NEG;
     uint8_t* zi = z ? z + (long)i * n_col : 0;
     int lastH = 0, prevH = 0;
     for (int j = mb; j < me; ++j) {
       int m = eh[j].h + q[query[j]], e = eh[j].e;
-      long long f0 = (long long)B2_MINUS_INF - (long long)(j - beg) * e_ins;  // the serial recurrence's start value
-      long long fs = pre - (long long)(j - 1) * e_ins;
-      int f = (int)(j == beg ? (long long)B2_MINUS_INF : (fs > f0 ? fs : f0));
+      const int f0 = B2_MINUS_INF - (j - beg) * e_ins;  // the serial recurrence's start value
+      const int fs = pre == NEG ? NEG : pre - (j - 1) * e_ins;
+      int f = j == beg ? B2_MINUS_INF : (fs > f0 ? fs : f0);
       uint8_t d = m >= e ? 0 : 1;
       int h = m >= e ? m : e;
       d = h >= f ? d : 2;
@@ -220,7 +228,7 @@ __device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* que
       d |= (f - e_ins) > t ? 2 << 4 : 0;
       if (zi) zi[j - beg] = d;
       if (j != mb) eh[j].h = prevH;
-      long long v = (long long)m - oe_ins + (long long)j * e_ins;
+      const int v = m - oe_ins + j * e_ins;
       pre = pre > v ? pre : v;
       prevH = h; lastH = h;
     }
@@ -271,6 +279,7 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
   }
   shift = (256 - shift) & 0xff;
   const int oe_d = o_del + e_del, oe_i = o_ins + e_ins;
+  const bool use_scan = o_ins >= 1 && e_ins >= 1 && !(xtra & B2_KSW_XLITERAL);
   B2Kswr r; r.score = 0; r.te = r.qe = r.score2 = r.te2 = r.tb = r.qb = -1;
   const int minsc = (xtra & B2_KSW_XSUBO) ? xtra & 0xffff : 0x10000;
   const int endsc = (xtra & B2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
@@ -316,7 +325,25 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
         h = H[j];
       }
     }
-    for (int k = 0, done = 0; k < 16 && !done; ++k) {  // lazy-F
+    if (use_scan) {  // carry of F across the lanes' column blocks (see b2_sw_local), then decay inside the block
+      int x = f;
+      const int D = slen * e_ins;
+#pragma unroll
+      for (int d = 1; d < 16; d <<= 1) {
+        int o = g.shfl_up(x, d) - d * D;
+        if (l >= d && o > x) x = o;
+      }
+      f = g.shfl_up(x, 1);
+      if (l == 0) f = 0;
+#pragma unroll
+      for (int j = 0; j < B2_SW_SLMAX; ++j) {
+        if (j < slen) {
+          H1[j] = H1[j] > f ? H1[j] : f;
+          f = f - e_ins; if (f < 0) f = 0;
+        }
+      }
+    } else
+    for (int k = 0, done = 0; k < 16 && !done; ++k) {  // lazy-F, literally
       f = g.shfl_up(f, 1);
       if (l == 0) f = 0;
 #pragma unroll
@@ -431,6 +458,21 @@ __device__ inline B2Kswr b2_sw_local_coop(const B2G& g, int size, int qlen, cons
         f = f > t ? f : t;
         h = H0[j * lanes + l];
       }
+      if (o_ins >= 1 && e_ins >= 1 && !(xtra & B2_KSW_XLITERAL)) {  // carry scan instead of the lazy-F loop (see b2_sw_local)
+        int x = f;
+        const int D = slen * e_ins;
+        for (int d = 1; d < lanes; d <<= 1) {
+          int o = __shfl_up_sync(amask, x, d, lanes) - d * D;
+          if (l >= d && o > x) x = o;
+        }
+        f = __shfl_up_sync(amask, x, 1, lanes);
+        if (l == 0) f = 0;
+        for (int j = 0; j < slen && f > 0; ++j) {
+          int hh = H1[j * lanes + l];
+          H1[j * lanes + l] = (int16_t)(hh > f ? hh : f);
+          f = f - e_ins;
+        }
+      } else
       // lazy-F
       for (int k = 0, done = 0; k < 16 && !done; ++k) {
         f = __shfl_up_sync(amask, f, 1, lanes);

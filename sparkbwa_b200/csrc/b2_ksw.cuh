@@ -169,6 +169,7 @@ B2_HD inline int b2_global2(int qlen, const uint8_t* query, int tlen, const uint
 #define B2_KSW_XSTOP 0x20000
 #define B2_KSW_XSUBO 0x40000
 #define B2_KSW_XSTART 0x80000
+#define B2_KSW_XLITERAL 0x100000  // test hook: run the reference's lazy-F loop literally
 
 struct B2Kswr { int score, te, qe, score2, te2, tb, qb; };
 
@@ -229,6 +230,23 @@ B2_HD inline B2Kswr b2_sw_local(int size, int qlen, const uint8_t* query, int tl
         hv[l] = H0[j * lanes + l];
       }
     }
+    if (o_ins >= 1 && e_ins >= 1 && !(xtra & B2_KSW_XLITERAL)) {
+      // What the reference's lazy-F loop converges to (checked against the literal loop
+      // below by tests/test_cpu.py::test_striped_sw_scan_equals_lazy_f): F entering a lane's column block is the
+      // max-plus carry  x_l = max(own_l, x_{l-1} - slen*e_ins)  of the blocks to its left, and inside the block
+      // it only decays (any H it raises re-opens a gap below what is already flowing).
+      int x[16];
+      for (int l = 0; l < lanes; ++l) x[l] = fv[l];
+      for (int l = 1; l < lanes; ++l) { int c = x[l - 1] - slen * e_ins; if (c < 0) c = 0; x[l] = x[l] > c ? x[l] : c; }
+      for (int l = lanes - 1; l > 0; --l) {
+        int f = x[l - 1];
+        for (int j = 0; j < slen && f > 0; ++j) {
+          int hh = H1[j * lanes + l];
+          H1[j * lanes + l] = (int16_t)(hh > f ? hh : f);
+          f = f - e_ins; if (f < 0) f = 0;
+        }
+      }
+    } else
     // lazy-F: propagate F across lane boundaries until it can no longer raise any H
     for (int k = 0, done = 0; k < 16 && !done; ++k) {
       for (int l = lanes - 1; l > 0; --l) fv[l] = fv[l - 1];
@@ -297,7 +315,7 @@ B2_HD inline B2Kswr b2_align2(int qlen, uint8_t* query, int tlen, uint8_t* targe
   if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
   b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target);
   B2Kswr rr = b2_sw_local(size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
-                          B2_KSW_XSTOP | r.score, work, bbuf, cells);
+                          B2_KSW_XSTOP | r.score | (xtra & B2_KSW_XLITERAL), work, bbuf, cells);
   b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target);
   if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
   return r;

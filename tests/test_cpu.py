@@ -152,3 +152,13 @@ def test_capacity_retry_paths(hostsim, workdir):
     env = dict(pu.HOSTSIM_ENV, B200BWA_SCRATCH="512", B200BWA_CAP_INTV="2", B200BWA_SLOT="64")
     our = pu.engine_sam(c, hostsim, env=env)
     assert not pu.first_diff(ref, our)
+
+
+def test_striped_sw_scan_equals_lazy_f(tmp_path):
+    """The mate-rescue SW replaces the reference's lazy-F loop (ksw.c:176-188) by a max-plus carry scan;
+    fuzz it against a literal emulation of that loop (byte and word mode, random scorings)."""
+    exe = str(tmp_path / "sw_fuzz")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "sparkbwa_b200", "csrc"), "-o", exe,
+                    os.path.join(ROOT, "tests", "sw_fuzz.cpp")], check=True)
+    r = subprocess.run([exe, "12000", "777"], stdout=subprocess.PIPE, check=False)
+    assert b"mismatches 0" in r.stdout, r.stdout
