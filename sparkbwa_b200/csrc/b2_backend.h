@@ -19,6 +19,7 @@ extern thread_local B2Dim b2_dim;
     b2_dim.grid = (_g); b2_dim.block = (_b);                             \
     for (int _t = 0; _t < (_g) * (_b); ++_t) { b2_dim.tid = _t; kern(__VA_ARGS__); } \
   } while (0)
+#define B2_LAUNCH_SMEM(kern, _g, _b, _smem, stream, ...) B2_LAUNCH(kern, _g, _b, stream, __VA_ARGS__)
 typedef int b2_stream_t;
 inline int b2_dev_malloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 inline void b2_dev_free(void* p) { free(p); }
@@ -30,7 +31,6 @@ inline int b2_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p
 inline void b2_host_free(void* p) { free(p); }
 #define B2_ATOMIC_OR(p, v) (*(p) |= (v))
 #define B2_ATOMIC_ADD(p, v) (*(p) += (v))
-#define B2_LANE_GROUP 1
 #define B2_TASK_GROUP 1
 #else
 #include <cuda_runtime.h>
@@ -38,6 +38,7 @@ inline void b2_host_free(void* p) { free(p); }
 #define B2_GTID() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
 #define B2_GSIZE() ((int)(gridDim.x * blockDim.x))
 #define B2_LAUNCH(kern, _g, _b, stream, ...) kern<<<(_g), (_b), 0, (stream)>>>(__VA_ARGS__)
+#define B2_LAUNCH_SMEM(kern, _g, _b, _smem, stream, ...) kern<<<(_g), (_b), (_smem), (stream)>>>(__VA_ARGS__)
 typedef cudaStream_t b2_stream_t;
 inline int b2_dev_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
 inline void b2_dev_free(void* p) { if (p) cudaFree(p); }
@@ -49,6 +50,5 @@ inline int b2_host_alloc(void** p, size_t n) { return cudaMallocHost(p, n ? n : 
 inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
-#define B2_LANE_GROUP B2_SEED_LANES
 #define B2_TASK_GROUP B2_TASK_LANES
 #endif

@@ -11,14 +11,12 @@
 //   bytes 32..63 : 128 symbols, 2 bits each, 16 per u32, most-significant pair first.
 // A rank query at k counts symbols [0, (k&127)] of block k>>7 (k already shifted past '$').
 //
-// On the device a "seeding group" of B2_SEED_LANES lanes serves one read: every lane runs the same
-// control flow and lane g fetches 16-byte chunk g of the two blocks a bidirectional extension
-// touches (one LDG.128 per lane per block => one 64-byte request per block per group), popcounts
-// its part and the partial ranks are exchanged with warp shuffles.
+// On the device one lane serves one read (32 independent searches per warp).  The search is written as a
+// state machine (B2SeedFsm below) so that every lane of a warp reaches the one expensive step -- a
+// bidirectional extension: two 64-byte block fetches and their popcounts -- at the same program point:
+// the nested loops of the reference would leave the 32 lanes in 32 different places.
 #pragma once
 #include "b2_types.h"
-
-#define B2_SEED_LANES 4
 
 B2_HD inline uint32_t b2_cnt_word(uint32_t w, int m) {
   // packed counts (A | C<<8 | G<<16 | T<<24) of the top m (0..16) symbols of a BWT word
@@ -139,54 +137,75 @@ struct B2OccScalar {
 };
 
 #if defined(__CUDACC__)
-// Group-cooperative form: lane g (0..3) of the group fetches, for each of the two blocks, the cumulative count of
-// symbol g (8 bytes) and BWT words 2g, 2g+1 (8 bytes = 32 symbols), popcounts its 32 symbols for all four
-// symbols, the packed partial counts are summed over the group with two butterfly steps, and lane g ends up
-// with rank_g(k), rank_g(l).  A suffix sum over the lanes gives x[b]; the child of symbol c is broadcast from lane c.
-struct B2OccCoop {
-  unsigned mask;  // lanes of this group inside the warp
-  int g;          // lane index inside the group (0..B2_SEED_LANES-1)
-  mutable unsigned long long n_blk = 0;
-  __device__ inline bool leader() const { return g == 0; }
-  __device__ inline uint64_t bc64(uint64_t v, int src) const {
-    return (uint64_t)__shfl_sync(mask, (unsigned)v, src, B2_SEED_LANES) |
-           (uint64_t)__shfl_sync(mask, (unsigned)(v >> 32), src, B2_SEED_LANES) << 32;
-  }
-  __device__ inline void child(const B2Index& ix, const B2Intv& ik, int c, int is_back, B2Intv& out) const {
-    const int f = !is_back;
-    const uint64_t k = ik.x[f] - 1, l = ik.x[f] - 1 + ik.x[2];
-    n_blk += b2_pair_blocks(ix, k, l);
+// Per-lane form used by k_seed (one read per lane, 32 independent searches per warp): the lane fetches the whole
+// 64-byte block with four 16-byte loads that bypass L1 allocation (the blocks are touched once; L1 is kept for the
+// read's own bases and the interval stack spill), and ranks all four symbols with 12 popcounts: the 128 symbols are
+// handled as four word pairs whose high/low bit planes are interleaved into one 32-bit lane each.
+struct B2Blk { uint4 c01, c23, w03, w47; };  // counts A,C | counts G,T | BWT words 0..3 | BWT words 4..7
+
+// 32-byte load that bypasses L1 allocation (sm_100: LDG.256): half the memory-pipe work of two 16-byte loads when
+// every lane addresses its own line
+__device__ inline void b2_ldg_stream32(const void* p, uint4& a, uint4& b) {
+  asm volatile("ld.global.nc.L1::no_allocate.v8.u32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+               : "=r"(a.x), "=r"(a.y), "=r"(a.z), "=r"(a.w), "=r"(b.x), "=r"(b.y), "=r"(b.z), "=r"(b.w) : "l"(p));
+}
+
+__device__ inline void b2_ld_blk(const uint32_t* p, B2Blk& b) {
+  b2_ldg_stream32(p, b.c01, b.c23);
+  b2_ldg_stream32(p + 8, b.w03, b.w47);
+}
+
+// counts of T, G, C among the top symbols of a word pair: ma2/mb2 = 2 * (symbols counted in word a / b), 0..32
+__device__ inline void b2_pair_cnt(uint32_t wa, uint32_t wb, int n2, uint32_t& T, uint32_t& G, uint32_t& C) {
+  const int ma2 = __vimin_s32_relu(n2, 32), mb2 = __vimin_s32_relu(n2 - 32, 32);
+  const uint32_t sa = ~__funnelshift_rc(0xFFFFFFFFu, 0u, ma2), sb = ~__funnelshift_rc(0xFFFFFFFFu, 0u, mb2);
+  const uint32_t K = (sa & 0x55555555u) | (sb & 0xAAAAAAAAu);
+  const uint32_t X = ((wa >> 1) & 0x55555555u) | (wb & 0xAAAAAAAAu);   // high bits: word a on even, word b on odd positions
+  const uint32_t Y = (wa & 0x55555555u) | ((wb << 1) & 0xAAAAAAAAu);   // low bits, same positions
+  T += __popc(X & Y & K); G += __popc(X & ~Y & K); C += __popc(~X & Y & K);
+}
+
+// ranks of A,C,G,T over symbols [0, n) of the block, n in 1..128, added to the block's cumulative counts
+__device__ inline void b2_rank4(const B2Blk& b, int n, uint64_t r[4]) {
+  uint32_t T = 0, G = 0, C = 0;
+  const int n2 = 2 * n;
+  b2_pair_cnt(b.w03.x, b.w03.y, n2, T, G, C);
+  b2_pair_cnt(b.w03.z, b.w03.w, n2 - 64, T, G, C);
+  b2_pair_cnt(b.w47.x, b.w47.y, n2 - 128, T, G, C);
+  b2_pair_cnt(b.w47.z, b.w47.w, n2 - 192, T, G, C);
+  r[0] = ((uint64_t)b.c01.y << 32 | b.c01.x) + ((uint32_t)n - T - G - C);
+  r[1] = ((uint64_t)b.c01.w << 32 | b.c01.z) + C;
+  r[2] = ((uint64_t)b.c23.y << 32 | b.c23.x) + G;
+  r[3] = ((uint64_t)b.c23.w << 32 | b.c23.z) + T;
+}
+
+struct B2OccLane {
+  unsigned long long n_blk = 0;
+  __device__ inline void child(const B2Index& ix, const B2Intv& ik, int c, int back, B2Intv& out) {
+    const uint64_t xf = back ? ik.x[0] : ik.x[1], xo = back ? ik.x[1] : ik.x[0];
+    const uint64_t k = xf - 1, l = xf - 1 + ik.x[2];
     const bool kv = (k != (uint64_t)-1), lv = (l != (uint64_t)-1);
     const uint64_t kk = k - (k >= ix.primary), ll = l - (l >= ix.primary);
-    uint64_t ck = 0, cl = 0, wk = 0, wl = 0;
-    if (kv) {
-      const uint64_t* b = reinterpret_cast<const uint64_t*>(ix.bwt + ((kk >> 7) << 4));
-      ck = __ldg(b + g);
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(b + 4 + g));
-      wk = (uint64_t)w.x << 32 | w.y;
-    }
-    if (lv) {
-      const uint64_t* b = reinterpret_cast<const uint64_t*>(ix.bwt + ((ll >> 7) << 4));
-      cl = __ldg(b + g);
-      const uint2 w = __ldg(reinterpret_cast<const uint2*>(b + 4 + g));
-      wl = (uint64_t)w.x << 32 | w.y;
-    }
-    uint32_t pk = kv ? b2_cnt_dword(wk, (int)(kk & 127) + 1 - 32 * g) : 0;
-    uint32_t pl = lv ? b2_cnt_dword(wl, (int)(ll & 127) + 1 - 32 * g) : 0;
-    pk += __shfl_xor_sync(mask, pk, 1, B2_SEED_LANES); pl += __shfl_xor_sync(mask, pl, 1, B2_SEED_LANES);
-    pk += __shfl_xor_sync(mask, pk, 2, B2_SEED_LANES); pl += __shfl_xor_sync(mask, pl, 2, B2_SEED_LANES);
-    const uint64_t tk = ck + (pk >> (8 * g) & 0xff), tl = cl + (pl >> (8 * g) & 0xff);  // ranks of symbol g
-    const uint64_t x2 = tl - tk;
-    // suffix sum of the child sizes over symbols > g
-    uint64_t suf = x2;
-    {
-      uint64_t o = bc64(suf, (g + 1) & 3); if (g + 1 < 4) suf += o;
-      o = bc64(suf, (g + 2) & 3); if (g + 2 < 4) suf += o;
-    }
-    const uint64_t xb = ik.x[is_back] + (ik.x[f] <= ix.primary && ik.x[f] + ik.x[2] - 1 >= ix.primary) + (suf - x2);
-    out.x[f] = bc64(ix.L2[g] + 1 + tk, c);
-    out.x[2] = bc64(x2, c);
-    out.x[is_back] = bc64(xb, c);
+    const bool same = kv && lv && (kk >> 7) == (ll >> 7);
+    n_blk += same ? 1u : (unsigned)kv + (unsigned)lv;
+    B2Blk bk, bl;
+    bk.c01 = bk.c23 = bk.w03 = bk.w47 = make_uint4(0, 0, 0, 0);
+    bl = bk;
+    if (kv) b2_ld_blk(ix.bwt + ((kk >> 7) << 4), bk);
+    if (lv && !same) b2_ld_blk(ix.bwt + ((ll >> 7) << 4), bl);
+    if (same) bl = bk;
+    uint64_t tk[4] = {0, 0, 0, 0}, tl[4] = {0, 0, 0, 0};
+    if (kv) b2_rank4(bk, (int)(kk & 127) + 1, tk);
+    if (lv) b2_rank4(bl, (int)(ll & 127) + 1, tl);
+    const uint64_t d0 = tl[0] - tk[0], d1 = tl[1] - tk[1], d2 = tl[2] - tk[2], d3 = tl[3] - tk[3];
+    const uint64_t dc = c == 0 ? d0 : c == 1 ? d1 : c == 2 ? d2 : d3;
+    const uint64_t tc = c == 0 ? tk[0] : c == 1 ? tk[1] : c == 2 ? tk[2] : tk[3];
+    const uint64_t suf = c == 0 ? d1 + d2 + d3 : c == 1 ? d2 + d3 : c == 2 ? d3 : 0;
+    const uint64_t of = ix.L2[c] + 1 + tc;
+    const uint64_t ob = xo + (xf <= ix.primary && xf + ik.x[2] - 1 >= ix.primary) + suf;
+    out.x[0] = back ? of : ob;
+    out.x[1] = back ? ob : of;
+    out.x[2] = dc;
   }
 };
 #endif
@@ -288,6 +307,8 @@ B2_HD inline int b2_seed_strategy1(const B2Index& ix, const Occ& occ, int len, c
   return len;
 }
 
+B2_HD inline void b2_sort_intv(B2Intv* a, int m);
+
 // Three seeding passes + sort by (start,end).  `out` has `cap` entries; returns the number of
 // intervals found (may exceed cap: the caller treats that as a capacity overflow and retries).
 // scratch: 3*(len+1) B2Intv.
@@ -328,13 +349,235 @@ B2_HD inline int b2_collect_intv(const B2Opt& opt, const B2Index& ix, const Occ&
       } else ++x;
     }
   }
-  // sort by info; equal keys denote the same substring hence identical intervals (any order is exact)
-  int m = n < cap ? n : cap;
-  for (int i = 1; i < m; ++i) {
-    B2Intv t = out[i];
-    int j = i - 1;
-    while (j >= 0 && out[j].info > t.info) { out[j + 1] = out[j]; --j; }
-    out[j + 1] = t;
-  }
+  b2_sort_intv(out, n < cap ? n : cap);
   return n;
+}
+
+// ---------------------------------------------------------------------------------------------
+// mem_collect_intv as a resumable state machine (one per lane).  consume() takes the child interval of the
+// pending request, does the lane-local bookkeeping and leaves the next request (interval `p`, symbol `rc`,
+// direction `rback`) or reports that the read is finished; the caller performs the extension for all lanes
+// of the warp together.  What differs from the nested-loop form above, without changing the result:
+//   * the work arrays of bwt_smem1a (`prev`/`curr`, bwa/bwt.c:296-343) are one interval stack: the forward
+//     phase pushes entries 0..top-1, the backward sweeps address entry k as stack[top-1-k] (longest match
+//     first, i.e. the reversed order) and compact in place (a sweep writes entry n_curr <= j after reading j);
+//   * SMEMs are filtered by min_seed_len and appended to `out` as found; `out` is left unsorted -- k_seed_fin
+//     sorts it by `info` (equal keys are identical intervals, so the sorted array does not depend on the
+//     order of insertion) -- and the re-seeding pass takes its candidates (bwamem.c:133-142) from a short
+//     list recorded when they are emitted rather than re-reading `out`;
+//   * everything touched per step (stack, read bases, candidate list) is in shared memory: a warp runs the
+//     32 lanes' divergent bookkeeping serially, so a global-memory access there would stall all of them.
+enum { B2S_IDLE = 0, B2S_FWD, B2S_BWD, B2S_S3 };
+enum { B2T_SCAN1 = 0, B2T_START, B2T_BEGIN_BWD, B2T_SWEEP_END, B2T_SWEEP_START, B2T_END_SMEM, B2T_SCAN2, B2T_SCAN3, B2T_DONE };
+
+struct B2SeedMemHost {  // plain arrays (host checker build)
+  B2Intv* stk; const uint8_t* qg; uint32_t* rsv;
+  B2_HD inline void load_query(const uint8_t* q, int) { qg = q; }
+  B2_HD inline int q(int i) const { return qg[i]; }
+  B2_HD inline void get(int i, B2Intv& v) const { v = stk[i]; v.x[1] = 0; }  // (x[1] is not tracked through the backward phase)
+  B2_HD inline void put(int i, const B2Intv& v) { stk[i] = v; }
+  B2_HD inline void rs_put(int k, uint32_t x, uint32_t mi) { rsv[2 * k] = x; rsv[2 * k + 1] = mi; }
+  B2_HD inline void rs_get(int k, uint32_t& x, uint32_t& mi) const { x = rsv[2 * k]; mi = rsv[2 * k + 1]; }
+};
+
+#if defined(__CUDACC__)
+// Device: per lane E stack entries of three words {x0.lo, x2.lo, x0.hi | x2.hi << 8 | info << 16} (the engine refuses
+// indexes of 2^40 symbols or more and runs reads of 65 536 bases or more through the spill path only), QW words of
+// 4-bit base codes and RS candidate pairs, all word-transposed over the block's lanes (bank-conflict free).
+// Deeper stack entries, longer reads and further candidates spill to a per-lane global array.
+// x[1] -- the interval of the reverse complement -- is not kept on the stack: backward extension only passes it
+// through, and nothing after seeding reads it (mem_chain uses x[0], x[2] and info; bwamem.c:273-301), so SMEMs
+// leave this kernel with x[1] = 0.  Forward walks (where x[1] drives the extension) keep it in registers.
+// The spill paths are out-of-line calls on purpose: inlined, the compiler predicates them, and a predicated-off
+// global load/store still occupies the memory pipe and a long-scoreboard slot in every trip of the hot loop.
+__device__ __noinline__ void b2_spill_get3(const uint32_t* a, uint32_t* w) { w[0] = a[0]; w[1] = a[1]; w[2] = a[2]; }
+__device__ __noinline__ void b2_spill_put3(uint32_t* a, uint32_t w0, uint32_t w1, uint32_t w2) { a[0] = w0; a[1] = w1; a[2] = w2; }
+__device__ __noinline__ void b2_spill_put2(uint32_t* a, uint32_t w0, uint32_t w1) { a[0] = w0; a[1] = w1; }
+__device__ __noinline__ int b2_spill_q(const uint8_t* q, int i) { return q[i]; }
+
+struct B2SeedMemDev {
+  uint32_t *s, *qs, *rs;   // shared: stack, bases, candidates (already offset by the lane)
+  uint32_t *g, *grs;       // global spill: stack entries >= E, candidates >= RS
+  const uint8_t* qg;
+  int stride, E, QW, RS;
+  __device__ inline void load_query(const uint8_t* q, int len) {
+    qg = q;
+    const int nw = (len + 7) >> 3 < QW ? (len + 7) >> 3 : QW;
+    for (int w = 0; w < nw; ++w) {
+      uint32_t v = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) { const int i = 8 * w + k; v |= (uint32_t)(i < len ? q[i] : 4) << (4 * k); }
+      qs[w * stride] = v;
+    }
+  }
+  __device__ inline int q(int i) const {
+    if (i < 8 * QW) return (int)(qs[(i >> 3) * stride] >> ((i & 7) * 4) & 15);
+    return b2_spill_q(qg, i);
+  }
+  __device__ inline void get(int i, B2Intv& v) const {
+    uint32_t w[3];
+    if (i < E) { const uint32_t* a = s + (size_t)i * 3 * stride; w[0] = a[0]; w[1] = a[stride]; w[2] = a[2 * stride]; }
+    else b2_spill_get3(g + (size_t)(i - E) * 3, w);
+    v.x[0] = (uint64_t)(w[2] & 0xff) << 32 | w[0];
+    v.x[1] = 0;
+    v.x[2] = (uint64_t)(w[2] >> 8 & 0xff) << 32 | w[1];
+    v.info = w[2] >> 16;
+  }
+  __device__ inline void put(int i, const B2Intv& v) {
+    const uint32_t w2 = (uint32_t)(v.x[0] >> 32) | (uint32_t)(v.x[2] >> 32) << 8 | (uint32_t)v.info << 16;
+    if (i < E) { uint32_t* a = s + (size_t)i * 3 * stride; a[0] = (uint32_t)v.x[0]; a[stride] = (uint32_t)v.x[2]; a[2 * stride] = w2; }
+    else b2_spill_put3(g + (size_t)(i - E) * 3, (uint32_t)v.x[0], (uint32_t)v.x[2], w2);
+  }
+  __device__ inline void rs_put(int k, uint32_t x, uint32_t mi) {
+    if (k < RS) { rs[2 * k * stride] = x; rs[(2 * k + 1) * stride] = mi; } else b2_spill_put2(grs + 2 * (k - RS), x, mi);
+  }
+  __device__ inline void rs_get(int k, uint32_t& x, uint32_t& mi) const {
+    if (k < RS) { x = rs[2 * k * stride]; mi = rs[(2 * k + 1) * stride]; }
+    else { uint32_t w[3]; b2_spill_get3(grs + 2 * (k - RS), w); x = w[0]; mi = w[1]; }
+  }
+};
+#endif
+
+template <class Mem, int MODE>
+struct B2SeedFsm {
+  Mem mem;
+  int len; B2Intv* out; int cap;
+  int phase, pass;
+  int x, i, j, n_prev, n_curr, top, n, nm_last, ret, k2, n_rs, rc, rback;
+  uint64_t min_intv, last_x2;
+  B2Intv ik, p;
+
+  B2_HD inline void emit(const B2Opt& opt, const B2Intv& v, int start) {
+    const int qend = (int)v.info;
+    nm_last = start;
+    if (qend - start >= opt.min_seed_len) {
+      if (n < cap) { B2Intv t = v; t.info = (uint64_t)start << 32 | (uint32_t)qend; out[n] = t; }
+      ++n;
+      if (pass == 1 && qend - start >= (int)(opt.min_seed_len * opt.split_factor + .499) && v.x[2] <= (uint64_t)opt.split_width)
+        mem.rs_put(n_rs++, (uint32_t)((start + qend) >> 1), (uint32_t)(v.x[2] + 1));
+    }
+  }
+
+  // First request of a task; returns 0 if it yields nothing to extend.  A read is two independent tasks, run by
+  // different lanes: mode 0 = SMEM passes 1+2 (entries out[0], out[1], ...), mode 1 = pass 3, the forward-only
+  // seeds of bwt_seed_strategy1 (entries out[cap-1], out[cap-2], ...); k_seed_fin joins and sorts them.
+  B2_HD inline int begin(const B2Opt& opt, const B2Index& ix, const uint8_t* q, int len_, B2Intv* out_, int cap_) {
+    len = len_; out = out_; cap = cap_;
+    mem.load_query(q, len);
+    n = 0; n_rs = 0; x = 0; pass = MODE ? 3 : 1;
+    if (MODE) return opt.max_mem_intv > 0 ? advance(opt, ix, B2T_SCAN3) : 0;
+    return advance(opt, ix, B2T_SCAN1);
+  }
+
+  // lane-local transitions until the next request (returns 1) or the end of the read (returns 0)
+  B2_HD inline int advance(const B2Opt& opt, const B2Index& ix, int t) {
+    for (;;) {
+      if (MODE == 0 && (t == B2T_START || t == B2T_SCAN1)) {
+        if (t == B2T_SCAN1) {
+          while (x < len && mem.q(x) > 3) ++x;
+          if (x >= len) { pass = 2; k2 = 0; t = B2T_SCAN2; continue; }
+          min_intv = 1;
+        }
+        b2_set_intv(ix, mem.q(x), ik);  // start of bwt_smem1a at x
+        ik.info = (uint64_t)(x + 1);
+        i = x + 1; n_curr = 0; phase = B2S_FWD; rback = 0;
+        if (i < len) { const int b = mem.q(i); if (b < 4) { p = ik; rc = 3 - b; return 1; } }
+        mem.put(n_curr++, ik); ret = (int)ik.info;
+        t = B2T_BEGIN_BWD;
+      } else if (MODE == 0 && (t == B2T_BEGIN_BWD || t == B2T_SWEEP_END || t == B2T_SWEEP_START)) {
+        if (t == B2T_BEGIN_BWD) { top = n_curr; n_prev = n_curr; i = x - 1; nm_last = 0x7fffffff; phase = B2S_BWD; rback = 1; }
+        else if (t == B2T_SWEEP_END) {
+          if (n_curr == 0) { t = B2T_END_SMEM; continue; }
+          n_prev = n_curr; --i;
+        }
+        j = 0; n_curr = 0;
+        int bc = -1;
+        if (i >= 0) { bc = mem.q(i); if (bc > 3) bc = -1; }
+        mem.get(top - 1, p);
+        if (bc < 0) {  // nothing extends: only the longest candidate can be reported
+          if (i + 1 < nm_last) emit(opt, p, i + 1);
+          t = B2T_END_SMEM;
+          continue;
+        }
+        rc = bc;
+        return 1;
+      } else if (MODE == 0 && t == B2T_END_SMEM) {
+        if (pass == 1) { x = ret; t = B2T_SCAN1; } else t = B2T_SCAN2;
+      } else if (MODE == 0 && t == B2T_SCAN2) {
+        if (k2 < n_rs) {
+          uint32_t rx, rmi;
+          mem.rs_get(k2++, rx, rmi);
+          x = (int)rx; min_intv = rmi; t = B2T_START;
+        } else t = B2T_DONE;
+      } else if (MODE == 1 && t == B2T_SCAN3) {
+        while (x < len && mem.q(x) > 3) ++x;
+        if (x >= len) { t = B2T_DONE; continue; }
+        b2_set_intv(ix, mem.q(x), ik);
+        i = x + 1; phase = B2S_S3; rback = 0;
+        if (i >= len) { t = B2T_DONE; continue; }
+        const int b = mem.q(i);
+        if (b < 4) { p = ik; rc = 3 - b; return 1; }
+        x = i + 1;
+      } else {
+        phase = B2S_IDLE;
+        return 0;
+      }
+    }
+  }
+
+  B2_HD inline int consume(const B2Opt& opt, const B2Index& ix, B2Intv okc) {
+    int t;
+    if (MODE == 0 && phase == B2S_BWD) {
+      if (okc.x[2] < min_intv) {
+        if (n_curr == 0 && i + 1 < nm_last) emit(opt, p, i + 1);
+      } else if (n_curr == 0 || okc.x[2] != last_x2) {
+        okc.info = p.info;
+        mem.put(top - 1 - n_curr, okc);
+        ++n_curr;
+        last_x2 = okc.x[2];
+      }
+      ++j;
+      if (j < n_prev) { mem.get(top - 1 - j, p); return 1; }
+      t = B2T_SWEEP_END;
+    } else {  // one more base of a forward walk: bwt_smem1a's first loop (B2S_FWD) or bwt_seed_strategy1 (B2S_S3)
+      const bool fwd = MODE == 0;
+      bool stop;
+      if (fwd) {
+        const bool changed = okc.x[2] != ik.x[2];
+        if (changed) { mem.put(n_curr++, ik); ret = (int)ik.info; }
+        stop = changed && okc.x[2] < min_intv;
+        t = B2T_BEGIN_BWD;
+      } else {
+        stop = okc.x[2] < opt.max_mem_intv && i - x >= opt.min_seed_len;
+        if (stop && okc.x[2] > 0) {
+          if (n < cap) { okc.info = (uint64_t)x << 32 | (uint64_t)(i + 1); out[cap - 1 - n] = okc; }
+          ++n;
+        }
+        if (stop) x = i + 1;  // where the next walk starts
+        t = B2T_SCAN3;
+      }
+      if (!stop) {
+        ik = okc; ik.info = (uint64_t)(i + 1);
+        ++i;
+        if (i < len) {
+          const int b = mem.q(i);
+          if (b < 4) { p = ik; rc = 3 - b; return 1; }
+        }
+        if (fwd) { mem.put(n_curr++, ik); ret = (int)ik.info; }  // ambiguous base or end of the read
+        else if (i >= len) t = B2T_DONE;
+        else x = i + 1;
+      }
+    }
+    return advance(opt, ix, t);
+  }
+};
+
+// sort by info (insertion sort: a handful of entries); equal keys denote the same substring hence identical intervals
+B2_HD inline void b2_sort_intv(B2Intv* a, int m) {
+  for (int i = 1; i < m; ++i) {
+    B2Intv t = a[i];
+    int j = i - 1;
+    while (j >= 0 && a[j].info > t.info) { a[j + 1] = a[j]; --j; }
+    a[j + 1] = t;
+  }
 }

@@ -61,7 +61,7 @@ struct Worker {
   DBuf<uint8_t> seq; DBuf<char> qual; DBuf<uint8_t> has_qual; DBuf<char> names, comments;
   DBuf<int64_t> seq_off, name_off, com_off; DBuf<int32_t> l_seq, l_name, l_com;
   // stages
-  DBuf<B2Intv> intv, seed_scratch; DBuf<int32_t> n_intv, n_tasks; DBuf<int64_t> seed_off;
+  DBuf<B2Intv> intv, seed_scratch; DBuf<uint32_t> seed_spill; DBuf<int32_t> n_intv, n_tasks; DBuf<int64_t> seed_off;
   DBuf<B2Seed> raw, cseeds; DBuf<int32_t> raw_rid; DBuf<B2Chain> chains; DBuf<int32_t> n_chain, reg_cap;
   DBuf<int64_t> reg_off; DBuf<B2Reg> regs; DBuf<int32_t> n_regs;
   DBuf<uint8_t> scratch; DBuf<int8_t> pe_dir; DBuf<int64_t> pe_is; DBuf<double> pairtab;
@@ -107,7 +107,11 @@ class B2EngineImpl {
     cfg = c; opt = o;
 #if !defined(B2_HOSTSIM)
     if (cudaSetDevice(cfg.device) != cudaSuccess) return fail("cudaSetDevice failed (no usable CUDA device)");
+    // a per-device function attribute, the same value from every engine of the process
+    if (cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail("cudaFuncSetAttribute(k_seed) failed");
 #endif
+    if (h.seq_len >= (1ull << 40)) return fail("index too large: the seeding kernel packs interval bounds into 40 bits");
     ix.primary = h.primary; ix.seq_len = h.seq_len;
     for (int i = 0; i < 5; ++i) ix.L2[i] = h.L2[i];
     ix.bwt_size = h.bwt_words ? h.bwt_words : h.bwt.size(); ix.n_sa = h.n_sa ? h.n_sa : h.sa.size();
@@ -178,7 +182,7 @@ class B2EngineImpl {
       for (DBuf<uint8_t>* b : {&w.seq, &w.has_qual, &w.scratch}) b->release();
       w.qual.release(); w.names.release(); w.comments.release(); w.seq_off.release(); w.name_off.release();
       w.com_off.release(); w.l_seq.release(); w.l_name.release(); w.l_com.release(); w.intv.release();
-      w.seed_scratch.release(); w.n_intv.release(); w.n_tasks.release(); w.seed_off.release(); w.raw.release();
+      w.seed_scratch.release(); w.seed_spill.release(); w.n_intv.release(); w.n_tasks.release(); w.seed_off.release(); w.raw.release();
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
@@ -287,17 +291,47 @@ class B2EngineImpl {
     int ev_begin = w.timer.mark();
 
     // ---- seeding ----
-    const int seed_groups = cfg.seed_grid * cfg.seed_block / B2_LANE_GROUP;
-    if (w.n_intv.ensure(n + 1) || w.n_tasks.ensure(n + 1) || w.seed_off.ensure(n + 2) ||
-        w.seed_scratch.ensure((size_t)seed_groups * 3 * (size_t)(w.max_len + 1)))
-      return fail("device allocation failed (seeding)");
+    // one read per lane; the lane count is what fits on the chip at once (shared-memory interval stacks), the
+    // lanes pull reads from a cursor
+    const int seed_block = cfg.seed_block;
+    int seed_QW = std::min((w.max_len + 7) / 8, 32), seed_RS = 4, seed_E;
+    {  // split the per-lane share of the SM's shared memory: bases, candidates, the rest for the interval stack
+      const int per_lane_words = (int)((227 * 1024 / cfg.seed_blocks_per_sm - 1024) / seed_block / 4);
+      seed_E = (per_lane_words - seed_QW - 2 * seed_RS) / 3;
+      if (cfg.seed_smem_entries > 0) seed_E = cfg.seed_smem_entries;
+      if (seed_E < 4) seed_E = 4;
+    }
+    const size_t seed_smem = (size_t)seed_block * (3 * seed_E + seed_QW + 2 * seed_RS) * sizeof(uint32_t);
+    const size_t seed3_smem = (size_t)seed_block * seed_QW * sizeof(uint32_t);
+    int seed_grid = std::min({(n + seed_block - 1) / seed_block, 148 * cfg.seed_blocks_per_sm, cfg.seed_grid});
+    int seed3_grid = std::min({(n + seed_block - 1) / seed_block, 148 * cfg.seed3_blocks_per_sm, cfg.seed_grid});
+    {  // bound the spill area for very long reads
+      const size_t per_lane = 5 * sizeof(uint32_t) * (size_t)(w.max_len + 1);
+      const size_t max_lanes = std::max<size_t>(((size_t)2 << 30) / per_lane, (size_t)seed_block);
+      seed_grid = (int)std::min<size_t>((size_t)seed_grid, max_lanes / seed_block);
+      seed3_grid = (int)std::min<size_t>((size_t)seed3_grid, max_lanes / seed_block);
+      if (seed_grid < 1) seed_grid = 1;
+      if (seed3_grid < 1) seed3_grid = 1;
+    }
+    const size_t seed_lanes = (size_t)std::max(seed_grid, seed3_grid) * seed_block;
+#if defined(B2_HOSTSIM)
+    if (w.seed_scratch.ensure(seed_lanes * (size_t)(w.max_len + 1))) return fail("device allocation failed (seeding)");
+    (void)seed_smem; (void)seed3_smem;
+#else
+    if (w.seed_spill.ensure(seed_lanes * 5 * (size_t)(w.max_len + 1) + 8)) return fail("device allocation failed (seeding)");
+    if (seed_smem > (size_t)227 * 1024) return fail("seeding shared-memory configuration exceeds 227 KB per block");
+#endif
+    if (w.n_intv.ensure(n + 1) || w.n_tasks.ensure(n + 1) || w.seed_off.ensure(n + 2)) return fail("device allocation failed (seeding)");
     for (;;) {
       if (w.intv.ensure((size_t)n * w.cap_intv)) return fail("device allocation failed (intervals)");
       c.intv = w.intv.p; c.cap_intv = w.cap_intv; c.n_intv = w.n_intv.p; c.n_tasks = w.n_tasks.p;
-      c.seed_scratch = w.seed_scratch.p;
-      b2_dev_memset(w.flags.p, 0, sizeof(int), w.stream);
-      B2_LAUNCH(k_seed, cfg.seed_grid, cfg.seed_block, w.stream, c);
-      ++w.times.launches;
+      c.seed_scratch = w.seed_scratch.p; c.seed_spill = w.seed_spill.p;
+      c.seed_E = seed_E; c.seed_QW = seed_QW; c.seed_RS = seed_RS;
+      b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);
+      B2_LAUNCH_SMEM(k_seed, seed_grid, seed_block, seed_smem, w.stream, c);
+      B2_LAUNCH_SMEM(k_seed3, seed3_grid, seed_block, seed3_smem, w.stream, c);
+      B2_LAUNCH(k_seed_fin, (n + 127) / 128, 128, w.stream, c);
+      w.times.launches += 3;
       if (read_flags(w, &flags)) return 1;
       if (!(flags & B2_FLAG_OVF_INTV)) break;
       if (w.cap_intv >= 8192) return fail("seed interval capacity exceeded");

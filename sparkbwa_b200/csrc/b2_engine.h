@@ -42,7 +42,10 @@ struct B2HostBatch {
 struct B2EngineConfig {
   int device = 0;
   int lane_grid = 148 * 4, lane_block = 128;   // lane-per-read kernels (persistent, grid-stride)
-  int seed_grid = 148 * 8, seed_block = 128;   // seeding groups of B2_SEED_LANES lanes
+  int seed_grid = 148 * 16, seed_block = 128;  // seeding: one task per lane; grid = min(tasks, SMs x blocks per SM, seed_grid)
+  int seed_blocks_per_sm = 4;                  // shared memory is split for this many resident seeding blocks per SM
+  int seed3_blocks_per_sm = 8;                 // forward-only pass: no stack, fewer registers
+  int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
   size_t scratch_per_lane = 48 << 10;
   size_t max_scratch_bytes = (size_t)64 << 30;
   int n_workers = 4;                           // independent stream/buffer sets (batches in flight)

@@ -665,6 +665,9 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_LANE_BLOCK"))) cfg->lane_block = atoi(s);
   if ((s = getenv("B200BWA_SEED_GRID"))) cfg->seed_grid = atoi(s);
   if ((s = getenv("B200BWA_SEED_BLOCK"))) cfg->seed_block = atoi(s);
+  if ((s = getenv("B200BWA_SEED_ENTRIES"))) cfg->seed_smem_entries = atoi(s);
+  if ((s = getenv("B200BWA_SEED_BPS"))) cfg->seed_blocks_per_sm = atoi(s);
+  if ((s = getenv("B200BWA_SEED3_BPS"))) cfg->seed3_blocks_per_sm = atoi(s);
   if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
   if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
   if ((s = getenv("B200BWA_WORKERS"))) cfg->n_workers = atoi(s);

@@ -1,5 +1,5 @@
 // Kernel bodies of the batch pipeline (mem_process_seqs, bwa/bwamem.c:1172-1201, re-staged for a GPU):
-//   k_seed    SMEM seeding, one B2_SEED_LANES-lane group per read           (mem_collect_intv)
+//   k_seed    SMEM seeding, one read per lane (state machine)                (mem_collect_intv)
 //   k_sa      one task per sampled suffix-array position                     (bwt_sa + bns_intv2rid)
 //   k_chain   chaining + chain filter, one read per lane                     (mem_chain, mem_chain_flt)
 //   k_extend  seed extension + de-dup, one read per lane                     (mem_chain2aln, mem_sort_dedup_patch)
@@ -55,7 +55,9 @@ struct B2Ctx {
   long long* dbg;                // optional per-item profile: [4*i] = {cycles, sw calls, glob calls, n regs}
   // seeding
   B2Intv* intv; int cap_intv; int32_t* n_intv; int32_t* n_tasks;
-  B2Intv* seed_scratch;   // per group: 3*(max_len+1)
+  B2Intv* seed_scratch;   // host checker build: per lane max_len+1 stack entries
+  uint32_t* seed_spill;   // device: per lane 5*(max_len+1) words for what does not fit the shared-memory part
+  int seed_E, seed_QW, seed_RS;  // per lane in shared memory: stack entries, words of 4-bit base codes, re-seed candidates
   // SA / chaining
   const int64_t* seed_off; int64_t n_seed_tasks;
   B2Seed* raw; int32_t* raw_rid;
@@ -85,29 +87,123 @@ B2_HD inline B2Read b2_make_read(const B2Batch& b, int r, int copy_comment) {
   return s;
 }
 
-B2_KERNEL k_seed(B2Ctx c) {
-  const int gid = B2_GTID() / B2_LANE_GROUP, n_groups = B2_GSIZE() / B2_LANE_GROUP;
+// One task per lane at a time; lanes pull tasks from the stage's work cursor.  Each trip of the outer loop performs
+// ONE bidirectional extension for every lane that has a request pending (convergent, expensive: two 64-byte block
+// fetches + popcounts) and then the lane-local bookkeeping of the search (divergent, cheap, shared memory only)
+// -- see B2SeedFsm.  MODE 0 = SMEM passes 1+2 of a read, MODE 1 = its forward-only pass 3; two kernels because the
+// second needs no interval stack and far fewer registers, so many more of its lanes fit an SM.
+// Shared memory per block: blockDim.x * (3*E + QW + 2*RS) words (MODE 1: E = RS = 0).
+template <int MODE>
+B2_D inline void b2_seed_body(const B2Ctx& c) {
 #if defined(B2_HOSTSIM)
   B2OccScalar occ;
+  B2SeedFsm<B2SeedMemHost, MODE> m;
+  m.mem.stk = c.seed_scratch + (size_t)B2_GTID() * (size_t)(c.max_len + 1);
+  m.mem.rsv = (uint32_t*)malloc(sizeof(uint32_t) * 2 * (size_t)(c.max_len + 1));
+  B2Intv* chk = (B2Intv*)malloc(sizeof(B2Intv) * (size_t)(2 * c.cap_intv + 3 * (c.max_len + 1)));
 #else
-  B2OccCoop occ;
-  occ.g = threadIdx.x & (B2_SEED_LANES - 1);
-  occ.mask = ((1u << B2_SEED_LANES) - 1) << ((threadIdx.x & 31) & ~(B2_SEED_LANES - 1));
-#endif
-  B2Intv* scratch = c.seed_scratch + (size_t)gid * 3 * (size_t)(c.max_len + 1);
-  for (int r = gid; r < c.b.n_reads; r += n_groups) {
-    const int len = c.b.l_seq[r];
-    int n = 0;
-    long tasks = 0;
-    B2Intv* out = c.intv + (size_t)r * c.cap_intv;
-    if (len >= c.opt.min_seed_len) {
-      n = b2_collect_intv(c.opt, c.ix, occ, len, c.b.seq + c.b.seq_off[r], out, c.cap_intv, scratch);
-      if (n > c.cap_intv) { if (occ.leader()) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_INTV); n = c.cap_intv; }
-      for (int i = 0; i < n; ++i) tasks += out[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)out[i].x[2];
-    }
-    if (occ.leader()) { c.n_intv[r] = n; c.n_tasks[r] = (int32_t)tasks; }
+  extern __shared__ uint32_t b2_seed_smem[];
+  B2OccLane occ;
+  B2SeedFsm<B2SeedMemDev, MODE> m;
+  {
+    const int T = blockDim.x;
+    const int E = MODE ? 0 : c.seed_E, RS = MODE ? 0 : c.seed_RS;
+    m.mem.stride = T; m.mem.E = E; m.mem.QW = c.seed_QW; m.mem.RS = RS;
+    m.mem.s = b2_seed_smem + threadIdx.x;
+    m.mem.qs = b2_seed_smem + (size_t)3 * E * T + threadIdx.x;
+    m.mem.rs = b2_seed_smem + (size_t)(3 * E + c.seed_QW) * T + threadIdx.x;
+    m.mem.g = c.seed_spill + (size_t)B2_GTID() * 5 * (size_t)(c.max_len + 1);
+    m.mem.grs = m.mem.g + 3 * (size_t)(c.max_len + 1);
   }
-  if (occ.leader() && occ.n_blk) B2_ATOMIC_ADD(&c.counters[B2_CNT_OCC_BLOCKS], occ.n_blk);
+#endif
+  m.phase = B2S_IDLE;
+  int r = -1, need = 0;
+  bool alive = true;
+  int32_t* n_out = MODE ? c.n_tasks : c.n_intv;  // (n_tasks holds the pass-3 count until k_seed_fin)
+  for (;;) {
+    while (alive && !need) {  // next task of this lane
+#if defined(__CUDA_ARCH__)
+      r = atomicAdd(c.work + MODE, 1);
+#else
+      r = c.work[MODE]++;
+#endif
+      if (r >= c.b.n_reads) { alive = false; break; }
+      const int len = c.b.l_seq[r];
+      n_out[r] = 0;
+      if (len < c.opt.min_seed_len) continue;
+      need = m.begin(c.opt, c.ix, c.b.seq + c.b.seq_off[r], len, c.intv + (size_t)r * c.cap_intv, c.cap_intv);
+    }
+    // the warp-wide vote is also the reconvergence point: every lane with a pending request runs the extension
+    // below in the same pass
+#if defined(__CUDA_ARCH__)
+    if (__ballot_sync(0xffffffffu, need) == 0) break;
+#else
+    if (!need) break;
+#endif
+    if (need) {
+      B2Intv okc;
+      okc.info = 0;
+      occ.child(c.ix, m.p, m.rc, m.rback, okc);
+#if defined(B2_HOSTSIM)
+      static const bool dump_steps = getenv("B200BWA_DEBUG_SEED_STEPS") != 0;
+      static long steps[4]; static int steps_read = -1;
+      if (dump_steps) { if (steps_read != r) { steps_read = r; steps[0] = steps[1] = steps[2] = steps[3] = 0; } ++steps[m.phase]; }
+#endif
+      need = m.consume(c.opt, c.ix, okc);
+#if defined(B2_HOSTSIM)
+      if (dump_steps && !need) fprintf(stderr, "[D::seed_steps] %d fwd %ld bwd %ld s3 %ld n %d\n", r, steps[B2S_FWD], steps[B2S_BWD], steps[B2S_S3], m.n);
+#endif
+      if (!need) {  // task finished; k_seed_fin joins the two runs, sorts the intervals and counts the SA tasks
+        int n = m.n;
+        if (n > c.cap_intv) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_INTV); n = c.cap_intv; }
+        n_out[r] = n;
+#if defined(B2_HOSTSIM)
+        if (MODE && c.n_intv[r] + n <= c.cap_intv) {  // cross-check against the plain nested-loop form (x[1] aside)
+          B2OccScalar occ2;
+          B2Intv* mine = chk + c.cap_intv + 3 * (c.max_len + 1);
+          const int n12 = c.n_intv[r];
+          memcpy(mine, m.out, sizeof(B2Intv) * (size_t)n12);
+          for (int k = 0; k < n; ++k) mine[n12 + k] = m.out[c.cap_intv - 1 - k];
+          n += n12;
+          b2_sort_intv(mine, n);
+          int n2 = b2_collect_intv(c.opt, c.ix, occ2, m.len, c.b.seq + c.b.seq_off[r], chk, c.cap_intv, chk + c.cap_intv);
+          int bad = n2 <= c.cap_intv && n2 != n;
+          for (int k = 0; !bad && k < n && n2 <= c.cap_intv; ++k)
+            bad = chk[k].x[0] != mine[k].x[0] || chk[k].x[2] != mine[k].x[2] || chk[k].info != mine[k].info ||
+                  (mine[k].x[1] != 0 && mine[k].x[1] != chk[k].x[1]);
+          if (bad) {
+            fprintf(stderr, "[hostsim] seeding state machine differs from the nested form on read %d (%d vs %d intervals)\n", r, n, n2);
+            abort();
+          }
+        }
+#endif
+      }
+    }
+  }
+  if (occ.n_blk) B2_ATOMIC_ADD(&c.counters[B2_CNT_OCC_BLOCKS], occ.n_blk);
+#if defined(B2_HOSTSIM)
+  free(chk); free(m.mem.rsv);
+#endif
+}
+
+B2_KERNEL k_seed(B2Ctx c) { b2_seed_body<0>(c); }
+B2_KERNEL k_seed3(B2Ctx c) { b2_seed_body<1>(c); }
+
+// per read: intervals sorted by (start, end) as mem_collect_intv leaves them (bwamem.c:161) + number of SA lookups
+B2_KERNEL k_seed_fin(B2Ctx c) {
+  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+    B2Intv* out = c.intv + (size_t)r * c.cap_intv;
+    const int n12 = c.n_intv[r], n3 = c.n_tasks[r];
+    if (n12 + n3 > c.cap_intv) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_INTV); c.n_tasks[r] = 0; continue; }
+    const int gap = c.cap_intv - n3 - n12;  // close the gap between the two runs (their order is irrelevant: sorted below)
+    for (int k = 0; k < n3 && k < gap; ++k) out[n12 + k] = out[c.cap_intv - 1 - k];
+    const int n = n12 + n3;
+    c.n_intv[r] = n;
+    b2_sort_intv(out, n);
+    long tasks = 0;
+    for (int i = 0; i < n; ++i) tasks += out[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)out[i].x[2];
+    c.n_tasks[r] = (int32_t)tasks;
+  }
 }
 
 B2_KERNEL k_sa(B2Ctx c) {
