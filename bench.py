@@ -31,7 +31,7 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
-LIB = os.path.join(ROOT, "sparkbwa_b200", "libbwa.so")
+LIB = os.environ.get("B200BWA_LIB", os.path.join(ROOT, "sparkbwa_b200", "libbwa.so"))
 ORACLE = os.path.join(ROOT, "oracle", "_ref", "bwa")
 
 

@@ -57,6 +57,10 @@ B2_HD inline int b2_extend2_any(B2Scratch& sc, int qlen, const uint8_t* query, i
 #if defined(__CUDA_ARCH__)
   if (sc.gsize > 1) {
     B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
+    int s;
+    if (b2_extend2_reg_try(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle, gtle,
+                           gscore, max_off, &sc.ext_cells, &s))
+      return s;
     return b2_extend2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle,
                            gtle, gscore, max_off, eh, &sc.ext_cells);
   }
@@ -72,6 +76,10 @@ B2_HD inline int b2_global2_any(B2Scratch& sc, int qlen, const uint8_t* query, i
 #if defined(__CUDA_ARCH__)
   if (sc.gsize > 1) {
     B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
+    int s;
+    if (b2_global2_diag_try(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, z, n_cigar_, cigar, cigar_cap,
+                            &sc.glob_cells, &s))
+      return s;
     return b2_global2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, eh, z, n_cigar_, cigar,
                            cigar_cap, &sc.glob_cells);
   }
@@ -180,7 +188,7 @@ B2_HD inline int b2_cal_max_gap(const B2Opt& opt, int qlen) {
 struct B2U64Lt { B2_HD bool operator()(uint64_t a, uint64_t b) const { return a < b; } };
 
 // lane-parallel variant of b2_get_seq for a task group (every lane ends up seeing the whole window)
-B2_HD inline int64_t b2_get_seq_g(B2Scratch& sc, int64_t l_pac, const uint8_t* pac, int64_t beg, int64_t end, uint8_t* seq) {
+B2_NOINLINE B2_HD inline int64_t b2_get_seq_g(B2Scratch& sc, int64_t l_pac, const uint8_t* pac, int64_t beg, int64_t end, uint8_t* seq) {
   if (end < beg) { int64_t t = beg; beg = end; end = t; }
   if (end > l_pac << 1) end = l_pac << 1;
   if (beg < 0) beg = 0;
@@ -207,7 +215,7 @@ struct B2ChainPrep {
   B2EH* eh;
 };
 
-B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, int l_query, const B2Chain& c, const B2Seed* seeds,
+B2_NOINLINE B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, int l_query, const B2Chain& c, const B2Seed* seeds,
                                B2ChainPrep& P, B2Scratch& sc) {
   if (P.ready) return 1;
   const int64_t l_pac = ix.l_pac;
@@ -239,7 +247,7 @@ B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, int l_query,
 
 // Left/right extension of one seed inside its chain's window -> the region it yields (bwamem.c:709-781).
 // Depends only on the seed, the chain and the read -- not on the regions found so far.
-B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, const uint8_t* query, const B2Chain& c, const B2Seed* seeds,
+B2_NOINLINE B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, const uint8_t* query, const B2Chain& c, const B2Seed* seeds,
                                  const B2Seed& s, const B2ChainPrep& P, B2Reg& a, B2Scratch& sc) {
   const int64_t* rmax = P.rmax;
   int max_off[2], aw[2], i;
@@ -387,7 +395,7 @@ B2_HD inline int b2_put_int(char* s, int l, int cap, long c) {
 
 // want_cigar == 0: score only.  Returns 0 when the reference would have returned a null cigar
 // without touching *score (reject conditions), 1 otherwise.
-B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int l_query, uint8_t* query, int64_t rb,
+B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int l_query, uint8_t* query, int64_t rb,
                                int64_t re, int* score, B2Cigar* out, B2Scratch& sc) {
   const int64_t l_pac = ix.l_pac;
   const int8_t* mat = opt.mat;
@@ -523,7 +531,7 @@ struct B2RegScLt {
   }
 };
 
-B2_HD inline int b2_sort_dedup_patch(const B2Opt& opt, const B2Index& ix, int have_ref, uint8_t* query, int n,
+B2_NOINLINE B2_HD inline int b2_sort_dedup_patch(const B2Opt& opt, const B2Index& ix, int have_ref, uint8_t* query, int n,
                                      B2Reg* a, B2Scratch& sc) {
   int m, i, j;
   if (n <= 1) return n;

@@ -12,6 +12,7 @@
 struct B2Dim { int grid, block, tid; };
 extern thread_local B2Dim b2_dim;
 #define B2_KERNEL static void
+#define B2_KERNEL_LB(threads, blocks_per_sm) static void
 #define B2_GTID() (b2_dim.tid)
 #define B2_GSIZE() (b2_dim.grid * b2_dim.block)
 #define B2_LAUNCH(kern, _g, _b, stream, ...)                             \
@@ -32,9 +33,15 @@ inline void b2_host_free(void* p) { free(p); }
 #define B2_ATOMIC_OR(p, v) (*(p) |= (v))
 #define B2_ATOMIC_ADD(p, v) (*(p) += (v))
 #define B2_TASK_GROUP 1
+#define B2_G_EXT 1
+#define B2_G_FINAL 1
+#define B2_G_RESC 1
+#define B2_LB_EXT 1
+#define B2_LB_FINAL 1
 #else
 #include <cuda_runtime.h>
 #define B2_KERNEL static __global__ void
+#define B2_KERNEL_LB(threads, blocks_per_sm) static __global__ void __launch_bounds__(threads, blocks_per_sm)
 #define B2_GTID() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
 #define B2_GSIZE() ((int)(gridDim.x * blockDim.x))
 #define B2_LAUNCH(kern, _g, _b, stream, ...) kern<<<(_g), (_b), 0, (stream)>>>(__VA_ARGS__)
@@ -51,4 +58,21 @@ inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2_TASK_GROUP B2_TASK_LANES
+// Lanes per task of the group-cooperative kernels.  A warp whose two halves follow different tasks keeps switching
+// between two instruction streams (ncu: stall_no_inst 49-67 % of the samples in k_final_pe / k_ext_chain with
+// 16-lane groups), so the control-flow-heavy kernels give a whole warp to a task; the rescue SW keeps the 16 lanes
+// of ksw_u8, whose two groups per warp run the same loop nearly in lock step.
+#ifndef B2_G_EXT
+#define B2_G_EXT 32
+#endif
+#ifndef B2_G_FINAL
+#define B2_G_FINAL 16
+#endif
+#define B2_G_RESC 16
+#ifndef B2_LB_EXT
+#define B2_LB_EXT 4
+#endif
+#ifndef B2_LB_FINAL
+#define B2_LB_FINAL 3
+#endif
 #endif

@@ -17,6 +17,7 @@
 //                     lazy-F loop with its early exit map one to one.
 #pragma once
 #include "b2_ksw.cuh"
+#include "b2_coopreg.cuh"
 
 #define B2_TASK_LANES 16
 
@@ -28,6 +29,7 @@ struct B2G {
   int size;       // power of two
   __device__ inline int shfl(int v, int src) const { return __shfl_sync(mask, v, src, size); }
   __device__ inline int shfl_up(int v, int d) const { return __shfl_up_sync(mask, v, d, size); }
+  __device__ inline int shfl_down(int v, int d) const { return __shfl_down_sync(mask, v, d, size); }
   __device__ inline int shfl_xor(int v, int m) const { return __shfl_xor_sync(mask, v, m, size); }
   __device__ inline long long shfl_xor64(long long v, int m) const { return __shfl_xor_sync(mask, v, m, size); }
   __device__ inline void sync() const { __syncwarp(mask); }
@@ -44,7 +46,22 @@ struct B2G {
   }
 };
 
-__device__ inline int b2_extend2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+// The same interface with the member mask known at compile time (low or high half of the warp): a shuffle with a
+// run-time mask costs five extra instructions (MATCH.ANY / REDUX / VOTE / LOP3 / BRA.DIV convergence check).
+template <unsigned MASK, int SIZE>
+struct B2GC {
+  int lane;
+  static constexpr int size = SIZE;
+  static constexpr unsigned mask = MASK;
+  __device__ inline int shfl(int v, int src) const { return __shfl_sync(MASK, v, src, SIZE); }
+  __device__ inline int shfl_up(int v, int d) const { return __shfl_up_sync(MASK, v, d, SIZE); }
+  __device__ inline int shfl_down(int v, int d) const { return __shfl_down_sync(MASK, v, d, SIZE); }
+  __device__ inline void sync() const { __syncwarp(MASK); }
+  __device__ inline int max_all(int v) const { return __reduce_max_sync(MASK, v); }
+  __device__ inline int min_all(int v) const { return __reduce_min_sync(MASK, v); }
+};
+
+B2_NOINLINE __device__ inline int b2_extend2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                       const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
                                       int zdrop, int h0, int* _qle, int* _tle, int* _gtle, int* _gscore, int* _max_off,
                                       B2EH* eh, unsigned long long* cells) {
@@ -174,7 +191,7 @@ __device__ inline int b2_extend2_coop(const B2G& g, int qlen, const uint8_t* que
 // max-plus scan  F[j] = max( MINUS_INF-(j-beg)*e_ins, max_{beg<=k<j}( M[k]-oe_ins-(j-1-k)*e_ins ) ), which is the
 // unrolled form of the reference's serial recurrence, so H, E, F and every direction bit (ties: m>=e, h>=f, e>t,
 // f>t) are the same integers.  The traceback (a few hundred dependent steps) stays serial.
-__device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+B2_NOINLINE __device__ inline int b2_global2_coop(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                       const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, B2EH* eh,
                                       uint8_t* z, int* n_cigar_, uint32_t* cigar, int cigar_cap, unsigned long long* cells) {
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
@@ -527,6 +544,69 @@ __device__ inline B2Kswr b2_sw_local_coop(const B2G& g, int size, int qlen, cons
   }
   g.sync();
   return r;
+}
+
+// ---- dispatch to the register-resident forms (b2_coopreg.cuh) -------------------------------------------------
+// Whole-warp groups only (the member mask is then the constant 0xffffffff: a shuffle with a run-time mask costs
+// five extra instructions -- MATCH.ANY / REDUX / VOTE / LOP3 / BRA.DIV -- for the convergence check).  One
+// out-of-line instance per cells-per-lane count, shared by the call sites (mem_chain2aln's two extensions, the
+// several users of bwa_gen_cigar2).  Returns false when the preconditions do not hold (the callers then use the
+// memory-resident forms above).
+typedef B2GC<0xffffffffu, 32> B2GW;
+
+template <int C>
+__device__ __noinline__ int b2_extend2_reg_dev(int lane, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                               const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
+                                               int zdrop, int h0, int* res5, unsigned long long* cells) {
+  B2GW g; g.lane = lane;
+  return b2_extend2_reg<C>(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, res5, res5 + 1,
+                           res5 + 2, res5 + 3, res5 + 4, cells);
+}
+
+__device__ inline bool b2_extend2_reg_try(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                          const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
+                                          int zdrop, int h0, int* qle, int* tle, int* gtle, int* gscore, int* max_off,
+                                          unsigned long long* cells, int* score) {
+  if (g.size != 32 || qlen + 1 > 32 * 8 || !b2_mat_simple(mat)) return false;
+  const int need = (qlen + 1 + 31) >> 5;
+  int r[5];
+  int s;
+#define B2_EXT_ARGS g.lane, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, r, cells
+  if (need <= 1) s = b2_extend2_reg_dev<1>(B2_EXT_ARGS);
+  else if (need <= 2) s = b2_extend2_reg_dev<2>(B2_EXT_ARGS);
+  else if (need <= 3) s = b2_extend2_reg_dev<3>(B2_EXT_ARGS);
+  else if (need <= 5) s = b2_extend2_reg_dev<5>(B2_EXT_ARGS);
+  else s = b2_extend2_reg_dev<8>(B2_EXT_ARGS);
+#undef B2_EXT_ARGS
+  if (qle) *qle = r[0];
+  if (tle) *tle = r[1];
+  if (gtle) *gtle = r[2];
+  if (gscore) *gscore = r[3];
+  if (max_off) *max_off = r[4];
+  *score = s;
+  return true;
+}
+
+template <int C>
+__device__ __noinline__ int b2_global2_diag_dev(int lane, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                                const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, uint8_t* z,
+                                                int* n_cigar_, uint32_t* cigar, int cigar_cap, unsigned long long* cells) {
+  B2GW g; g.lane = lane;
+  return b2_global2_diag<C>(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, z, n_cigar_, cigar, cigar_cap, cells);
+}
+
+__device__ inline bool b2_global2_diag_try(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                           const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, uint8_t* z,
+                                           int* n_cigar_, uint32_t* cigar, int cigar_cap, unsigned long long* cells, int* score) {
+  const int dl = qlen > tlen ? qlen - tlen : tlen - qlen;
+  if (g.size != 32 || qlen < 1 || tlen < 1 || dl > w || 2 * w + 1 > 32 * 4 || !b2_mat_simple(mat)) return false;
+  const int need = (2 * w + 1 + 31) >> 5;
+#define B2_GLB_ARGS g.lane, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, z, n_cigar_, cigar, cigar_cap, cells
+  if (need <= 1) *score = b2_global2_diag_dev<1>(B2_GLB_ARGS);
+  else if (need <= 2) *score = b2_global2_diag_dev<2>(B2_GLB_ARGS);
+  else *score = b2_global2_diag_dev<4>(B2_GLB_ARGS);
+#undef B2_GLB_ARGS
+  return true;
 }
 
 #endif  // __CUDACC__

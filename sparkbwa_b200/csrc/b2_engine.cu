@@ -82,7 +82,7 @@ struct Worker {
   int n_reads_run = 0;
   B2StageTimes times;
   std::vector<int8_t> h_dir; std::vector<int64_t> h_is; std::vector<char> h_sam;
-  void* pin_sam = nullptr; size_t pin_sam_cap = 0;
+  void* pin_sam = nullptr; size_t pin_sam_cap = 0, last_sam_bytes = 0;
 };
 
 }  // namespace
@@ -254,7 +254,9 @@ class B2EngineImpl {
 
   // Runs the pipeline over reads [first, first+count) of the batch resident on `src` using the stream and
   // buffers of `w` (src == w for the ordinary one-batch call).
-  int run(Worker& w, const B2Pes* pes0, std::string* sam, Worker* srcp = nullptr, int first = 0, int count = -1) {
+  int run(Worker& w, const B2Pes* pes0, std::string* sam, Worker* srcp = nullptr, int first = 0, int count = -1,
+          bool view = false) {
+    w.last_sam_bytes = 0;
     bind_device();
     Worker& src = srcp ? *srcp : w;
     if (!src.resident) return fail("no resident batch");
@@ -396,7 +398,7 @@ class B2EngineImpl {
       if (ensure_scratch()) return 1;
       if (TC > 0) {
         b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-        const int64_t blocks_needed = (TC * B2_TASK_GROUP + cfg.lane_block - 1) / cfg.lane_block;
+        const int64_t blocks_needed = (TC * B2_G_EXT + cfg.lane_block - 1) / cfg.lane_block;
         B2_LAUNCH(k_ext_chain, (int)std::min<int64_t>(blocks_needed, cfg.lane_grid), cfg.lane_block, w.stream, c);
         ++w.times.launches;
         if (read_flags(w, &flags)) return 1;
@@ -468,7 +470,7 @@ class B2EngineImpl {
         for (;;) {
           if (ensure_scratch()) return 1;
           b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-          const int64_t groups_needed = (T * B2_TASK_GROUP + cfg.lane_block - 1) / cfg.lane_block;
+          const int64_t groups_needed = (T * B2_G_RESC + cfg.lane_block - 1) / cfg.lane_block;
           const int grid = (int)std::min<int64_t>(groups_needed, cfg.lane_grid);
           B2_LAUNCH(k_resc_sw, grid, cfg.lane_block, w.stream, c);
           ++w.times.launches;
@@ -545,7 +547,7 @@ class B2EngineImpl {
     int ev_gat = w.timer.mark();
     w.times.sam_bytes = total;
     int ev_d2h = ev_gat;
-    if (sam) {
+    if (sam || view) {
       if ((size_t)total > w.pin_sam_cap) {
         if (w.pin_sam) b2_host_free(w.pin_sam);
         w.pin_sam_cap = (size_t)total + (size_t)total / 4 + 4096;
@@ -556,7 +558,8 @@ class B2EngineImpl {
       b2_g_d2h_bytes += (size_t)total;
       ev_d2h = w.timer.mark();
       if (b2_sync(w.stream)) return fail("device synchronisation failed");
-      sam->append((const char*)w.pin_sam, (size_t)total);
+      if (sam) sam->append((const char*)w.pin_sam, (size_t)total);
+      w.last_sam_bytes = (size_t)total;
     } else {
       if (b2_sync(w.stream)) return fail("device synchronisation failed");
     }
@@ -645,6 +648,14 @@ int B2Engine::process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam,
   Worker& w = impl_->workers[worker];
   if (impl_->upload(w, b)) return 1;
   return impl_->run(w, pes0, &sam);
+}
+int B2Engine::process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, const char** data, size_t* len) {
+  Worker& w = impl_->workers[worker];
+  *data = 0; *len = 0;
+  if (impl_->upload(w, b)) return 1;
+  if (impl_->run(w, pes0, nullptr, nullptr, 0, -1, true)) return 1;
+  *data = (const char*)w.pin_sam; *len = w.last_sam_bytes;
+  return 0;
 }
 int B2Engine::upload(const B2HostBatch& b, int worker) { return impl_->upload(impl_->workers[worker], b); }
 int B2Engine::run_resident(const B2Pes* pes0, std::string* sam, int worker) {

@@ -74,6 +74,8 @@ class B2Engine {
   // Aligns one batch and appends its SAM text to `sam`.  PE iff opt.flag & B2_F_PE.  pes0: user-supplied
   // insert-size distribution (-I) or null.  `worker` selects one of the independent stream/buffer sets.
   int process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam, int worker = 0);
+  // same, leaving the SAM text in the worker's pinned host buffer: *data stays valid until the next call on `worker`
+  int process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, const char** data, size_t* len);
   // device-resident variant used by the benchmark: upload once, run the kernels many times
   int upload(const B2HostBatch& b, int worker = 0);
   int run_resident(const B2Pes* pes0, std::string* sam, int worker = 0);

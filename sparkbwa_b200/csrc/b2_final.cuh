@@ -110,7 +110,7 @@ B2_HD inline void b2_mark_primary_core(const B2Opt& opt, int n, B2Reg* a, int* z
   }
 }
 
-B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* a, int64_t id, int* z) {
+B2_NOINLINE B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* a, int64_t id, int* z) {
   int i, n_pri;
   if (n == 0) return 0;
   for (i = n_pri = 0; i < n; ++i) {
@@ -186,7 +186,7 @@ B2_HD inline int b2_get_rlen(int n_cigar, const uint32_t* cigar) {
 
 // ar == null: unmapped record.  qwork: l_query bytes of scratch holding a private copy of the read.
 // The cigar/MD of the result live in `sc` (not released here).
-B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, int l_query,
+B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, int l_query,
                               const uint8_t* query_, const B2Reg* ar, B2Scratch& sc, int* err) {
   B2Aln a;
   a.pos = 0; a.rid = 0; a.flag = 0; a.is_rev = a.is_alt = a.mapq = a.NM = 0; a.n_cigar = 0;
@@ -258,7 +258,7 @@ B2_HD inline int b2_pri_idx(double XA_drop_ratio, const B2Reg* a, int i) {
   return -1;
 }
 
-B2_HD inline char** b2_gen_alt(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, int n, const B2Reg* a,
+B2_NOINLINE B2_HD inline char** b2_gen_alt(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, int n, const B2Reg* a,
                                int l_query, const uint8_t* query, B2Scratch& sc, int* err) {
   if (n == 0) return 0;
   int* cnt = (int*)sc.alloc(sizeof(int) * (size_t)n, 4);
@@ -334,7 +334,7 @@ B2_HD inline void b2_put_f3(B2Out& o, double x) {
   o.putc_('0' + f / 100); o.putc_('0' + f / 10 % 10); o.putc_('0' + f % 10);
 }
 
-B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, const B2Fmt& fmt, B2Out& str, const B2Read& s, int n,
+B2_NOINLINE B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, const B2Fmt& fmt, B2Out& str, const B2Read& s, int n,
                              const B2Aln* list, int which, const B2Aln* m_) {
   B2Aln ptmp = list[which], *p = &ptmp, mtmp, *m = 0;
   int i;
@@ -440,7 +440,7 @@ B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, const B2Fmt& f
 }
 
 // SE record set of one read (also the unpaired branch of PE).
-B2_HD inline void b2_reg2sam(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Fmt& fmt, B2Out& str,
+B2_NOINLINE B2_HD inline void b2_reg2sam(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Fmt& fmt, B2Out& str,
                              const B2Read& s, int n, B2Reg* a, int extra_flag, const B2Aln* m, B2Scratch& sc, int* err) {
   const size_t mk = sc.mark();
   char** XA = 0;
@@ -610,7 +610,7 @@ B2_HD inline B2Kswr b2_rescue_sw(const B2Opt& opt, const B2Index& ix, const B2Re
 }
 
 // Mate rescue.  ma[*n_ma] may grow up to cap_ma.
-B2_HD inline int b2_matesw(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const B2Reg* a, int l_ms,
+B2_NOINLINE B2_HD inline int b2_matesw(const B2Opt& opt, const B2Index& ix, const B2Pes pes[4], const B2Reg* a, int l_ms,
                            const uint8_t* ms, B2Reg* ma, int* n_ma, int cap_ma, B2Scratch& sc, int end_i, int anchor_j,
                            const B2RescCache* cache) {
   const int64_t l_pac = ix.l_pac;
@@ -668,7 +668,7 @@ struct B2Pair64Lt {
 };
 
 // Best proper pair.  `id` is deliberately an int and `id<<8` wraps in 32 bits like the reference.
-B2_HD inline int b2_pair(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Pes pes[4], const B2Reg* a0,
+B2_NOINLINE B2_HD inline int b2_pair(const B2Opt& opt, const B2Index& ix, const B2Tables& tb, const B2Pes pes[4], const B2Reg* a0,
                          const B2Reg* a1, int id, int* sub, int* n_sub, int z[2], const int n_pri[2], B2Scratch& sc,
                          int* err) {
   const int64_t l_pac = ix.l_pac;

@@ -11,7 +11,11 @@
 #include <stdio.h>
 #include <stdlib.h>
 #include <string.h>
+#include <fcntl.h>
+#include <sys/mman.h>
 #include <sys/resource.h>
+#include <sys/stat.h>
+#include <unistd.h>
 #include <sys/time.h>
 #include <zlib.h>
 
@@ -463,22 +467,34 @@ static const unsigned char nt4_table[256] = {
 
 const unsigned char* b2_nt4_table() { return nt4_table; }
 
+// A record either lives in the reader's own strings (general kseq path: gzip, pipes, FASTA, multi-line
+// records, CR/LF, ...) or, for the common case of a plain 4-line FASTQ in a regular file, is a set of
+// pointers into the memory-mapped file found with four memchr calls (`stable`: valid until close()).
+// The mapped fast path is taken record by record and only when the record has exactly the shape for
+// which kseq_read's result is the four line bodies; anything else falls through to the general parser,
+// which continues from the same position in the same buffer.
 struct B2SeqReader::Impl {
   gzFile fp = 0;
-  std::vector<unsigned char> buf;
+  std::vector<unsigned char> store;      // gz mode: refill buffer
+  const unsigned char* data = 0;          // current buffer (store.data() or the mapping)
   size_t begin = 0, end = 0;
   bool is_eof = false;
   int last_char = 0;
+  const unsigned char* map = 0;
+  size_t map_size = 0;
   std::string name, comment, seq, qual;
+  bool refill() {
+    if (map || is_eof) { is_eof = true; return false; }
+    begin = 0;
+    int n = gzread(fp, store.data(), (unsigned)store.size());
+    end = n > 0 ? (size_t)n : 0;
+    data = store.data();
+    if (end == 0) { is_eof = true; return false; }
+    return true;
+  }
   int getc_() {
-    if (is_eof && begin >= end) return -1;
-    if (begin >= end) {
-      begin = 0;
-      int n = gzread(fp, buf.data(), (unsigned)buf.size());
-      end = n > 0 ? (size_t)n : 0;
-      if (end == 0) { is_eof = true; return -1; }
-    }
-    return buf[begin++];
+    if (begin >= end && !refill()) return -1;
+    return data[begin++];
   }
   // delimiter: 0 = any whitespace, 2 = newline.  Returns length or -1 at EOF without data.
   int getuntil(int delim, std::string& str, int* dret, bool append) {
@@ -486,25 +502,18 @@ struct B2SeqReader::Impl {
     if (dret) *dret = 0;
     if (!append) str.clear();
     for (;;) {
-      if (begin >= end) {
-        if (!is_eof) {
-          begin = 0;
-          int n = gzread(fp, buf.data(), (unsigned)buf.size());
-          end = n > 0 ? (size_t)n : 0;
-          if (end == 0) { is_eof = true; break; }
-        } else break;
-      }
+      if (begin >= end && !refill()) break;
       size_t i;
       if (delim == 2) {
-        const unsigned char* q = (const unsigned char*)memchr(buf.data() + begin, '\n', end - begin);
-        i = q ? (size_t)(q - buf.data()) : end;
+        const unsigned char* q = (const unsigned char*)memchr(data + begin, '\n', end - begin);
+        i = q ? (size_t)(q - data) : end;
       } else {
-        for (i = begin; i < end; ++i) if (isspace(buf[i])) break;
+        for (i = begin; i < end; ++i) if (isspace(data[i])) break;
       }
       gotany = true;
-      str.append((const char*)buf.data() + begin, i - begin);
+      str.append((const char*)data + begin, i - begin);
       begin = i + 1;
-      if (i < end) { if (dret) *dret = buf[i]; break; }
+      if (i < end) { if (dret) *dret = data[i]; break; }
     }
     if (!gotany && is_eof && begin >= end) return -1;
     if (delim == 2 && str.size() > 1 && str[str.size() - 1] == '\r') str.resize(str.size() - 1);
@@ -534,85 +543,188 @@ struct B2SeqReader::Impl {
     if (seq.size() != qual.size()) return -2;
     return (int)seq.size();
   }
+  // plain 4-line record at the current position of the mapping?  (see the comment above)
+  bool fast(B2RecView* v) {
+    if (!map || last_char != 0) return false;
+    const unsigned char* p = data + begin;
+    const unsigned char* e = data + end;
+    if (p >= e || *p != '@') return false;
+    const unsigned char* nl = (const unsigned char*)memchr(p + 1, '\n', e - (p + 1));
+    if (!nl || nl[-1] == '\r') return false;
+    const unsigned char* q = p + 1;
+    while (q < nl && !isspace(*q)) ++q;
+    if (memchr(p + 1, 0, q - (p + 1))) return false;
+    const unsigned char* s = nl + 1;
+    if (s >= e || *s == '\n' || *s == '>' || *s == '+' || *s == '@') return false;
+    const unsigned char* nl2 = (const unsigned char*)memchr(s, '\n', e - s);
+    if (!nl2 || nl2[-1] == '\r') return false;
+    const size_t ls = nl2 - s;
+    if (memchr(s, 0, ls)) return false;
+    const unsigned char* p3 = nl2 + 1;
+    if (p3 >= e || *p3 != '+') return false;
+    const unsigned char* nl3 = (const unsigned char*)memchr(p3, '\n', e - p3);
+    if (!nl3) return false;
+    const unsigned char* qs = nl3 + 1;
+    if (qs + ls > e || (qs + ls < e && qs[ls] != '\n') || memchr(qs, '\n', ls)) return false;
+    v->name = (const char*)p + 1; v->l_name = (int)(q - (p + 1));
+    if (q < nl) { v->comment = (const char*)q + 1; v->l_comment = (int)(nl - (q + 1)); }
+    else { v->comment = 0; v->l_comment = 0; }
+    v->seq = (const char*)s; v->l_seq = (int)ls;
+    v->qual = (const char*)qs; v->l_qual = (int)ls;
+    begin = (size_t)(qs + ls - data) + (qs + ls < e ? 1 : 0);
+    return true;
+  }
 };
 
 B2SeqReader::B2SeqReader() : impl_(new Impl) {}
 B2SeqReader::~B2SeqReader() { close(); delete impl_; }
 int B2SeqReader::open(const char* fn) {
+  close();
+  *impl_ = Impl();
+  if (strcmp(fn, "-") && !getenv("B200BWA_NO_MMAP")) {  // regular, non-empty, not gzip: map it
+    int fd = ::open(fn, O_RDONLY);
+    if (fd < 0) return 1;
+    struct stat st;
+    unsigned char magic[2] = {0, 0};
+    if (fstat(fd, &st) == 0 && S_ISREG(st.st_mode) && st.st_size > 2 && pread(fd, magic, 2, 0) == 2 &&
+        !(magic[0] == 0x1f && magic[1] == 0x8b)) {
+      void* m = mmap(0, (size_t)st.st_size, PROT_READ, MAP_PRIVATE, fd, 0);
+      if (m != MAP_FAILED) {
+        madvise(m, (size_t)st.st_size, MADV_SEQUENTIAL);
+        impl_->map = (const unsigned char*)m; impl_->map_size = (size_t)st.st_size;
+        impl_->data = impl_->map; impl_->begin = 0; impl_->end = impl_->map_size;
+      }
+    }
+    ::close(fd);
+    if (impl_->map) return 0;
+  }
   impl_->fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(0, "r");
   if (!impl_->fp) return 1;
   gzbuffer(impl_->fp, 1 << 20);
-  impl_->buf.resize(1 << 20);
+  impl_->store.resize(1 << 20);
   return 0;
 }
-void B2SeqReader::close() { if (impl_->fp) { gzclose(impl_->fp); impl_->fp = 0; } }
+void B2SeqReader::close() {
+  if (impl_->fp) { gzclose(impl_->fp); impl_->fp = 0; }
+  if (impl_->map) { munmap((void*)impl_->map, impl_->map_size); impl_->map = 0; impl_->data = 0; impl_->begin = impl_->end = 0; }
+}
 int B2SeqReader::next() { return impl_->read(); }
+int B2SeqReader::next_view(B2RecView* v, bool* stable) {
+  if (impl_->fast(v)) { *stable = true; return v->l_seq; }
+  *stable = false;
+  int r = impl_->read();
+  if (r < 0) return r;
+  v->name = impl_->name.data(); v->l_name = (int)impl_->name.size();
+  v->comment = impl_->comment.data(); v->l_comment = (int)impl_->comment.size();
+  v->seq = impl_->seq.data(); v->l_seq = (int)impl_->seq.size();
+  v->qual = impl_->qual.data(); v->l_qual = (int)impl_->qual.size();
+  return r;
+}
 const std::string& B2SeqReader::name() const { return impl_->name; }
 const std::string& B2SeqReader::comment() const { return impl_->comment; }
 const std::string& B2SeqReader::seq() const { return impl_->seq; }
 const std::string& B2SeqReader::qual() const { return impl_->qual; }
 
-static void append_read(B2HostBatch* b, B2SeqReader* ks, int copy_comment) {
-  std::string name = ks->name();
-  // strlen semantics of the reference's strdup'ed strings: cut at an embedded NUL
-  size_t z = name.find('\0');
-  if (z != std::string::npos) name.resize(z);
-  size_t l = name.size();
-  if (l > 2 && name[l - 2] == '/' && isdigit((unsigned char)name[l - 1])) name.resize(l - 2);  // trim_readno
-  const std::string& s = ks->seq();
-  size_t ls = s.size();
-  z = s.find('\0');
-  if (z != std::string::npos) ls = z;
-  b->seq_off.push_back((int64_t)b->seq.size());
-  b->l_seq.push_back((int32_t)ls);
-  size_t o = b->seq.size();
-  b->seq.resize(o + ls);
-  for (size_t i = 0; i < ls; ++i) { unsigned char c = nt4_table[(unsigned char)s[i]]; b->seq[o + i] = c; }
-  b->qual.resize(o + ls);
-  if (!ks->qual().empty()) {
-    memcpy(b->qual.data() + o, ks->qual().data(), ls);
-    b->has_qual.push_back(1);
-  } else {
-    memset(b->qual.data() + o, 0, ls);
-    b->has_qual.push_back(0);
+char* B2RawBatch::hold(const char* p, size_t n) {
+  if (n == 0) return 0;
+  if (arena.empty() || arena_used + n > arena_cap) {
+    arena_cap = n > ((size_t)4 << 20) ? n : ((size_t)4 << 20);
+    arena.emplace_back(new char[arena_cap]);
+    arena_used = 0;
   }
-  b->name_off.push_back((int64_t)b->names.size());
-  b->l_name.push_back((int32_t)name.size());
-  b->names.insert(b->names.end(), name.begin(), name.end());
-  if (copy_comment && !ks->comment().empty()) {
-    b->com_off.push_back((int64_t)b->comments.size());
-    b->l_com.push_back((int32_t)ks->comment().size());
-    b->comments.insert(b->comments.end(), ks->comment().begin(), ks->comment().end());
-  } else {
-    b->com_off.push_back(0);
-    b->l_com.push_back(-1);
-  }
-  ++b->n_reads;
-  b->n_bases += (int64_t)ls;
-  if ((int)ls > b->max_len) b->max_len = (int)ls;
+  char* d = arena.back().get() + arena_used;
+  memcpy(d, p, n);
+  arena_used += n;
+  return d;
 }
 
-// one batch exactly as bseq_read cuts it; returns the number of reads
-int b2_read_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, int copy_comment, B2HostBatch* b) {
-  b->clear();
+static inline int take_record(B2SeqReader* ks, B2RawBatch* rb) {
+  B2RecView v;
+  bool stable = false;
+  if (ks->next_view(&v, &stable) < 0) return -1;
+  if (!stable) {  // the reader's strings are overwritten by its next record
+    v.name = rb->hold(v.name, v.l_name); v.comment = rb->hold(v.comment, v.l_comment);
+    v.seq = rb->hold(v.seq, v.l_seq); v.qual = rb->hold(v.qual, v.l_qual);
+  }
+  // strlen semantics of the reference's strdup'ed sequence: cut at an embedded NUL (never on the mapped path)
+  if (!stable && v.l_seq > 0) { const void* z = memchr(v.seq, 0, v.l_seq); if (z) v.l_seq = (int)((const char*)z - v.seq); }
+  rb->recs.push_back(v);
+  return v.l_seq;
+}
+
+// one batch exactly as bseq_read cuts it (bwa/bwa.c:42-75), as record views; returns the number of reads
+int b2_read_raw_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, B2RawBatch* rb) {
+  rb->clear();
   int size = 0;
-  while (ks->next() >= 0) {
-    if (ks2 && ks2->next() < 0) {
-      fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n");
-      break;
-    }
-    append_read(b, ks, copy_comment);
-    size += b->l_seq.back();
+  for (;;) {
+    int l = take_record(ks, rb);
+    if (l < 0) break;
     if (ks2) {
-      append_read(b, ks2, copy_comment);
-      size += b->l_seq.back();
+      int l2 = take_record(ks2, rb);
+      if (l2 < 0) {
+        fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n");
+        rb->recs.pop_back();
+        break;
+      }
+      size += l2;
     }
-    if (size >= chunk_size && (b->n_reads & 1) == 0) break;
+    size += l;
+    if (size >= chunk_size && (rb->recs.size() & 1) == 0) break;
   }
   if (size == 0) {
-    if (ks2 && ks2->next() >= 0) fprintf(stderr, "[W::bseq_read] the 1st file has fewer sequences.\n");
+    B2RecView v; bool st;
+    if (ks2 && ks2->next_view(&v, &st) >= 0) fprintf(stderr, "[W::bseq_read] the 1st file has fewer sequences.\n");
   }
-  return b->n_reads;
+  rb->n_bases = size;
+  return (int)rb->recs.size();
+}
+
+// record views -> the packed arrays the engine uploads (name trimming of bwa/bwa.c:27-31, nst_nt4_table codes)
+void b2_pack_batch(const B2RawBatch& rb, int copy_comment, B2HostBatch* b) {
+  b->clear();
+  const size_t n = rb.recs.size();
+  size_t tot_seq = 0, tot_name = 0, tot_com = 0;
+  for (const B2RecView& v : rb.recs) { tot_seq += v.l_seq; tot_name += v.l_name; tot_com += v.l_comment; }
+  b->seq.resize(tot_seq); b->qual.resize(tot_seq); b->names.resize(tot_name);
+  if (copy_comment) b->comments.resize(tot_com);
+  b->has_qual.resize(n); b->seq_off.resize(n); b->name_off.resize(n); b->com_off.resize(n);
+  b->l_seq.resize(n); b->l_name.resize(n); b->l_com.resize(n);
+  size_t so = 0, no = 0, co = 0;
+  int max_len = 0;
+  for (size_t i = 0; i < n; ++i) {
+    const B2RecView& v = rb.recs[i];
+    size_t l = v.l_name ? strnlen(v.name, v.l_name) : 0;
+    if (l > 2 && v.name[l - 2] == '/' && isdigit((unsigned char)v.name[l - 1])) l -= 2;  // trim_readno
+    const size_t ls = v.l_seq;
+    b->seq_off[i] = (int64_t)so;
+    b->l_seq[i] = (int32_t)ls;
+    uint8_t* ds = b->seq.data() + so;
+    for (size_t k = 0; k < ls; ++k) ds[k] = nt4_table[(unsigned char)v.seq[k]];
+    if (v.l_qual > 0) { memcpy(b->qual.data() + so, v.qual, ls); b->has_qual[i] = 1; }
+    else { memset(b->qual.data() + so, 0, ls); b->has_qual[i] = 0; }
+    so += ls;
+    b->name_off[i] = (int64_t)no;
+    b->l_name[i] = (int32_t)l;
+    if (l) memcpy(b->names.data() + no, v.name, l);
+    no += l;
+    if (copy_comment && v.l_comment > 0) {
+      b->com_off[i] = (int64_t)co;
+      b->l_com[i] = v.l_comment;
+      memcpy(b->comments.data() + co, v.comment, v.l_comment);
+      co += v.l_comment;
+    } else { b->com_off[i] = 0; b->l_com[i] = -1; }
+    if ((int)ls > max_len) max_len = (int)ls;
+  }
+  b->seq.resize(so); b->qual.resize(so); b->names.resize(no); b->comments.resize(co);
+  b->n_reads = (int)n; b->n_bases = (int64_t)so; b->max_len = max_len;
+  b->n_processed = rb.n_processed;
+}
+
+int b2_read_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, int copy_comment, B2HostBatch* b) {
+  B2RawBatch rb;
+  int n = b2_read_raw_batch(chunk_size, ks, ks2, &rb);
+  b2_pack_batch(rb, copy_comment, b);
+  return n;
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -681,8 +793,11 @@ namespace {
 struct Job {
   int64_t index = 0;
   int n_reads = 0;
-  std::unique_ptr<B2HostBatch> batch;
-  std::string sam;
+  std::unique_ptr<B2RawBatch> raw;
+  std::string sam;           // ordered-writer mode only
+  size_t sam_size = 0;
+  int64_t offset = -1;       // positioned-write mode: file offset of this batch's SAM block
+  bool size_known = false;
   int rc = 0;
   bool done = false;
 };
@@ -731,36 +846,64 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   B2Engine* eng = b2_get_engine(m.positional[0].c_str(), device, m.ignore_alt, opt, m.rg_id.c_str(), m.verbose, &host);
   if (!eng) return 1;
 
+  // Output.  A regular file (what SparkBWA passes with -f) is written with positioned writes issued by the GPU
+  // worker threads straight from their pinned D2H buffers: a batch's offset is the header plus the sizes of all
+  // earlier batches, known as soon as those have left the GPU.  Anything else (stdout, pipes) goes through the
+  // ordered writer below.
   FILE* out = stdout;
+  int out_fd = -1;
   if (out_path) {
-    out = fopen(out_path, "wb");
-    if (!out) { fprintf(stderr, "[E::main_mem] fail to open output `%s'.\n", out_path); return set_err("fail to open output `%s'", out_path); }
-    setvbuf(out, 0, _IOFBF, 1 << 22);
+    out_fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    if (out_fd < 0) { fprintf(stderr, "[E::main_mem] fail to open output `%s'.\n", out_path); return set_err("fail to open output `%s'", out_path); }
+    struct stat st;
+    if (fstat(out_fd, &st) != 0 || !S_ISREG(st.st_mode) || getenv("B200BWA_ORDERED_WRITER")) {
+      out = fdopen(out_fd, "wb");
+      if (!out) { ::close(out_fd); return set_err("fail to open output `%s'", out_path); }
+      setvbuf(out, 0, _IOFBF, 1 << 22);
+      out_fd = -1;
+    } else out = 0;
   }
+  const bool positioned = out_fd >= 0;
+  auto pwrite_all = [&](const char* p, size_t n, int64_t off) -> bool {
+    while (n > 0) {
+      ssize_t k = ::pwrite(out_fd, p, n, (off_t)off);
+      if (k < 0) { if (errno == EINTR) continue; return false; }
+      p += k; n -= (size_t)k; off += k;
+    }
+    return true;
+  };
   // Multi-GPU sharding: B200BWA_SHARD=<rank>/<world> makes this call align only the -K batches
   // b with b % world == rank (each still tagged with its absolute n_processed).  Rank 0 writes the header; every
   // rank writes "<out>.batches" (batch index, reads, SAM bytes per line) so the pieces can be merged in order.
   int shard_rank = 0, shard_world = 1;
   if (const char* sh = getenv("B200BWA_SHARD")) {
     if (sscanf(sh, "%d/%d", &shard_rank, &shard_world) != 2 || shard_world < 1 || shard_rank < 0 || shard_rank >= shard_world) {
-      if (out_path) fclose(out);
+      if (out_path) { if (out) fclose(out); else ::close(out_fd); }
       return set_err("bad B200BWA_SHARD '%s' (want rank/world)", sh);
     }
   }
   FILE* fidx = 0;
   if (shard_world > 1 && out_path) fidx = fopen((std::string(out_path) + ".batches").c_str(), "w");
   std::string hdr = b2_sam_header(*host, m.hdr_line, pg_cmdline ? pg_cmdline : "");
-  if (shard_rank == 0) fwrite(hdr.data(), 1, hdr.size(), out);
+  int64_t next_off = 0;  // positioned mode: where the next unassigned batch goes
+  bool write_failed = false;
+  if (shard_rank == 0) {
+    if (positioned) { if (!pwrite_all(hdr.data(), hdr.size(), 0)) write_failed = true; next_off = (int64_t)hdr.size(); }
+    else fwrite(hdr.data(), 1, hdr.size(), out);
+  }
 
   const int chunk = m.fixed_chunk_size > 0 ? m.fixed_chunk_size : opt.chunk_size * opt.n_threads;
   const B2Pes* pes0 = m.has_pes0 ? m.pes0 : 0;
   const int n_workers = eng->n_workers();
 
-  // Pipeline (kt_pipeline's three ordered steps): reader thread -> GPU workers -> ordered writer (this thread).
+  // Pipeline (kt_pipeline's three ordered steps): reader thread (record boundaries only) -> GPU workers (pack,
+  // upload, kernels, download, positioned write) -> this thread (ordered bookkeeping / ordered writer).
   std::mutex mu;
   std::condition_variable cv;
   std::deque<std::shared_ptr<Job>> todo, inorder;
-  bool read_done = false, failed = false;
+  std::deque<std::shared_ptr<Job>> unassigned;  // positioned mode: jobs in order whose offset is not yet known
+  bool read_done = false, failed = write_failed;
+  std::string errmsg;
   const size_t max_inflight = (size_t)n_workers + 2;
 
   std::thread reader([&]() {
@@ -768,20 +911,21 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     int64_t batch_index = 0;
     for (;;) {
       std::shared_ptr<Job> j(new Job);
-      j->batch.reset(new B2HostBatch);
-      int n = b2_read_batch(chunk, &ks, have2 ? &ks2 : 0, m.copy_comment, j->batch.get());
+      j->raw.reset(new B2RawBatch);
+      int n = b2_read_raw_batch(chunk, &ks, have2 ? &ks2 : 0, j->raw.get());
       if (n == 0) break;
-      j->batch->n_processed = n_processed;
+      j->raw->n_processed = n_processed;
       j->index = batch_index;
       j->n_reads = n;
       n_processed += n;
       if (batch_index++ % shard_world != shard_rank) continue;
-      if (m.verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)j->batch->n_bases);
+      if (m.verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)j->raw->n_bases);
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
       if (failed) break;
       todo.push_back(j);
       inorder.push_back(j);
+      if (positioned) unassigned.push_back(j);
       cv.notify_all();
     }
     std::lock_guard<std::mutex> lk(mu);
@@ -792,6 +936,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   std::vector<std::thread> gpu;
   for (int wi = 0; wi < n_workers; ++wi)
     gpu.emplace_back([&, wi]() {
+      B2HostBatch hb;
       for (;;) {
         std::shared_ptr<Job> j;
         {
@@ -802,26 +947,46 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           todo.pop_front();
         }
         double ct = b2_cputime(), rt = b2_realtime();
-        int rc = eng->process(*j->batch, pes0, j->sam, wi);
+        b2_pack_batch(*j->raw, m.copy_comment, &hb);
+        j->raw.reset();
+        const char* data = 0;
+        size_t len = 0;
+        int rc = positioned ? eng->process_view(hb, pes0, wi, &data, &len) : eng->process(hb, pes0, j->sam, wi);
         if (m.verbose >= 3 && !rc)
-          fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", j->batch->n_reads,
+          fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", hb.n_reads,
                   b2_cputime() - ct, b2_realtime() - rt);
         if (getenv("B200BWA_TIMES") && !rc) {
           const B2StageTimes& t = eng->times(wi);
           fprintf(stderr, "[T::b200bwa] worker %d reads %d: h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f rescue %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
-                  wi, j->batch->n_reads, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
+                  wi, hb.n_reads, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
                   t.launches, (long)t.n_seed_tasks, (long)t.n_regs, (long)t.sam_bytes);
         }
-        j->batch.reset();
+        if (positioned && !rc) {
+          std::unique_lock<std::mutex> lk(mu);
+          j->sam_size = len; j->size_known = true;
+          while (!unassigned.empty() && unassigned.front()->size_known) {  // hand out offsets along the known prefix
+            unassigned.front()->offset = next_off;
+            next_off += (int64_t)unassigned.front()->sam_size;
+            unassigned.pop_front();
+          }
+          cv.notify_all();
+          cv.wait(lk, [&] { return j->offset >= 0 || failed; });
+          const bool ok = j->offset >= 0;
+          lk.unlock();
+          if (ok && !pwrite_all(data, len, j->offset)) {
+            std::lock_guard<std::mutex> lk2(mu);
+            rc = 1; errmsg = "write error on SAM output";
+          }
+        }
         std::lock_guard<std::mutex> lk(mu);
         j->rc = rc; j->done = true;
-        if (rc) { failed = true; b2_tls_error = eng->last_error(); }
+        if (rc) failed = true;
         cv.notify_all();
       }
     });
 
-  int rc = 0;
-  std::string errmsg;
+  int rc = write_failed ? 1 : 0;
+  if (write_failed) errmsg = "write error on SAM output";
   for (;;) {
     std::shared_ptr<Job> j;
     {
@@ -833,8 +998,8 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       inorder.pop_front();
       cv.notify_all();
     }
-    if (fidx) fprintf(fidx, "%ld\t%d\t%zu\n", (long)j->index, j->n_reads, j->sam.size());
-    if (fwrite(j->sam.data(), 1, j->sam.size(), out) != j->sam.size()) {
+    if (fidx) fprintf(fidx, "%ld\t%d\t%zu\n", (long)j->index, j->n_reads, positioned ? j->sam_size : j->sam.size());
+    if (!positioned && fwrite(j->sam.data(), 1, j->sam.size(), out) != j->sam.size()) {
       std::lock_guard<std::mutex> lk(mu);
       failed = true; rc = 1; errmsg = "write error on SAM output";
       cv.notify_all();
@@ -850,7 +1015,8 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   for (auto& t : gpu) t.join();
   if (rc) set_err("%s", errmsg.empty() ? eng->last_error() : errmsg.c_str());
   if (fidx) fclose(fidx);
-  if (out_path) { if (fclose(out) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }
+  if (positioned) { if (::close(out_fd) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }
+  else if (out_path) { if (fclose(out) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }
   else fflush(out);
   if (rc == 0 && m.verbose >= 3) {
     fprintf(stderr, "[main] Version: %s\n", B200BWA_VERSION);

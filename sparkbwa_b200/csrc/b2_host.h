@@ -1,5 +1,6 @@
 // Host-side driver interface (option block, index loader, FASTA/Q batching, main_mem twin).
 #pragma once
+#include <memory>
 #include <string>
 #include <vector>
 #include "b2_engine.h"
@@ -21,6 +22,22 @@ int b2_load_index(const char* hint, B2IndexHost* ix, int verbose, int meta_only)
 std::string b2_sam_header(const B2IndexHost& ix, const std::string& hdr_line, const std::string& pg);  // bwa/bwa.c:370
 const unsigned char* b2_nt4_table();
 
+// One FASTA/Q record as pointers (into a memory-mapped input file, or into storage owned by the batch).
+struct B2RecView {
+  const char *name, *comment, *seq, *qual;
+  int l_name, l_comment, l_seq, l_qual;
+};
+
+// One -K batch as record views: what the reader thread produces; a GPU worker thread packs it (b2_pack_batch).
+struct B2RawBatch {
+  std::vector<B2RecView> recs;
+  int64_t n_bases = 0, n_processed = 0;
+  std::vector<std::unique_ptr<char[]>> arena;  // copies of the records that do not live in a mapped file
+  size_t arena_used = 0, arena_cap = 0;
+  char* hold(const char* p, size_t n);
+  void clear() { recs.clear(); arena.clear(); arena_used = arena_cap = 0; n_bases = 0; }
+};
+
 class B2SeqReader {  // kseq_read semantics, bwa/kseq.h:175-215
  public:
   B2SeqReader();
@@ -28,6 +45,8 @@ class B2SeqReader {  // kseq_read semantics, bwa/kseq.h:175-215
   int open(const char* fn);
   void close();
   int next();  // >= 0 length, -1 EOF, -2 truncated quality
+  // same, returning views; *stable: the views stay valid until close() (mapped file), else until the next call
+  int next_view(B2RecView* v, bool* stable);
   const std::string& name() const;
   const std::string& comment() const;
   const std::string& seq() const;
@@ -38,6 +57,8 @@ class B2SeqReader {  // kseq_read semantics, bwa/kseq.h:175-215
 };
 
 int b2_read_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, int copy_comment, B2HostBatch* b);  // bseq_read
+int b2_read_raw_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, B2RawBatch* rb);                  // its cut, views only
+void b2_pack_batch(const B2RawBatch& rb, int copy_comment, B2HostBatch* b);
 void b2_engine_config_from_env(B2EngineConfig* cfg);
 B2Engine* b2_get_engine(const char* prefix, int device, int ignore_alt, const B2Opt& opt, const char* rg_id, int verbose,
                         B2IndexHost** host_out);

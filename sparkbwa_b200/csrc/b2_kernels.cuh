@@ -245,14 +245,14 @@ B2_HD inline B2Scratch b2_lane_scratch(const B2Ctx& c, int lane) {
 }
 
 // scratch + lane-group identity of a task group (B2_TASK_GROUP lanes per read / pair)
-B2_HD inline B2Scratch b2_group_scratch(const B2Ctx& c, int* gid, int* n_groups) {
-  *gid = B2_GTID() / B2_TASK_GROUP;
-  *n_groups = B2_GSIZE() / B2_TASK_GROUP;
+B2_HD inline B2Scratch b2_group_scratch(const B2Ctx& c, int* gid, int* n_groups, const int G) {
+  *gid = B2_GTID() / G;
+  *n_groups = B2_GSIZE() / G;
   B2Scratch sc = b2_lane_scratch(c, *gid);
 #if defined(__CUDA_ARCH__)
-  sc.gsize = B2_TASK_GROUP;
-  sc.lane = threadIdx.x & (B2_TASK_GROUP - 1);
-  sc.gmask = (B2_TASK_GROUP == 32 ? 0xffffffffu : ((1u << B2_TASK_GROUP) - 1)) << ((threadIdx.x & 31) & ~(B2_TASK_GROUP - 1));
+  sc.gsize = G;
+  sc.lane = threadIdx.x & (G - 1);
+  sc.gmask = (G == 32 ? 0xffffffffu : ((1u << G) - 1)) << ((threadIdx.x & 31) & ~(G - 1));
 #endif
   return sc;
 }
@@ -308,9 +308,9 @@ B2_KERNEL k_chain(B2Ctx c) {
 // One task group per (read, kept chain): extends the chain's seeds against a chain-local region list and
 // leaves every region it computes in cand[] for the serial per-read pass below (mem_chain2aln's DP, hoisted
 // out of the per-read control flow so that a read with hundreds of chains is spread over as many groups).
-B2_KERNEL k_ext_chain(B2Ctx c) {
+B2_KERNEL_LB(128, B2_LB_EXT) k_ext_chain(B2Ctx c) {
   int gid, n_groups;
-  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_EXT);
   for (int64_t t = b2_next_task(c, sc); t < c.n_chain_tasks; t = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
@@ -334,7 +334,7 @@ B2_KERNEL k_ext_chain(B2Ctx c) {
 
 // Serial per-read pass of the extension stage (one lane per read): decides which seeds are extended in the
 // reference's order, taking the regions from cand[], then mem_sort_dedup_patch.
-B2_KERNEL k_extend(B2Ctx c) {
+B2_KERNEL_LB(128, 4) k_extend(B2Ctx c) {
   B2Scratch sc = b2_lane_scratch(c, B2_GTID());
   for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     const int64_t off = c.seed_off[r];
@@ -400,7 +400,7 @@ B2_KERNEL k_resc_plan(B2Ctx c, int mode) {
 // one task group per planned attempt: local SW of the mate against the rescue window
 B2_KERNEL k_resc_sw(B2Ctx c) {
   int gid, n_groups;
-  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_RESC);
   for (int t = b2_next_task(c, sc); t < c.n_resc; t = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
@@ -413,9 +413,9 @@ B2_KERNEL k_resc_sw(B2Ctx c) {
   b2_flush_counters(c, sc);
 }
 
-B2_KERNEL k_final_se(B2Ctx c) {
+B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
   int gid, n_groups;
-  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
   for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
@@ -439,9 +439,9 @@ B2_KERNEL k_final_se(B2Ctx c) {
   b2_flush_counters(c, sc);
 }
 
-B2_KERNEL k_final_pe(B2Ctx c) {
+B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) {
   int gid, n_groups;
-  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups);
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
   const int n_pairs = c.b.n_reads >> 1;
   for (int i = b2_next_task(c, sc); i < n_pairs; i = b2_next_task(c, sc)) {
     sc.gsync();

@@ -15,7 +15,7 @@
 struct B2EH { int32_t h, e; };
 
 // query/target: codes 0..4; eh: qlen+1 entries of scratch.  Returns the best extension score.
-B2_HD inline int b2_extend2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat,
+B2_NOINLINE B2_HD inline int b2_extend2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat,
                             int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus, int zdrop, int h0,
                             int* _qle, int* _tle, int* _gtle, int* _gscore, int* _max_off, B2EH* eh,
                             unsigned long long* cells = 0) {
@@ -102,7 +102,7 @@ B2_HD inline int b2_push_cigar(uint32_t* cigar, int n, int op, int len) {
 
 // Banded global alignment.  z: backtrack matrix of min(qlen,2w+1)*tlen bytes, or null for score only.
 // cigar (capacity cigar_cap) receives the operations; *n_cigar < 0 signals capacity overflow.
-B2_HD inline int b2_global2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat,
+B2_NOINLINE B2_HD inline int b2_global2(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat,
                             int o_del, int e_del, int o_ins, int e_ins, int w, B2EH* eh, uint8_t* z,
                             int* n_cigar_, uint32_t* cigar, int cigar_cap, unsigned long long* cells = 0) {
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
@@ -176,7 +176,7 @@ struct B2Kswr { int score, te, qe, score2, te2, tb, qb; };
 // Striped local SW.  size: 1 = saturating bytes, 16 lanes; 2 = 16-bit words, 8 lanes.
 // work: 4*slen*lanes int16 (H0,H1,E,Hmax); bbuf: tlen entries of (score<<32|row) scratch for the
 // sub-optimal list (bounded by tlen because consecutive rows are merged).
-B2_HD inline B2Kswr b2_sw_local(int size, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+B2_NOINLINE B2_HD inline B2Kswr b2_sw_local(int size, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                 const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra,
                                 int16_t* work, uint64_t* bbuf, unsigned long long* cells = 0) {
   const int lanes = size == 1 ? 16 : 8;
@@ -307,7 +307,7 @@ B2_HD inline void b2_revseq(int l, uint8_t* s) {
 }
 
 // query/target are modified in place and restored (as the reference does).
-B2_HD inline B2Kswr b2_align2(int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat, int o_del,
+B2_NOINLINE B2_HD inline B2Kswr b2_align2(int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat, int o_del,
                               int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf,
                               unsigned long long* cells = 0) {
   const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;

@@ -14,9 +14,17 @@
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__
 #define B2_D __device__
+// Big leaf routines are kept out of line on the device: the finalisation kernel inlined to 123 k instructions and
+// spent half of its issue slots waiting for instruction fetch (ncu: stall_no_inst 49 %, profiles/r1c).
+#if defined(B2_INLINE_ALL)
+#define B2_NOINLINE
+#else
+#define B2_NOINLINE __noinline__
+#endif
 #else
 #define B2_HD
 #define B2_D
+#define B2_NOINLINE
 #endif
 
 #define B2_F_PE 0x2

@@ -162,3 +162,15 @@ def test_striped_sw_scan_equals_lazy_f(tmp_path):
                     os.path.join(ROOT, "tests", "sw_fuzz.cpp")], check=True)
     r = subprocess.run([exe, "12000", "777"], stdout=subprocess.PIPE, check=False)
     assert b"mismatches 0" in r.stdout, r.stdout
+
+
+def test_register_resident_coop_dp_equals_scalar(tmp_path):
+    """The device runs ksw_extend2 / ksw_global2 as register-resident lane-group routines (b2_coopreg.cuh);
+    the same templates, driven by a coroutine emulation of the lane group (simt_emu.h), are fuzzed against the
+    scalar forms that the host checker build pins to the oracle (scores, end points, CIGARs, direction
+    matrices and the algorithmic cell counts must all agree)."""
+    exe = str(tmp_path / "coop_fuzz")
+    subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + os.path.join(ROOT, "sparkbwa_b200", "csrc"),
+                    "-I" + os.path.join(ROOT, "tests"), "-o", exe, os.path.join(ROOT, "tests", "coop_fuzz.cpp")], check=True)
+    r = subprocess.run([exe, "1200", "31337"], stdout=subprocess.PIPE, check=False)
+    assert r.returncode == 0 and b"mismatches 0; global" in r.stdout and r.stdout.rstrip().endswith(b"mismatches 0"), r.stdout

@@ -148,3 +148,45 @@ def test_repeat_call_same_process(tmp_path):
         assert rc == 0
         outs.append(pu.sam_digest(out))
     assert outs[0] == outs[1]
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_config1_scale_matches_oracle(tmp_path_factory):
+    """BASELINE.json configs[1] at its full index size: 2x150 bp pairs against a 100 Mbp reference with -K 10000000
+    (several batches, so the per-batch insert-size statistics matter).  B200BWA_FULL_PAIRS (default 150000; the
+    round's own visit runs 1000000) sets the read count; the oracle is `bwa mem -t <host cores>` on the same files,
+    the index files are written by the GPU builder and are byte-identical to `bwa index`'s (test below on a prefix)."""
+    import sys
+    sys.path.insert(0, ROOT)
+    from sparkbwa_b200 import synth, index
+    pairs = int(os.environ.get("B200BWA_FULL_PAIRS", "150000"))
+    ref_len = int(os.environ.get("B200BWA_FULL_REF", "100000000"))
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path_factory.mktemp("cfg1"))
+    d = os.path.join(base, f"b2cfg1_L{ref_len}_P{pairs}")
+    os.makedirs(d, exist_ok=True)
+    prefix = os.path.join(d, "ref")
+    ctg = synth.make_reference(ref_len, n_contigs=4, seed=1, repeat_frac=0.02)
+    if not os.path.exists(prefix + ".sa"):
+        index.build_index(ctg, prefix + ".tmp")
+        for e in ("pac", "ann", "amb", "bwt", "sa"):
+            os.replace(prefix + ".tmp." + e, prefix + "." + e)
+    f1, f2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
+    s1, s2 = [], []
+    for a, b in synth.simulate_pairs_fast(ctg, pairs, 150, seed=4242, sub=0.01, indel=0.001):
+        s1.append(a); s2.append(b)
+    synth.write_fastq_fixed(f1, s1, 0, b"/1")
+    synth.write_fastq_fixed(f2, s2, 0, b"/2")
+    del ctg, s1, s2
+    ours, ref = os.path.join(d, "ours.sam"), os.path.join(d, "oracle.sam")
+    lib = _lib()
+    rc = _main_to(lib, ["bwa", "mem", "-v", "1", "-K", "10000000", prefix, f1, f2], ours)
+    assert rc == 0, lib.b200bwa_last_error()
+    with open(ref, "wb") as f:
+        subprocess.run([pu.ORACLE, "mem", "-v", "1", "-t", str(os.cpu_count() or 1), "-K", "10000000", prefix, f1, f2], check=True,
+                       stdout=f, stderr=subprocess.DEVNULL)
+    diff = pu.first_diff(ref, ours)
+    n_lines = len(pu.sam_body(ours))
+    assert not diff, diff
+    assert n_lines >= 2 * pairs
+    for p in (ours, ref, f1, f2):
+        os.remove(p)
