@@ -9,6 +9,7 @@
 #include "b2_sort.cuh"
 #include "b2_ksw.cuh"
 #include "b2_coop.cuh"
+#include "b2_galn.cuh"
 
 // Per-task bump scratch (stack discipline via mark/reset).
 struct B2Scratch {
@@ -21,6 +22,7 @@ struct B2Scratch {
   // lane group serving this task (device: B2_TASK_LANES lanes running the same control flow)
   int lane = 0, gsize = 1;
   unsigned gmask = 0;
+  const B2GalnCache* galn = 0;  // global alignments computed ahead of the finalisation kernel (b2_galn.cuh)
   B2_HD inline void gsync() const {
 #if defined(__CUDA_ARCH__)
     if (gsize > 1) __syncwarp(gmask);
@@ -49,6 +51,11 @@ struct B2Scratch {
   B2_HD inline size_t mark() const { return used; }
   B2_HD inline void reset(size_t m) { used = m; }
 };
+
+// in-place reversal split over the lanes of the group (each lane swaps its own pairs)
+B2_HD inline void b2_revseq_g(const B2Scratch& sc, int l, uint8_t* s) {
+  for (int i = sc.lane; i < l >> 1; i += sc.gsize) { uint8_t t = s[i]; s[i] = s[l - 1 - i]; s[l - 1 - i] = t; }
+}
 
 B2_HD inline int b2_extend2_any(B2Scratch& sc, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                 const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
@@ -395,8 +402,9 @@ B2_HD inline int b2_put_int(char* s, int l, int cap, long c) {
 
 // want_cigar == 0: score only.  Returns 0 when the reference would have returned a null cigar
 // without touching *score (reject conditions), 1 otherwise.
+// pre: result of the speculative inter-task pass for exactly this (query, rb, re, w_), or null.
 B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, int w_, int l_query, uint8_t* query, int64_t rb,
-                               int64_t re, int* score, B2Cigar* out, B2Scratch& sc) {
+                               int64_t re, int* score, B2Cigar* out, B2Scratch& sc, const B2GalnRes* pre = 0) {
   const int64_t l_pac = ix.l_pac;
   const int8_t* mat = opt.mat;
   if (out) { out->n_cigar = 0; out->NM = -1; out->l_md = 0; if (out->md_cap > 0) out->md[0] = 0; }
@@ -408,7 +416,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
   if (re - rb != rlen) { sc.reset(mk); return 0; }
   if (rb >= l_pac) {  // reverse both so that indels are placed leftmost on the forward strand
     sc.gsync();
-    if (sc.lane == 0) { b2_revseq(l_query, query); b2_revseq((int)rlen, rseq); }
+    b2_revseq_g(sc, l_query, query); b2_revseq_g(sc, (int)rlen, rseq);
     sc.gsync();
   }
   if (l_query == re - rb && w_ == 0) {
@@ -417,16 +425,13 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
     for (int i = sc.lane; i < l_query; i += sc.gsize) s += mat[rseq[i] * 5 + query[i]];
     *score = sc.gsum(s);
   } else {
-    int w, max_gap, max_ins, max_del, min_w;
-    max_ins = (int)((double)(((l_query + 1) >> 1) * mat[0] - opt.o_ins) / opt.e_ins + 1.);
-    max_del = (int)((double)(((l_query + 1) >> 1) * mat[0] - opt.o_del) / opt.e_del + 1.);
-    max_gap = max_ins > max_del ? max_ins : max_del;
-    max_gap = max_gap > 1 ? max_gap : 1;
-    int dl = (int)(rlen - l_query); dl = dl < 0 ? -dl : dl;
-    w = (max_gap + dl + 1) >> 1;
-    w = w < w_ ? w : w_;
-    min_w = dl + 3;
-    w = w > min_w ? w : min_w;
+    const int w = b2_cigar_band(opt, l_query, (int)rlen, w_);
+    if (pre && out && pre->n_cigar >= 0 && pre->n_cigar <= out->cap) {  // computed ahead by k_galn
+      *score = pre->score;
+      for (int k = sc.lane; k < pre->n_cigar; k += sc.gsize) out->cigar[k] = pre->cigar[k];
+      out->n_cigar = pre->n_cigar;
+      sc.gsync();
+    } else {
     B2EH* eh = (B2EH*)sc.alloc(sizeof(B2EH) * (size_t)(l_query + 2), 8);
     uint8_t* z = 0;
     if (out) {
@@ -434,7 +439,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
       z = (uint8_t*)sc.alloc((size_t)n_col * (size_t)rlen, 1);
     }
     if (sc.overflow) {
-      if (rb >= l_pac) { sc.gsync(); if (sc.lane == 0) b2_revseq(l_query, query); sc.gsync(); }
+      if (rb >= l_pac) { sc.gsync(); b2_revseq_g(sc, l_query, query); sc.gsync(); }
       sc.reset(mk);
       return 0;
     }
@@ -445,6 +450,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
     if (out) {
       if (nc < 0) { sc.overflow = 1; nc = 0; }
       out->n_cigar = nc;
+    }
     }
   }
   if (out) {  // NM and MD
@@ -490,7 +496,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
     out->l_md = l;
     out->NM = n_mm + n_gap;
   }
-  if (rb >= l_pac) { sc.gsync(); if (sc.lane == 0) b2_revseq(l_query, query); sc.gsync(); }
+  if (rb >= l_pac) { sc.gsync(); b2_revseq_g(sc, l_query, query); sc.gsync(); }
   sc.reset(mk);
   return 1;
 }

@@ -32,6 +32,8 @@ inline int b2_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p
 inline void b2_host_free(void* p) { free(p); }
 #define B2_ATOMIC_OR(p, v) (*(p) |= (v))
 #define B2_ATOMIC_ADD(p, v) (*(p) += (v))
+#define B2_ATOMIC_CAS(p, cmp, val) (*(p) == (cmp) ? (*(p) = (val), (cmp)) : *(p))
+#define B2_WARP_LANES 1
 #define B2_TASK_GROUP 1
 #define B2_G_EXT 1
 #define B2_G_FINAL 1
@@ -57,6 +59,8 @@ inline int b2_host_alloc(void** p, size_t n) { return cudaMallocHost(p, n ? n : 
 inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
+#define B2_ATOMIC_CAS(p, cmp, val) atomicCAS((p), (cmp), (val))
+#define B2_WARP_LANES 32
 #define B2_TASK_GROUP B2_TASK_LANES
 // Lanes per task of the group-cooperative kernels.  A warp whose two halves follow different tasks keeps switching
 // between two instruction streams (ncu: stall_no_inst 49-67 % of the samples in k_final_pe / k_ext_chain with

@@ -70,6 +70,7 @@ struct Worker {
   DBuf<long long> dbg;
   DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
+  DBuf<int32_t> galn_cnt, galn_table; DBuf<int64_t> galn_off; DBuf<B2GalnTask> galn_tasks; DBuf<B2GalnRes> galn_res;
   DBuf<unsigned long long> counters;
   unsigned long long h_counters[16] = {0};
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;
@@ -189,6 +190,7 @@ class B2EngineImpl {
       w.flags.release(); w.counters.release(); w.dbg.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
+      w.galn_cnt.release(); w.galn_table.release(); w.galn_off.release(); w.galn_tasks.release(); w.galn_res.release();
       if (w.pin_sam) b2_host_free(w.pin_sam);
 #if !defined(B2_HOSTSIM)
       if (w.stream) cudaStreamDestroy(w.stream);
@@ -254,8 +256,9 @@ class B2EngineImpl {
 
   // Runs the pipeline over reads [first, first+count) of the batch resident on `src` using the stream and
   // buffers of `w` (src == w for the ordinary one-batch call).
+  // pe_mode: -1 = as the options say; 0 / 1 = this batch single-end / paired-end (smart pairing runs both kinds)
   int run(Worker& w, const B2Pes* pes0, std::string* sam, Worker* srcp = nullptr, int first = 0, int count = -1,
-          bool view = false) {
+          bool view = false, int pe_mode = -1, std::vector<int32_t>* item_len = nullptr) {
     w.last_sam_bytes = 0;
     bind_device();
     Worker& src = srcp ? *srcp : w;
@@ -263,9 +266,8 @@ class B2EngineImpl {
     if (count < 0) count = src.n_reads - first;
     if (first < 0 || first + count > src.n_reads) return fail("resident range out of bounds");
     const int n = count;
-    const bool pe = (opt.flag & B2_F_PE) != 0;
+    const bool pe = pe_mode >= 0 ? pe_mode != 0 : (opt.flag & B2_F_PE) != 0;
     if (pe && (n & 1)) return fail("paired-end batch with an odd number of reads");
-    if (opt.flag & B2_F_SMARTPE) return fail("smart pairing (-p) is not supported by this build");
     w.timer.reset();
     float t_h2d = w.times.h2d;
     w.times = B2StageTimes();
@@ -274,6 +276,7 @@ class B2EngineImpl {
     B2Ctx c;
     memset(&c, 0, sizeof(c));
     c.opt = opt; c.ix = ix; c.fmt = fmt;
+    c.opt.flag = (c.opt.flag & ~(B2_F_PE | B2_F_SMARTPE)) | (pe ? B2_F_PE : 0);
     c.tb.logtab = d_logtab.p; c.tb.n_log = n_log;
     c.n_processed = src.n_processed + first; c.max_len = src.max_len;
     w.max_len = src.max_len;
@@ -482,6 +485,45 @@ class B2EngineImpl {
     }
     int ev_pes = w.timer.mark();
 
+    // ---- end-point-constrained global alignments, one per lane, ahead of the finalisation (b2_galn.cuh) ----
+    memset(&c.galn, 0, sizeof(c.galn));
+    {
+      const size_t half = ((size_t)w.max_len + 64 + 15) & ~(size_t)15;
+      const size_t pool_need = 32 * 2 * half + ((size_t)w.max_len + 64) * 7 * 32 * 4;
+      if (!cfg.no_galn && b2_mat_simple(opt.mat) && !ensure_scratch() && pool_need <= 32 * w.scratch_per_lane) {
+        if (w.galn_cnt.ensure((size_t)B2_GALN_CLASSES * (n + 1)) || w.galn_off.ensure((size_t)B2_GALN_CLASSES * (n + 2)))
+          return fail("device allocation failed (alignment plan)");
+        c.galn_cnt = w.galn_cnt.p; c.galn_off = w.galn_off.p;
+        B2_LAUNCH(k_galn_plan, (n + 127) / 128, 128, w.stream, c, 0);
+        for (int k = 0; k < B2_GALN_CLASSES; ++k)
+          B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)(w.galn_cnt.p + (size_t)k * (n + 1)), w.galn_off.p + (size_t)k * (n + 2), n);
+        w.times.launches += 1 + B2_GALN_CLASSES;
+        int64_t tot[B2_GALN_CLASSES], T = 0;
+        for (int k = 0; k < B2_GALN_CLASSES; ++k) b2_d2h(&tot[k], w.galn_off.p + (size_t)k * (n + 2) + n, sizeof(int64_t), w.stream);
+        if (b2_sync(w.stream)) return fail("device synchronisation failed");
+        for (int k = 0; k < B2_GALN_CLASSES; ++k) { c.galn_base[k] = T; c.galn_n[k] = tot[k]; T += tot[k]; }
+        if (getenv("B200BWA_DEBUG_GALN")) fprintf(stderr, "[D::galn] reads %d tasks %ld (%ld, %ld, %ld)\n", n, (long)T, (long)tot[0], (long)tot[1], (long)tot[2]);
+        if (T > 0 && T < (1 << 29)) {
+          size_t tsz = 2;
+          while (tsz < (size_t)2 * T) tsz <<= 1;
+          if (w.galn_tasks.ensure(T + 1) || w.galn_res.ensure(T + 1) || w.galn_table.ensure(tsz))
+            return fail("device allocation failed (alignment tasks)");
+          b2_dev_memset(w.galn_table.p, 0xff, tsz * sizeof(int32_t), w.stream);
+          c.galn_tasks = w.galn_tasks.p; c.galn_res = w.galn_res.p; c.galn_table = w.galn_table.p;
+          c.galn.tasks = w.galn_tasks.p; c.galn.res = w.galn_res.p; c.galn.table = w.galn_table.p;
+          c.galn.mask = (uint32_t)(tsz - 1); c.galn.seq_base = c.b.seq;
+          B2_LAUNCH(k_galn_plan, (n + 127) / 128, 128, w.stream, c, 1);
+          ++w.times.launches;
+          // one-warp blocks: a batch has only a few hundred warps of these tasks, spread them over all SMs
+          const int blk = std::min(cfg.lane_block, 32);
+          auto grid_for = [&](int64_t cnt) { return (int)std::min<int64_t>((cnt + blk - 1) / blk, (int64_t)cfg.lane_grid * cfg.lane_block / blk); };
+          if (tot[0] > 0) { B2_LAUNCH(k_galn9, grid_for(tot[0]), blk, w.stream, c); ++w.times.launches; }
+          if (tot[1] > 0) { B2_LAUNCH(k_galn17, grid_for(tot[1]), blk, w.stream, c); ++w.times.launches; }
+          if (tot[2] > 0) { B2_LAUNCH(k_galn33, grid_for(tot[2]), blk, w.stream, c); ++w.times.launches; }
+        }
+      }
+    }
+
     // ---- finalisation + SAM text ----
     if (w.sam_len.ensure(n_items + 1) || w.sam_off.ensure(n_items + 2)) return fail("device allocation failed");
     c.sam_len = w.sam_len.p;
@@ -546,6 +588,10 @@ class B2EngineImpl {
     }
     int ev_gat = w.timer.mark();
     w.times.sam_bytes = total;
+    if (item_len) {
+      item_len->resize(n_items);
+      b2_d2h(item_len->data(), w.sam_len.p, (size_t)n_items * sizeof(int32_t), w.stream);
+    }
     int ev_d2h = ev_gat;
     if (sam || view) {
       if ((size_t)total > w.pin_sam_cap) {
@@ -656,6 +702,12 @@ int B2Engine::process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, 
   if (impl_->run(w, pes0, nullptr, nullptr, 0, -1, true)) return 1;
   *data = (const char*)w.pin_sam; *len = w.last_sam_bytes;
   return 0;
+}
+int B2Engine::process_items(const B2HostBatch& b, const B2Pes* pes0, int worker, int paired, std::string& sam,
+                            std::vector<int32_t>& item_len) {
+  Worker& w = impl_->workers[worker];
+  if (impl_->upload(w, b)) return 1;
+  return impl_->run(w, pes0, &sam, nullptr, 0, -1, false, paired ? 1 : 0, &item_len);
 }
 int B2Engine::upload(const B2HostBatch& b, int worker) { return impl_->upload(impl_->workers[worker], b); }
 int B2Engine::run_resident(const B2Pes* pes0, std::string* sam, int worker) {

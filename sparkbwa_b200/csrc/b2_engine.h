@@ -47,6 +47,7 @@ struct B2EngineConfig {
   int seed3_blocks_per_sm = 8;                 // forward-only pass: no stack, fewer registers
   int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
   size_t scratch_per_lane = 48 << 10;
+  int no_galn = 0;                             // 1: skip the speculative inter-task global alignments (B200BWA_NO_GALN)
   size_t max_scratch_bytes = (size_t)64 << 30;
   int n_workers = 4;                           // independent stream/buffer sets (batches in flight)
   int cap_intv = 64;
@@ -76,6 +77,10 @@ class B2Engine {
   int process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam, int worker = 0);
   // same, leaving the SAM text in the worker's pinned host buffer: *data stays valid until the next call on `worker`
   int process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, const char** data, size_t* len);
+  // one batch forced single-end (paired = 0) or paired-end (1), also returning the SAM bytes of every read / pair:
+  // the two halves of a smart-pairing batch (bwa/fastmap.c:64-83)
+  int process_items(const B2HostBatch& b, const B2Pes* pes0, int worker, int paired, std::string& sam,
+                    std::vector<int32_t>& item_len);
   // device-resident variant used by the benchmark: upload once, run the kernels many times
   int upload(const B2HostBatch& b, int worker = 0);
   int run_resident(const B2Pes* pes0, std::string* sam, int worker = 0);

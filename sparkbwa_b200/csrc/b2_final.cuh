@@ -178,6 +178,17 @@ B2_HD inline int b2_infer_bw(int l1, int l2, int score, int a, int q, int r) {
   return w;
 }
 
+// band of the first attempt of mem_reg2aln's loop (bwa/bwamem.c:1072-1080)
+B2_HD inline int b2_reg2aln_w0(const B2Opt& opt, const B2Reg* ar) {
+  const int qb = ar->qb, qe = ar->qe;
+  const int64_t rb = ar->rb, re = ar->re;
+  int tmp = b2_infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_del, opt.e_del);
+  int w2 = b2_infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_ins, opt.e_ins);
+  w2 = w2 > tmp ? w2 : tmp;
+  if (w2 > opt.w) w2 = w2 < ar->w ? w2 : ar->w;
+  return w2 < opt.w << 2 ? w2 : opt.w << 2;
+}
+
 B2_HD inline int b2_get_rlen(int n_cigar, const uint32_t* cigar) {
   int l = 0;
   for (int k = 0; k < n_cigar; ++k) { int op = cigar[k] & 0xf; if (op == 0 || op == 2) l += cigar[k] >> 4; }
@@ -196,10 +207,8 @@ B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, c
   int64_t pos, rb = ar->rb, re = ar->re;
   a.mapq = (uint32_t)(ar->secondary < 0 ? b2_approx_mapq_se(opt, tb, ar, err) : 0) & 0xff;
   if (ar->secondary >= 0) a.flag |= 0x100;
-  tmp = b2_infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_del, opt.e_del);
-  w2 = b2_infer_bw(qe - qb, (int)(re - rb), ar->truesc, opt.a, opt.o_ins, opt.e_ins);
-  w2 = w2 > tmp ? w2 : tmp;
-  if (w2 > opt.w) w2 = w2 < ar->w ? w2 : ar->w;
+  w2 = b2_reg2aln_w0(opt, ar);  // (the loop's own clamp to 4*opt.w is idempotent)
+  (void)tmp;
   B2Cigar cg;
   cg.cap = (qe - qb) + (int)(re - rb) + 4;
   cg.cigar = (uint32_t*)sc.alloc(sizeof(uint32_t) * (size_t)cg.cap, 4);
@@ -214,7 +223,8 @@ B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, c
   i = 0;
   do {
     w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
-    b2_gen_cigar2(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cg, sc);
+    b2_gen_cigar2(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cg, sc,
+                  i == 0 ? b2_galn_lookup(sc.galn, query_, qb, qe, rb, re, w2) : 0);
     if (score == last_sc || w2 == opt.w << 2) break;
     last_sc = score;
     w2 <<= 1;

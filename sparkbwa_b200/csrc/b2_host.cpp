@@ -785,6 +785,7 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_WORKERS"))) cfg->n_workers = atoi(s);
   if ((s = getenv("B200BWA_CAP_INTV"))) cfg->cap_intv = atoi(s);
   if ((s = getenv("B200BWA_SLOT"))) cfg->slot_per_read = atoi(s);
+  if ((s = getenv("B200BWA_NO_GALN"))) cfg->no_galn = atoi(s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -803,13 +804,85 @@ struct Job {
 };
 }  // namespace
 
+// bseq_classify (bwa/bwa.c:77-93): adjacent reads with equal names form a pair, everything else is single-end
+static void classify_smart(const B2HostBatch& b, std::vector<int>& se, std::vector<int>& pe) {
+  const int n = b.n_reads;
+  auto same = [&](int x, int y) {
+    return b.l_name[x] == b.l_name[y] && memcmp(b.names.data() + b.name_off[x], b.names.data() + b.name_off[y], b.l_name[x]) == 0;
+  };
+  int i, has_last;
+  for (i = 1, has_last = 1; i < n; ++i) {
+    if (has_last) {
+      if (same(i, i - 1)) { pe.push_back(i - 1); pe.push_back(i); has_last = 0; }
+      else se.push_back(i - 1);
+    } else has_last = 1;
+  }
+  if (has_last && n > 0) se.push_back(i - 1);
+}
+
+static void subset_batch(const B2HostBatch& src, const std::vector<int>& idx, B2HostBatch* dst) {
+  dst->clear();
+  for (int r : idx) {
+    const size_t ls = src.l_seq[r];
+    dst->seq_off.push_back((int64_t)dst->seq.size());
+    dst->l_seq.push_back(src.l_seq[r]);
+    dst->seq.insert(dst->seq.end(), src.seq.begin() + src.seq_off[r], src.seq.begin() + src.seq_off[r] + ls);
+    dst->qual.insert(dst->qual.end(), src.qual.begin() + src.seq_off[r], src.qual.begin() + src.seq_off[r] + ls);
+    dst->has_qual.push_back(src.has_qual[r]);
+    dst->name_off.push_back((int64_t)dst->names.size());
+    dst->l_name.push_back(src.l_name[r]);
+    dst->names.insert(dst->names.end(), src.names.begin() + src.name_off[r], src.names.begin() + src.name_off[r] + src.l_name[r]);
+    if (src.l_com[r] >= 0) {
+      dst->com_off.push_back((int64_t)dst->comments.size());
+      dst->l_com.push_back(src.l_com[r]);
+      dst->comments.insert(dst->comments.end(), src.comments.begin() + src.com_off[r], src.comments.begin() + src.com_off[r] + src.l_com[r]);
+    } else { dst->com_off.push_back(0); dst->l_com.push_back(-1); }
+    ++dst->n_reads;
+    dst->n_bases += (int64_t)ls;
+    if ((int)ls > dst->max_len) dst->max_len = (int)ls;
+  }
+}
+
+// One smart-pairing batch (bwa/fastmap.c:64-83): the single-end reads first (ids from n_processed), then the pairs
+// (ids from n_processed + #single), SAM records returned in the input order.
+static int process_smart(B2Engine* eng, const B2HostBatch& hb, const B2Pes* pes0, int wi, int verbose, std::string& out) {
+  std::vector<int> se, pe;
+  classify_smart(hb, se, pe);
+  if (verbose >= 3) fprintf(stderr, "[M::process] %d single-end sequences; %d paired-end sequences\n", (int)se.size(), (int)pe.size());
+  B2HostBatch sub;
+  std::string sam[2];
+  std::vector<int32_t> len[2];
+  if (!se.empty()) {
+    subset_batch(hb, se, &sub);
+    sub.n_processed = hb.n_processed;
+    if (eng->process_items(sub, 0, wi, 0, sam[0], len[0])) return 1;
+  }
+  if (!pe.empty()) {
+    subset_batch(hb, pe, &sub);
+    sub.n_processed = hb.n_processed + (int64_t)se.size();
+    if (eng->process_items(sub, pes0, wi, 1, sam[1], len[1])) return 1;
+  }
+  // merge: walk the reads in input order; a pair's block (both mates) sits at its first read
+  size_t is = 0, ip = 0, os = 0, op = 0;
+  for (int i = 0; i < hb.n_reads;) {
+    if (ip < pe.size() && pe[ip] == i) {
+      out.append(sam[1], op, (size_t)len[1][ip >> 1]); op += (size_t)len[1][ip >> 1];
+      ip += 2; i += 2;
+    } else {
+      out.append(sam[0], os, (size_t)len[0][is]); os += (size_t)len[0][is];
+      ++is; ++i;
+    }
+  }
+  return 0;
+}
+
 int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdline) {
   B2MemArgs m;
   double t_real = b2_realtime();
   if (b2_parse_mem_args(argc, argv, &m)) return 1;
   if (m.positional.size() < 2 || m.positional.size() > 3) {
     fprintf(stderr, "\nUsage: bwa mem [options] <idxbase> <in1.fq> [in2.fq]\n\n");
-    fprintf(stderr, "b200bwa accepts the option set of bwa-0.7.15 `mem` (see bwa.1); -p is not supported.\n\n");
+    fprintf(stderr, "b200bwa accepts the option set of bwa-0.7.15 `mem` (see bwa.1).\n\n");
     return 1;
   }
   std::lock_guard<std::mutex> run_lock(g_run_mu);
@@ -839,10 +912,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       opt.flag |= B2_F_PE;
     }
   }
-  if (opt.flag & B2_F_SMARTPE) {
-    fprintf(stderr, "[E::main_mem] smart pairing (-p) is not supported by b200bwa\n");
-    return set_err("smart pairing (-p) is not supported");
-  }
+  const bool smart = (opt.flag & B2_F_SMARTPE) != 0;  // interleaved input: pairs are adjacent reads with equal names
   B2Engine* eng = b2_get_engine(m.positional[0].c_str(), device, m.ignore_alt, opt, m.rg_id.c_str(), m.verbose, &host);
   if (!eng) return 1;
 
@@ -951,7 +1021,11 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
         j->raw.reset();
         const char* data = 0;
         size_t len = 0;
-        int rc = positioned ? eng->process_view(hb, pes0, wi, &data, &len) : eng->process(hb, pes0, j->sam, wi);
+        int rc;
+        if (smart) {
+          rc = process_smart(eng, hb, pes0, wi, m.verbose, j->sam);
+          data = j->sam.data(); len = j->sam.size();
+        } else rc = positioned ? eng->process_view(hb, pes0, wi, &data, &len) : eng->process(hb, pes0, j->sam, wi);
         if (m.verbose >= 3 && !rc)
           fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", hb.n_reads,
                   b2_cputime() - ct, b2_realtime() - rt);

@@ -72,6 +72,11 @@ struct B2Ctx {
   int8_t* pe_dir; int64_t* pe_is;
   // planned mate-rescue attempts
   int32_t* resc_cnt; const int64_t* resc_off; B2RescTask* resc_tasks; B2Kswr* resc_res; int64_t n_resc;
+  // global alignments computed ahead of the finalisation kernel (b2_galn.cuh)
+  int32_t* galn_cnt; const int64_t* galn_off;   // [class][read] counts and their exclusive scans (row strides n+1, n+2)
+  int64_t galn_base[B2_GALN_CLASSES], galn_n[B2_GALN_CLASSES];
+  B2GalnTask* galn_tasks; B2GalnRes* galn_res; int32_t* galn_table;
+  B2GalnCache galn;
   // SAM
   char* slots; int slot_size; int32_t* sam_len; const int64_t* sam_off; char* sam_out;
 };
@@ -413,9 +418,80 @@ B2_KERNEL k_resc_sw(B2Ctx c) {
   b2_flush_counters(c, sc);
 }
 
+// ---- speculative global alignments (b2_galn.cuh) ----------------------------------------------------------------
+// mode 0: count the alignments worth computing ahead, per band class; mode 1: write them (class-major task ids) and
+// enter them into the hash table.  One lane per read; mirrors the entry conditions of mem_reg2aln / bwa_gen_cigar2.
+B2_KERNEL k_galn_plan(B2Ctx c, int mode) {
+  const int n = c.b.n_reads;
+  const int64_t l_pac = c.ix.l_pac;
+  for (int r = B2_GTID(); r < n; r += B2_GSIZE()) {
+    int cnt[B2_GALN_CLASSES];
+    for (int k = 0; k < B2_GALN_CLASSES; ++k) cnt[k] = 0;
+    const B2Reg* a = c.regs + c.reg_off[r];
+    const int nr = c.n_regs[r];
+    for (int k = 0; k < nr && k < B2_GALN_MAXREGS; ++k) {
+      const B2Reg* ar = &a[k];
+      if (ar->rb < 0 || ar->re < 0) continue;
+      const int qb = ar->qb, qe = ar->qe, l_query = qe - qb;
+      const int64_t rb = ar->rb, re = ar->re;
+      if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac) || re - rb > l_query + 64) continue;
+      const int w_in = b2_reg2aln_w0(c.opt, ar);
+      if (l_query == re - rb && w_in == 0) continue;  // gap-free: no DP (bwa/bwa.c:131)
+      const int w = b2_cigar_band(c.opt, l_query, (int)(re - rb), w_in);
+      const int cls = b2_galn_class(w);
+      const int dl = l_query > (int)(re - rb) ? l_query - (int)(re - rb) : (int)(re - rb) - l_query;
+      if (cls < 0 || dl > w) continue;
+      if (mode) {
+        const int64_t id = c.galn_base[cls] + c.galn_off[(size_t)cls * (n + 2) + r] + cnt[cls];
+        B2GalnTask t;
+        t.seq_off = c.b.seq_off[r]; t.rb = rb; t.re = re; t.read = r; t.qb = qb; t.qe = qe; t.w_in = w_in; t.w = w;
+        c.galn_tasks[id] = t;
+        c.galn_res[id].n_cigar = -1;
+        uint32_t h = b2_galn_hash(t.seq_off, qb, qe, rb, re, w_in) & c.galn.mask;
+        while (B2_ATOMIC_CAS(&c.galn_table[h], -1, (int32_t)id) != -1) h = (h + 1) & c.galn.mask;
+      }
+      ++cnt[cls];
+    }
+    if (!mode) for (int k = 0; k < B2_GALN_CLASSES; ++k) c.galn_cnt[(size_t)k * (n + 1) + r] = cnt[k];
+  }
+}
+
+// one alignment per lane; the lanes of a warp share a pool made of their scratch regions: per-lane staging of the
+// two sequences, then the lane-interleaved direction words.
+template <int ND>
+B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
+  const int LW = B2_WARP_LANES;
+  const int lane = B2_GTID() & (LW - 1);
+  uint8_t* pool = c.scratch + (size_t)(B2_GTID() - lane) * c.scratch_per_lane;
+  const int half = (c.max_len + 64 + 15) & ~15;
+  uint8_t* q = pool + (size_t)lane * 2 * half;
+  uint8_t* tg = q + half;
+  uint32_t* zw = (uint32_t*)(pool + (size_t)LW * 2 * half) + lane;
+  const int64_t first = c.galn_base[cls], last = first + c.galn_n[cls];
+  for (int64_t t = first + B2_GTID(); t < last; t += B2_GSIZE()) {
+    const B2GalnTask task = c.galn_tasks[t];
+    B2GalnRes* res = &c.galn_res[t];
+    const int qlen = task.qe - task.qb, tlen = (int)(task.re - task.rb);
+    if (qlen > c.max_len || tlen > c.max_len + 64) continue;  // (n_cigar stays -1: not available)
+    if (b2_get_seq(c.ix.l_pac, c.ix.pac, task.rb, task.re, tg) != tlen) continue;
+    const uint8_t* src = c.b.seq + task.seq_off + task.qb;
+    if (task.rb >= c.ix.l_pac) {  // reverse both, as bwa_gen_cigar2 does for the reverse strand (bwa/bwa.c:127-130)
+      for (int k = 0; k < qlen; ++k) q[k] = src[qlen - 1 - k];
+      b2_revseq(tlen, tg);
+    } else {
+      for (int k = 0; k < qlen; ++k) q[k] = src[k];
+    }
+    b2_galn_one<ND>(qlen, q, tlen, tg, c.opt.mat, c.opt.o_del, c.opt.e_del, c.opt.o_ins, c.opt.e_ins, task.w, zw, LW, res);
+  }
+}
+B2_KERNEL k_galn9(B2Ctx c) { b2_galn_run<9>(c, 0); }
+B2_KERNEL k_galn17(B2Ctx c) { b2_galn_run<17>(c, 1); }
+B2_KERNEL k_galn33(B2Ctx c) { b2_galn_run<33>(c, 2); }
+
 B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
+  sc.galn = &c.galn;
   for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
@@ -442,6 +518,7 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
 B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
+  sc.galn = &c.galn;
   const int n_pairs = c.b.n_reads >> 1;
   for (int i = b2_next_task(c, sc); i < n_pairs; i = b2_next_task(c, sc)) {
     sc.gsync();

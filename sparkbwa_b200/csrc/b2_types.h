@@ -14,12 +14,14 @@
 #if defined(__CUDACC__)
 #define B2_HD __host__ __device__
 #define B2_D __device__
-// Big leaf routines are kept out of line on the device: the finalisation kernel inlined to 123 k instructions and
-// spent half of its issue slots waiting for instruction fetch (ncu: stall_no_inst 49 %, profiles/r1c).
-#if defined(B2_INLINE_ALL)
-#define B2_NOINLINE
-#else
+// Build experiment (-DB2_OUTLINE): keep the big leaf routines out of line on the device.  The finalisation kernel
+// inlines to 123 k instructions and waits for instruction fetch half of the time (ncu stall_no_inst 49 %), but the
+// out-of-line build (43 k instructions) measured SLOWER on the B200 (k_final_pe 10.3 -> 15.7 ms: by-reference
+// arguments force the kernel parameter block into local memory), so inlining stays the default.
+#if defined(B2_OUTLINE)
 #define B2_NOINLINE __noinline__
+#else
+#define B2_NOINLINE
 #endif
 #else
 #define B2_HD

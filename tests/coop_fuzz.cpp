@@ -7,6 +7,7 @@
 #include <vector>
 #include "b2_ksw.cuh"
 #include "b2_coopreg.cuh"
+#include "b2_galn.cuh"
 #include "simt_emu.h"
 
 static const int GS = 32;  // lanes per group, as the device runs them (whole warps)
@@ -63,7 +64,7 @@ int main(int argc, char** argv) {
   int trials = argc > 1 ? atoi(argv[1]) : 3000;
   srand48(argc > 2 ? atol(argv[2]) : 4242);
   EmuWarp W;
-  long bad_e = 0, bad_g = 0, n_e = 0, n_g = 0;
+  long bad_e = 0, bad_g = 0, n_e = 0, n_g = 0, n_l = 0, bad_l = 0;
   for (int tr = 0; tr < trials; ++tr) {
     int a = 1 + lrand48() % 3, b = 1 + lrand48() % 6;
     int o_del = lrand48() % 9, e_del = 1 + lrand48() % 3, o_ins = lrand48() % 9, e_ins = 1 + lrand48() % 3;
@@ -140,11 +141,27 @@ int main(int argc, char** argv) {
       bool bad = s0 != s1 || nc0 != nc1 || c0 != c1;
       if (!bad && want_cigar && nc0 > 0 && memcmp(cg0.data(), cg1.data(), sizeof(uint32_t) * nc0)) bad = true;
       if (!bad && want_cigar && z0 != z1) bad = true;
+      // the inter-task (one alignment per lane) form of b2_galn.cuh, with a lane stride as on the device
+      if (!bad && want_cigar && cap > 3 && b2_galn_class(w) >= 0) {
+        B2GalnRes gr; gr.n_cigar = -7; gr.score = 0;
+        const int zs = 1 + (int)(lrand48() % 3);
+        std::vector<uint32_t> zw((size_t)(tlen + 1) * 7 * zs + 8, 0xdeadbeef);
+        const int cls = b2_galn_class(w);
+        if (cls == 0) b2_galn_one<9>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
+        else if (cls == 1) b2_galn_one<17>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
+        else b2_galn_one<33>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
+        ++n_l;
+        if (gr.score != s0) bad = true;
+        if (gr.n_cigar >= 0) { if (gr.n_cigar != nc0 || memcmp(gr.cigar, cg0.data(), sizeof(uint32_t) * nc0)) bad = true; }
+        else if (nc0 <= B2_GALN_MAXCIG) bad = true;  // may only give up when the CIGAR does not fit
+        if (bad) ++bad_l;
+      }
       if (bad && ++bad_g <= 5)
         fprintf(stderr, "GLOB mismatch trial %d qlen %d tlen %d w %d cigar %d: score %d nc %d cells %llu vs %d %d %llu\n", tr, qlen, tlen, w,
                 (int)want_cigar, s0, nc0, c0, s1, nc1, c1);
     }
   }
+  printf("lane-per-alignment trials %ld mismatches %ld; ", n_l, bad_l);
   printf("extend trials %ld mismatches %ld; global trials %ld mismatches %ld\n", n_e, bad_e, n_g, bad_g);
-  return (bad_e || bad_g) ? 1 : 0;
+  return (bad_e || bad_g || bad_l) ? 1 : 0;
 }

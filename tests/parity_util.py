@@ -132,3 +132,22 @@ def first_diff(a, b, limit=3):
 
 HOSTSIM_ENV = {"B200BWA_LANE_GRID": "1", "B200BWA_LANE_BLOCK": "1", "B200BWA_SEED_GRID": "1",
                "B200BWA_SEED_BLOCK": "1", "B200BWA_SCRATCH": str(4 << 20)}
+
+
+def make_interleaved(case, drop_every=7):
+    """Interleaved FASTQ for smart pairing (-p): the two mate files merged pair by pair, with mate 2 of every
+    `drop_every`-th pair and mate 1 of every (drop_every+4)-th pair removed so that single-end reads occur too."""
+    out = os.path.join(case["dir"], "inter.fq")
+    with open(case["fq"][0], "rb") as f1, open(case["fq"][1], "rb") as f2, open(out, "wb") as fo:
+        k = 0
+        while True:
+            a = [f1.readline() for _ in range(4)]
+            b = [f2.readline() for _ in range(4)]
+            if not a[0] or not b[0]:
+                break
+            if k % (drop_every + 4) != 3:
+                fo.writelines(a)
+            if k % drop_every != 5:
+                fo.writelines(b)
+            k += 1
+    return out

@@ -151,6 +151,17 @@ def test_repeat_call_same_process(tmp_path):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_smart_pairing(workdir):
+    """-p: interleaved input, single-end reads mixed in, several batches (bwa/fastmap.c:64-83, bwa/bwa.c:77-93)."""
+    c = pu.make_case(workdir, "pe_small")
+    inter = pu.make_interleaved(c)
+    c2 = dict(c, fq=[inter], opts=["-p", "-K", "30000"])
+    ref = pu.oracle_sam(c2)
+    our = pu.engine_sam(c2, pu.CLI)
+    assert not pu.first_diff(ref, our)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_config1_scale_matches_oracle(tmp_path_factory):
     """BASELINE.json configs[1] at its full index size: 2x150 bp pairs against a 100 Mbp reference with -K 10000000
     (several batches, so the per-batch insert-size statistics matter).  B200BWA_FULL_PAIRS (default 150000; the
