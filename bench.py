@@ -183,7 +183,7 @@ def main():
     ap.add_argument("--ref-len", type=int, default=100_000_000)
     ap.add_argument("--K", type=int, default=10_000_000)
     ap.add_argument("--seed", type=int, default=1)
-    ap.add_argument("--workers", type=int, default=4)
+    ap.add_argument("--workers", type=int, default=6)
     ap.add_argument("--cpu-sample-pairs", type=int, default=200_000)
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -278,7 +278,7 @@ def main():
         raise SystemExit("upload failed: " + lib.b200bwa_last_error().decode())
     del inter
     batches = cut_batches(n_reads, 150, args.K)
-    n_workers = max(1, min(args.workers, int(os.environ.get("B200BWA_WORKERS", "4"))))
+    n_workers = max(1, min(args.workers, int(os.environ.get("B200BWA_WORKERS", "6"))))
 
     def one_pass(collect=None):
         lock = threading.Lock()

@@ -10,6 +10,7 @@
 #include "b2_ksw.cuh"
 #include "b2_coop.cuh"
 #include "b2_galn.cuh"
+#include "b2_xext.cuh"
 
 // Per-task bump scratch (stack discipline via mark/reset).
 struct B2Scratch {
@@ -222,11 +223,11 @@ struct B2ChainPrep {
   B2EH* eh;
 };
 
-B2_NOINLINE B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, int l_query, const B2Chain& c, const B2Seed* seeds,
-                               B2ChainPrep& P, B2Scratch& sc) {
-  if (P.ready) return 1;
+// reference window [rmax0, rmax1) of a chain (bwamem.c:641-660): every seed with the largest gaps, clamped to one
+// strand and one contig
+B2_HD inline void b2_chain_window(const B2Opt& opt, const B2Index& ix, int l_query, const B2Chain& c, const B2Seed* seeds,
+                                  int64_t* rmax) {
   const int64_t l_pac = ix.l_pac;
-  int64_t* rmax = P.rmax;
   rmax[0] = l_pac << 1; rmax[1] = 0;
   for (int i = 0; i < c.n; ++i) {
     const B2Seed& t = seeds[i];
@@ -241,6 +242,14 @@ B2_NOINLINE B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, 
     if (seeds[0].rbeg < l_pac) rmax[1] = l_pac; else rmax[0] = l_pac;
   }
   b2_fetch_bounds(ix, &rmax[0], seeds[0].rbeg, &rmax[1]);
+}
+
+B2_NOINLINE B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, int l_query, const B2Chain& c, const B2Seed* seeds,
+                               B2ChainPrep& P, B2Scratch& sc) {
+  if (P.ready) return 1;
+  const int64_t l_pac = ix.l_pac;
+  int64_t* rmax = P.rmax;
+  b2_chain_window(opt, ix, l_query, c, seeds, rmax);
   const int64_t rlen = rmax[1] - rmax[0];
   P.rseq = (uint8_t*)sc.alloc((size_t)rlen + 1, 1);
   P.qs = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
@@ -254,26 +263,37 @@ B2_NOINLINE B2_HD inline int b2_chain_prep(const B2Opt& opt, const B2Index& ix, 
 
 // Left/right extension of one seed inside its chain's window -> the region it yields (bwamem.c:709-781).
 // Depends only on the seed, the chain and the read -- not on the regions found so far.
-B2_NOINLINE B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, const uint8_t* query, const B2Chain& c, const B2Seed* seeds,
-                                 const B2Seed& s, const B2ChainPrep& P, B2Reg& a, B2Scratch& sc) {
-  const int64_t* rmax = P.rmax;
+// xr: results of the inter-task pass for this seed ([0] left, [1] right; b2_xext.cuh) or null.  The reference window
+// and the work buffers (P) are set up only if some DP has to run here.  Returns 0 on scratch overflow.
+B2_NOINLINE B2_HD inline int b2_extend_seed(const B2Opt& opt, const B2Index& ix, int l_query, const uint8_t* query, const B2Chain& c,
+                                const B2Seed* seeds, const B2Seed& s, B2ChainPrep& P, B2Reg& a, B2Scratch& sc,
+                                const B2XextRes* xr = 0) {
   int max_off[2], aw[2], i;
   { B2Reg z = B2Reg(); a = z; }
   a.w = aw[0] = aw[1] = opt.w;
   a.score = a.truesc = -1;
   a.rid = c.rid;
   if (s.qbeg) {  // left extension on reversed prefixes
-    int qle, tle, gtle, gscore;
-    const int64_t tmp = s.rbeg - rmax[0];
-    sc.gsync();
-    for (i = sc.lane; i < s.qbeg; i += sc.gsize) P.qs[i] = query[s.qbeg - 1 - i];
-    for (int64_t j = sc.lane; j < tmp; j += sc.gsize) P.rs[j] = P.rseq[tmp - 1 - j];
-    sc.gsync();
+    int qle = 0, tle = 0, gtle = 0, gscore = 0;
+    bool staged = false;
     for (i = 0; i < 2; ++i) {
       int prev = a.score;
       aw[0] = opt.w << i;
-      a.score = b2_extend2_any(sc, s.qbeg, P.qs, (int)tmp, P.rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
-                               opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], P.eh);
+      if (i == 0 && xr && xr[0].w == aw[0] && xr[0].h0 == s.len * opt.a) {
+        a.score = xr[0].score; qle = xr[0].qle; tle = xr[0].tle; gtle = xr[0].gtle; gscore = xr[0].gscore; max_off[0] = xr[0].max_off;
+      } else {
+        if (!b2_chain_prep(opt, ix, l_query, c, seeds, P, sc)) return 0;
+        const int64_t tmp = s.rbeg - P.rmax[0];
+        if (!staged) {
+          sc.gsync();
+          for (int k = sc.lane; k < s.qbeg; k += sc.gsize) P.qs[k] = query[s.qbeg - 1 - k];
+          for (int64_t j = sc.lane; j < tmp; j += sc.gsize) P.rs[j] = P.rseq[tmp - 1 - j];
+          sc.gsync();
+          staged = true;
+        }
+        a.score = b2_extend2_any(sc, s.qbeg, P.qs, (int)tmp, P.rs, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, aw[0],
+                                 opt.pen_clip5, opt.zdrop, s.len * opt.a, &qle, &tle, &gtle, &gscore, &max_off[0], P.eh);
+      }
       if (a.score == prev || max_off[0] < (aw[0] >> 1) + (aw[0] >> 2)) break;
     }
     if (gscore <= 0 || gscore <= a.score - opt.pen_clip5) {
@@ -286,22 +306,27 @@ B2_NOINLINE B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, cons
   } else { a.score = a.truesc = s.len * opt.a; a.qb = 0; a.rb = s.rbeg; }
 
   if (s.qbeg + s.len != l_query) {  // right extension
-    int qle, tle, qe, re, gtle, gscore, sc0 = a.score;
+    int qle = 0, tle = 0, qe, gtle = 0, gscore = 0, sc0 = a.score;
     qe = s.qbeg + s.len;
-    re = (int)(s.rbeg + s.len - rmax[0]);
     for (i = 0; i < 2; ++i) {
       int prev = a.score;
       aw[1] = opt.w << i;
-      a.score = b2_extend2_any(sc, l_query - qe, query + qe, (int)(rmax[1] - rmax[0] - re), P.rseq + re, opt.mat, opt.o_del,
-                               opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
-                               &gscore, &max_off[1], P.eh);
+      if (i == 0 && xr && xr[1].w == aw[1] && xr[1].h0 == sc0) {
+        a.score = xr[1].score; qle = xr[1].qle; tle = xr[1].tle; gtle = xr[1].gtle; gscore = xr[1].gscore; max_off[1] = xr[1].max_off;
+      } else {
+        if (!b2_chain_prep(opt, ix, l_query, c, seeds, P, sc)) return 0;
+        const int re = (int)(s.rbeg + s.len - P.rmax[0]);
+        a.score = b2_extend2_any(sc, l_query - qe, query + qe, (int)(P.rmax[1] - P.rmax[0] - re), P.rseq + re, opt.mat, opt.o_del,
+                                 opt.e_del, opt.o_ins, opt.e_ins, aw[1], opt.pen_clip3, opt.zdrop, sc0, &qle, &tle, &gtle,
+                                 &gscore, &max_off[1], P.eh);
+      }
       if (a.score == prev || max_off[1] < (aw[1] >> 1) + (aw[1] >> 2)) break;
     }
     if (gscore <= 0 || gscore <= a.score - opt.pen_clip3) {
-      a.qe = qe + qle; a.re = rmax[0] + re + tle;
+      a.qe = qe + qle; a.re = s.rbeg + s.len + tle;
       a.truesc += a.score - sc0;
     } else {
-      a.qe = l_query; a.re = rmax[0] + re + gtle;
+      a.qe = l_query; a.re = s.rbeg + s.len + gtle;
       a.truesc += gscore - sc0;
     }
   } else { a.qe = l_query; a.re = s.rbeg + s.len; }
@@ -314,6 +339,7 @@ B2_NOINLINE B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, cons
   a.w = aw[0] > aw[1] ? aw[0] : aw[1];
   a.seedlen0 = s.len;
   a.frac_rep = c.frac_rep;
+  return 1;
 }
 
 // Extend the seeds of one chain, longest first, skipping seeds already covered by a region in av[] (bwamem.c:632-786).
@@ -325,12 +351,12 @@ B2_NOINLINE B2_HD inline void b2_extend_seed(const B2Opt& opt, int l_query, cons
 // srt: c.n u64 scratch.
 B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query, const uint8_t* query,
                                const B2Chain& c, const B2Seed* seeds, B2Reg* av, int* n_av, int cap_av,
-                               uint64_t* srt, B2Scratch& sc, int mode = 0, B2Reg* cand = 0, uint8_t* cand_ok = 0) {
+                               uint64_t* srt, B2Scratch& sc, int mode = 0, B2Reg* cand = 0, uint8_t* cand_ok = 0,
+                               const B2XextRes* xres = 0) {
   if (c.n == 0) return;
   const size_t mk = sc.mark();
   B2ChainPrep P;
   P.ready = 0;
-  if (mode != 2 && !b2_chain_prep(opt, ix, l_query, c, seeds, P, sc)) { sc.reset(mk); return; }
   if (mode == 1) for (int i = sc.lane; i < c.n; i += sc.gsize) cand_ok[i] = 0;
 
   for (int i = 0; i < c.n; ++i) srt[i] = (uint64_t)seeds[i].score << 32 | (uint32_t)i;
@@ -368,8 +394,7 @@ B2_HD inline void b2_chain2aln(const B2Opt& opt, const B2Index& ix, int l_query,
     if (*n_av >= cap_av) { sc.overflow = 1; break; }
     B2Reg& a = av[(*n_av)++];
     if (mode == 2 && cand_ok[si]) { a = cand[si]; continue; }
-    if (!b2_chain_prep(opt, ix, l_query, c, seeds, P, sc)) break;
-    b2_extend_seed(opt, l_query, query, c, seeds, s, P, a, sc);
+    if (!b2_extend_seed(opt, ix, l_query, query, c, seeds, s, P, a, sc, xres ? xres + 2 * si : 0)) break;
     if (mode == 1) {
       sc.gsync();
       if (sc.lane == 0) { cand[si] = a; cand_ok[si] = 1; }

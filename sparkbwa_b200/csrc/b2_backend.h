@@ -31,7 +31,9 @@ inline int b2_sync(b2_stream_t) { return 0; }
 inline int b2_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 inline void b2_host_free(void* p) { free(p); }
 #define B2_ATOMIC_OR(p, v) (*(p) |= (v))
-#define B2_ATOMIC_ADD(p, v) (*(p) += (v))
+template <class T, class V>
+inline T b2_host_fetch_add(T* p, V v) { T o = *p; *p += (T)v; return o; }
+#define B2_ATOMIC_ADD(p, v) b2_host_fetch_add((p), (v))
 #define B2_ATOMIC_CAS(p, cmp, val) (*(p) == (cmp) ? (*(p) = (val), (cmp)) : *(p))
 #define B2_WARP_LANES 1
 #define B2_TASK_GROUP 1

@@ -70,6 +70,7 @@ struct Worker {
   DBuf<long long> dbg;
   DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
+  DBuf<B2XextTask> xext_tasks; DBuf<B2XextRes> xext_res; DBuf<int32_t> xext_key, xext_hist, xext_perm; DBuf<int64_t> xext_hoff;
   DBuf<int32_t> galn_cnt, galn_table; DBuf<int64_t> galn_off; DBuf<B2GalnTask> galn_tasks; DBuf<B2GalnRes> galn_res;
   DBuf<unsigned long long> counters;
   unsigned long long h_counters[16] = {0};
@@ -111,6 +112,8 @@ class B2EngineImpl {
     // a per-device function attribute, the same value from every engine of the process
     if (cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail("cudaFuncSetAttribute(k_seed) failed");
+    if (cudaFuncSetAttribute(k_xext_run, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+      return fail("cudaFuncSetAttribute(k_xext_run) failed");
 #endif
     if (h.seq_len >= (1ull << 40)) return fail("index too large: the seeding kernel packs interval bounds into 40 bits");
     ix.primary = h.primary; ix.seq_len = h.seq_len;
@@ -190,6 +193,7 @@ class B2EngineImpl {
       w.flags.release(); w.counters.release(); w.dbg.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
+      w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
       w.galn_cnt.release(); w.galn_table.release(); w.galn_off.release(); w.galn_tasks.release(); w.galn_res.release();
       if (w.pin_sam) b2_host_free(w.pin_sam);
 #if !defined(B2_HOSTSIM)
@@ -397,6 +401,33 @@ class B2EngineImpl {
     b2_d2h(&TC, w.chain_off.p + n, sizeof(int64_t), w.stream);
     if (b2_sync(w.stream)) return fail("device synchronisation failed");
     c.chain_off = w.chain_off.p; c.n_chain_tasks = TC; c.cand = w.cand.p; c.cand_ok = w.cand_ok.p;
+    // inter-task extension of every chain's best seed, left then right, ahead of the group-cooperative kernel
+    c.xext_res = nullptr; c.xext_tasks = nullptr;
+    if (TC > 0 && !cfg.no_xext && b2_mat_simple(opt.mat) && S < (1 << 29)) {
+      c.xext_qcap = w.max_len; c.xext_tcap = w.max_len + 2 * opt.w + 64;
+      const size_t words = (size_t)32 * ((size_t)c.xext_qcap + 2 + c.xext_qcap / 8 + 1 + c.xext_tcap / 8 + 1);
+      const size_t smem = words * sizeof(uint32_t);
+      if (smem <= (size_t)227 * 1024) {
+        const int bins = c.xext_qcap + 1;
+        if (w.xext_tasks.ensure(TC + 1) || w.xext_res.ensure(2 * (size_t)S + 2) || w.xext_key.ensure(TC + 1) || w.xext_perm.ensure(TC + 1) ||
+            w.xext_hist.ensure(2 * (size_t)bins + 2) || w.xext_hoff.ensure((size_t)bins + 2))
+          return fail("device allocation failed (extension tasks)");
+        c.xext_tasks = w.xext_tasks.p; c.xext_res = w.xext_res.p; c.xext_key = w.xext_key.p; c.xext_perm = w.xext_perm.p;
+        c.xext_hist = w.xext_hist.p; c.xext_cur = w.xext_hist.p + bins + 1; c.xext_hoff = w.xext_hoff.p;
+        b2_dev_memset(w.xext_res.p, 0xff, (2 * (size_t)S + 2) * sizeof(B2XextRes), w.stream);  // w = -1: no result
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)227 * 1024) / smem));
+        const int xgrid = (int)std::min<int64_t>((TC + 31) / 32, (int64_t)148 * per_sm);
+        const int pgrid = (int)std::min<int64_t>((TC + 127) / 128, 148 * 8);
+        for (int side = 0; side < 2; ++side) {
+          b2_dev_memset(w.xext_hist.p, 0, (2 * (size_t)bins + 2) * sizeof(int32_t), w.stream);
+          B2_LAUNCH(k_xext_plan, pgrid, 128, w.stream, c, side);
+          B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.xext_hist.p, w.xext_hoff.p, bins);
+          B2_LAUNCH(k_xext_scatter, pgrid, 128, w.stream, c);
+          B2_LAUNCH_SMEM(k_xext_run, xgrid, 32, smem, w.stream, c);
+          w.times.launches += 4;
+        }
+      }
+    }
     for (;;) {
       if (ensure_scratch()) return 1;
       if (TC > 0) {

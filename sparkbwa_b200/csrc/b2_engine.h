@@ -47,9 +47,10 @@ struct B2EngineConfig {
   int seed3_blocks_per_sm = 8;                 // forward-only pass: no stack, fewer registers
   int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
   size_t scratch_per_lane = 48 << 10;
+  int no_xext = 0;                             // 1: skip the inter-task seed extensions (B200BWA_NO_XEXT)
   int no_galn = 0;                             // 1: skip the speculative inter-task global alignments (B200BWA_NO_GALN)
   size_t max_scratch_bytes = (size_t)64 << 30;
-  int n_workers = 4;                           // independent stream/buffer sets (batches in flight)
+  int n_workers = 6;                           // independent stream/buffer sets (batches in flight)
   int cap_intv = 64;
   int slot_per_read = 0;                       // 0: derived from the longest read of the batch
   int verbose = 3;

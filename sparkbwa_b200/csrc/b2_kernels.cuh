@@ -72,6 +72,11 @@ struct B2Ctx {
   int8_t* pe_dir; int64_t* pe_is;
   // planned mate-rescue attempts
   int32_t* resc_cnt; const int64_t* resc_off; B2RescTask* resc_tasks; B2Kswr* resc_res; int64_t n_resc;
+  // seed extensions computed ahead of the chain-extension kernel (b2_xext.cuh)
+  B2XextTask* xext_tasks; B2XextRes* xext_res;  // one task per (read, chain) and side; two result slots per seed
+  int xext_qcap, xext_tcap;                     // staging capacity per lane (bases)
+  int32_t *xext_key, *xext_hist, *xext_cur, *xext_perm;  // counting sort of the tasks by query length (longest first):
+  const int64_t* xext_hoff;                              // the lanes of a warp then run extensions of similar size
   // global alignments computed ahead of the finalisation kernel (b2_galn.cuh)
   int32_t* galn_cnt; const int64_t* galn_off;   // [class][read] counts and their exclusive scans (row strides n+1, n+2)
   int64_t galn_base[B2_GALN_CLASSES], galn_n[B2_GALN_CLASSES];
@@ -310,6 +315,107 @@ B2_KERNEL k_chain(B2Ctx c) {
   }
 }
 
+// ---- inter-task seed extension ahead of k_ext_chain (b2_xext.cuh) ----------------------------------------------
+// side 0: the first band try of the LEFT extension of every chain's best seed (the seed mem_chain2aln extends
+// first: largest score, ties to the later one); side 1: of its RIGHT extension, whose start score is the left
+// result (so it is planned once the left pass has run, and only when that first try was final).
+B2_KERNEL k_xext_plan(B2Ctx c, int side) {
+  for (int64_t t = B2_GTID(); t < c.n_chain_tasks; t += B2_GSIZE()) {
+    int lo = 0, hi = c.b.n_reads;
+    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.chain_off[mid] <= t) lo = mid; else hi = mid; }
+    const int r = lo;
+    const int64_t off = c.seed_off[r];
+    const B2Chain& ch = c.chains[off + (t - c.chain_off[r])];
+    const B2Seed* seeds = c.cseeds + off + ch.seed_head;
+    const int l_seq = c.b.l_seq[r];
+    B2XextTask task;
+    task.qlen = -1;
+    if (ch.n > 0) {
+      int si = 0;
+      for (int i = 1; i < ch.n; ++i) if (seeds[i].score >= seeds[si].score) si = i;
+      const B2Seed s = seeds[si];
+      const int64_t gidx = off + ch.seed_head + si;
+      int64_t rmax[2];
+      b2_chain_window(c.opt, c.ix, l_seq, ch, seeds, rmax);
+      if (side == 0) {
+        if (s.qbeg > 0) {
+          task.tpos = s.rbeg - 1; task.tdir = -1; task.tlen = (int)(s.rbeg - rmax[0]);
+          task.qsrc = c.b.seq_off[r] + s.qbeg - 1; task.qdir = -1; task.qlen = s.qbeg;
+          task.h0 = s.len * c.opt.a; task.w = c.opt.w; task.end_bonus = c.opt.pen_clip5; task.slot = (int32_t)(2 * gidx);
+        }
+      } else if (s.qbeg + s.len != l_seq) {
+        int sc0 = s.len * c.opt.a;
+        bool ok = true;
+        if (s.qbeg > 0) {
+          const B2XextRes L = c.xext_res[2 * gidx];
+          ok = L.w == c.opt.w && L.h0 == sc0 && L.max_off < (c.opt.w >> 1) + (c.opt.w >> 2);
+          sc0 = L.score;
+        }
+        if (ok) {
+          const int qe = s.qbeg + s.len;
+          task.tpos = s.rbeg + s.len; task.tdir = 1; task.tlen = (int)(rmax[1] - (s.rbeg + s.len));
+          task.qsrc = c.b.seq_off[r] + qe; task.qdir = 1; task.qlen = l_seq - qe;
+          task.h0 = sc0; task.w = c.opt.w; task.end_bonus = c.opt.pen_clip3; task.slot = (int32_t)(2 * gidx + 1);
+        }
+      }
+      if (task.qlen >= 0 && (task.qlen < 1 || task.qlen > c.xext_qcap || task.tlen < 0 || task.tlen > c.xext_tcap ||
+                             task.h0 + task.qlen * c.opt.a >= 65000 || 2 * gidx + 1 > 0x7fffffff))
+        task.qlen = -1;
+    }
+    c.xext_tasks[t] = task;
+    const int key = task.qlen < 0 ? c.xext_qcap : c.xext_qcap - task.qlen;  // invalid tasks go to the last bin
+    c.xext_key[t] = key;
+    B2_ATOMIC_ADD(&c.xext_hist[key], 1);
+  }
+}
+
+B2_KERNEL k_xext_scatter(B2Ctx c) {
+  for (int64_t t = B2_GTID(); t < c.n_chain_tasks; t += B2_GSIZE()) {
+    const int key = c.xext_key[t];
+    const int64_t pos = c.xext_hoff[key] + B2_ATOMIC_ADD(&c.xext_cur[key], 1);
+    c.xext_perm[pos] = (int32_t)t;
+  }
+}
+
+// one extension per lane; the warp's shared-memory block holds, lane-interleaved, eh[] and the two staged sequences
+B2_KERNEL k_xext_run(B2Ctx c) {
+  const int qw = c.xext_qcap / 8 + 1, tw = c.xext_tcap / 8 + 1;
+  B2XMem M;
+#if defined(B2_HOSTSIM)
+  M.stride = 1;
+  M.eh = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(c.xext_qcap + 2 + qw + tw));
+  M.q = M.eh + c.xext_qcap + 2; M.t = M.q + qw;
+#else
+  extern __shared__ uint32_t b2_xext_smem[];
+  const int lane = threadIdx.x & 31;
+  uint32_t* base = b2_xext_smem + (size_t)(threadIdx.x >> 5) * 32 * (size_t)(c.xext_qcap + 2 + qw + tw);
+  M.stride = 32;
+  M.eh = base + lane; M.q = base + (size_t)32 * (c.xext_qcap + 2) + lane; M.t = M.q + (size_t)32 * qw;
+#endif
+  unsigned long long cells = 0, calls = 0;
+  const int64_t n_valid = c.xext_hoff[c.xext_qcap];  // the invalid tasks sit in the last bin
+  for (int64_t t = B2_GTID(); t < n_valid; t += B2_GSIZE()) {
+    const B2XextTask task = c.xext_tasks[c.xext_perm[t]];
+    const uint8_t* qs = c.b.seq + task.qsrc;
+    const int qdir = task.qdir;
+    b2_xext_stage(M.q, M.stride, task.qlen, [&](int k) { return (int)qs[(int64_t)k * qdir]; });
+    const int64_t tpos = task.tpos, l_pac = c.ix.l_pac;
+    const int tdir = task.tdir;
+    const uint8_t* pac = c.ix.pac;
+    b2_xext_stage(M.t, M.stride, task.tlen, [&](int k) { return b2_base_at(pac, l_pac, tpos + (int64_t)k * tdir); });
+    B2XextRes res;
+    res.w = task.w; res.h0 = task.h0;
+    res.score = b2_xext_one(M, task.qlen, task.tlen, c.opt.mat, c.opt.o_del, c.opt.e_del, c.opt.o_ins, c.opt.e_ins, task.w,
+                            task.end_bonus, c.opt.zdrop, task.h0, &res.qle, &res.tle, &res.gtle, &res.gscore, &res.max_off, &cells);
+    ++calls;
+    c.xext_res[task.slot] = res;
+  }
+  if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], calls); }
+#if defined(B2_HOSTSIM)
+  free(M.eh);
+#endif
+}
+
 // One task group per (read, kept chain): extends the chain's seeds against a chain-local region list and
 // leaves every region it computes in cand[] for the serial per-read pass below (mem_chain2aln's DP, hoisted
 // out of the per-read control flow so that a read with hundreds of chains is spread over as many groups).
@@ -330,7 +436,8 @@ B2_KERNEL_LB(128, B2_LB_EXT) k_ext_chain(B2Ctx c) {
     if (!sc.overflow) {
       int n_av = 0;
       b2_chain2aln(c.opt, c.ix, l_seq, c.b.seq + c.b.seq_off[r], ch, c.cseeds + off + ch.seed_head, av, &n_av, ch.n, srt, sc, 1,
-                   c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head);
+                   c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head,
+                   c.xext_res ? c.xext_res + 2 * (off + ch.seed_head) : 0);
     }
     if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
   }

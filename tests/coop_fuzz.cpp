@@ -8,6 +8,7 @@
 #include "b2_ksw.cuh"
 #include "b2_coopreg.cuh"
 #include "b2_galn.cuh"
+#include "b2_xext.cuh"
 #include "simt_emu.h"
 
 static const int GS = 32;  // lanes per group, as the device runs them (whole warps)
@@ -64,7 +65,7 @@ int main(int argc, char** argv) {
   int trials = argc > 1 ? atoi(argv[1]) : 3000;
   srand48(argc > 2 ? atol(argv[2]) : 4242);
   EmuWarp W;
-  long bad_e = 0, bad_g = 0, n_e = 0, n_g = 0, n_l = 0, bad_l = 0;
+  long bad_e = 0, bad_g = 0, n_e = 0, n_g = 0, n_l = 0, bad_l = 0, n_x = 0, bad_x = 0;
   for (int tr = 0; tr < trials; ++tr) {
     int a = 1 + lrand48() % 3, b = 1 + lrand48() % 6;
     int o_del = lrand48() % 9, e_del = 1 + lrand48() % 3, o_ins = lrand48() % 9, e_ins = 1 + lrand48() % 3;
@@ -98,6 +99,19 @@ int main(int argc, char** argv) {
       else if (need <= 5) s1 = run_ext<5>(W, qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, r1, &c1);
       else s1 = run_ext<8>(W, qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, r1, &c1);
       ++n_e;
+      if (h0 + qlen * a < 65000) {  // the inter-task (one extension per lane) form of b2_xext.cuh, lane-strided storage
+        const int zs = 1 + (int)(lrand48() % 3);
+        std::vector<uint32_t> ehv((size_t)(qlen + 2) * zs + 8), qv((size_t)(qlen / 8 + 2) * zs + 8), tv((size_t)(tlen / 8 + 2) * zs + 8);
+        B2XMem M; M.eh = ehv.data(); M.q = qv.data(); M.t = tv.data(); M.stride = zs;
+        b2_xext_stage(M.q, zs, qlen, [&](int k) { return (int)q[k]; });
+        b2_xext_stage(M.t, zs, tlen, [&](int k) { return (int)t[k]; });
+        int r2[5]; unsigned long long c2 = 0;
+        int s2 = b2_xext_one(M, qlen, tlen, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, &r2[0], &r2[1], &r2[2], &r2[3], &r2[4], &c2);
+        ++n_x;
+        if (s2 != s0 || memcmp(r0, r2, sizeof(r0)) || c2 != c0) {
+          if (++bad_x <= 5) fprintf(stderr, "XEXT mismatch trial %d qlen %d tlen %d w %d h0 %d: %d vs %d\n", tr, qlen, tlen, w, h0, s0, s2);
+        }
+      }
       if (s0 != s1 || memcmp(r0, r1, sizeof(r0)) || c0 != c1) {
         if (++bad_e <= 5)
           fprintf(stderr, "EXT mismatch trial %d qlen %d tlen %d w %d h0 %d zdrop %d: %d (%d %d %d %d %d) cells %llu vs %d (%d %d %d %d %d) cells %llu\n", tr,
@@ -161,7 +175,7 @@ int main(int argc, char** argv) {
                 (int)want_cigar, s0, nc0, c0, s1, nc1, c1);
     }
   }
-  printf("lane-per-alignment trials %ld mismatches %ld; ", n_l, bad_l);
+  printf("lane-per-extension trials %ld mismatches %ld; lane-per-alignment trials %ld mismatches %ld; ", n_x, bad_x, n_l, bad_l);
   printf("extend trials %ld mismatches %ld; global trials %ld mismatches %ld\n", n_e, bad_e, n_g, bad_g);
-  return (bad_e || bad_g || bad_l) ? 1 : 0;
+  return (bad_e || bad_g || bad_l || bad_x) ? 1 : 0;
 }
