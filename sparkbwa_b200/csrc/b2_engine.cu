@@ -11,6 +11,11 @@
 
 #if defined(B2_HOSTSIM)
 thread_local B2Dim b2_dim;
+#if defined(B2_GALN_STATS)
+long b2_galn_stats[16];
+struct B2GalnStatsPrinter { ~B2GalnStatsPrinter() { fprintf(stderr, "[D::galn] reg2aln attempts: no-DP %ld, hit %ld, retry-miss %ld, wide-miss %ld, other-miss %ld; missed cells %ld\n",
+  b2_galn_stats[0], b2_galn_stats[1], b2_galn_stats[2], b2_galn_stats[3], b2_galn_stats[4], b2_galn_stats[8]); } } b2_galn_stats_printer;
+#endif
 #endif
 
 #include <atomic>
@@ -520,7 +525,7 @@ class B2EngineImpl {
     memset(&c.galn, 0, sizeof(c.galn));
     {
       const size_t half = ((size_t)w.max_len + 64 + 15) & ~(size_t)15;
-      const size_t pool_need = 32 * 2 * half + ((size_t)w.max_len + 64) * 7 * 32 * 4;
+      const size_t pool_need = 32 * 2 * half + ((size_t)w.max_len + 64) * B2_GALN_MAX_ZWORDS * 32 * 4;
       if (!cfg.no_galn && b2_mat_simple(opt.mat) && !ensure_scratch() && pool_need <= 32 * w.scratch_per_lane) {
         if (w.galn_cnt.ensure((size_t)B2_GALN_CLASSES * (n + 1)) || w.galn_off.ensure((size_t)B2_GALN_CLASSES * (n + 2)))
           return fail("device allocation failed (alignment plan)");
@@ -533,7 +538,7 @@ class B2EngineImpl {
         for (int k = 0; k < B2_GALN_CLASSES; ++k) b2_d2h(&tot[k], w.galn_off.p + (size_t)k * (n + 2) + n, sizeof(int64_t), w.stream);
         if (b2_sync(w.stream)) return fail("device synchronisation failed");
         for (int k = 0; k < B2_GALN_CLASSES; ++k) { c.galn_base[k] = T; c.galn_n[k] = tot[k]; T += tot[k]; }
-        if (getenv("B200BWA_DEBUG_GALN")) fprintf(stderr, "[D::galn] reads %d tasks %ld (%ld, %ld, %ld)\n", n, (long)T, (long)tot[0], (long)tot[1], (long)tot[2]);
+        if (getenv("B200BWA_DEBUG_GALN")) fprintf(stderr, "[D::galn] reads %d tasks %ld (%ld, %ld, %ld, %ld)\n", n, (long)T, (long)tot[0], (long)tot[1], (long)tot[2], (long)tot[3]);
         if (T > 0 && T < (1 << 29)) {
           size_t tsz = 2;
           while (tsz < (size_t)2 * T) tsz <<= 1;
@@ -551,6 +556,7 @@ class B2EngineImpl {
           if (tot[0] > 0) { B2_LAUNCH(k_galn9, grid_for(tot[0]), blk, w.stream, c); ++w.times.launches; }
           if (tot[1] > 0) { B2_LAUNCH(k_galn17, grid_for(tot[1]), blk, w.stream, c); ++w.times.launches; }
           if (tot[2] > 0) { B2_LAUNCH(k_galn33, grid_for(tot[2]), blk, w.stream, c); ++w.times.launches; }
+          if (tot[3] > 0) { B2_LAUNCH(k_galn65, grid_for(tot[3]), blk, w.stream, c); ++w.times.launches; }
         }
       }
     }

@@ -223,8 +223,14 @@ B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, c
   i = 0;
   do {
     w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
-    b2_gen_cigar2(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cg, sc,
-                  i == 0 ? b2_galn_lookup(sc.galn, query_, qb, qe, rb, re, w2) : 0);
+    const B2GalnRes* pre = i == 0 ? b2_galn_lookup(sc.galn, query_, qb, qe, rb, re, w2) : 0;
+#if defined(B2_HOSTSIM) && defined(B2_GALN_STATS)
+    { extern long b2_galn_stats[16]; const int wb = b2_cigar_band(opt, qe - qb, (int)(re - rb), w2);
+      const bool nodp = (qe - qb == re - rb && w2 == 0);
+      ++b2_galn_stats[nodp ? 0 : (pre ? 1 : (i > 0 ? 2 : (b2_galn_class(wb) < 0 ? 3 : 4)))];
+      if (!nodp && !pre) b2_galn_stats[8] += (long)(2 * wb + 1 < qe - qb ? 2 * wb + 1 : qe - qb) * (re - rb); }
+#endif
+    b2_gen_cigar2(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cg, sc, pre);
     if (score == last_sc || w2 == opt.w << 2) break;
     last_sc = score;
     w2 <<= 1;

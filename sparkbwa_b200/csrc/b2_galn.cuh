@@ -20,7 +20,7 @@
 #include "b2_coopreg.cuh"
 
 #define B2_GALN_MAXCIG 12
-#define B2_GALN_CLASSES 3
+#define B2_GALN_CLASSES 4
 #define B2_GALN_MAXREGS 2   // regions per read planned ahead (they are sorted by score)
 
 struct B2GalnTask {
@@ -71,15 +71,17 @@ B2_HD inline const B2GalnRes* b2_galn_lookup(const B2GalnCache* gc, const uint8_
   return 0;
 }
 
-// band class of a ksw_global2 band: 2w+1 diagonals in 9 / 17 / 33 registers; -1: too wide for this path
-B2_HD inline int b2_galn_class(int w) { return w <= 4 ? 0 : (w <= 8 ? 1 : (w <= 16 ? 2 : -1)); }
+// band class of a ksw_global2 band: 2w+1 diagonals in 9 / 17 / 33 / 65 registers; -1: too wide for this path
+B2_HD inline int b2_galn_class(int w) { return w <= 4 ? 0 : (w <= 8 ? 1 : (w <= 16 ? 2 : (w <= 32 ? 3 : -1))); }
+#define B2_GALN_MAX_ZWORDS 13  // direction words per row of the widest class
 
 // One alignment, entirely lane-local.  query/target: base codes (already reversed for the reverse strand, as
 // bwa_gen_cigar2 does); zw: direction words of this lane, word k of row i at zw[(i * NWZ + k) * zstride].
 // Preconditions: the substitution matrix has bwa_fill_scmat's shape, 2w+1 <= ND, |qlen - tlen| <= w, qlen, tlen >= 1.
 template <int ND>
 B2_HD inline void b2_galn_one(int qlen, const uint8_t* query, int tlen, const uint8_t* target, const int8_t* mat, int o_del,
-                              int e_del, int o_ins, int e_ins, int w, uint32_t* zw, int zstride, B2GalnRes* res) {
+                              int e_del, int o_ins, int e_ins, int w, uint32_t* zw, int zstride, B2GalnRes* res,
+                              unsigned long long* cells = 0) {
   constexpr int NWZ = (ND + 4) / 5;
   constexpr int NQ = (ND + 9) / 10;
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
@@ -105,6 +107,7 @@ B2_UNROLL
     const int hb = i ? -(o_del + e_del * i) : 0;
     int f = B2_MINUS_INF;
     uint32_t zword = 0;
+    if (cells) *cells += (unsigned long long)(dend - dmin);  // = end - beg of the reference's row (bwa/ksw.c:530-531)
 B2_UNROLL
     for (int d = 0; d < ND; ++d) {
       if (d >= dmin && d < dend) {

@@ -575,6 +575,7 @@ B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
   uint8_t* tg = q + half;
   uint32_t* zw = (uint32_t*)(pool + (size_t)LW * 2 * half) + lane;
   const int64_t first = c.galn_base[cls], last = first + c.galn_n[cls];
+  unsigned long long cells = 0, calls = 0;
   for (int64_t t = first + B2_GTID(); t < last; t += B2_GSIZE()) {
     const B2GalnTask task = c.galn_tasks[t];
     B2GalnRes* res = &c.galn_res[t];
@@ -588,12 +589,15 @@ B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
     } else {
       for (int k = 0; k < qlen; ++k) q[k] = src[k];
     }
-    b2_galn_one<ND>(qlen, q, tlen, tg, c.opt.mat, c.opt.o_del, c.opt.e_del, c.opt.o_ins, c.opt.e_ins, task.w, zw, LW, res);
+    b2_galn_one<ND>(qlen, q, tlen, tg, c.opt.mat, c.opt.o_del, c.opt.e_del, c.opt.o_ins, c.opt.e_ins, task.w, zw, LW, res, &cells);
+    ++calls;
   }
+  if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CELLS], cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CALLS], calls); }
 }
 B2_KERNEL k_galn9(B2Ctx c) { b2_galn_run<9>(c, 0); }
 B2_KERNEL k_galn17(B2Ctx c) { b2_galn_run<17>(c, 1); }
 B2_KERNEL k_galn33(B2Ctx c) { b2_galn_run<33>(c, 2); }
+B2_KERNEL k_galn65(B2Ctx c) { b2_galn_run<65>(c, 3); }
 
 B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
   int gid, n_groups;

@@ -159,11 +159,12 @@ int main(int argc, char** argv) {
       if (!bad && want_cigar && cap > 3 && b2_galn_class(w) >= 0) {
         B2GalnRes gr; gr.n_cigar = -7; gr.score = 0;
         const int zs = 1 + (int)(lrand48() % 3);
-        std::vector<uint32_t> zw((size_t)(tlen + 1) * 7 * zs + 8, 0xdeadbeef);
+        std::vector<uint32_t> zw((size_t)(tlen + 1) * B2_GALN_MAX_ZWORDS * zs + 8, 0xdeadbeef);
         const int cls = b2_galn_class(w);
         if (cls == 0) b2_galn_one<9>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
         else if (cls == 1) b2_galn_one<17>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
-        else b2_galn_one<33>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
+        else if (cls == 2) b2_galn_one<33>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
+        else b2_galn_one<65>(qlen, q.data(), tlen, t.data(), mat, o_del, e_del, o_ins, e_ins, w, zw.data(), zs, &gr);
         ++n_l;
         if (gr.score != s0) bad = true;
         if (gr.n_cigar >= 0) { if (gr.n_cigar != nc0 || memcmp(gr.cigar, cg0.data(), sizeof(uint32_t) * nc0)) bad = true; }
