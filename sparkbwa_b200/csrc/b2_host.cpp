@@ -1020,6 +1020,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
         double ct = b2_cputime(), rt = b2_realtime();
         b2_pack_batch(*j->raw, m.copy_comment, &hb);
         j->raw.reset();
+        const double t_packed = b2_realtime();
         const char* data = 0;
         size_t len = 0;
         int rc;
@@ -1030,8 +1031,11 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
         if (m.verbose >= 3 && !rc)
           fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", hb.n_reads,
                   b2_cputime() - ct, b2_realtime() - rt);
+        const double t_gpu = b2_realtime();
         if (getenv("B200BWA_TIMES") && !rc) {
           const B2StageTimes& t = eng->times(wi);
+          fprintf(stderr, "[T::b200bwa] worker %d batch %ld: start %.1f ms, pack %.1f ms, upload+kernels+download %.1f ms (wall)\n", wi,
+                  (long)j->index, (rt - t_real) * 1e3, (t_packed - rt) * 1e3, (t_gpu - t_packed) * 1e3);
           fprintf(stderr, "[T::b200bwa] worker %d reads %d: h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f rescue %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
                   wi, hb.n_reads, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
                   t.launches, (long)t.n_seed_tasks, (long)t.n_regs, (long)t.sam_bytes);
@@ -1048,7 +1052,10 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           cv.wait(lk, [&] { return j->offset >= 0 || failed; });
           const bool ok = j->offset >= 0;
           lk.unlock();
-          if (ok && !pwrite_all(data, len, j->offset)) {
+          const double t_w0 = b2_realtime();
+          const bool wrote = !ok || pwrite_all(data, len, j->offset);
+          if (getenv("B200BWA_TIMES")) fprintf(stderr, "[T::b200bwa] worker %d batch %ld: offset wait %.1f ms, write %.1f ms, done at %.1f ms\n", wi, (long)j->index, (t_w0 - t_gpu) * 1e3, (b2_realtime() - t_w0) * 1e3, (b2_realtime() - t_real) * 1e3);
+          if (!wrote) {
             std::lock_guard<std::mutex> lk2(mu);
             rc = 1; errmsg = "write error on SAM output";
           }

@@ -161,19 +161,13 @@ def test_smart_pairing(workdir):
     assert not pu.first_diff(ref, our)
 
 
-@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
-def test_config1_scale_matches_oracle(tmp_path_factory):
-    """BASELINE.json configs[1] at its full index size: 2x150 bp pairs against a 100 Mbp reference with -K 10000000
-    (several batches, so the per-batch insert-size statistics matter).  B200BWA_FULL_PAIRS (default 150000; the
-    round's own visit runs 1000000) sets the read count; the oracle is `bwa mem -t <host cores>` on the same files,
-    the index files are written by the GPU builder and are byte-identical to `bwa index`'s (test below on a prefix)."""
+def _config_scale_index(tmp_path_factory, ref_len):
+    """100 Mbp-class synthetic reference + index files written by the GPU builder, cached in /dev/shm."""
     import sys
     sys.path.insert(0, ROOT)
     from sparkbwa_b200 import synth, index
-    pairs = int(os.environ.get("B200BWA_FULL_PAIRS", "150000"))
-    ref_len = int(os.environ.get("B200BWA_FULL_REF", "100000000"))
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path_factory.mktemp("cfg1"))
-    d = os.path.join(base, f"b2cfg1_L{ref_len}_P{pairs}")
+    base = "/dev/shm" if os.path.isdir("/dev/shm") else str(tmp_path_factory.mktemp("cfg"))
+    d = os.path.join(base, f"b2cfg_L{ref_len}")
     os.makedirs(d, exist_ok=True)
     prefix = os.path.join(d, "ref")
     ctg = synth.make_reference(ref_len, n_contigs=4, seed=1, repeat_frac=0.02)
@@ -181,6 +175,35 @@ def test_config1_scale_matches_oracle(tmp_path_factory):
         index.build_index(ctg, prefix + ".tmp")
         for e in ("pac", "ann", "amb", "bwt", "sa"):
             os.replace(prefix + ".tmp." + e, prefix + "." + e)
+    return d, prefix, ctg
+
+
+def _compare_with_oracle(lib, d, tag, opts, prefix, fqs, min_lines):
+    ours, ref = os.path.join(d, f"ours_{tag}.sam"), os.path.join(d, f"oracle_{tag}.sam")
+    rc = _main_to(lib, ["bwa", "mem", "-v", "1"] + opts + [prefix] + fqs, ours)
+    assert rc == 0, lib.b200bwa_last_error()
+    with open(ref, "wb") as f:
+        subprocess.run([pu.ORACLE, "mem", "-v", "1", "-t", str(os.cpu_count() or 1)] + opts + [prefix] + fqs, check=True,
+                       stdout=f, stderr=subprocess.DEVNULL)
+    diff = pu.first_diff(ref, ours)
+    n_lines = len(pu.sam_body(ours))
+    for p in (ours, ref):
+        os.remove(p)
+    assert not diff, diff
+    assert n_lines >= min_lines
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_config1_scale_matches_oracle(tmp_path_factory):
+    """BASELINE.json configs[1] at its full index size: 2x150 bp pairs against a 100 Mbp reference with -K 10000000
+    (several batches, so the per-batch insert-size statistics matter).  B200BWA_FULL_PAIRS (default 150000; the
+    round's own visit runs 1000000) sets the read count; the oracle is `bwa mem -t <host cores>` on the same files,
+    the index files are written by the GPU builder (byte-identical to `bwa index`'s).  configs[4]'s batch-size
+    sweep is covered on the same reads with -K 1000000 and -K 100000000 (different batch cuts, different pestat)."""
+    from sparkbwa_b200 import synth
+    pairs = int(os.environ.get("B200BWA_FULL_PAIRS", "150000"))
+    ref_len = int(os.environ.get("B200BWA_FULL_REF", "100000000"))
+    d, prefix, ctg = _config_scale_index(tmp_path_factory, ref_len)
     f1, f2 = os.path.join(d, "r_1.fq"), os.path.join(d, "r_2.fq")
     s1, s2 = [], []
     for a, b in synth.simulate_pairs_fast(ctg, pairs, 150, seed=4242, sub=0.01, indel=0.001):
@@ -188,16 +211,29 @@ def test_config1_scale_matches_oracle(tmp_path_factory):
     synth.write_fastq_fixed(f1, s1, 0, b"/1")
     synth.write_fastq_fixed(f2, s2, 0, b"/2")
     del ctg, s1, s2
-    ours, ref = os.path.join(d, "ours.sam"), os.path.join(d, "oracle.sam")
     lib = _lib()
-    rc = _main_to(lib, ["bwa", "mem", "-v", "1", "-K", "10000000", prefix, f1, f2], ours)
-    assert rc == 0, lib.b200bwa_last_error()
-    with open(ref, "wb") as f:
-        subprocess.run([pu.ORACLE, "mem", "-v", "1", "-t", str(os.cpu_count() or 1), "-K", "10000000", prefix, f1, f2], check=True,
-                       stdout=f, stderr=subprocess.DEVNULL)
-    diff = pu.first_diff(ref, ours)
-    n_lines = len(pu.sam_body(ours))
-    assert not diff, diff
-    assert n_lines >= 2 * pairs
-    for p in (ours, ref, f1, f2):
-        os.remove(p)
+    try:
+        _compare_with_oracle(lib, d, "K1e7", ["-K", "10000000"], prefix, [f1, f2], 2 * pairs)
+        if pairs <= 200000:
+            _compare_with_oracle(lib, d, "K1e6", ["-K", "1000000"], prefix, [f1, f2], 2 * pairs)
+            _compare_with_oracle(lib, d, "K1e8", ["-K", "100000000"], prefix, [f1, f2], 2 * pairs)
+    finally:
+        for p in (f1, f2):
+            os.remove(p)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_config3_scale_single_end_250bp(tmp_path_factory):
+    """BASELINE.json configs[3]: single-end 250 bp reads at 3.5 % substitutions + 1.5 % indels (wide ksw_extend2 bands,
+    band retries in mem_reg2aln) against the 100 Mbp index."""
+    from sparkbwa_b200 import synth
+    n = int(os.environ.get("B200BWA_FULL_SE", "30000"))
+    d, prefix, ctg = _config_scale_index(tmp_path_factory, int(os.environ.get("B200BWA_FULL_REF", "100000000")))
+    fq = os.path.join(d, "se250.fq")
+    r1, _ = synth.simulate_reads(ctg, n=n, read_len=250, paired=False, seed=99, sub=0.035, indel=0.015)
+    synth.write_fastq(fq, r1)
+    del ctg, r1
+    try:
+        _compare_with_oracle(_lib(), d, "se250", [], prefix, [fq], n)
+    finally:
+        os.remove(fq)
