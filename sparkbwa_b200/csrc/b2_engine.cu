@@ -389,6 +389,21 @@ class B2EngineImpl {
       if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
       w.scratch_per_lane *= 2;
     }
+    {  // mem_flt_chained_seeds acts only on long reads (5.5 ln l <= 0.05 l: l >= 725 with the default options)
+      const double min_l = opt.min_chain_weight ? (double)(1.1f * (float)opt.min_chain_weight) : 5.5 * log((double)w.max_len);
+      if (!(min_l > (double)(0.05f * (float)w.max_len)) && !getenv("B200BWA_DEBUG_NO_SEED_FILTER")) {  // (the switch exists to show the filter matters)
+        for (;;) {
+          if (ensure_scratch()) return 1;
+          b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+          B2_LAUNCH(k_flt_seeds, cfg.lane_grid, cfg.lane_block, w.stream, c);
+          ++w.times.launches;
+          if (read_flags(w, &flags)) return 1;
+          if (flags & B2_FLAG_ERR_TABLE) return fail("log table index out of range (read too long)");
+          if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
+          w.scratch_per_lane *= 2;
+        }
+      }
+    }
     int ev_chain = w.timer.mark();
     B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.reg_cap.p, w.reg_off.p, n);
     ++w.times.launches;

@@ -73,6 +73,53 @@ B2_HD inline double b2_log_int(const B2Tables& tb, long v, int* err) {
 }
 
 // ---------------------------------------------------------------------------------------------
+// ---------------------------------------------------------------------------------------------
+// mem_flt_chained_seeds (bwa/bwamem.c:598-615) and mem_seed_sw (:571-596): for long reads, every seed of every kept
+// chain is re-scored by a local SW of the seed +-50 bp and dropped when that score is too low.
+#define B2_SHORT_EXT 50
+#define B2_SHORT_LEN 200
+
+// returns 0 when the reference returns before doing anything (short reads); else 1 and the minimum HSP score
+B2_HD inline int b2_flt_seeds_threshold(const B2Opt& opt, const B2Tables& tb, int l_query, int* min_hsp, int* err) {
+  const double min_l = opt.min_chain_weight ? (double)(1.1f * (float)opt.min_chain_weight) : (double)5.5f * b2_log_int(tb, l_query, err);
+  *min_hsp = (int)(opt.a * min_l + .499);
+  return !(min_l > (double)(0.05f * (float)l_query));
+}
+
+// -1: no need to test this seed
+B2_HD inline int b2_seed_sw(const B2Opt& opt, const B2Index& ix, int l_query, const uint8_t* query, const B2Seed& s, B2Scratch& sc) {
+  const int64_t l_pac = ix.l_pac;
+  if (s.len >= B2_SHORT_LEN) return -1;
+  int qb = s.qbeg, qe = s.qbeg + s.len;
+  int64_t rb = s.rbeg, re = s.rbeg + s.len;
+  const int64_t mid = (rb + re) >> 1;
+  qb -= B2_SHORT_EXT; qb = qb > 0 ? qb : 0;
+  qe += B2_SHORT_EXT; qe = qe < l_query ? qe : l_query;
+  rb -= B2_SHORT_EXT; rb = rb > 0 ? rb : 0;
+  re += B2_SHORT_EXT; re = re < l_pac << 1 ? re : l_pac << 1;
+  if (rb < l_pac && l_pac < re) {
+    if (mid < l_pac) re = l_pac;
+    else rb = l_pac;
+  }
+  if (qe - qb >= B2_SHORT_LEN || re - rb >= B2_SHORT_LEN) return -1;
+  b2_fetch_bounds(ix, &rb, mid, &re);  // bns_fetch_seq: clamp to the contig holding mid
+  const size_t mk = sc.mark();
+  const int ql = qe - qb, tl = (int)(re - rb);
+  const int npad = ((ql + 7) / 8) * 8;
+  uint8_t* q = (uint8_t*)sc.alloc((size_t)ql + 1, 1);
+  uint8_t* ref = (uint8_t*)sc.alloc((size_t)tl + 1, 1);
+  int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
+  uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
+  if (sc.overflow) { sc.reset(mk); return -1; }
+  sc.gsync();
+  for (int k = sc.lane; k < ql; k += sc.gsize) q[k] = query[qb + k];
+  b2_get_seq_g(sc, l_pac, ix.pac, rb, re, ref);
+  sc.gsync();
+  B2Kswr x = b2_align2_any(sc, ql, q, tl, ref, opt.mat, opt.o_del, opt.e_del, opt.o_ins, opt.e_ins, B2_KSW_XSTART, work, bbuf);
+  sc.reset(mk);
+  return x.score;
+}
+
 struct B2RegHashLt {
   B2_HD bool operator()(const B2Reg& a, const B2Reg& b) const {
     return a.score > b.score || (a.score == b.score && (a.is_alt < b.is_alt || (a.is_alt == b.is_alt && a.hash < b.hash)));

@@ -315,6 +315,49 @@ B2_KERNEL k_chain(B2Ctx c) {
   }
 }
 
+// mem_flt_chained_seeds: one lane group per read (only launched when the batch holds reads long enough for the
+// filter to act at all); compacts the seeds of every kept chain in place.
+B2_KERNEL k_flt_seeds(B2Ctx c) {
+  int gid, n_groups;
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_RESC);
+  for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
+    sc.gsync();
+    sc.reset(0);
+    const int l_seq = c.b.l_seq[r];
+    int min_hsp = 0, err = 0;
+    if (!b2_flt_seeds_threshold(c.opt, c.tb, l_seq, &min_hsp, &err)) { if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE); continue; }
+    if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE);
+    const int64_t off = c.seed_off[r];
+    const uint8_t* query = c.b.seq + c.b.seq_off[r];
+    int cap = 0;
+    for (int i = 0; i < c.n_chain[r]; ++i) {
+      B2Chain& ch = c.chains[off + i];
+      B2Seed* seeds = c.cseeds + off + ch.seed_head;
+      int k = 0;
+      for (int j = 0; j < ch.n; ++j) {
+        B2Seed s = seeds[j];
+        int score = b2_seed_sw(c.opt, c.ix, l_seq, query, s, sc);
+        if (sc.overflow) break;
+        if (score < 0 || score >= min_hsp) {
+          s.score = score < 0 ? s.len * c.opt.a : score;
+          sc.gsync();
+          if (sc.lane == 0) seeds[k] = s;
+          sc.gsync();
+          ++k;
+        }
+      }
+      if (sc.overflow) break;
+      sc.gsync();
+      if (sc.lane == 0) ch.n = k;
+      sc.gsync();
+      cap += k;
+    }
+    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; continue; }
+    if (sc.lane == 0) c.reg_cap[r] = cap;
+  }
+  b2_flush_counters(c, sc);
+}
+
 // ---- inter-task seed extension ahead of k_ext_chain (b2_xext.cuh) ----------------------------------------------
 // side 0: the first band try of the LEFT extension of every chain's best seed (the seed mem_chain2aln extends
 // first: largest score, ties to the later one); side 1: of its RIGHT extension, whose start score is the left

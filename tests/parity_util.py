@@ -44,6 +44,12 @@ CASES = {
     # short and ragged reads: below min_seed_len, empty alignments, length 1
     "se_short": (dict(total_len=200_000, n_contigs=1, seed=35, repeat_frac=0.02),
                  dict(n=600, read_len=60, paired=False, seed=37, sub=0.03, indel=0.003, n_frac=0.02, ragged=True), []),
+    # long reads: mem_flt_chained_seeds re-scores every seed (reads >= 725 bp); repeats + chimeras make it drop some
+    "se_long900": (dict(total_len=300_000, n_contigs=2, seed=61, repeat_frac=0.5, rep_len=(100, 800), rep_copies=(5, 40), rep_div=0.08),
+                   dict(n=150, read_len=900, paired=False, seed=63, sub=0.08, indel=0.03, junk_frac=0.05, chimeric_frac=0.3), []),
+    # the pacbio preset (-x pacbio: a=b=o=e=1, -k17 -W40 -r10 -L0) on 1.5 kb reads at 14 % error
+    "se_pacbio1500": (dict(total_len=300_000, n_contigs=2, seed=71, repeat_frac=0.5, rep_len=(100, 800), rep_copies=(5, 40), rep_div=0.08),
+                      dict(n=100, read_len=1500, paired=False, seed=73, sub=0.10, indel=0.04, chimeric_frac=0.3), ["-x", "pacbio"]),
     "pe_small": (dict(total_len=200_000, n_contigs=2, seed=41, repeat_frac=0.20, rep_len=(200, 1500), rep_copies=(2, 12)),
                  dict(n=400, read_len=125, paired=True, seed=43, sub=0.015, indel=0.002, mate2_sub=0.05, chimeric_frac=0.05), []),
 }
