@@ -64,15 +64,15 @@ inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_ATOMIC_CAS(p, cmp, val) atomicCAS((p), (cmp), (val))
 #define B2_WARP_LANES 32
 #define B2_TASK_GROUP B2_TASK_LANES
-// Lanes per task of the group-cooperative kernels.  A warp whose two halves follow different tasks keeps switching
-// between two instruction streams (ncu: stall_no_inst 49-67 % of the samples in k_final_pe / k_ext_chain with
-// 16-lane groups), so the control-flow-heavy kernels give a whole warp to a task; the rescue SW keeps the 16 lanes
-// of ksw_u8, whose two groups per warp run the same loop nearly in lock step.
+// Lanes per task of the group-cooperative kernels.  The chain-extension kernel runs the register-resident row-parallel
+// ksw_extend2 on whole warps (constant member mask); the rescue SW keeps the 16 lanes of ksw_u8, whose two groups per
+// warp run the same loop nearly in lock step; the finalisation kernel, whose DP now runs ahead of it (b2_galn.cuh),
+// is serial bookkeeping plus bulk copies, and does best with small groups: more pairs in flight per register.
 #ifndef B2_G_EXT
 #define B2_G_EXT 32
 #endif
 #ifndef B2_G_FINAL
-#define B2_G_FINAL 16
+#define B2_G_FINAL 4   // measured on the B200 (profiles/r1d/variants_group_size.jsonl): 32: 5.20, 16: 5.38, 8: 5.69, 4: 5.83, 2: 5.34, 1: 5.36 M reads/s
 #endif
 #define B2_G_RESC 16
 #ifndef B2_LB_EXT

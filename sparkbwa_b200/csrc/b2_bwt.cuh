@@ -537,8 +537,24 @@ struct B2SeedFsm {
         last_x2 = okc.x[2];
       }
       ++j;
-      if (j < n_prev) { mem.get(top - 1 - j, p); return 1; }
-      t = B2T_SWEEP_END;
+      // The end of a sweep (j == n_prev) is the COMMON case -- a sweep has one to three candidates -- so the
+      // transition to the next sweep is taken here, in line with the lanes that stay inside their sweep, instead of
+      // through advance() (whose state loop ran at ~5 of 32 lanes and made up 40 % of the kernel's instructions).
+      if (j >= n_prev) {
+        if (n_curr == 0) return advance(opt, ix, B2T_END_SMEM);
+        n_prev = n_curr; --i;
+        j = 0; n_curr = 0;
+        int bc = -1;
+        if (i >= 0) { bc = mem.q(i); if (bc > 3) bc = -1; }
+        if (bc < 0) {  // nothing extends: only the longest candidate can be reported
+          mem.get(top - 1, p);
+          if (i + 1 < nm_last) emit(opt, p, i + 1);
+          return advance(opt, ix, B2T_END_SMEM);
+        }
+        rc = bc;
+      }
+      mem.get(top - 1 - j, p);
+      return 1;
     } else {  // one more base of a forward walk: bwt_smem1a's first loop (B2S_FWD) or bwt_seed_strategy1 (B2S_S3)
       const bool fwd = MODE == 0;
       bool stop;
