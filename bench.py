@@ -278,7 +278,8 @@ def main():
         raise SystemExit("upload failed: " + lib.b200bwa_last_error().decode())
     del inter
     batches = cut_batches(n_reads, 150, args.K)
-    n_workers = max(1, min(args.workers, int(os.environ.get("B200BWA_WORKERS", "6"))))
+    lib.b200bwa_n_workers.argtypes = [ctypes.c_void_p]
+    n_workers = max(1, min(args.workers, int(lib.b200bwa_n_workers(ix))))
 
     def one_pass(collect=None):
         lock = threading.Lock()

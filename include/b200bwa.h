@@ -86,11 +86,13 @@ int b200bwa_upload_batch(b200bwa_index_t* idx, int n_reads, const char* seq, con
 int b200bwa_run_resident(b200bwa_index_t* idx, int paired, int want_sam, char** sam_out, size_t* sam_len);
 
 /* Runs reads [first, first+count) of the batch uploaded by b200bwa_upload_batch on stream/buffer set
- * `worker` (0..2; sets may run concurrently from different host threads).  Pairing mode comes from
+ * `worker` (0 .. b200bwa_n_workers()-1, else rc 1; sets may run concurrently from different host threads).  Pairing mode comes from
  * b200bwa_set_paired.  `t` (may be NULL) receives the device stage times of this call. */
 int b200bwa_run_resident_range(b200bwa_index_t* idx, int worker, int first, int count, int paired, int want_sam,
                                char** sam_out, size_t* sam_len, b200bwa_times_t* t);
 int b200bwa_set_paired(b200bwa_index_t* idx, int paired);
+/* Number of independent stream/buffer sets of this index's engine (B200BWA_WORKERS, default 6, at most 8). */
+int b200bwa_n_workers(b200bwa_index_t* idx);
 
 /* Algorithmic-work counters accumulated by the kernels of one worker: [0] 64-byte occ-block touches of
  * SMEM seeding, [1] SA lookups, [2] SA walk steps, [3] ksw_extend2 cells, [4] calls, [5] ksw_global2

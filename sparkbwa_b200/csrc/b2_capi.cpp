@@ -271,6 +271,10 @@ int b200bwa_run_resident_range(b200bwa_index_t* ix, int worker, int first, int c
                                char** sam_out, size_t* sam_len, b200bwa_times_t* t) {
   try {
     if (!ix) return 1;
+    if (worker < 0 || worker >= ix->engine->n_workers()) {
+      b2_tls_error = "worker index out of range (the engine has " + std::to_string(ix->engine->n_workers()) + " stream/buffer sets)";
+      return 1;
+    }
     // options are set once by the caller (b200bwa_set_options / b200bwa_set_paired); concurrent workers share them
     std::string sam;
     if (ix->engine->run_resident_range(ix->args.has_pes0 ? ix->args.pes0 : 0, want_sam ? &sam : 0, worker, 0, first, count)) {
@@ -289,6 +293,8 @@ int b200bwa_run_resident_range(b200bwa_index_t* ix, int worker, int first, int c
   } catch (const std::exception& e) { b2_tls_error = e.what(); return 1; }
 }
 
+int b200bwa_n_workers(b200bwa_index_t* ix) { return ix ? ix->engine->n_workers() : 0; }
+
 int b200bwa_set_paired(b200bwa_index_t* ix, int paired) {
   if (!ix) return 1;
   if (paired) ix->args.opt.flag |= B2_F_PE; else ix->args.opt.flag &= ~B2_F_PE;
@@ -297,7 +303,7 @@ int b200bwa_set_paired(b200bwa_index_t* ix, int paired) {
 }
 
 int b200bwa_counters(b200bwa_index_t* ix, int worker, unsigned long long out[16], int reset) {
-  if (!ix) return 1;
+  if (!ix || worker < 0 || worker >= ix->engine->n_workers()) return 1;
   return ix->engine->counters(worker, out, 0, 0, reset);
 }
 

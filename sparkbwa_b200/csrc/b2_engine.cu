@@ -27,9 +27,11 @@ template <class T>
 struct DBuf {
   T* p = nullptr;
   size_t cap = 0;
-  int ensure(size_t n) {
+  int ensure(size_t n, bool exact = false) {
     if (n <= cap) return 0;
-    size_t want = n + n / 4 + 16;
+    // generous headroom: a cudaFree/cudaMalloc pair synchronises the whole device, i.e. stalls every other stream,
+    // and per-batch sizes (seeds, regions, rescue windows, SAM bytes) keep creeping up for the first dozen batches
+    size_t want = exact ? n : n + n / 2 + 4096;
     b2_dev_free(p);
     p = nullptr; cap = 0;
     void* q = nullptr;
@@ -376,7 +378,7 @@ class B2EngineImpl {
     // ---- lane-per-read stages with retry on scratch overflow ----
     auto ensure_scratch = [&]() -> int {
       if ((size_t)lanes * w.scratch_per_lane > cfg.max_scratch_bytes) return fail("per-lane scratch limit exceeded");
-      if (w.scratch.ensure((size_t)lanes * w.scratch_per_lane)) return fail("device allocation failed (scratch)");
+      if (w.scratch.ensure((size_t)lanes * w.scratch_per_lane, true)) return fail("device allocation failed (scratch)");
       c.scratch = w.scratch.p; c.scratch_per_lane = w.scratch_per_lane;
       return 0;
     };
