@@ -396,13 +396,17 @@ def main():
             raise SystemExit("e2e failed: " + lib.b200bwa_last_error().decode())
         lib.b200bwa_process_counters(pc, 1)
         barrier()
-        t0 = time.time()
-        n_e2e = max(1, min(2, args.steps))
+        n_e2e = max(1, min(3, args.steps))
+        per_call = []
         for _ in range(n_e2e):
+            t0 = time.time()
             if lib.b200bwa_main_to(len(argv), arr, sam.encode()) != 0:
                 raise SystemExit("e2e failed: " + lib.b200bwa_last_error().decode())
+            per_call.append(time.time() - t0)
         torch.cuda.synchronize()
-        dt = (time.time() - t0) / n_e2e
+        # median of the calls: a single call is 0.4 s, so one host hiccup (another tenant of the box, a page-cache
+        # flush) would otherwise dominate the figure; every call's time is reported next to it
+        dt = float(np.median(per_call))
         tt = torch.tensor([dt], dtype=torch.float64, device="cuda")
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -410,7 +414,8 @@ def main():
         lib.b200bwa_process_counters(pc, 0)
         out["e2e"] = {"value": world * 2 * e2e_pairs / dt, "unit": "reads/s", "h2d_bytes_per_step": int(pc[0] // n_e2e),
                       "d2h_bytes_per_step": int(pc[1] // n_e2e), "path": "b200bwa_main_to: FASTQ files (tmpfs) -> SAM file (tmpfs)",
-                      "sam_bytes": os.path.getsize(sam), "seconds_per_step": dt}
+                      "sam_bytes": os.path.getsize(sam), "seconds_per_step": dt,
+                      "seconds_per_call": [round(x, 4) for x in per_call], "statistic": "median of the calls"}
         try:
             os.remove(sam)
         except OSError:

@@ -650,7 +650,7 @@ class B2EngineImpl {
     if (sam || view) {
       if ((size_t)total > w.pin_sam_cap) {
         if (w.pin_sam) b2_host_free(w.pin_sam);
-        w.pin_sam_cap = (size_t)total + (size_t)total / 4 + 4096;
+        w.pin_sam_cap = (size_t)total + (size_t)total / 2 + ((size_t)1 << 20);  // (cudaFreeHost/cudaMallocHost stall the device too)
         if (b2_host_alloc(&w.pin_sam, w.pin_sam_cap)) return fail("pinned host allocation failed");
       }
       b2_d2h(w.pin_sam, w.sam_out.p, (size_t)total, w.stream);
