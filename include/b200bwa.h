@@ -50,7 +50,8 @@ b200bwa_index_t* b200bwa_index_load(const char* prefix, int device);
 void b200bwa_index_free(b200bwa_index_t* idx);
 
 /* Sets bwa-mem options from an option string as given to `-w` of SparkBWA / the bwa command line
- * (e.g. "-t 4 -K 10000000 -M"); NULL or "" = defaults.  Returns 0 on success. */
+ * (e.g. "-t 4 -K 10000000 -M"); NULL or "" = defaults.  Returns 0 on success.  Smart pairing (-p, bwa/fastmap.c:64-83)
+ * is a property of the file-driven entry points above; b200bwa_align_batch takes its pairing from `paired`. */
 int b200bwa_set_options(b200bwa_index_t* idx, const char* mem_options);
 
 /* Aligns one batch held in HOST memory and returns the SAM records (no header) in a malloc'ed
