@@ -188,3 +188,49 @@ def test_hostsim_smart_pairing(hostsim, workdir):
     our = pu.engine_sam(c2, hostsim, env=pu.HOSTSIM_ENV)
     assert not pu.first_diff(ref, our)
     assert len(pu.sam_body(our)) > 700
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_reader_paths_match_oracle(hostsim, workdir):
+    """The reader takes a memory-mapped fast path for plain 4-line FASTQ and the kseq-exact general parser for
+    everything else; all of them must cut the same batches and yield the same records as the reference's kseq:
+    gzip input, the general parser forced on a plain file, CR/LF line ends, multi-line FASTA, and a file that
+    switches between the two parsers record by record (FASTQ records followed by FASTA records)."""
+    import gzip
+    c = pu.make_case(workdir, "pe_small")
+    d = c["dir"]
+    ref = pu.oracle_sam(c)
+    # (1) general parser forced on the plain files
+    our = pu.engine_sam(c, hostsim, env=dict(pu.HOSTSIM_ENV, B200BWA_NO_MMAP="1"))
+    assert not pu.first_diff(ref, our)
+    # (2) gzip-compressed mates
+    gz = []
+    for f in c["fq"]:
+        g = f + ".gz"
+        with open(f, "rb") as fi, gzip.open(g, "wb", compresslevel=1) as fo:
+            fo.write(fi.read())
+        gz.append(g)
+    our = pu.engine_sam(dict(c, fq=gz), hostsim, env=pu.HOSTSIM_ENV)
+    assert not pu.first_diff(ref, our)
+    # (3) CR/LF line ends, (4) multi-line FASTA after FASTQ records in one single-end file
+    recs = open(c["fq"][0], "rb").read().split(b"\n")
+    crlf = os.path.join(d, "crlf.fq")
+    with open(crlf, "wb") as f:
+        f.write(b"\r\n".join(recs))
+    mixed = os.path.join(d, "mixed.fq")
+    with open(mixed, "wb") as f:
+        n_rec = (len(recs) - 1) // 4
+        for k in range(n_rec):
+            name, seq, _, qual = recs[4 * k:4 * k + 4]
+            if k % 3 == 2:   # FASTA, sequence folded at 60 columns
+                f.write(b">" + name[1:] + b" some comment\n")
+                for p in range(0, len(seq), 60):
+                    f.write(seq[p:p + 60] + b"\n")
+            else:
+                f.write(b"\n".join([name, seq, b"+" + (name[1:] if k % 5 == 0 else b""), qual]) + b"\n")
+    for fq in (crlf, mixed):
+        c1 = dict(c, fq=[fq], opts=["-K", "40000"])
+        r1 = pu.oracle_sam(c1)
+        o1 = pu.engine_sam(c1, hostsim, env=pu.HOSTSIM_ENV)
+        assert not pu.first_diff(r1, o1), fq
+        assert len(pu.sam_body(o1)) > 300
