@@ -681,12 +681,13 @@ int b2_read_raw_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, B2RawBa
 
 // record views -> the packed arrays the engine uploads (name trimming of bwa/bwa.c:27-31, nst_nt4_table codes)
 void b2_pack_batch(const B2RawBatch& rb, int copy_comment, B2HostBatch* b) {
-  b->clear();
+  // (no clear(): every array is resized to its exact length below, and a vector that only shrinks or regrows within
+  // its old size is not zero-filled again -- 20 MB of memset per batch otherwise)
   const size_t n = rb.recs.size();
   size_t tot_seq = 0, tot_name = 0, tot_com = 0;
   for (const B2RecView& v : rb.recs) { tot_seq += v.l_seq; tot_name += v.l_name; tot_com += v.l_comment; }
   b->seq.resize(tot_seq); b->qual.resize(tot_seq); b->names.resize(tot_name);
-  if (copy_comment) b->comments.resize(tot_com);
+  b->comments.resize(copy_comment ? tot_com : 0);
   b->has_qual.resize(n); b->seq_off.resize(n); b->name_off.resize(n); b->com_off.resize(n);
   b->l_seq.resize(n); b->l_name.resize(n); b->l_com.resize(n);
   size_t so = 0, no = 0, co = 0;
