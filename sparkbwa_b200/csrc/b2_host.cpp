@@ -483,6 +483,62 @@ struct B2SeqReader::Impl {
   const unsigned char* map = 0;
   size_t map_size = 0;
   std::string name, comment, seq, qual;
+  // Scan-ahead thread (mapped files only): runs fast() over the mapping and hands the record views over in blocks,
+  // so that the two mate files are scanned concurrently with each other and with the batch cutting.  It stops at the
+  // first record that is not a plain 4-line FASTQ record (or at EOF); the consumer then continues from that position
+  // with the synchronous code (fast() / read() record by record).
+  struct Block { std::vector<B2RecView> v; };
+  std::thread pre_thread;
+  std::mutex pre_mu;
+  std::condition_variable pre_cv;
+  std::deque<std::unique_ptr<Block>> pre_q;
+  bool pre_on = false, pre_done = false, pre_stop = false;
+  std::unique_ptr<Block> cur;
+  size_t cur_i = 0;
+  void pre_start() {
+    if (!map || pre_on) return;
+    pre_on = true; pre_done = false; pre_stop = false;
+    pre_thread = std::thread([this]() {
+      for (;;) {
+        std::unique_ptr<Block> b(new Block);
+        b->v.reserve(4096);
+        B2RecView v;
+        while (b->v.size() < 4096 && fast(&v)) b->v.push_back(v);
+        const bool last = b->v.size() < 4096;
+        std::unique_lock<std::mutex> lk(pre_mu);
+        pre_cv.wait(lk, [&] { return pre_q.size() < 16 || pre_stop; });
+        if (pre_stop) { pre_done = true; pre_cv.notify_all(); return; }
+        if (!b->v.empty()) pre_q.push_back(std::move(b));
+        if (last) { pre_done = true; pre_cv.notify_all(); return; }
+        pre_cv.notify_all();
+      }
+    });
+  }
+  // next scanned-ahead view; false once the scan-ahead thread has ended and its blocks are used up
+  bool pre_next(B2RecView* v) {
+    for (;;) {
+      if (cur && cur_i < cur->v.size()) { *v = cur->v[cur_i++]; return true; }
+      std::unique_lock<std::mutex> lk(pre_mu);
+      pre_cv.wait(lk, [&] { return !pre_q.empty() || pre_done; });
+      if (pre_q.empty()) {
+        lk.unlock();
+        pre_thread.join();
+        pre_on = false; cur.reset();
+        return false;
+      }
+      cur = std::move(pre_q.front());
+      pre_q.pop_front();
+      cur_i = 0;
+      pre_cv.notify_all();
+    }
+  }
+  void pre_shutdown() {
+    if (!pre_on) return;
+    { std::lock_guard<std::mutex> lk(pre_mu); pre_stop = true; }
+    pre_cv.notify_all();
+    pre_thread.join();
+    pre_on = false; pre_q.clear(); cur.reset();
+  }
   bool refill() {
     if (map || is_eof) { is_eof = true; return false; }
     begin = 0;
@@ -580,7 +636,8 @@ B2SeqReader::B2SeqReader() : impl_(new Impl) {}
 B2SeqReader::~B2SeqReader() { close(); delete impl_; }
 int B2SeqReader::open(const char* fn) {
   close();
-  *impl_ = Impl();
+  delete impl_;
+  impl_ = new Impl;
   if (strcmp(fn, "-") && !getenv("B200BWA_NO_MMAP")) {  // regular, non-empty, not gzip: map it
     int fd = ::open(fn, O_RDONLY);
     if (fd < 0) return 1;
@@ -596,7 +653,10 @@ int B2SeqReader::open(const char* fn) {
       }
     }
     ::close(fd);
-    if (impl_->map) return 0;
+    if (impl_->map) {
+      if (!getenv("B200BWA_NO_SCAN_AHEAD")) impl_->pre_start();
+      return 0;
+    }
   }
   impl_->fp = strcmp(fn, "-") ? gzopen(fn, "r") : gzdopen(0, "r");
   if (!impl_->fp) return 1;
@@ -605,11 +665,25 @@ int B2SeqReader::open(const char* fn) {
   return 0;
 }
 void B2SeqReader::close() {
+  impl_->pre_shutdown();
   if (impl_->fp) { gzclose(impl_->fp); impl_->fp = 0; }
   if (impl_->map) { munmap((void*)impl_->map, impl_->map_size); impl_->map = 0; impl_->data = 0; impl_->begin = impl_->end = 0; }
 }
-int B2SeqReader::next() { return impl_->read(); }
+int B2SeqReader::next() {  // string-returning form: same record stream as next_view
+  B2RecView v;
+  bool stable = false;
+  const int r = next_view(&v, &stable);
+  if (r >= 0 && stable) {
+    impl_->name.assign(v.name, v.l_name); impl_->comment.assign(v.comment ? v.comment : "", v.l_comment);
+    impl_->seq.assign(v.seq, v.l_seq); impl_->qual.assign(v.qual, v.l_qual);
+  }
+  return r;
+}
 int B2SeqReader::next_view(B2RecView* v, bool* stable) {
+  if (impl_->pre_on) {
+    if (impl_->pre_next(v)) { *stable = true; return v->l_seq; }
+    // the scan-ahead thread has ended (EOF or a record for the general parser): carry on from its position
+  }
   if (impl_->fast(v)) { *stable = true; return v->l_seq; }
   *stable = false;
   int r = impl_->read();
