@@ -28,7 +28,10 @@ extern "C" {
 #endif
 
 /* argv-compatible with `bwa` (argv[0] = program name, argv[1] = "mem", then bwa-mem options,
- * index prefix, reads [, mates]).  SAM goes to stdout.  Other sub-commands return 1. */
+ * index prefix, reads [, mates]).  SAM goes to stdout.  Other sub-commands return 1.
+ * One call aligns ONE job on every visible GPU (B200BWA_DEVICES="all" | "0,2,5", or B200BWA_DEVICE=n for one):
+ * the -K batches are dealt round-robin over the devices and their SAM blocks are written in input order, as
+ * kt_pipeline orders them (bwa/kthread.c:92-102, bwa/fastmap.c:84-89). */
 int b200bwa_main(int argc, char** argv);
 
 /* Same, but the SAM text is written to `out_path` (what the JNI glue achieves with
@@ -37,6 +40,11 @@ int b200bwa_main_to(int argc, char** argv, const char* out_path);
 
 /* argv as main_mem sees it: argv[0] = "mem". out_path may be NULL (stdout). */
 int b200bwa_mem(int argc, char** argv, const char* out_path);
+
+/* The file-driven entry points keep the device image of an index cached across calls (keyed by prefix and the
+ * size/mtime of <prefix>.bwt), the way `bwa shm` keeps it in host shared memory (bwa/bwashm.c:87-118).  This
+ * releases every cached image that no running call uses; returns the number released. */
+int b200bwa_index_cache_evict(void);
 
 /* Last error message of the calling thread's most recent failing call ("" if none). */
 const char* b200bwa_last_error(void);

@@ -61,6 +61,8 @@ int b200bwa_main_to(int argc, char** argv, const char* out_path) {
 
 int b200bwa_main(int argc, char** argv) { return b200bwa_main_to(argc, argv, 0); }
 
+int b200bwa_index_cache_evict(void) { return b2_index_cache_evict(); }
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

@@ -19,6 +19,7 @@ struct B2GalnStatsPrinter { ~B2GalnStatsPrinter() { fprintf(stderr, "[D::galn] r
 #endif
 
 #include <atomic>
+#include <mutex>
 std::atomic<unsigned long long> b2_g_h2d_bytes{0}, b2_g_d2h_bytes{0}, b2_g_launches{0};
 
 namespace {
@@ -92,6 +93,10 @@ struct Worker {
   B2StageTimes times;
   std::vector<int8_t> h_dir; std::vector<int64_t> h_is; std::vector<char> h_sam;
   void* pin_sam = nullptr; size_t pin_sam_cap = 0, last_sam_bytes = 0;
+  // raw-FASTQ ingest: pinned staging of the batch's file bytes + record descriptors, and its device image
+  void* pin_in = nullptr; size_t pin_in_cap = 0;
+  DBuf<uint8_t> raw_in; DBuf<int32_t> com_cnt;
+  int ev_in0 = -1, ev_in1 = -1;
 };
 
 }  // namespace
@@ -109,8 +114,14 @@ class B2EngineImpl {
   B2Fmt fmt{};
   std::vector<Worker> workers;
   std::string err;
+  mutable std::mutex err_mu;  // fail() is called from every GPU worker thread
 
-  int fail(const std::string& m) { err = m; if (cfg.verbose >= 1) fprintf(stderr, "[E::b200bwa] %s\n", m.c_str()); return 1; }
+  int fail(const std::string& m) {
+    { std::lock_guard<std::mutex> lk(err_mu); err = m; }
+    if (cfg.verbose >= 1) fprintf(stderr, "[E::b200bwa] %s\n", m.c_str());
+    return 1;
+  }
+  std::string last_error() const { std::lock_guard<std::mutex> lk(err_mu); return err; }
 
   int common_init(const B2IndexHost& h, const B2Opt& o, const char* rg_id, const B2EngineConfig& c) {
     cfg = c; opt = o;
@@ -180,9 +191,37 @@ class B2EngineImpl {
     return common_init(h, o, rg_id, c);
   }
 
+  // index image copied device to device from an engine of another GPU of this process
+  int init_peer(const B2IndexHost& h, B2EngineImpl& src, const B2Opt& o, const char* rg_id, const B2EngineConfig& c) {
+    cfg = c;
+    bwt_bytes = src.bwt_bytes; sa_bytes = src.sa_bytes; pac_bytes = src.pac_bytes;
+#if !defined(B2_HOSTSIM)
+    if (cudaSetDevice(c.device) != cudaSuccess) return fail("cudaSetDevice failed (no usable CUDA device)");
+    if (c.device != src.cfg.device) {
+      int can = 0;
+      if (cudaDeviceCanAccessPeer(&can, c.device, src.cfg.device) == cudaSuccess && can)
+        if (cudaDeviceEnablePeerAccess(src.cfg.device, 0) != cudaSuccess) cudaGetLastError();  // already enabled: fine
+    }
+#endif
+    if (d_bwt.ensure(bwt_bytes / 4 + 16) || d_sa.ensure(sa_bytes / 8 + 1) || d_pac.ensure(pac_bytes + 8))
+      return fail("device allocation failed (index image)");
+#if !defined(B2_HOSTSIM)
+    if (cudaMemcpyPeerAsync(d_bwt.p, c.device, src.ix.bwt, src.cfg.device, bwt_bytes, 0) != cudaSuccess ||
+        cudaMemcpyPeerAsync(d_sa.p, c.device, src.ix.sa, src.cfg.device, sa_bytes, 0) != cudaSuccess ||
+        cudaMemcpyPeerAsync(d_pac.p, c.device, src.ix.pac, src.cfg.device, pac_bytes, 0) != cudaSuccess)
+      return fail("peer copy of the index image failed");
+#else
+    memcpy(d_bwt.p, src.ix.bwt, bwt_bytes); memcpy(d_sa.p, src.ix.sa, sa_bytes); memcpy(d_pac.p, src.ix.pac, pac_bytes);
+#endif
+    ix.bwt = d_bwt.p; ix.sa = d_sa.p; ix.pac = d_pac.p;
+    return common_init(h, o, rg_id, c);
+  }
+
   int init_device(const B2IndexHost& h, const void* bwt, const void* sa, const void* pac, const B2Opt& o,
                   const char* rg_id, const B2EngineConfig& c) {
     owns_index = false;
+    bwt_bytes = (h.bwt_words ? h.bwt_words : h.bwt.size()) * 4; sa_bytes = (h.n_sa ? h.n_sa : h.sa.size()) * 8;
+    pac_bytes = (size_t)(h.l_pac / 4 + 1);
     ix.bwt = (const uint32_t*)bwt; ix.sa = (const uint64_t*)sa; ix.pac = (const uint8_t*)pac;
     return common_init(h, o, rg_id, c);
   }
@@ -203,6 +242,8 @@ class B2EngineImpl {
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
       w.galn_cnt.release(); w.galn_table.release(); w.galn_off.release(); w.galn_tasks.release(); w.galn_res.release();
       if (w.pin_sam) b2_host_free(w.pin_sam);
+      if (w.pin_in) b2_host_free(w.pin_in);
+      w.raw_in.release(); w.com_cnt.release();
 #if !defined(B2_HOSTSIM)
       if (w.stream) cudaStreamDestroy(w.stream);
 #endif
@@ -259,6 +300,69 @@ class B2EngineImpl {
     return check_cuda("upload");
   }
 
+  // One batch given as raw FASTQ bytes (B2RawInput): the byte range its records span in each mapped file goes to a
+  // pinned staging buffer together with the record descriptors, one H2D copy, then the ingest kernels build the
+  // packed batch on the device.  No synchronisation: everything is queued on the worker's stream ahead of run().
+  int upload_raw(Worker& w, const B2RawInput& in) {
+    bind_device();
+    const int n = in.n_reads;
+    w.timer.reset();
+    w.times = B2StageTimes();
+    w.ev_in0 = w.timer.mark();
+    size_t lo[2] = {0, 0}, sz[2] = {0, 0}, tot_name = 0, tot_com = 0;
+    for (int f = 0; f < in.n_files; ++f) {
+      const B2Rec* r = in.recs[f];
+      const size_t m = in.n_recs[f];
+      if (m == 0) return fail("raw batch without records");
+      lo[f] = r[0].off;
+      sz[f] = (size_t)(r[m - 1].off + r[m - 1].qual_rel + r[m - 1].l_seq - lo[f]);
+      for (size_t i = 0; i < m; ++i) { tot_name += r[i].l_name; tot_com += r[i].l_hdr - r[i].l_name; }
+    }
+    if ((size_t)n != in.n_recs[0] + in.n_recs[1]) return fail("raw batch: record count mismatch");
+    auto up16 = [](size_t x) { return (x + 15) & ~(size_t)15; };
+    const size_t o1 = up16(sz[0]), orec0 = up16(o1 + sz[1]), orec1 = orec0 + in.n_recs[0] * sizeof(B2Rec);
+    const size_t total = orec1 + in.n_recs[1] * sizeof(B2Rec);
+    if (total > w.pin_in_cap) {
+      if (w.pin_in) b2_host_free(w.pin_in);
+      w.pin_in = nullptr;
+      w.pin_in_cap = total + total / 2 + ((size_t)1 << 20);
+      if (b2_host_alloc(&w.pin_in, w.pin_in_cap)) { w.pin_in_cap = 0; return fail("pinned host allocation failed"); }
+    }
+    uint8_t* st = (uint8_t*)w.pin_in;
+    memcpy(st, in.base[0] + lo[0], sz[0]);
+    if (in.n_files == 2) memcpy(st + o1, in.base[1] + lo[1], sz[1]);
+    memcpy(st + orec0, in.recs[0], in.n_recs[0] * sizeof(B2Rec));
+    if (in.n_files == 2) memcpy(st + orec1, in.recs[1], in.n_recs[1] * sizeof(B2Rec));
+    const size_t nb = (size_t)in.n_bases;
+    if (w.raw_in.ensure(total + 16) || w.seq.ensure(nb + 8) || w.qual.ensure(nb + 8) || w.has_qual.ensure(n + 1) ||
+        w.names.ensure(tot_name + 8) || w.comments.ensure((in.copy_comment ? tot_com : 0) + 8) || w.seq_off.ensure(n + 2) ||
+        w.name_off.ensure(n + 2) || w.com_off.ensure(n + 2) || w.l_seq.ensure(n + 1) || w.l_name.ensure(n + 1) ||
+        w.l_com.ensure(n + 1) || w.com_cnt.ensure(n + 1))
+      return fail("device allocation failed (read batch)");
+    b2_h2d(w.raw_in.p, st, total, w.stream);
+    b2_g_h2d_bytes += total;
+    w.h2d_bytes += total;
+    B2Ingest g;
+    memset(&g, 0, sizeof(g));
+    g.raw = w.raw_in.p;
+    g.recs[0] = (const B2Rec*)(w.raw_in.p + orec0); g.recs[1] = (const B2Rec*)(w.raw_in.p + orec1);
+    g.adj[0] = -(int64_t)lo[0]; g.adj[1] = (int64_t)o1 - (int64_t)lo[1];
+    g.n_files = in.n_files; g.n_reads = n; g.copy_comment = in.copy_comment;
+    g.seq = w.seq.p; g.qual = w.qual.p; g.has_qual = w.has_qual.p; g.names = w.names.p; g.comments = w.comments.p;
+    g.seq_off = w.seq_off.p; g.name_off = w.name_off.p; g.com_off = w.com_off.p;
+    g.l_seq = w.l_seq.p; g.l_name = w.l_name.p; g.l_com = w.l_com.p; g.com_cnt = w.com_cnt.p;
+    const int grid = std::min((n + 127) / 128, 148 * 8);
+    B2_LAUNCH(k_ingest_len, grid, 128, w.stream, g);
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.l_seq.p, w.seq_off.p, n);
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.l_name.p, w.name_off.p, n);
+    B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.com_cnt.p, w.com_off.p, n);
+    B2_LAUNCH(k_ingest_copy, std::min((4 * n + 127) / 128, 148 * 16), 128, w.stream, g);
+    w.ev_in1 = w.timer.mark();
+    w.n_reads = n; w.max_len = in.max_len; w.n_processed = in.n_processed;
+    w.resident = true;
+    return check_cuda("upload_raw");
+  }
+
   int read_flags(Worker& w, int* f) {
     b2_d2h(f, w.flags.p, sizeof(int), w.stream);
     if (b2_sync(w.stream)) return fail("device synchronisation failed (kernel fault?)");
@@ -279,10 +383,14 @@ class B2EngineImpl {
     const int n = count;
     const bool pe = pe_mode >= 0 ? pe_mode != 0 : (opt.flag & B2_F_PE) != 0;
     if (pe && (n & 1)) return fail("paired-end batch with an odd number of reads");
-    w.timer.reset();
+    const bool ingest = w.ev_in0 >= 0;   // upload_raw queued the ingest ahead of this call: its events are still pending
+    if (!ingest) w.timer.reset();
     float t_h2d = w.times.h2d;
     w.times = B2StageTimes();
     w.times.h2d = t_h2d;
+    if (ingest) w.times.launches = 5;
+    const int ev_in0 = w.ev_in0, ev_in1 = w.ev_in1;
+    w.ev_in0 = w.ev_in1 = -1;
     if (n == 0) return 0;
     B2Ctx c;
     memset(&c, 0, sizeof(c));
@@ -675,6 +783,7 @@ class B2EngineImpl {
     w.times.gather = w.timer.ms(ev_fin, ev_gat);
     w.times.d2h = w.timer.ms(ev_gat, ev_d2h);
     w.times.total = w.timer.ms(ev_begin, ev_d2h);
+    if (ingest) w.times.h2d = w.timer.ms(ev_in0, ev_in1);
     return 0;
   }
 };
@@ -735,6 +844,17 @@ void b2_pestat_host(const B2Opt& opt, int n_pairs, const int8_t* dir, const int6
 }
 
 // ---------------------------------------------------------------------------------------------
+int b2_device_count() {
+#if defined(B2_HOSTSIM)
+  const char* s = getenv("B200BWA_HOSTSIM_DEVICES");  // the host checker build pretends to have this many devices
+  return s ? atoi(s) : 1;
+#else
+  int n = 0;
+  if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+  return n;
+#endif
+}
+
 B2Engine::B2Engine() : impl_(new B2EngineImpl) {}
 B2Engine::~B2Engine() { delete impl_; }
 int B2Engine::init(const B2IndexHost& idx, const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg) {
@@ -744,6 +864,10 @@ int B2Engine::init_device_index(const B2IndexHost& meta, const void* d_bwt, cons
                                 const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg) {
   return impl_->init_device(meta, d_bwt, d_sa, d_pac, opt, rg_id, cfg);
 }
+int B2Engine::init_from_peer(const B2IndexHost& meta, B2Engine& src, const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg) {
+  return impl_->init_peer(meta, *src.impl_, opt, rg_id, cfg);
+}
+int B2Engine::device() const { return impl_->cfg.device; }
 int B2Engine::process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam, int worker) {
   Worker& w = impl_->workers[worker];
   if (impl_->upload(w, b)) return 1;
@@ -753,6 +877,19 @@ int B2Engine::process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, 
   Worker& w = impl_->workers[worker];
   *data = 0; *len = 0;
   if (impl_->upload(w, b)) return 1;
+  if (impl_->run(w, pes0, nullptr, nullptr, 0, -1, true)) return 1;
+  *data = (const char*)w.pin_sam; *len = w.last_sam_bytes;
+  return 0;
+}
+int B2Engine::process_raw(const B2RawInput& in, const B2Pes* pes0, std::string& sam, int worker) {
+  Worker& w = impl_->workers[worker];
+  if (impl_->upload_raw(w, in)) return 1;
+  return impl_->run(w, pes0, &sam);
+}
+int B2Engine::process_raw_view(const B2RawInput& in, const B2Pes* pes0, int worker, const char** data, size_t* len) {
+  Worker& w = impl_->workers[worker];
+  *data = 0; *len = 0;
+  if (impl_->upload_raw(w, in)) return 1;
   if (impl_->run(w, pes0, nullptr, nullptr, 0, -1, true)) return 1;
   *data = (const char*)w.pin_sam; *len = w.last_sam_bytes;
   return 0;
@@ -790,7 +927,11 @@ int B2Engine::counters(int worker, unsigned long long out[16], unsigned long lon
   }
   return 0;
 }
-const char* B2Engine::last_error() const { return impl_->err.c_str(); }
+const char* B2Engine::last_error() const {
+  static thread_local std::string copy;  // the engine's string may be rewritten by a failing worker thread
+  copy = impl_->last_error();
+  return copy.c_str();
+}
 int B2Engine::n_workers() const { return (int)impl_->workers.size(); }
 void B2Engine::index_device_ptrs(void** bwt, size_t* bb, void** sa, size_t* sb, void** pac, size_t* pb) {
   *bwt = (void*)impl_->ix.bwt; *bb = impl_->bwt_bytes; *sa = (void*)impl_->ix.sa; *sb = impl_->sa_bytes;

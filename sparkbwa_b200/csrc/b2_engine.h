@@ -39,6 +39,17 @@ struct B2HostBatch {
   }
 };
 
+// One -K batch as raw file bytes: per input file the records' descriptors and the mapping they point into.  The engine
+// copies the byte range the records span to the device and parses / trims / encodes there (k_ingest_*).
+// Paired-end input from two files: read 2i = record i of file 0, read 2i+1 = record i of file 1.
+struct B2RawInput {
+  int n_files = 0, n_reads = 0, max_len = 0, copy_comment = 0;
+  int64_t n_bases = 0, n_processed = 0;
+  const unsigned char* base[2] = {0, 0};
+  const B2Rec* recs[2] = {0, 0};
+  size_t n_recs[2] = {0, 0};
+};
+
 struct B2EngineConfig {
   int device = 0;
   int lane_grid = 148 * 4, lane_block = 128;   // lane-per-read kernels (persistent, grid-stride)
@@ -73,9 +84,16 @@ class B2Engine {
   // adopt an index image that already lives in device memory (NCCL-broadcast by the caller)
   int init_device_index(const B2IndexHost& meta, const void* d_bwt, const void* d_sa, const void* d_pac,
                         const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg);
+  // replicate the index image of `src` (an engine of another device of this process) into this engine's device:
+  // device-to-device copies over NVLink (cudaMemcpyPeerAsync), no second trip through host memory
+  int init_from_peer(const B2IndexHost& meta, B2Engine& src, const B2Opt& opt, const char* rg_id, const B2EngineConfig& cfg);
+  int device() const;
   // Aligns one batch and appends its SAM text to `sam`.  PE iff opt.flag & B2_F_PE.  pes0: user-supplied
   // insert-size distribution (-I) or null.  `worker` selects one of the independent stream/buffer sets.
   int process(const B2HostBatch& b, const B2Pes* pes0, std::string& sam, int worker = 0);
+  // the same two calls for a batch given as raw FASTQ bytes (packing on the device)
+  int process_raw(const B2RawInput& in, const B2Pes* pes0, std::string& sam, int worker);
+  int process_raw_view(const B2RawInput& in, const B2Pes* pes0, int worker, const char** data, size_t* len);
   // same, leaving the SAM text in the worker's pinned host buffer: *data stays valid until the next call on `worker`
   int process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, const char** data, size_t* len);
   // one batch forced single-end (paired = 0) or paired-end (1), also returning the SAM bytes of every read / pair:
@@ -104,6 +122,9 @@ class B2Engine {
  private:
   B2EngineImpl* impl_;
 };
+
+// number of usable CUDA devices (0 when there is none)
+int b2_device_count();
 
 // mem_pestat second half (bwa/bwamem_pair.c:66-108) on the host: candidates -> pes[4]
 void b2_pestat_host(const B2Opt& opt, int n_pairs, const int8_t* dir, const int64_t* is, B2Pes pes[4], int verbose);

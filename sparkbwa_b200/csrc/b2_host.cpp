@@ -483,61 +483,207 @@ struct B2SeqReader::Impl {
   const unsigned char* map = 0;
   size_t map_size = 0;
   std::string name, comment, seq, qual;
-  // Scan-ahead thread (mapped files only): runs fast() over the mapping and hands the record views over in blocks,
-  // so that the two mate files are scanned concurrently with each other and with the batch cutting.  It stops at the
-  // first record that is not a plain 4-line FASTQ record (or at EOF); the consumer then continues from that position
-  // with the synchronous code (fast() / read() record by record).
-  struct Block { std::vector<B2RecView> v; };
-  std::thread pre_thread;
+  // Parallel scan-ahead (mapped files only).  The mapping is cut into fixed-size chunks; scanner threads take the
+  // chunks in order, each finding the first record start inside its chunk speculatively (a line that parses as a plain
+  // 4-line record and is followed by another one) and then parsing record after record into compact descriptors.  The
+  // consumer accepts chunk k only if its start equals the position where chunk k-1 ended -- the scan from a given
+  // position is deterministic, so an accepted chunk holds exactly the records a sequential scan would have found;
+  // otherwise it re-scans the chunk itself from the right position.  The scan ends at EOF or at the first record that
+  // is not a plain 4-line FASTQ record; the consumer then continues from that position with the synchronous code
+  // (fast() / read() record by record).
+  struct Chunk {
+    size_t lo = 0, hi = 0, start = 0, end_pos = 0;
+    bool stopped = false, done = false;   // stopped: an irregular record begins at end_pos
+    std::vector<B2Rec> recs;
+  };
+  static constexpr size_t kNoStart = (size_t)-1;
+  std::vector<std::thread> pre_threads;
   std::mutex pre_mu;
   std::condition_variable pre_cv;
-  std::deque<std::unique_ptr<Block>> pre_q;
-  bool pre_on = false, pre_done = false, pre_stop = false;
-  std::unique_ptr<Block> cur;
-  size_t cur_i = 0;
+  std::vector<std::unique_ptr<Chunk>> chunks;
+  size_t chunk_bytes = (size_t)8 << 20, pre_next_chunk = 0, pre_consumed = 0, pre_window = 8;
+  bool pre_on = false, pre_stop = false;
+  size_t cur_chunk = 0, cur_i = 0, cur_expected = 0;
+  bool cur_ready = false;
+
+  // one plain 4-line record at `pos` (the conditions under which kseq_read's result is the four line bodies)
+  static bool parse_rec(const unsigned char* data, size_t size, size_t pos, B2Rec* r, size_t* next) {
+    const unsigned char* p = data + pos;
+    const unsigned char* e = data + size;
+    if (p >= e || *p != '@') return false;
+    const unsigned char* nl = (const unsigned char*)memchr(p + 1, '\n', e - (p + 1));
+    if (!nl || nl[-1] == '\r') return false;
+    const unsigned char* q = p + 1;
+    while (q < nl && !isspace(*q)) ++q;
+    if (memchr(p + 1, 0, q - (p + 1))) return false;
+    const unsigned char* s = nl + 1;
+    if (s >= e || *s == '\n' || *s == '>' || *s == '+' || *s == '@') return false;
+    const unsigned char* nl2 = (const unsigned char*)memchr(s, '\n', e - s);
+    if (!nl2 || nl2[-1] == '\r') return false;
+    const size_t ls = nl2 - s;
+    if (memchr(s, 0, ls)) return false;
+    const unsigned char* p3 = nl2 + 1;
+    if (p3 >= e || *p3 != '+') return false;
+    const unsigned char* nl3 = (const unsigned char*)memchr(p3, '\n', e - p3);
+    if (!nl3) return false;
+    const unsigned char* qs = nl3 + 1;
+    if (qs + ls > e || (qs + ls < e && qs[ls] != '\n') || memchr(qs, '\n', ls)) return false;
+    if ((size_t)(qs - p) > 0xffffffffu || ls > 0x7fffffffu) return false;
+    r->off = pos; r->l_seq = (uint32_t)ls; r->l_hdr = (uint32_t)(nl - (p + 1)); r->l_name = (uint32_t)(q - (p + 1));
+    r->qual_rel = (uint32_t)(qs - p);
+    *next = (size_t)(qs + ls - data) + (qs + ls < e ? 1 : 0);
+    return true;
+  }
+  static void rec_view(const unsigned char* data, const B2Rec& r, B2RecView* v) {
+    const char* p = (const char*)data + r.off;
+    v->name = p + 1; v->l_name = (int)r.l_name;
+    if (r.l_name < r.l_hdr) { v->comment = p + 1 + r.l_name + 1; v->l_comment = (int)(r.l_hdr - r.l_name - 1); }
+    else { v->comment = 0; v->l_comment = 0; }
+    v->seq = p + 1 + r.l_hdr + 1; v->l_seq = (int)r.l_seq;
+    v->qual = p + r.qual_rel; v->l_qual = (int)r.l_seq;
+  }
+  // records whose '@' lies in [pos, hi), blank lines between records skipped (kseq skips to the next '@' or '>')
+  void scan_range(Chunk* c, size_t pos) const {
+    const unsigned char* d = map;
+    const size_t size = map_size;
+    c->start = pos; c->stopped = false; c->recs.clear();
+    for (;;) {
+      size_t q = pos;
+      while (q < size && d[q] == '\n') ++q;
+      if (q >= size) { c->end_pos = size; return; }
+      if (q >= c->hi) { c->end_pos = q; return; }
+      B2Rec r;
+      size_t next;
+      if (!parse_rec(d, size, q, &r, &next)) { c->end_pos = q; c->stopped = true; return; }
+      c->recs.push_back(r);
+      pos = next;
+    }
+  }
+  // first position in [lo, hi) that looks like the start of a record (kNoStart: none)
+  size_t find_start(size_t lo, size_t hi) const {
+    const unsigned char* d = map;
+    const size_t size = map_size;
+    size_t p = lo;
+    if (lo > 0 && d[lo - 1] != '\n') {
+      const unsigned char* nl = (const unsigned char*)memchr(d + lo, '\n', size - lo);
+      if (!nl) return kNoStart;
+      p = (size_t)(nl - d) + 1;
+    }
+    for (int tries = 0; tries < 256; ++tries) {
+      while (p < size && d[p] == '\n') ++p;
+      if (p >= hi || p >= size) return kNoStart;
+      B2Rec r;
+      size_t next;
+      if (d[p] == '@' && parse_rec(d, size, p, &r, &next)) {
+        size_t q = next;
+        while (q < size && d[q] == '\n') ++q;
+        size_t n2;
+        if (q >= size || parse_rec(d, size, q, &r, &n2)) return p;
+      }
+      const unsigned char* nl = (const unsigned char*)memchr(d + p, '\n', size - p);
+      if (!nl) return kNoStart;
+      p = (size_t)(nl - d) + 1;
+    }
+    return kNoStart;
+  }
   void pre_start() {
     if (!map || pre_on) return;
-    pre_on = true; pre_done = false; pre_stop = false;
-    pre_thread = std::thread([this]() {
-      for (;;) {
-        std::unique_ptr<Block> b(new Block);
-        b->v.reserve(4096);
-        B2RecView v;
-        while (b->v.size() < 4096 && fast(&v)) b->v.push_back(v);
-        const bool last = b->v.size() < 4096;
-        std::unique_lock<std::mutex> lk(pre_mu);
-        pre_cv.wait(lk, [&] { return pre_q.size() < 16 || pre_stop; });
-        if (pre_stop) { pre_done = true; pre_cv.notify_all(); return; }
-        if (!b->v.empty()) pre_q.push_back(std::move(b));
-        if (last) { pre_done = true; pre_cv.notify_all(); return; }
-        pre_cv.notify_all();
-      }
-    });
+    if (const char* s = getenv("B200BWA_SCAN_CHUNK")) { long v = atol(s); if (v >= 64) chunk_bytes = (size_t)v; }
+    const size_t n_chunks = (map_size + chunk_bytes - 1) / chunk_bytes;
+    int n_threads = 4;
+    if (const char* s = getenv("B200BWA_SCAN_THREADS")) n_threads = atoi(s);
+    if (n_threads < 1) n_threads = 1;
+    if ((size_t)n_threads > n_chunks) n_threads = (int)n_chunks;
+    chunks.clear();
+    chunks.resize(n_chunks);
+    pre_window = (size_t)2 * n_threads + 2;
+    pre_next_chunk = 0; pre_consumed = 0; pre_stop = false; pre_on = true;
+    cur_chunk = 0; cur_i = 0; cur_expected = 0; cur_ready = false;
+    for (int t = 0; t < n_threads; ++t)
+      pre_threads.emplace_back([this, n_chunks]() {
+        for (;;) {
+          size_t k;
+          {
+            std::unique_lock<std::mutex> lk(pre_mu);
+            pre_cv.wait(lk, [&] { return pre_stop || pre_next_chunk >= n_chunks || pre_next_chunk < pre_consumed + pre_window; });
+            if (pre_stop || pre_next_chunk >= n_chunks) return;
+            k = pre_next_chunk++;
+          }
+          std::unique_ptr<Chunk> c(new Chunk);
+          c->lo = k * chunk_bytes;
+          c->hi = std::min(map_size, c->lo + chunk_bytes);
+          c->recs.reserve((c->hi - c->lo) / 256 + 16);
+          const size_t st = k == 0 ? 0 : find_start(c->lo, c->hi);
+          if (st == kNoStart) { c->start = kNoStart; c->end_pos = kNoStart; }
+          else scan_range(c.get(), st);
+          c->done = true;
+          std::lock_guard<std::mutex> lk(pre_mu);
+          chunks[k] = std::move(c);
+          pre_cv.notify_all();
+        }
+      });
   }
-  // next scanned-ahead view; false once the scan-ahead thread has ended and its blocks are used up
-  bool pre_next(B2RecView* v) {
+  // Makes chunk cur_chunk current and validated.  False when the scan-ahead has ended (EOF, or an irregular record at
+  // `begin`, which then holds the position to continue from).
+  bool pre_load() {
     for (;;) {
-      if (cur && cur_i < cur->v.size()) { *v = cur->v[cur_i++]; return true; }
-      std::unique_lock<std::mutex> lk(pre_mu);
-      pre_cv.wait(lk, [&] { return !pre_q.empty() || pre_done; });
-      if (pre_q.empty()) {
-        lk.unlock();
-        pre_thread.join();
-        pre_on = false; cur.reset();
-        return false;
+      if (cur_ready) {
+        Chunk* c = chunks[cur_chunk].get();
+        if (cur_i < c->recs.size()) return true;
+        // chunk used up
+        const size_t endp = c->end_pos;
+        const bool stopped = c->stopped;
+        {
+          std::lock_guard<std::mutex> lk(pre_mu);
+          chunks[cur_chunk].reset();
+          pre_consumed = cur_chunk + 1;
+          pre_cv.notify_all();
+        }
+        cur_expected = endp;
+        cur_ready = false;
+        ++cur_chunk;
+        if (stopped || cur_chunk >= chunks.size() || endp >= map_size) { pre_finish(endp); return false; }
       }
-      cur = std::move(pre_q.front());
-      pre_q.pop_front();
+      {
+        std::unique_lock<std::mutex> lk(pre_mu);
+        pre_cv.wait(lk, [&] { return chunks[cur_chunk] != nullptr; });
+      }
+      Chunk* c = chunks[cur_chunk].get();
+      if (cur_expected >= c->hi) {           // the previous chunk's last record covers this chunk entirely
+        c->recs.clear(); c->end_pos = cur_expected; c->stopped = false;
+      } else if (c->start != cur_expected) {  // speculation missed: scan it here from the right position
+        scan_range(c, cur_expected);
+      }
       cur_i = 0;
-      pre_cv.notify_all();
+      cur_ready = true;
     }
+  }
+  void pre_finish(size_t pos) {
+    pre_shutdown();
+    begin = pos;
+  }
+  bool pre_span(const B2Rec** p, size_t* n) {
+    if (!pre_on || !pre_load()) return false;
+    Chunk* c = chunks[cur_chunk].get();
+    *p = c->recs.data() + cur_i; *n = c->recs.size() - cur_i;
+    return true;
+  }
+  // next scanned-ahead view; false once the scan-ahead has ended and its records are used up
+  bool pre_next(B2RecView* v) {
+    const B2Rec* p;
+    size_t n;
+    if (!pre_span(&p, &n)) return false;
+    rec_view(map, *p, v);
+    ++cur_i;
+    return true;
   }
   void pre_shutdown() {
     if (!pre_on) return;
     { std::lock_guard<std::mutex> lk(pre_mu); pre_stop = true; }
     pre_cv.notify_all();
-    pre_thread.join();
-    pre_on = false; pre_q.clear(); cur.reset();
+    for (auto& t : pre_threads) t.join();
+    pre_threads.clear();
+    pre_on = false; chunks.clear(); cur_ready = false;
   }
   bool refill() {
     if (map || is_eof) { is_eof = true; return false; }
@@ -602,32 +748,13 @@ struct B2SeqReader::Impl {
   // plain 4-line record at the current position of the mapping?  (see the comment above)
   bool fast(B2RecView* v) {
     if (!map || last_char != 0) return false;
-    const unsigned char* p = data + begin;
-    const unsigned char* e = data + end;
-    if (p >= e || *p != '@') return false;
-    const unsigned char* nl = (const unsigned char*)memchr(p + 1, '\n', e - (p + 1));
-    if (!nl || nl[-1] == '\r') return false;
-    const unsigned char* q = p + 1;
-    while (q < nl && !isspace(*q)) ++q;
-    if (memchr(p + 1, 0, q - (p + 1))) return false;
-    const unsigned char* s = nl + 1;
-    if (s >= e || *s == '\n' || *s == '>' || *s == '+' || *s == '@') return false;
-    const unsigned char* nl2 = (const unsigned char*)memchr(s, '\n', e - s);
-    if (!nl2 || nl2[-1] == '\r') return false;
-    const size_t ls = nl2 - s;
-    if (memchr(s, 0, ls)) return false;
-    const unsigned char* p3 = nl2 + 1;
-    if (p3 >= e || *p3 != '+') return false;
-    const unsigned char* nl3 = (const unsigned char*)memchr(p3, '\n', e - p3);
-    if (!nl3) return false;
-    const unsigned char* qs = nl3 + 1;
-    if (qs + ls > e || (qs + ls < e && qs[ls] != '\n') || memchr(qs, '\n', ls)) return false;
-    v->name = (const char*)p + 1; v->l_name = (int)(q - (p + 1));
-    if (q < nl) { v->comment = (const char*)q + 1; v->l_comment = (int)(nl - (q + 1)); }
-    else { v->comment = 0; v->l_comment = 0; }
-    v->seq = (const char*)s; v->l_seq = (int)ls;
-    v->qual = (const char*)qs; v->l_qual = (int)ls;
-    begin = (size_t)(qs + ls - data) + (qs + ls < e ? 1 : 0);
+    size_t q = begin;
+    while (q < end && data[q] == '\n') ++q;   // blank lines between records (SparkBWA writes one after every record)
+    B2Rec r;
+    size_t next;
+    if (q >= end || !parse_rec(data, end, q, &r, &next)) return false;
+    rec_view(data, r, v);
+    begin = next;
     return true;
   }
 };
@@ -694,6 +821,10 @@ int B2SeqReader::next_view(B2RecView* v, bool* stable) {
   v->qual = impl_->qual.data(); v->l_qual = (int)impl_->qual.size();
   return r;
 }
+bool B2SeqReader::span(const B2Rec** p, size_t* n) { return impl_->pre_span(p, n); }
+void B2SeqReader::advance(size_t k) { impl_->cur_i += k; }
+const unsigned char* B2SeqReader::map_base() const { return impl_->map; }
+void B2SeqReader::view_of(const unsigned char* base, const B2Rec& r, B2RecView* v) { Impl::rec_view(base, r, v); }
 const std::string& B2SeqReader::name() const { return impl_->name; }
 const std::string& B2SeqReader::comment() const { return impl_->comment; }
 const std::string& B2SeqReader::seq() const { return impl_->seq; }
@@ -726,31 +857,121 @@ static inline int take_record(B2SeqReader* ks, B2RawBatch* rb) {
   return v.l_seq;
 }
 
-// one batch exactly as bseq_read cuts it (bwa/bwa.c:42-75), as record views; returns the number of reads
+// compact descriptors -> views, in read order (two files: interleaved)
+static void expand_compact(B2RawBatch* rb) {
+  if (!rb->compact) return;
+  const size_t n0 = rb->crec[0].size(), n1 = rb->crec[1].size();
+  rb->recs.reserve(n0 + n1 + 64);
+  B2RecView v;
+  for (size_t i = 0; i < n0; ++i) {
+    B2SeqReader::view_of(rb->cbase[0], rb->crec[0][i], &v);
+    rb->recs.push_back(v);
+    if (i < n1) { B2SeqReader::view_of(rb->cbase[1], rb->crec[1][i], &v); rb->recs.push_back(v); }
+  }
+  rb->compact = false; rb->crec[0].clear(); rb->crec[1].clear();
+}
+
+// one batch exactly as bseq_read cuts it (bwa/bwa.c:42-75); returns the number of reads.  While every reader has
+// scanned-ahead plain FASTQ records to offer the batch is collected as descriptors (rb->compact); the first record that
+// needs the general parser turns it into views.
 int b2_read_raw_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, B2RawBatch* rb) {
   rb->clear();
-  int size = 0;
-  for (;;) {
-    int l = take_record(ks, rb);
-    if (l < 0) break;
-    if (ks2) {
-      int l2 = take_record(ks2, rb);
-      if (l2 < 0) {
-        fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n");
-        rb->recs.pop_back();
-        break;
+  int size = 0, max_len = 0;
+  bool full = false;
+  if (!getenv("B200BWA_NO_COMPACT")) {
+    rb->compact = true; rb->n_files = ks2 ? 2 : 1;
+    rb->cbase[0] = ks->map_base(); rb->cbase[1] = ks2 ? ks2->map_base() : 0;
+    while (!full) {
+      const B2Rec *p1 = 0, *p2 = 0;
+      size_t n1 = 0, n2 = 0;
+      if (!ks->span(&p1, &n1)) break;
+      if (ks2 && !ks2->span(&p2, &n2)) break;
+      const size_t m = ks2 ? std::min(n1, n2) : n1;
+      size_t i = 0;
+      if (ks2) {
+        while (i < m) {
+          const int l1 = (int)p1[i].l_seq, l2 = (int)p2[i].l_seq;
+          size += l1 + l2; ++i;
+          if (l1 > max_len) max_len = l1;
+          if (l2 > max_len) max_len = l2;
+          if (size >= chunk_size) { full = true; break; }
+        }
+        rb->crec[1].insert(rb->crec[1].end(), p2, p2 + i);
+        ks2->advance(i);
+      } else {
+        const size_t have = rb->crec[0].size();
+        while (i < m) {
+          const int l1 = (int)p1[i].l_seq;
+          size += l1; ++i;
+          if (l1 > max_len) max_len = l1;
+          if (size >= chunk_size && ((have + i) & 1) == 0) { full = true; break; }
+        }
       }
-      size += l2;
+      rb->crec[0].insert(rb->crec[0].end(), p1, p1 + i);
+      ks->advance(i);
     }
-    size += l;
-    if (size >= chunk_size && (rb->recs.size() & 1) == 0) break;
+    if (rb->crec[0].empty()) rb->compact = false;
+    // the device addresses the raw bytes of a batch with 32-bit offsets
+    if (rb->compact) {
+      uint64_t span = 0;
+      for (int f = 0; f < rb->n_files; ++f) {
+        const std::vector<B2Rec>& c = rb->crec[f];
+        span += c.back().off + c.back().qual_rel + c.back().l_seq + 1 - c.front().off;
+      }
+      if (span >= ((uint64_t)1 << 31)) expand_compact(rb);
+    }
+  }
+  if (!full) {
+    for (;;) {
+      B2RawBatch one;  // (records of the general parser are copied into the batch's arena by take_record)
+      const size_t before = rb->recs.size();
+      if (rb->compact) {
+        // peek: does another record exist at all?  only then leave the compact form
+        B2RawBatch* dst = &one;
+        int l = take_record(ks, dst);
+        if (l < 0) break;
+        expand_compact(rb);
+        B2RecView v = one.recs[0];
+        if (!one.arena.empty()) {  // re-home the copies
+          v.name = rb->hold(v.name, v.l_name); v.comment = rb->hold(v.comment, v.l_comment);
+          v.seq = rb->hold(v.seq, v.l_seq); v.qual = rb->hold(v.qual, v.l_qual);
+        }
+        rb->recs.push_back(v);
+        if (ks2) {
+          int l2 = take_record(ks2, rb);
+          if (l2 < 0) {
+            fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n");
+            rb->recs.pop_back();
+            break;
+          }
+          size += l2;
+        }
+        size += l;
+      } else {
+        int l = take_record(ks, rb);
+        if (l < 0) break;
+        if (ks2) {
+          int l2 = take_record(ks2, rb);
+          if (l2 < 0) {
+            fprintf(stderr, "[W::bseq_read] the 2nd file has fewer sequences.\n");
+            rb->recs.pop_back();
+            break;
+          }
+          size += l2;
+        }
+        size += l;
+      }
+      (void)before;
+      if (size >= chunk_size && (rb->recs.size() & 1) == 0) break;
+    }
   }
   if (size == 0) {
     B2RecView v; bool st;
     if (ks2 && ks2->next_view(&v, &st) >= 0) fprintf(stderr, "[W::bseq_read] the 1st file has fewer sequences.\n");
   }
   rb->n_bases = size;
-  return (int)rb->recs.size();
+  rb->max_len = max_len;
+  return (int)rb->n_reads();
 }
 
 // record views -> the packed arrays the engine uploads (name trimming of bwa/bwa.c:27-31, nst_nt4_table codes)
@@ -804,46 +1025,131 @@ int b2_read_batch(int chunk_size, B2SeqReader* ks, B2SeqReader* ks2, int copy_co
 
 // ---------------------------------------------------------------------------------------------
 // Index cache: like `bwa shm` keeps the index in host shared memory (bwa/bwashm.c:87-118), the
-// device image stays resident across calls in one executor process, keyed by prefix.
-struct CachedIndex {
+// device images stay resident across calls in one executor process.  An entry is keyed by the index
+// prefix plus the size and mtime of its .bwt file (a rebuilt index under the same name is reloaded)
+// and holds one engine per device it has been used on; the first engine is filled from the files,
+// every further one by a device-to-device copy.  A call holds the entry's lock while it runs: calls on
+// different indices run concurrently, calls on the same index take turns (they share the engines'
+// stream/buffer sets).
+struct B2CachedIndex {
   std::string prefix;
-  int device;
+  long long bwt_size = 0, bwt_mtime_ns = 0;
+  bool ignore_alt = false;
   std::unique_ptr<B2IndexHost> host;
-  std::unique_ptr<B2Engine> engine;
-  bool ignore_alt;
+  std::vector<std::unique_ptr<B2Engine>> engines;  // one per device, in order of first use
+  std::mutex run_mu;
+  // the ord-th engine on device d (a device listed twice in B200BWA_DEVICES gets two engines: that is how the
+  // multi-engine path is exercised on a box with a single GPU)
+  B2Engine* on_device(int d, int ord = 0) {
+    for (auto& e : engines) if (e->device() == d && ord-- == 0) return e.get();
+    return 0;
+  }
 };
 static std::mutex g_cache_mu;
-static std::vector<std::unique_ptr<CachedIndex>> g_cache;
-static std::mutex g_run_mu;  // one aligning call at a time per process (the reference is not re-entrant either)
+static std::vector<std::shared_ptr<B2CachedIndex>> g_cache;
+
+static bool stat_bwt(const char* hint, long long* size, long long* mtime_ns) {
+  std::string prefix = infer_prefix(hint);
+  struct stat st;
+  if (prefix.empty() || stat((prefix + ".bwt").c_str(), &st) != 0) return false;
+  *size = (long long)st.st_size;
+  *mtime_ns = (long long)st.st_mtim.tv_sec * 1000000000ll + st.st_mtim.tv_nsec;
+  return true;
+}
+
+// engines for `devices` (all on one index), created on first use; null on failure
+static std::shared_ptr<B2CachedIndex> b2_get_engines(const char* prefix, const std::vector<int>& devices, int ignore_alt,
+                                                     int verbose, std::vector<B2Engine*>* out) {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  long long sz = 0, mt = 0;
+  if (!stat_bwt(prefix, &sz, &mt)) {
+    if (verbose >= 1) fprintf(stderr, "[E::bwa_idx_load_from_disk] fail to locate the index files\n");
+    set_err("fail to locate the index files for '%s'", prefix);
+    return nullptr;
+  }
+  std::shared_ptr<B2CachedIndex> c;
+  for (size_t i = 0; i < g_cache.size(); ++i) {
+    B2CachedIndex& e = *g_cache[i];
+    if (e.prefix != prefix || e.ignore_alt != (ignore_alt != 0)) continue;
+    if (e.bwt_size != sz || e.bwt_mtime_ns != mt) {  // the files changed under this name: forget the stale image
+      g_cache.erase(g_cache.begin() + i);
+      break;
+    }
+    c = g_cache[i];
+    break;
+  }
+  B2Opt opt0;
+  b2_opt_init(&opt0);
+  bool fresh = false;
+  if (!c) {
+    c.reset(new B2CachedIndex);
+    c->prefix = prefix; c->bwt_size = sz; c->bwt_mtime_ns = mt; c->ignore_alt = ignore_alt != 0;
+    c->host.reset(new B2IndexHost);
+    fresh = true;
+  }
+  for (size_t di = 0; di < devices.size(); ++di) {
+    const int d = devices[di];
+    int ord = 0;
+    for (size_t k = 0; k < di; ++k) if (devices[k] == d) ++ord;
+    if (c->on_device(d, ord)) continue;
+    std::unique_ptr<B2Engine> e(new B2Engine);
+    B2EngineConfig cfg;
+    cfg.verbose = verbose;
+    b2_engine_config_from_env(&cfg);
+    cfg.device = d;
+    if (c->engines.empty()) {
+      if (b2_load_index(prefix, c->host.get(), verbose, 0)) return nullptr;
+      if (ignore_alt) for (auto& a : c->host->anns) a.is_alt = 0;
+      if (e->init(*c->host, opt0, "", cfg)) { set_err("%s", e->last_error()); return nullptr; }
+      // the host copies of the big arrays are no longer needed once they are in HBM
+      std::vector<uint32_t>().swap(c->host->bwt);
+      std::vector<uint64_t>().swap(c->host->sa);
+      std::vector<uint8_t>().swap(c->host->pac);
+    } else {
+      // fan out: copy from the engine that was created log2 steps ago (0 -> 1, then 0 -> 2 and 1 -> 3, ...), so the
+      // sources of successive copies are different GPUs (the copies themselves are queued per destination device)
+      size_t k = c->engines.size(), p2 = 1;
+      while (p2 * 2 <= k) p2 *= 2;
+      if (e->init_from_peer(*c->host, *c->engines[k - p2], opt0, "", cfg)) { set_err("%s", e->last_error()); return nullptr; }
+    }
+    c->engines.push_back(std::move(e));
+  }
+  if (fresh) g_cache.push_back(c);
+  if (out) {
+    out->clear();
+    for (size_t di = 0; di < devices.size(); ++di) {
+      int ord = 0;
+      for (size_t k = 0; k < di; ++k) if (devices[k] == devices[di]) ++ord;
+      out->push_back(c->on_device(devices[di], ord));
+    }
+  }
+  return c;
+}
 
 B2Engine* b2_get_engine(const char* prefix, int device, int ignore_alt, const B2Opt& opt, const char* rg_id, int verbose,
                         B2IndexHost** host_out) {
-  std::lock_guard<std::mutex> lk(g_cache_mu);
-  for (auto& c : g_cache)
-    if (c->prefix == prefix && c->device == device && c->ignore_alt == (ignore_alt != 0)) {
-      c->engine->set_options(opt, rg_id, verbose);
-      if (host_out) *host_out = c->host.get();
-      return c->engine.get();
-    }
-  std::unique_ptr<CachedIndex> c(new CachedIndex);
-  c->prefix = prefix; c->device = device; c->ignore_alt = ignore_alt != 0;
-  c->host.reset(new B2IndexHost);
-  if (b2_load_index(prefix, c->host.get(), verbose, 0)) return 0;
-  if (ignore_alt) for (auto& a : c->host->anns) a.is_alt = 0;
-  c->engine.reset(new B2Engine);
-  B2EngineConfig cfg;
-  cfg.device = device;
-  cfg.verbose = verbose;
-  b2_engine_config_from_env(&cfg);
-  if (c->engine->init(*c->host, opt, rg_id, cfg)) { set_err("%s", c->engine->last_error()); return 0; }
-  // the host copies of the big arrays are no longer needed once they are in HBM
-  std::vector<uint32_t>().swap(c->host->bwt);
-  std::vector<uint64_t>().swap(c->host->sa);
-  std::vector<uint8_t>().swap(c->host->pac);
+  std::vector<B2Engine*> engs;
+  std::shared_ptr<B2CachedIndex> c = b2_get_engines(prefix, std::vector<int>(1, device), ignore_alt, verbose, &engs);
+  if (!c) return 0;
+  B2Engine* e = engs[0];
+  e->set_options(opt, rg_id, verbose);
   if (host_out) *host_out = c->host.get();
-  B2Engine* e = c->engine.get();
-  g_cache.push_back(std::move(c));
   return e;
+}
+
+// drops every cached device image that no call is using (the executor is about to load a different index, or wants
+// its HBM back); returns the number of entries released
+int b2_index_cache_evict() {
+  std::lock_guard<std::mutex> lk(g_cache_mu);
+  int n = 0;
+  for (size_t i = 0; i < g_cache.size();) {
+    if (g_cache[i].use_count() == 1 && g_cache[i]->run_mu.try_lock()) {
+      g_cache[i]->run_mu.unlock();
+      g_cache.erase(g_cache.begin() + i);
+      ++n;
+    } else ++i;
+  }
+  return n;
 }
 
 void b2_engine_config_from_env(B2EngineConfig* cfg) {
@@ -961,18 +1267,52 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     fprintf(stderr, "b200bwa accepts the option set of bwa-0.7.15 `mem` (see bwa.1).\n\n");
     return 1;
   }
-  std::lock_guard<std::mutex> run_lock(g_run_mu);
   B2Opt opt = m.opt;
   B2SeqReader ks, ks2;
   bool have2 = false;
+  const int chunk = m.fixed_chunk_size > 0 ? m.fixed_chunk_size : opt.chunk_size * opt.n_threads;
+  // Devices of this call (the -K batches of ONE job are dealt over the GPUs of the box, batch b to
+  // device b mod G, each carrying its absolute n_processed; one ordered output).  B200BWA_DEVICES = "all" or a
+  // comma-separated list; B200BWA_DEVICE = one device; default: every visible device, but no more than the input
+  // can keep busy (estimated from the file sizes: about 45 % of a FASTQ file's bytes are bases).
+  std::vector<int> devices;
+  {
+    const char* ds = getenv("B200BWA_DEVICES");
+    const int n_vis = b2_device_count();
+    if (ds && strcmp(ds, "all") != 0) {
+      for (const char* p = ds; *p;) {
+        char* e;
+        long v = strtol(p, &e, 10);
+        if (e == p) break;
+        devices.push_back((int)v);
+        p = *e == ',' ? e + 1 : e;
+      }
+    } else if (!ds && getenv("B200BWA_DEVICE")) devices.push_back(atoi(getenv("B200BWA_DEVICE")));
+    else {
+      double bases = 0;
+      bool known = true;
+      for (size_t i = 1; i < m.positional.size(); ++i) {
+        struct stat st;
+        if (stat(m.positional[i].c_str(), &st) == 0 && S_ISREG(st.st_mode)) bases += 0.45 * (double)st.st_size;
+        else known = false;
+      }
+      int want = n_vis < 1 ? 1 : n_vis;
+      if (known && !ds) { double nb = ceil(bases / (double)(chunk > 0 ? chunk : 1)); if (nb < want) want = nb < 1 ? 1 : (int)nb; }
+      for (int d = 0; d < want; ++d) devices.push_back(d);
+    }
+    if (devices.empty()) devices.push_back(0);
+  }
+  const int G = (int)devices.size();
   // index first (same order of failure modes as the reference: index, then reads)
-  B2IndexHost* host = 0;
-  int device = 0;
-  if (getenv("B200BWA_DEVICE")) device = atoi(getenv("B200BWA_DEVICE"));
+  std::vector<B2Engine*> engs;
+  std::shared_ptr<B2CachedIndex> cached;
+  auto get_engines = [&]() -> bool {
+    cached = b2_get_engines(m.positional[0].c_str(), devices, m.ignore_alt, m.verbose, &engs);
+    return cached != nullptr;
+  };
   if (ks.open(m.positional[1].c_str())) {
     // the reference loads the index before opening the reads; keep its message and code
-    B2Engine* probe = b2_get_engine(m.positional[0].c_str(), device, m.ignore_alt, opt, m.rg_id.c_str(), m.verbose, &host);
-    if (!probe) return 1;
+    if (!get_engines()) return 1;
     if (m.verbose >= 1) fprintf(stderr, "[E::main_mem] fail to open file `%s'.\n", m.positional[1].c_str());
     return set_err("fail to open file `%s'", m.positional[1].c_str());
   }
@@ -989,8 +1329,12 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     }
   }
   const bool smart = (opt.flag & B2_F_SMARTPE) != 0;  // interleaved input: pairs are adjacent reads with equal names
-  B2Engine* eng = b2_get_engine(m.positional[0].c_str(), device, m.ignore_alt, opt, m.rg_id.c_str(), m.verbose, &host);
-  if (!eng) return 1;
+  if (!get_engines()) return 1;
+  // one aligning call at a time per index (the engines' stream/buffer sets and options are per index); calls on
+  // other indices proceed concurrently
+  std::lock_guard<std::mutex> run_lock(cached->run_mu);
+  B2IndexHost* host = cached->host.get();
+  for (B2Engine* e : engs) e->set_options(opt, m.rg_id.c_str(), m.verbose);
 
   // Output.  A regular file (what SparkBWA passes with -f) is written with positioned writes issued by the GPU
   // worker threads straight from their pinned D2H buffers: a batch's offset is the header plus the sizes of all
@@ -1038,23 +1382,23 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     else fwrite(hdr.data(), 1, hdr.size(), out);
   }
 
-  const int chunk = m.fixed_chunk_size > 0 ? m.fixed_chunk_size : opt.chunk_size * opt.n_threads;
   const B2Pes* pes0 = m.has_pes0 ? m.pes0 : 0;
-  const int n_workers = eng->n_workers();
+  const int n_workers = engs[0]->n_workers();
 
   // Pipeline (kt_pipeline's three ordered steps): reader thread (record boundaries only) -> GPU workers (pack,
   // upload, kernels, download, positioned write) -> this thread (ordered bookkeeping / ordered writer).
   std::mutex mu;
   std::condition_variable cv;
-  std::deque<std::shared_ptr<Job>> todo, inorder;
+  std::vector<std::deque<std::shared_ptr<Job>>> todo(G);  // one queue per device
+  std::deque<std::shared_ptr<Job>> inorder;
   std::deque<std::shared_ptr<Job>> unassigned;  // positioned mode: jobs in order whose offset is not yet known
   bool read_done = false, failed = write_failed;
   std::string errmsg;
-  const size_t max_inflight = (size_t)n_workers + 2;
+  const size_t max_inflight = (size_t)G * ((size_t)n_workers + 2);
 
   std::thread reader([&]() {
     int64_t n_processed = 0;
-    int64_t batch_index = 0;
+    int64_t batch_index = 0, dealt = 0;
     for (;;) {
       std::shared_ptr<Job> j(new Job);
       j->raw.reset(new B2RawBatch);
@@ -1069,7 +1413,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
       if (failed) break;
-      todo.push_back(j);
+      todo[dealt++ % G].push_back(j);
       inorder.push_back(j);
       if (positioned) unassigned.push_back(j);
       cv.notify_all();
@@ -1080,39 +1424,57 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   });
 
   std::vector<std::thread> gpu;
-  for (int wi = 0; wi < n_workers; ++wi)
-    gpu.emplace_back([&, wi]() {
+  for (int dv = 0; dv < G; ++dv)
+   for (int wi = 0; wi < n_workers; ++wi)
+    gpu.emplace_back([&, dv, wi]() {
       B2HostBatch hb;
+      B2Engine* eng = engs[dv];
+      std::deque<std::shared_ptr<Job>>& q = todo[dv];
       for (;;) {
         std::shared_ptr<Job> j;
         {
           std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&] { return !todo.empty() || read_done || failed; });
-          if (failed || (todo.empty() && read_done)) return;
-          j = todo.front();
-          todo.pop_front();
+          cv.wait(lk, [&] { return !q.empty() || read_done || failed; });
+          if (failed || (q.empty() && read_done)) return;
+          j = q.front();
+          q.pop_front();
         }
         double ct = b2_cputime(), rt = b2_realtime();
-        b2_pack_batch(*j->raw, m.copy_comment, &hb);
-        j->raw.reset();
-        const double t_packed = b2_realtime();
         const char* data = 0;
         size_t len = 0;
         int rc;
-        if (smart) {
+        const bool raw_path = j->raw->compact && !smart;
+        int n_reads_job = (int)j->raw->n_reads();
+        if (raw_path) {
+          // plain FASTQ from mapped files: ship the bytes, the device packs (k_ingest_*)
+          B2RawInput in;
+          const B2RawBatch& rb = *j->raw;
+          in.n_files = rb.n_files; in.n_reads = n_reads_job; in.max_len = rb.max_len; in.copy_comment = m.copy_comment;
+          in.n_bases = rb.n_bases; in.n_processed = rb.n_processed;
+          for (int f = 0; f < rb.n_files; ++f) { in.base[f] = rb.cbase[f]; in.recs[f] = rb.crec[f].data(); in.n_recs[f] = rb.crec[f].size(); }
+          rc = positioned ? eng->process_raw_view(in, pes0, wi, &data, &len) : eng->process_raw(in, pes0, j->sam, wi);
+          j->raw.reset();
+        } else {
+          expand_compact(j->raw.get());
+          b2_pack_batch(*j->raw, m.copy_comment, &hb);
+          j->raw.reset();
+        }
+        const double t_packed = b2_realtime();
+        if (raw_path) {
+        } else if (smart) {
           rc = process_smart(eng, hb, pes0, wi, m.verbose, j->sam);
           data = j->sam.data(); len = j->sam.size();
         } else rc = positioned ? eng->process_view(hb, pes0, wi, &data, &len) : eng->process(hb, pes0, j->sam, wi);
         if (m.verbose >= 3 && !rc)
-          fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", hb.n_reads,
+          fprintf(stderr, "[M::mem_process_seqs] Processed %d reads in %.3f CPU sec, %.3f real sec\n", n_reads_job,
                   b2_cputime() - ct, b2_realtime() - rt);
         const double t_gpu = b2_realtime();
         if (getenv("B200BWA_TIMES") && !rc) {
           const B2StageTimes& t = eng->times(wi);
-          fprintf(stderr, "[T::b200bwa] worker %d batch %ld: start %.1f ms, pack %.1f ms, upload+kernels+download %.1f ms (wall)\n", wi,
-                  (long)j->index, (rt - t_real) * 1e3, (t_packed - rt) * 1e3, (t_gpu - t_packed) * 1e3);
+          fprintf(stderr, "[T::b200bwa] device %d worker %d batch %ld (%s): start %.1f ms, pack %.1f ms, upload+kernels+download %.1f ms (wall)\n", eng->device(), wi,
+                  (long)j->index, raw_path ? "device ingest" : "host pack", (rt - t_real) * 1e3, (t_packed - rt) * 1e3, (t_gpu - t_packed) * 1e3);
           fprintf(stderr, "[T::b200bwa] worker %d reads %d: h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f rescue %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
-                  wi, hb.n_reads, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
+                  wi, n_reads_job, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
                   t.launches, (long)t.n_seed_tasks, (long)t.n_regs, (long)t.sam_bytes);
         }
         if (positioned && !rc) {
@@ -1170,7 +1532,11 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   }
   reader.join();
   for (auto& t : gpu) t.join();
-  if (rc) set_err("%s", errmsg.empty() ? eng->last_error() : errmsg.c_str());
+  if (rc) {
+    std::string em = errmsg;
+    for (B2Engine* e : engs) if (em.empty() && e->last_error()[0]) em = e->last_error();
+    set_err("%s", em.c_str());
+  }
   if (fidx) fclose(fidx);
   if (positioned) { if (::close(out_fd) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }
   else if (out_path) { if (fclose(out) != 0 && !rc) { rc = 1; set_err("close error on SAM output"); } }

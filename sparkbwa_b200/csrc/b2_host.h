@@ -29,13 +29,23 @@ struct B2RecView {
 };
 
 // One -K batch as record views: what the reader thread produces; a GPU worker thread packs it (b2_pack_batch).
+// Two forms: `compact` (every record is a plain 4-line FASTQ record of a mapped file: descriptors only, the device
+// does the packing) or views (anything else: packed on the host by b2_pack_batch).
 struct B2RawBatch {
   std::vector<B2RecView> recs;
   int64_t n_bases = 0, n_processed = 0;
+  bool compact = false;
+  int n_files = 0, max_len = 0;
+  const unsigned char* cbase[2] = {0, 0};
+  std::vector<B2Rec> crec[2];
+  size_t n_reads() const { return compact ? crec[0].size() + crec[1].size() : recs.size(); }
   std::vector<std::unique_ptr<char[]>> arena;  // copies of the records that do not live in a mapped file
   size_t arena_used = 0, arena_cap = 0;
   char* hold(const char* p, size_t n);
-  void clear() { recs.clear(); arena.clear(); arena_used = arena_cap = 0; n_bases = 0; }
+  void clear() {
+    recs.clear(); arena.clear(); arena_used = arena_cap = 0; n_bases = 0;
+    compact = false; n_files = 0; max_len = 0; crec[0].clear(); crec[1].clear(); cbase[0] = cbase[1] = 0;
+  }
 };
 
 class B2SeqReader {  // kseq_read semantics, bwa/kseq.h:175-215
@@ -47,6 +57,12 @@ class B2SeqReader {  // kseq_read semantics, bwa/kseq.h:175-215
   int next();  // >= 0 length, -1 EOF, -2 truncated quality
   // same, returning views; *stable: the views stay valid until close() (mapped file), else until the next call
   int next_view(B2RecView* v, bool* stable);
+  // the records the scan-ahead has ready, as descriptors into the mapping (false: none, use next_view); advance(k)
+  // consumes the first k of them
+  bool span(const B2Rec** p, size_t* n);
+  void advance(size_t k);
+  const unsigned char* map_base() const;
+  static void view_of(const unsigned char* base, const B2Rec& r, B2RecView* v);
   const std::string& name() const;
   const std::string& comment() const;
   const std::string& seq() const;
@@ -62,6 +78,7 @@ void b2_pack_batch(const B2RawBatch& rb, int copy_comment, B2HostBatch* b);
 void b2_engine_config_from_env(B2EngineConfig* cfg);
 B2Engine* b2_get_engine(const char* prefix, int device, int ignore_alt, const B2Opt& opt, const char* rg_id, int verbose,
                         B2IndexHost** host_out);
+int b2_index_cache_evict();  // releases every cached device image no call is using; returns how many
 // argv[0] = "mem"; out_path null = stdout; pg_cmdline = full @PG line or null
 int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdline);
 

@@ -763,3 +763,73 @@ B2_KERNEL k_gather(B2Ctx c, int n_items) {
     for (int k = b; k < e; ++k) dst[k] = src[k];
   }
 }
+
+// ---------------------------------------------------------------------------------------------
+// Read ingest on the device (bseq_read's per-record work, bwa/bwa.c:42-75): the host ships the raw FASTQ bytes of a
+// batch plus one descriptor per record; these kernels trim the read-number suffix of the name (trim_readno,
+// bwa/bwa.c:27-31), split off the comment (kseq: the header up to the first white space is the name, bwa/kseq.h:181-193),
+// translate the bases with nst_nt4_table (bwa/bwamem.c:1025) and lay the batch out as B2Batch.
+struct B2Ingest {
+  const uint8_t* raw;        // staged file bytes
+  const B2Rec* recs[2];      // per input file
+  int64_t adj[2];            // raw + rec.off + adj[f] = address of the record's '@'
+  int n_files, n_reads, copy_comment;
+  uint8_t* seq; char* qual; uint8_t* has_qual; char* names; char* comments;
+  const int64_t *seq_off, *name_off, *com_off;
+  int32_t *l_seq, *l_name, *l_com, *com_cnt;
+};
+
+B2_HD inline const uint8_t* b2_ingest_rec(const B2Ingest& g, int r, B2Rec* rec) {
+  const int f = g.n_files == 2 ? (r & 1) : 0;
+  const int i = g.n_files == 2 ? (r >> 1) : r;
+  *rec = g.recs[f][i];
+  return g.raw + (int64_t)rec->off + g.adj[f];
+}
+
+B2_KERNEL k_ingest_len(B2Ingest g) {
+  for (int r = B2_GTID(); r < g.n_reads; r += B2_GSIZE()) {
+    B2Rec rec;
+    const uint8_t* p = b2_ingest_rec(g, r, &rec);
+    uint32_t l = rec.l_name;
+    if (l > 2 && p[1 + l - 2] == '/' && p[1 + l - 1] >= '0' && p[1 + l - 1] <= '9') l -= 2;
+    g.l_seq[r] = (int32_t)rec.l_seq;
+    g.l_name[r] = (int32_t)l;
+    const int lc = (g.copy_comment && rec.l_hdr > rec.l_name + 1) ? (int)(rec.l_hdr - rec.l_name - 1) : -1;
+    g.l_com[r] = lc;
+    g.com_cnt[r] = lc > 0 ? lc : 0;
+    g.has_qual[r] = 1;
+  }
+}
+
+B2_KERNEL k_ingest_copy(B2Ingest g) {
+  const int64_t total = (int64_t)g.n_reads * 4;
+  for (int64_t t = B2_GTID(); t < total; t += B2_GSIZE()) {
+    const int r = (int)(t >> 2), part = (int)(t & 3);
+    B2Rec rec;
+    const uint8_t* p = b2_ingest_rec(g, r, &rec);
+    if (part == 0) {
+      const uint8_t* src = p + 1 + rec.l_hdr + 1;
+      uint8_t* dst = g.seq + g.seq_off[r];
+      for (uint32_t k = 0; k < rec.l_seq; ++k) {
+        const uint32_t ch = src[k] | 0x20u;  // nst_nt4_table: A/a 0, C/c 1, G/g 2, T/t 3, everything else 4
+        dst[k] = ch == 'a' ? 0 : ch == 'c' ? 1 : ch == 'g' ? 2 : ch == 't' ? 3 : 4;
+      }
+    } else if (part == 1) {
+      const uint8_t* src = p + rec.qual_rel;
+      char* dst = g.qual + g.seq_off[r];
+      for (uint32_t k = 0; k < rec.l_seq; ++k) dst[k] = (char)src[k];
+    } else if (part == 2) {
+      const uint8_t* src = p + 1;
+      char* dst = g.names + g.name_off[r];
+      const int l = g.l_name[r];
+      for (int k = 0; k < l; ++k) dst[k] = (char)src[k];
+    } else {
+      const int l = g.l_com[r];
+      if (l > 0) {
+        const uint8_t* src = p + 1 + rec.l_name + 1;
+        char* dst = g.comments + g.com_off[r];
+        for (int k = 0; k < l; ++k) dst[k] = (char)src[k];
+      }
+    }
+  }
+}

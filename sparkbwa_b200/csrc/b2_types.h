@@ -111,6 +111,11 @@ struct B2Reg {
   uint64_t hash;
 };
 
+// A plain 4-line FASTQ record inside a memory-mapped input file, as found by the reader's scan: position of its '@',
+// sequence length, header-line length (after '@'), name length (up to the first white space), offset of the quality
+// line relative to the '@'.  The device parses / trims / encodes reads from these (k_ingest_*).
+struct B2Rec { uint64_t off; uint32_t l_seq, l_hdr, l_name, qual_rel; };
+
 struct B2Pes {
   int low, high;
   int failed;

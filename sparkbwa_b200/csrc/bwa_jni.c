@@ -21,7 +21,6 @@
 
 #ifdef B2_HAVE_JNI_H
 #include <jni.h>
-#define B2_CALL(env, slot, name) ((*env)->name)
 #else
 typedef int jint;
 typedef int jsize;
@@ -58,15 +57,23 @@ JNIEXPORT jint JNICALL Java_com_github_sparkbwa_BwaJni_bwa_1jni(JNIEnv* env, job
   const char** utf = (const char**)calloc((size_t)n, sizeof(char*));
   char** argv = (char**)calloc((size_t)n + 1, sizeof(char*));
   const char* out = 0;
-  int i, na = 0, ret;
-  for (i = 0; i < n; ++i) {
+  int i, na = 0, ret = 1, bad = 0;
+  if (!js || !utf || !argv) { free(js); free(utf); free(argv); return 1; }
+  for (i = 0; i < n && !bad; ++i) {
+    /* a null String element, or a NULL from GetStringUTFChars (out of memory, exception pending): give up with
+     * rc 1 after releasing what was acquired -- nothing may crash the executor JVM */
 #ifdef B2_HAVE_JNI_H
     js[i] = (jstring)(*env)->GetObjectArrayElement(env, stringArray, i);
-    utf[i] = (*env)->GetStringUTFChars(env, js[i], 0);
+    utf[i] = js[i] ? (*env)->GetStringUTFChars(env, js[i], 0) : 0;
 #else
     js[i] = (jstring)GetObjectArrayElement(env, stringArray, i);
-    utf[i] = GetStringUTFChars(env, js[i], 0);
+    utf[i] = js[i] ? GetStringUTFChars(env, js[i], 0) : 0;
 #endif
+    if (!utf[i]) bad = 1;
+  }
+  if (bad) {
+    fprintf(stderr, "[%s] null or unreadable argument string; nothing run\n", __func__);
+    goto release;
   }
   for (i = 0; i < n; ++i) {
     if (strcmp(utf[i], "-f") == 0 && i < n - 1) { out = utf[++i]; continue; } /* output file, not an aligner option */
@@ -75,7 +82,9 @@ JNIEXPORT jint JNICALL Java_com_github_sparkbwa_BwaJni_bwa_1jni(JNIEnv* env, job
   fprintf(stderr, "[%s] %d arguments, output '%s'\n", __func__, na, out ? out : "(stdout)");
   ret = b200bwa_main_to(na, argv, out);
   fprintf(stderr, "[%s] Return code from BWA %d.\n", __func__, ret);
+release:
   for (i = 0; i < n; ++i) {
+    if (!utf[i]) continue;
 #ifdef B2_HAVE_JNI_H
     (*env)->ReleaseStringUTFChars(env, js[i], utf[i]);
 #else

@@ -10,7 +10,8 @@ static char** g_args; static int g_n; static int g_released;
 static const char* GetStringUTFChars(JNIEnv* e, void* s, unsigned char* c) { (void)e; (void)c; return (const char*)s; }
 static void ReleaseStringUTFChars(JNIEnv* e, void* s, const char* u) { (void)e; (void)s; (void)u; ++g_released; }
 static int GetArrayLength(JNIEnv* e, void* a) { (void)e; (void)a; return g_n; }
-static void* GetObjectArrayElement(JNIEnv* e, void* a, int i) { (void)e; (void)a; return g_args[i]; }
+/* the literal argument "@NULL@" stands for a null String element */
+static void* GetObjectArrayElement(JNIEnv* e, void* a, int i) { (void)e; (void)a; return strcmp(g_args[i], "@NULL@") ? g_args[i] : 0; }
 int main(int argc, char** argv) {
   void* h = dlopen(argv[1], RTLD_NOW);
   if (!h) { fprintf(stderr, "dlopen: %s\n", dlerror()); return 99; }

@@ -142,6 +142,9 @@ def test_jni_symbol_through_fake_env(tmp_path):
                        stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert b"rc=1 released=6" in r.stdout, (r.stdout, r.stderr)
     assert b"invalid option" not in r.stderr
+    # a null String element must not reach strcmp(): rc 1, the strings acquired so far are released
+    r = subprocess.run([exe, LIB, "bwa", "mem", "@NULL@", "r.fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert b"rc=1 released=2" in r.stdout, (r.stdout, r.stderr)
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
@@ -234,3 +237,52 @@ def test_reader_paths_match_oracle(hostsim, workdir):
         o1 = pu.engine_sam(c1, hostsim, env=pu.HOSTSIM_ENV)
         assert not pu.first_diff(r1, o1), fq
         assert len(pu.sam_body(o1)) > 300
+
+
+# ---- one job over several devices; parallel scan + device-side ingest -----------------------------
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_hostsim_one_job_over_several_engines(hostsim, workdir):
+    """b2_mem_main deals the -K batches of ONE job over G engines (batch b -> engine b mod G, each batch carrying its
+    absolute n_processed) and writes one ordered SAM (kt_pipeline's ordering, bwa/kthread.c:92-102, bwa/fastmap.c:84-89).
+    The host checker build pretends to have three devices; the SAM must not depend on G."""
+    c = pu.make_case(workdir, "pe150")
+    ref = pu.oracle_sam(c)
+    for devs in ("0", "0,1,2", "1,1"):
+        our = pu.engine_sam(c, hostsim, env=dict(pu.HOSTSIM_ENV, B200BWA_DEVICES=devs, B200BWA_WORKERS="2",
+                                                 B200BWA_HOSTSIM_DEVICES="3"))
+        assert not pu.first_diff(ref, our), devs
+    # through a pipe (ordered-writer path instead of positioned writes)
+    our = pu.engine_sam(c, hostsim, env=dict(pu.HOSTSIM_ENV, B200BWA_DEVICES="0,1,2", B200BWA_WORKERS="2"), via_f=False)
+    assert not pu.first_diff(ref, our)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_parallel_scan_and_device_ingest(hostsim, workdir):
+    """The mapped input is scanned in chunks by several threads, each guessing its first record start; the reader
+    accepts a chunk only if it starts where the previous one ended.  Tiny chunks (every record straddles a boundary),
+    one or many threads, SparkBWA's own file shape (a blank line after every record, BwaPairedAlignment.java:86-105) and
+    a last record without newline must all give the batches -- and through the device-side packing (k_ingest_*: name
+    trimming, nt4 codes) the SAM -- of the reference's kseq + bseq_read."""
+    c = pu.make_case(workdir, "pe_small")
+    sp = []
+    for f in c["fq"]:
+        g = f + ".spark"
+        recs = open(f, "rb").read().split(b"\n")
+        with open(g, "wb") as fo:
+            n = (len(recs) - 1) // 4
+            for k in range(n):
+                fo.write(b"\n".join(recs[4 * k:4 * k + 4]) + b"\n" + (b"\n" if k < n - 1 else b""))
+        sp.append(g)
+    c_sp = dict(c, fq=sp)
+    for K in ("30000", "7000"):
+        ref = pu.oracle_sam(dict(c_sp, opts=["-K", K, "-C"]))
+        assert not pu.first_diff(ref, pu.oracle_sam(dict(c, opts=["-K", K, "-C"])))
+        for env in ({}, {"B200BWA_SCAN_CHUNK": "100"}, {"B200BWA_SCAN_CHUNK": "1000", "B200BWA_SCAN_THREADS": "7"},
+                    {"B200BWA_SCAN_CHUNK": "64", "B200BWA_SCAN_THREADS": "1"}, {"B200BWA_NO_COMPACT": "1"}):
+            for cc in (c, c_sp):
+                r = subprocess.run([hostsim, "mem", "-K", K, "-C", "-f", os.path.join(c["dir"], "scan.sam"), cc["ref"]] + cc["fq"],
+                                   env=dict(os.environ, B200BWA_TIMES="1", **pu.HOSTSIM_ENV, **env), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+                assert r.returncode == 0, r.stderr[-1000:]
+                assert not pu.first_diff(ref, os.path.join(c["dir"], "scan.sam")), (K, env)
+                want = b"host pack" if "B200BWA_NO_COMPACT" in env else b"device ingest"
+                assert want in r.stderr and (b"host pack" if want == b"device ingest" else b"device ingest") not in r.stderr

@@ -237,3 +237,34 @@ def test_config3_scale_single_end_250bp(tmp_path_factory):
         _compare_with_oracle(_lib(), d, "se250", [], prefix, [fq], n)
     finally:
         os.remove(fq)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_one_job_over_several_engines_matches_oracle(workdir):
+    """ONE call, several engines: the -K batches of the job are dealt round-robin over the devices (each with its absolute
+    n_processed), SAM blocks land in input order (bwa/kthread.c:92-102, bwa/fastmap.c:84-89).  On a multi-GPU box this
+    uses every visible GPU (index fanned out device to device); on a single GPU the same device is listed twice, which
+    gives two engines with their own index copy, streams and buffers -- the same dealing/ordering code."""
+    import torch
+    n = torch.cuda.device_count()
+    devs = "all" if n >= 2 else "0,0"
+    c = pu.make_case(workdir, "pe150")   # -K 300000: three batches
+    ref = pu.oracle_sam(c)
+    our = pu.engine_sam(c, pu.CLI, env={"B200BWA_DEVICES": devs, "B200BWA_TIMES": "1"})
+    assert not pu.first_diff(ref, our)
+    # smaller batches: 15 of them over the engines, and through a pipe (ordered writer instead of positioned writes)
+    c2 = dict(c, opts=["-K", "60000"])
+    ref2 = pu.oracle_sam(c2)
+    for via_f in (True, False):
+        our2 = pu.engine_sam(c2, pu.CLI, env={"B200BWA_DEVICES": devs}, via_f=via_f)
+        assert not pu.first_diff(ref2, our2)
+
+
+def test_device_ingest_is_the_path_taken(tmp_path):
+    """Plain FASTQ files are packed on the device (k_ingest_*), not by host threads."""
+    out = str(tmp_path / "o.sam")
+    r = subprocess.run([pu.CLI, "mem", "-K", "20000", "-f", out, os.path.join(GOLD, "ref.fa"), os.path.join(GOLD, "pe_1.fq"),
+                        os.path.join(GOLD, "pe_2.fq")], env=dict(os.environ, B200BWA_TIMES="1"), stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr[-2000:]
+    assert b"device ingest" in r.stderr and b"host pack" not in r.stderr
+    assert pu.sam_body(out) == pu.sam_body(os.path.join(GOLD, "pe.sam"))
