@@ -46,6 +46,18 @@ int b200bwa_mem(int argc, char** argv, const char* out_path);
  * releases every cached image that no running call uses; returns the number released. */
 int b200bwa_index_cache_evict(void);
 
+/* The steps either side of the path, Spark-free:
+ * b200bwa_reduce_sam     SparkBWA's reducer, java/com/github/sparkbwa/BwaInterpreter.java:342-376: concatenates the
+ *                        partitions' SAM files in order, keeps '@' lines of the first file only, deletes the inputs
+ *                        when delete_inputs != 0 (the reference always does).
+ * b200bwa_run_partitions the map step, BwaInterpreter.java:301-319 over BwaPairedAlignment / BwaSingleAlignment:
+ *                        partition p (fq1[p] [, fq2[p]]; fq2 may be NULL) -> one `mem` call with the option tokens
+ *                        `opts` -> <out_dir>/<app_name>-<p>.sam (BwaAlignmentBase.java:176-178); reduce != 0 then merges
+ *                        them into <out_dir>/FullOutput.sam. */
+int b200bwa_reduce_sam(int n_inputs, const char* const* inputs, const char* out_path, int delete_inputs);
+int b200bwa_run_partitions(int n_opts, char** opts, const char* idxbase, int n_parts, const char* const* fq1,
+                           const char* const* fq2, const char* out_dir, const char* app_name, int reduce);
+
 /* Last error message of the calling thread's most recent failing call ("" if none). */
 const char* b200bwa_last_error(void);
 

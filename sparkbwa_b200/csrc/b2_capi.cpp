@@ -63,6 +63,17 @@ int b200bwa_main(int argc, char** argv) { return b200bwa_main_to(argc, argv, 0);
 
 int b200bwa_index_cache_evict(void) { return b2_index_cache_evict(); }
 
+int b200bwa_reduce_sam(int n_inputs, const char* const* inputs, const char* out_path, int delete_inputs) {
+  try { b2_tls_error.clear(); return b2_reduce_sam(n_inputs, inputs, out_path, delete_inputs); }
+  catch (const std::exception& e) { b2_tls_error = e.what(); return 1; }
+}
+
+int b200bwa_run_partitions(int n_opts, char** opts, const char* idxbase, int n_parts, const char* const* fq1,
+                           const char* const* fq2, const char* out_dir, const char* app_name, int reduce) {
+  try { b2_tls_error.clear(); return b2_run_partitions(n_opts, opts, idxbase, n_parts, fq1, fq2, out_dir, app_name, reduce); }
+  catch (const std::exception& e) { b2_tls_error = e.what(); return 1; }
+}
+
 }  // extern "C"
 
 // ---------------------------------------------------------------------------------------------

@@ -84,6 +84,8 @@ struct Worker {
   unsigned long long h_counters[16] = {0};
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;
   size_t scratch_per_lane = 0;
+  int clean_batches = 0, decay_wait = 4;   // batches without a scratch overflow / how many of them before the size is halved again
+  bool tried_decay = false;
   int cap_intv = 0, slot_size = 0;
   // resident batch metadata
   int n_reads = 0, max_len = 0;
@@ -92,7 +94,10 @@ struct Worker {
   int n_reads_run = 0;
   B2StageTimes times;
   std::vector<int8_t> h_dir; std::vector<int64_t> h_is; std::vector<char> h_sam;
-  void* pin_sam = nullptr; size_t pin_sam_cap = 0, last_sam_bytes = 0;
+  // two pinned SAM buffers used in turn: the caller may still be writing batch i's text to the output file while
+  // batch i+1 is computed and downloaded (process_view's pointer stays valid until the second next call)
+  void* pin_sams[2] = {nullptr, nullptr}; size_t pin_sam_caps[2] = {0, 0}; int sam_flip = 0;
+  void* pin_sam = nullptr; size_t last_sam_bytes = 0;
   // raw-FASTQ ingest: pinned staging of the batch's file bytes + record descriptors, and its device image
   void* pin_in = nullptr; size_t pin_in_cap = 0;
   DBuf<uint8_t> raw_in; DBuf<int32_t> com_cnt;
@@ -241,7 +246,7 @@ class B2EngineImpl {
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
       w.galn_cnt.release(); w.galn_table.release(); w.galn_off.release(); w.galn_tasks.release(); w.galn_res.release();
-      if (w.pin_sam) b2_host_free(w.pin_sam);
+      for (void* q : w.pin_sams) if (q) b2_host_free(q);
       if (w.pin_in) b2_host_free(w.pin_in);
       w.raw_in.release(); w.com_cnt.release();
 #if !defined(B2_HOSTSIM)
@@ -410,7 +415,17 @@ class B2EngineImpl {
     c.dbg = nullptr;
     // k_chain uses one lane per read, k_extend/k_final one B2_TASK_GROUP-lane group per read/pair; the scratch
     // region is indexed by lane resp. group, so size it for the larger count
-    const int lanes = cfg.lane_grid * cfg.lane_block;
+    // the scratch area is [lanes of the launch] x [bytes per lane]: when one read needs far more than the common
+    // case (long reads, wide bands: the traceback matrix of a global alignment is band x length bytes), the stage is
+    // re-run with FEWER lanes rather than with that size for every lane -- the total stays within max_scratch_bytes
+    int lane_grid = cfg.lane_grid;
+    bool overflowed = false;
+    if (w.scratch_per_lane > cfg.scratch_per_lane && w.clean_batches >= w.decay_wait) {
+      // an outlier batch grew the per-lane size: try the smaller size again (and hand the memory back)
+      w.scratch_per_lane = std::max(cfg.scratch_per_lane, w.scratch_per_lane / 2);
+      w.tried_decay = true;
+      if (w.scratch.cap > ((size_t)2 << 30)) w.scratch.release();
+    }
     int flags = 0;
     int ev_begin = w.timer.mark();
 
@@ -485,19 +500,21 @@ class B2EngineImpl {
 
     // ---- lane-per-read stages with retry on scratch overflow ----
     auto ensure_scratch = [&]() -> int {
-      if ((size_t)lanes * w.scratch_per_lane > cfg.max_scratch_bytes) return fail("per-lane scratch limit exceeded");
-      if (w.scratch.ensure((size_t)lanes * w.scratch_per_lane, true)) return fail("device allocation failed (scratch)");
+      const size_t fit = cfg.max_scratch_bytes / w.scratch_per_lane / (size_t)cfg.lane_block;
+      if (fit < 1) return fail("per-lane scratch limit exceeded (a single read needs more than B200BWA_MAX_SCRATCH)");
+      lane_grid = (int)std::min<size_t>((size_t)cfg.lane_grid, fit);
+      if (w.scratch.ensure((size_t)lane_grid * cfg.lane_block * w.scratch_per_lane, true)) return fail("device allocation failed (scratch)");
       c.scratch = w.scratch.p; c.scratch_per_lane = w.scratch_per_lane;
       return 0;
     };
     for (;;) {
       if (ensure_scratch()) return 1;
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-      B2_LAUNCH(k_chain, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      B2_LAUNCH(k_chain, lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
       if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-      w.scratch_per_lane *= 2;
+      { w.scratch_per_lane *= 2; overflowed = true; }
     }
     {  // mem_flt_chained_seeds acts only on long reads (5.5 ln l <= 0.05 l: l >= 725 with the default options)
       const double min_l = opt.min_chain_weight ? (double)(1.1f * (float)opt.min_chain_weight) : 5.5 * log((double)w.max_len);
@@ -505,12 +522,12 @@ class B2EngineImpl {
         for (;;) {
           if (ensure_scratch()) return 1;
           b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-          B2_LAUNCH(k_flt_seeds, cfg.lane_grid, cfg.lane_block, w.stream, c);
+          B2_LAUNCH(k_flt_seeds, lane_grid, cfg.lane_block, w.stream, c);
           ++w.times.launches;
           if (read_flags(w, &flags)) return 1;
           if (flags & B2_FLAG_ERR_TABLE) return fail("log table index out of range (read too long)");
           if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-          w.scratch_per_lane *= 2;
+          { w.scratch_per_lane *= 2; overflowed = true; }
         }
       }
     }
@@ -563,17 +580,17 @@ class B2EngineImpl {
       if (TC > 0) {
         b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
         const int64_t blocks_needed = (TC * B2_G_EXT + cfg.lane_block - 1) / cfg.lane_block;
-        B2_LAUNCH(k_ext_chain, (int)std::min<int64_t>(blocks_needed, cfg.lane_grid), cfg.lane_block, w.stream, c);
+        B2_LAUNCH(k_ext_chain, (int)std::min<int64_t>(blocks_needed, lane_grid), cfg.lane_block, w.stream, c);
         ++w.times.launches;
         if (read_flags(w, &flags)) return 1;
-        if (flags & B2_FLAG_OVF_SCRATCH) { w.scratch_per_lane *= 2; continue; }
+        if (flags & B2_FLAG_OVF_SCRATCH) { { w.scratch_per_lane *= 2; overflowed = true; } continue; }
       }
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-      B2_LAUNCH(k_extend, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      B2_LAUNCH(k_extend, lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
       if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-      w.scratch_per_lane *= 2;
+      { w.scratch_per_lane *= 2; overflowed = true; }
     }
     int ev_ext = w.timer.mark();
 
@@ -635,12 +652,12 @@ class B2EngineImpl {
           if (ensure_scratch()) return 1;
           b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
           const int64_t groups_needed = (T * B2_G_RESC + cfg.lane_block - 1) / cfg.lane_block;
-          const int grid = (int)std::min<int64_t>(groups_needed, cfg.lane_grid);
+          const int grid = (int)std::min<int64_t>(groups_needed, lane_grid);
           B2_LAUNCH(k_resc_sw, grid, cfg.lane_block, w.stream, c);
           ++w.times.launches;
           if (read_flags(w, &flags)) return 1;
           if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-          w.scratch_per_lane *= 2;
+          { w.scratch_per_lane *= 2; overflowed = true; }
         }
       }
     }
@@ -677,7 +694,7 @@ class B2EngineImpl {
           ++w.times.launches;
           // one-warp blocks: a batch has only a few hundred warps of these tasks, spread them over all SMs
           const int blk = std::min(cfg.lane_block, 32);
-          auto grid_for = [&](int64_t cnt) { return (int)std::min<int64_t>((cnt + blk - 1) / blk, (int64_t)cfg.lane_grid * cfg.lane_block / blk); };
+          auto grid_for = [&](int64_t cnt) { return (int)std::min<int64_t>((cnt + blk - 1) / blk, (int64_t)lane_grid * cfg.lane_block / blk); };
           if (tot[0] > 0) { B2_LAUNCH(k_galn9, grid_for(tot[0]), blk, w.stream, c); ++w.times.launches; }
           if (tot[1] > 0) { B2_LAUNCH(k_galn17, grid_for(tot[1]), blk, w.stream, c); ++w.times.launches; }
           if (tot[2] > 0) { B2_LAUNCH(k_galn33, grid_for(tot[2]), blk, w.stream, c); ++w.times.launches; }
@@ -703,13 +720,13 @@ class B2EngineImpl {
         c.dbg = w.dbg.p;
       }
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-      if (pe) B2_LAUNCH(k_final_pe, cfg.lane_grid, cfg.lane_block, w.stream, c);
-      else B2_LAUNCH(k_final_se, cfg.lane_grid, cfg.lane_block, w.stream, c);
+      if (pe) B2_LAUNCH(k_final_pe, lane_grid, cfg.lane_block, w.stream, c);
+      else B2_LAUNCH(k_final_se, lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
       if (flags & B2_FLAG_ERR_TABLE) return fail("log/pairing table index out of range");
       if (!(flags & (B2_FLAG_OVF_SCRATCH | B2_FLAG_OVF_SLOT))) break;
-      if (flags & B2_FLAG_OVF_SCRATCH) w.scratch_per_lane *= 2;
+      if (flags & B2_FLAG_OVF_SCRATCH) { w.scratch_per_lane *= 2; overflowed = true; }
       if (flags & B2_FLAG_OVF_SLOT) {
         if (w.slot_size > (1 << 24)) return fail("SAM slot limit exceeded");
         w.slot_size *= 2;
@@ -756,11 +773,15 @@ class B2EngineImpl {
     }
     int ev_d2h = ev_gat;
     if (sam || view) {
-      if ((size_t)total > w.pin_sam_cap) {
-        if (w.pin_sam) b2_host_free(w.pin_sam);
-        w.pin_sam_cap = (size_t)total + (size_t)total / 2 + ((size_t)1 << 20);  // (cudaFreeHost/cudaMallocHost stall the device too)
-        if (b2_host_alloc(&w.pin_sam, w.pin_sam_cap)) return fail("pinned host allocation failed");
+      const int fl = w.sam_flip;
+      w.sam_flip ^= 1;
+      if ((size_t)total > w.pin_sam_caps[fl]) {
+        if (w.pin_sams[fl]) b2_host_free(w.pin_sams[fl]);
+        w.pin_sams[fl] = nullptr;
+        w.pin_sam_caps[fl] = (size_t)total + (size_t)total / 2 + ((size_t)1 << 20);  // (cudaFreeHost/cudaMallocHost stall the device too)
+        if (b2_host_alloc(&w.pin_sams[fl], w.pin_sam_caps[fl])) { w.pin_sam_caps[fl] = 0; return fail("pinned host allocation failed"); }
       }
+      w.pin_sam = w.pin_sams[fl];
       b2_d2h(w.pin_sam, w.sam_out.p, (size_t)total, w.stream);
       w.d2h_bytes += (size_t)total;
       b2_g_d2h_bytes += (size_t)total;
@@ -784,6 +805,14 @@ class B2EngineImpl {
     w.times.d2h = w.timer.ms(ev_gat, ev_d2h);
     w.times.total = w.timer.ms(ev_begin, ev_d2h);
     if (ingest) w.times.h2d = w.timer.ms(ev_in0, ev_in1);
+    if (overflowed) {
+      if (w.tried_decay) w.decay_wait = std::min(w.decay_wait * 4, 4096);  // the smaller size was not enough: ask less often
+      w.clean_batches = 0;
+    } else {
+      if (w.tried_decay) w.decay_wait = 4;
+      ++w.clean_batches;
+    }
+    w.tried_decay = false;
     return 0;
   }
 };
@@ -894,6 +923,7 @@ int B2Engine::process_raw_view(const B2RawInput& in, const B2Pes* pes0, int work
   *data = (const char*)w.pin_sam; *len = w.last_sam_bytes;
   return 0;
 }
+int B2Engine::next_view_slot(int worker) const { return impl_->workers[worker].sam_flip; }
 int B2Engine::process_items(const B2HostBatch& b, const B2Pes* pes0, int worker, int paired, std::string& sam,
                             std::vector<int32_t>& item_len) {
   Worker& w = impl_->workers[worker];

@@ -60,7 +60,7 @@ struct B2EngineConfig {
   size_t scratch_per_lane = 48 << 10;
   int no_xext = 0;                             // 1: skip the inter-task seed extensions (B200BWA_NO_XEXT)
   int no_galn = 0;                             // 1: skip the speculative inter-task global alignments (B200BWA_NO_GALN)
-  size_t max_scratch_bytes = (size_t)64 << 30;
+  size_t max_scratch_bytes = (size_t)16 << 30;    // per stream/buffer set; a stage that needs more per lane runs with fewer lanes
   int n_workers = 6;                           // independent stream/buffer sets (batches in flight)
   int cap_intv = 64;
   int slot_per_read = 0;                       // 0: derived from the longest read of the batch
@@ -94,7 +94,9 @@ class B2Engine {
   // the same two calls for a batch given as raw FASTQ bytes (packing on the device)
   int process_raw(const B2RawInput& in, const B2Pes* pes0, std::string& sam, int worker);
   int process_raw_view(const B2RawInput& in, const B2Pes* pes0, int worker, const char** data, size_t* len);
-  // same, leaving the SAM text in the worker's pinned host buffer: *data stays valid until the next call on `worker`
+  // same, leaving the SAM text in one of the worker's two pinned host buffers (used in turn): *data stays valid until
+  // the SECOND next call on `worker`, so the caller can write batch i out while batch i+1 is computed
+  int next_view_slot(int worker) const;   // which of the two buffers the next *_view call on `worker` will fill
   int process_view(const B2HostBatch& b, const B2Pes* pes0, int worker, const char** data, size_t* len);
   // one batch forced single-end (paired = 0) or paired-end (1), also returning the SAM bytes of every read / pair:
   // the two halves of a smart-pairing batch (bwa/fastmap.c:64-83)

@@ -1162,6 +1162,7 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_SEED_BPS"))) cfg->seed_blocks_per_sm = atoi(s);
   if ((s = getenv("B200BWA_SEED3_BPS"))) cfg->seed3_blocks_per_sm = atoi(s);
   if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
+  if ((s = getenv("B200BWA_MAX_SCRATCH"))) cfg->max_scratch_bytes = (size_t)atoll(s);
   if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
   if ((s = getenv("B200BWA_WORKERS"))) cfg->n_workers = atoi(s);
   if ((s = getenv("B200BWA_CAP_INTV"))) cfg->cap_intv = atoi(s);
@@ -1181,6 +1182,9 @@ struct Job {
   size_t sam_size = 0;
   int64_t offset = -1;       // positioned-write mode: file offset of this batch's SAM block
   bool size_known = false;
+  const char* wdata = 0;     // positioned-write mode: the text (in a pinned buffer of the worker, or in `sam`)
+  int wslot = -1;            // which of the worker's pinned buffers (index into `busy`), -1: none
+  double t_gpu = 0;
   int rc = 0;
   bool done = false;
 };
@@ -1397,7 +1401,9 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   const size_t max_inflight = (size_t)G * ((size_t)n_workers + 2);
 
   std::thread reader([&]() {
-    int64_t n_processed = 0;
+    // B200BWA_FIRST_READ: absolute index of this input's first read within a larger run (a partition of a job that
+    // was split upstream); it enters the hash tie-breaks exactly like n_processed of bwa/fastmap.c:85
+    int64_t n_processed = getenv("B200BWA_FIRST_READ") ? atoll(getenv("B200BWA_FIRST_READ")) : 0;
     int64_t batch_index = 0, dealt = 0;
     for (;;) {
       std::shared_ptr<Job> j(new Job);
@@ -1423,6 +1429,40 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     cv.notify_all();
   });
 
+  // Positioned mode: the file writes are done by a few writer threads, so that a GPU worker starts its next batch
+  // as soon as the SAM text of the current one sits in its pinned buffer (each worker has two, used in turn).
+  std::deque<std::shared_ptr<Job>> wq;                      // jobs with an assigned offset, waiting to be written
+  std::vector<char> busy((size_t)G * n_workers * 2, 0);    // pinned buffer [device][worker][slot] still being written out
+  int gpu_active = G * n_workers;
+  const bool times = getenv("B200BWA_TIMES") != 0;
+  std::vector<std::thread> writers;
+  if (positioned) {
+    int n_writers = 2 * G;
+    if (const char* s = getenv("B200BWA_WRITERS")) n_writers = atoi(s);
+    if (n_writers < 1) n_writers = 1;
+    for (int t = 0; t < n_writers; ++t)
+      writers.emplace_back([&]() {
+        for (;;) {
+          std::shared_ptr<Job> j;
+          {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return !wq.empty() || failed || gpu_active == 0; });
+            if (failed || wq.empty()) return;
+            j = wq.front();
+            wq.pop_front();
+          }
+          const double t_w0 = b2_realtime();
+          const bool wrote = pwrite_all(j->wdata, j->sam_size, j->offset);
+          if (times) fprintf(stderr, "[T::b200bwa] batch %ld: queued for writing %.1f ms, write %.1f ms, done at %.1f ms\n", (long)j->index, (t_w0 - j->t_gpu) * 1e3, (b2_realtime() - t_w0) * 1e3, (b2_realtime() - t_real) * 1e3);
+          std::lock_guard<std::mutex> lk(mu);
+          if (j->wslot >= 0) busy[j->wslot] = 0;
+          if (!wrote) { j->rc = 1; failed = true; errmsg = "write error on SAM output"; }
+          j->done = true;
+          cv.notify_all();
+        }
+      });
+  }
+
   std::vector<std::thread> gpu;
   for (int dv = 0; dv < G; ++dv)
    for (int wi = 0; wi < n_workers; ++wi)
@@ -1430,14 +1470,21 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       B2HostBatch hb;
       B2Engine* eng = engs[dv];
       std::deque<std::shared_ptr<Job>>& q = todo[dv];
+      struct Leave { std::mutex& m; std::condition_variable& c; int& n; ~Leave() { std::lock_guard<std::mutex> lk(m); --n; c.notify_all(); } } leave{mu, cv, gpu_active};
       for (;;) {
         std::shared_ptr<Job> j;
+        int slot = -1;
         {
           std::unique_lock<std::mutex> lk(mu);
           cv.wait(lk, [&] { return !q.empty() || read_done || failed; });
           if (failed || (q.empty() && read_done)) return;
           j = q.front();
           q.pop_front();
+          if (positioned && !smart) {  // the pinned buffer this batch's text will land in must have been written out
+            slot = (dv * n_workers + wi) * 2 + eng->next_view_slot(wi);
+            cv.wait(lk, [&] { return !busy[slot] || failed; });
+            if (failed) return;
+          }
         }
         double ct = b2_cputime(), rt = b2_realtime();
         const char* data = 0;
@@ -1478,24 +1525,17 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
                   t.launches, (long)t.n_seed_tasks, (long)t.n_regs, (long)t.sam_bytes);
         }
         if (positioned && !rc) {
-          std::unique_lock<std::mutex> lk(mu);
-          j->sam_size = len; j->size_known = true;
+          std::lock_guard<std::mutex> lk(mu);
+          j->sam_size = len; j->size_known = true; j->wdata = data; j->wslot = slot; j->t_gpu = t_gpu;
+          if (slot >= 0) busy[slot] = 1;
           while (!unassigned.empty() && unassigned.front()->size_known) {  // hand out offsets along the known prefix
             unassigned.front()->offset = next_off;
             next_off += (int64_t)unassigned.front()->sam_size;
+            wq.push_back(unassigned.front());
             unassigned.pop_front();
           }
           cv.notify_all();
-          cv.wait(lk, [&] { return j->offset >= 0 || failed; });
-          const bool ok = j->offset >= 0;
-          lk.unlock();
-          const double t_w0 = b2_realtime();
-          const bool wrote = !ok || pwrite_all(data, len, j->offset);
-          if (getenv("B200BWA_TIMES")) fprintf(stderr, "[T::b200bwa] worker %d batch %ld: offset wait %.1f ms, write %.1f ms, done at %.1f ms\n", wi, (long)j->index, (t_w0 - t_gpu) * 1e3, (b2_realtime() - t_w0) * 1e3, (b2_realtime() - t_real) * 1e3);
-          if (!wrote) {
-            std::lock_guard<std::mutex> lk2(mu);
-            rc = 1; errmsg = "write error on SAM output";
-          }
+          continue;   // a writer thread marks the job done
         }
         std::lock_guard<std::mutex> lk(mu);
         j->rc = rc; j->done = true;
@@ -1532,6 +1572,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   }
   reader.join();
   for (auto& t : gpu) t.join();
+  for (auto& t : writers) t.join();
   if (rc) {
     std::string em = errmsg;
     for (B2Engine* e : engs) if (em.empty() && e->last_error()[0]) em = e->last_error();
@@ -1548,4 +1589,68 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     fprintf(stderr, "\n[main] Real time: %.3f sec; CPU: %.3f sec\n", b2_realtime() - t_real, b2_cputime());
   }
   return rc;
+}
+
+// ---------------------------------------------------------------------------------------------
+// The step after the path: SparkBWA's reducer (BwaInterpreter.java:342-376) concatenates the SAM
+// files of the partitions in partition order, keeping lines that start with '@' only from the first file, every line
+// terminated by '\n', and deletes the inputs.
+int b2_reduce_sam(int n_inputs, const char* const* inputs, const char* out_path, int delete_inputs) {
+  FILE* out = fopen(out_path, "wb");
+  if (!out) return set_err("fail to open output `%s'", out_path);
+  setvbuf(out, 0, _IOFBF, 1 << 22);
+  std::vector<char> buf((size_t)1 << 22);
+  for (int i = 0; i < n_inputs; ++i) {
+    FILE* in = fopen(inputs[i], "rb");
+    if (!in) { fclose(out); return set_err("fail to open file `%s'", inputs[i]); }
+    bool at_line_start = true, keep = true, any = false;
+    size_t got;
+    while ((got = fread(buf.data(), 1, buf.size(), in)) > 0) {
+      size_t p = 0;
+      while (p < got) {
+        if (at_line_start) { keep = i == 0 || buf[p] != '@'; at_line_start = false; }
+        const char* nl = (const char*)memchr(buf.data() + p, '\n', got - p);
+        const size_t e = nl ? (size_t)(nl - buf.data()) + 1 : got;
+        if (keep && fwrite(buf.data() + p, 1, e - p, out) != e - p) { fclose(in); fclose(out); return set_err("write error on `%s'", out_path); }
+        any = true;
+        if (nl) at_line_start = true;
+        p = e;
+      }
+    }
+    if (any && !at_line_start && keep) fputc('\n', out);  // readLine() + "\n": an unterminated last line gets its newline
+    fclose(in);
+  }
+  if (fclose(out) != 0) return set_err("close error on `%s'", out_path);
+  if (delete_inputs) for (int i = 0; i < n_inputs; ++i) unlink(inputs[i]);
+  return 0;
+}
+
+// Spark-free driver of the same shape as SparkBWA's map step (BwaInterpreter.java:301-319 over
+// BwaPairedAlignment/BwaSingleAlignment): partition p of the reads -> one `mem` call -> <out_dir>/<app>-<p>.sam
+// (BwaAlignmentBase.java:176-178), then optionally the reducer into <out_dir>/FullOutput.sam.
+int b2_run_partitions(int n_opts, char** opts, const char* idxbase, int n_parts, const char* const* fq1, const char* const* fq2,
+                      const char* out_dir, const char* app, int reduce) {
+  std::vector<std::string> outs;
+  for (int p = 0; p < n_parts; ++p) {
+    char num[32];
+    snprintf(num, sizeof(num), "-%d.sam", p);
+    outs.push_back(std::string(out_dir) + "/" + (app ? app : "SparkBWA") + num);
+    std::vector<std::string> a;
+    a.push_back("mem");
+    for (int i = 0; i < n_opts; ++i) a.push_back(opts[i]);
+    a.push_back(idxbase);
+    a.push_back(fq1[p]);
+    if (fq2 && fq2[p]) a.push_back(fq2[p]);
+    std::vector<char*> argv;
+    for (auto& x : a) argv.push_back(&x[0]);
+    std::string pg = "@PG\tID:bwa\tPN:bwa\tVN:" B200BWA_VERSION "\tCL:bwa";
+    for (auto& x : a) { pg += ' '; pg += x; }
+    if (b2_mem_main((int)argv.size(), argv.data(), outs.back().c_str(), pg.c_str())) return 1;
+  }
+  if (reduce) {
+    std::vector<const char*> in;
+    for (auto& o : outs) in.push_back(o.c_str());
+    return b2_reduce_sam((int)in.size(), in.data(), (std::string(out_dir) + "/FullOutput.sam").c_str(), 1);
+  }
+  return 0;
 }

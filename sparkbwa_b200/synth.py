@@ -50,6 +50,38 @@ def make_reference(total_len: int, n_contigs: int = 1, seed: int = 1, repeat_fra
     return [(f"chr{i + 1}", codes[bounds[i]:bounds[i + 1]]) for i in range(n_contigs)]
 
 
+def add_alt_contigs(contigs, n_alt: int = 4, alt_len=(1500, 4000), div: float = 0.02, seed: int = 5):
+    """ALT haplotypes: near-copies (substitutions at rate `div` plus one small indel) of segments of the primary
+    contigs, appended as contigs named <chr>_alt<k>.  Returns (all contigs, [ALT names]) -- the names go into
+    <prefix>.alt (bwa/bntseq.c:179-204) so that the ALT-aware branches run (bwa/bwamem.c:535-551,
+    bwa/bwamem_pair.c:340-347, bwa/bwamem_extra.c:98-140)."""
+    rng = np.random.default_rng(seed)
+    out = list(contigs)
+    names = []
+    for k in range(n_alt):
+        ci = int(rng.integers(0, len(contigs)))
+        name, codes = contigs[ci]
+        L = int(rng.integers(alt_len[0], alt_len[1] + 1))
+        L = min(L, len(codes) // 2)
+        st = int(rng.integers(0, len(codes) - L))
+        cp = codes[st:st + L].copy()
+        nmut = rng.binomial(L, div)
+        if nmut:
+            pos = rng.integers(0, L, size=nmut)
+            cp[pos] = (cp[pos] + rng.integers(1, 4, size=nmut, dtype=np.uint8)) & 3
+        cut = int(rng.integers(L // 4, 3 * L // 4))
+        if k % 2 == 0:   # a short deletion
+            cp = np.concatenate([cp[:cut], cp[cut + int(rng.integers(1, 9)):]])
+        else:            # a short insertion
+            cp = np.concatenate([cp[:cut], rng.integers(0, 4, size=int(rng.integers(1, 9)), dtype=np.uint8), cp[cut:]])
+        if k % 3 == 2:
+            cp = (3 - cp[::-1]).astype(np.uint8)
+        nm = f"{name}_alt{k}"
+        out.append((nm, cp))
+        names.append(nm)
+    return out, names
+
+
 def write_fasta(path: str, contigs, width: int = 60):
     with open(path, "wb") as f:
         for name, codes in contigs:

@@ -17,9 +17,13 @@ from sparkbwa_b200 import synth  # noqa: E402
 ORACLE = os.path.join(ROOT, "oracle", "_ref", "bwa")
 CLI = os.path.join(ROOT, "sparkbwa_b200", "b200bwa")
 HOSTSIM = os.path.join(ROOT, "tests", "hostsim", "_build", "b200bwa_hostsim")
+ORACLE_BATCH = os.path.join(ROOT, "oracle", "_ref", "oracle_batch")
 
 # name -> (reference kwargs, reads kwargs, extra bwa-mem options)
 CASES = {
+    # BASELINE.json configs[0] at its stated size: 10 k x 100 bp single-end reads, 2 % error, vs a 5 Mbp reference
+    "cfg0_se100_5Mbp": (dict(total_len=5_000_000, n_contigs=1, seed=1, repeat_frac=0.02),
+                        dict(n=10000, read_len=100, paired=False, seed=21, sub=0.02, indel=0.0), []),
     # config 1 shape (scaled): single-end 100 bp, 2 % error
     "se100": (dict(total_len=1_000_000, n_contigs=3, seed=1, repeat_frac=0.05),
               dict(n=2000, read_len=100, paired=False, seed=3, sub=0.02, indel=0.002, n_frac=0.002, junk_frac=0.01), []),
@@ -50,6 +54,17 @@ CASES = {
     # the pacbio preset (-x pacbio: a=b=o=e=1, -k17 -W40 -r10 -L0) on 1.5 kb reads at 14 % error
     "se_pacbio1500": (dict(total_len=300_000, n_contigs=2, seed=71, repeat_frac=0.5, rep_len=(100, 800), rep_copies=(5, 40), rep_div=0.08),
                       dict(n=100, read_len=1500, paired=False, seed=73, sub=0.10, indel=0.04, chimeric_frac=0.3), ["-x", "pacbio"]),
+    # ALT contigs listed in ref.fa.alt: ALT-aware primary marking, ALT supplementary records, XA with max_XA_hits_alt
+    "pe_alt": (dict(total_len=300_000, n_contigs=2, seed=81, repeat_frac=0.05, alt=dict(n_alt=8, alt_len=(1200, 4000), div=0.02, seed=83)),
+               dict(n=1500, read_len=150, paired=True, seed=85, sub=0.01, indel=0.001, chimeric_frac=0.05), []),
+    "se_alt": (dict(total_len=200_000, n_contigs=2, seed=87, repeat_frac=0.10, rep_len=(200, 1500), rep_copies=(2, 8),
+                    alt=dict(n_alt=10, alt_len=(800, 3000), div=0.03, seed=89)),
+               dict(n=1500, read_len=120, paired=False, seed=91, sub=0.015, indel=0.002), ["-a"]),
+    # the other two presets of bwa/fastmap.c:288-317
+    "se_ont2d1200": (dict(total_len=300_000, n_contigs=2, seed=93, repeat_frac=0.3, rep_len=(100, 800), rep_copies=(3, 20), rep_div=0.08),
+                     dict(n=80, read_len=1200, paired=False, seed=95, sub=0.10, indel=0.05, chimeric_frac=0.2), ["-x", "ont2d"]),
+    "se_intractg2000": (dict(total_len=300_000, n_contigs=2, seed=97, repeat_frac=0.3, rep_len=(100, 800), rep_copies=(3, 20), rep_div=0.05),
+                        dict(n=80, read_len=2000, paired=False, seed=99, sub=0.01, indel=0.002, chimeric_frac=0.3), ["-x", "intractg"]),
     "pe_small": (dict(total_len=200_000, n_contigs=2, seed=41, repeat_frac=0.20, rep_len=(200, 1500), rep_copies=(2, 12)),
                  dict(n=400, read_len=125, paired=True, seed=43, sub=0.015, indel=0.002, mate2_sub=0.05, chimeric_frac=0.05), []),
 }
@@ -66,20 +81,34 @@ def run(cmd, **kw):
 def make_case(workdir: str, name: str):
     """Generate reference + reads + index (+ oracle SAM).  Returns dict of paths and options."""
     ref_kw, reads_kw, opts = CASES[name]
+    ref_kw = dict(ref_kw)
+    alt_kw = ref_kw.pop("alt", None)
+
+    def reference():
+        ctg = synth.make_reference(**ref_kw)
+        alt = []
+        if alt_kw:
+            ctg, alt = synth.add_alt_contigs(ctg, **alt_kw)
+        return ctg, alt
     d = os.path.join(workdir, name)
     os.makedirs(d, exist_ok=True)
     fa = os.path.join(d, "ref.fa")
     out = {"dir": d, "ref": fa, "opts": list(opts), "paired": reads_kw["paired"]}
     ctg = None
     if not os.path.exists(fa + ".bwt"):
-        ctg = synth.make_reference(**ref_kw)
+        ctg, alt = reference()
         synth.write_fasta(fa, ctg)
+        if alt:  # bwakit's .alt is a SAM file of the ALT contigs against the primary assembly; only column 1 is read
+            with open(fa + ".alt", "w") as f:
+                f.write("@SQ\tSN:chr1\tLN:1\n")
+                for nm in alt:
+                    f.write(f"{nm}\t0\tchr1\t1\t60\t100M\t*\t0\t0\t*\t*\n")
         run([ORACLE, "index", fa])
     fq1 = os.path.join(d, "r_1.fq")
     fq2 = os.path.join(d, "r_2.fq")
     if not os.path.exists(fq1):
         if ctg is None:
-            ctg = synth.make_reference(**ref_kw)
+            ctg, _ = reference()
         r1, r2 = synth.simulate_reads(ctg, **reads_kw)
         synth.write_fastq(fq1, r1)
         if r2 is not None:
@@ -157,3 +186,23 @@ def make_interleaved(case, drop_every=7):
                 fo.writelines(b)
             k += 1
     return out
+
+
+def check_first_read_offsets(case, binary, env=None, offsets=(0, (1 << 24) + 2 * 4321, (1 << 25) - 2, (1 << 31) + 6)):
+    """The absolute read index (n_processed, bwa/fastmap.c:85) feeds hash_64 tie-breaks (bwa/bwamem.c:527,1162,1167)
+    and, as a 32-bit `id<<8`, mem_pair (bwa/bwamem_pair.c:222), where it wraps for pair indices >= 2^23.
+    oracle/_ref/oracle_batch runs the reference's mem_process_seqs on the case's reads as ONE batch with a chosen
+    n_processed; the engine gets the same offset through B200BWA_FIRST_READ.  Returns how many SAM lines of the
+    oracle change with the offset (the check is only meaningful if some do)."""
+    base, moved = None, 0
+    for n0 in offsets:
+        r = subprocess.run([ORACLE_BATCH, case["ref"], str(n0)] + case["fq"], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+        ref = r.stdout.splitlines(True)
+        our = engine_sam(case, binary, extra=["-K", "2000000000"], env=dict(env or {}, B200BWA_FIRST_READ=str(n0)))
+        ours = [l for l in sam_body(our) if not l.startswith(b"@")]
+        assert ours == ref, f"SAM differs from the reference's mem_process_seqs at n_processed={n0}"
+        if base is None:
+            base = ref
+        else:
+            moved = max(moved, sum(1 for a, b in zip(ref, base) if a != b))
+    return moved

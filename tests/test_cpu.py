@@ -64,7 +64,7 @@ def test_hostsim_matches_golden(hostsim, tmp_path, args, gold):
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["se100", "pe150", "se250", "pe_rescue", "pe_repeat", "pe250", "pe_chimeric", "se_short", "se_long900",
-                                  "se_pacbio1500"])
+                                  "se_pacbio1500", "pe_alt", "se_alt", "se_ont2d1200", "se_intractg2000"])
 def test_hostsim_matches_oracle(hostsim, workdir, name):
     c = pu.make_case(workdir, name)
     ref = pu.oracle_sam(c)
@@ -156,6 +156,15 @@ def test_capacity_retry_paths(hostsim, workdir):
     env = dict(pu.HOSTSIM_ENV, B200BWA_SCRATCH="512", B200BWA_CAP_INTV="2", B200BWA_SLOT="64")
     our = pu.engine_sam(c, hostsim, env=env)
     assert not pu.first_diff(ref, our)
+    # per-lane scratch beyond the budget: the stage re-runs with fewer lanes instead of giving up (wide-band long
+    # reads must not abort a run the reference completes); a budget no single read fits fails loudly
+    c = pu.make_case(workdir, "se_long900")
+    ref = pu.oracle_sam(c)
+    env = dict(pu.HOSTSIM_ENV, B200BWA_LANE_GRID="8", B200BWA_SCRATCH="512", B200BWA_MAX_SCRATCH=str(1 << 20), B200BWA_WORKERS="1")
+    our = pu.engine_sam(c, hostsim, env=env)
+    assert not pu.first_diff(ref, our)
+    with pytest.raises(RuntimeError, match="scratch limit"):
+        pu.engine_sam(c, hostsim, env=dict(env, B200BWA_MAX_SCRATCH="4096"))
 
 
 def test_striped_sw_scan_equals_lazy_f(tmp_path):
@@ -286,3 +295,65 @@ def test_parallel_scan_and_device_ingest(hostsim, workdir):
                 assert not pu.first_diff(ref, os.path.join(c["dir"], "scan.sam")), (K, env)
                 want = b"host pack" if "B200BWA_NO_COMPACT" in env else b"device ingest"
                 assert want in r.stderr and (b"host pack" if want == b"device ingest" else b"device ingest") not in r.stderr
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_alt_contig_paths(hostsim, workdir):
+    """ALT contigs (<prefix>.alt, bwa/bntseq.c:179-204): the fixture must actually reach the ALT-aware code -- @SQ ... AH:*
+    header lines, pa:f: tags (bwa/bwamem.c:926: a primary that also has an ALT hit), ALT supplementary records
+    (bwa/bwamem_pair.c:340-347) and XA lists beyond max_XA_hits (bwa/bwamem_extra.c:98-140, max_XA_hits_alt) -- and
+    -j (ignore the .alt file) must give the plain result."""
+    c = pu.make_case(workdir, "pe_alt")
+    ref = pu.oracle_sam(c)
+    body = pu.sam_body(ref)
+    assert sum(1 for l in body if l.startswith(b"@SQ") and l.rstrip().endswith(b"AH:*")) == 8
+    assert sum(1 for l in body if b"\tpa:f:" in l) > 50
+    assert sum(1 for l in body if b"\tXA:Z:" in l) > 100
+    assert not pu.first_diff(ref, pu.engine_sam(c, hostsim, env=pu.HOSTSIM_ENV))
+    for extra in (["-j"], ["-h", "2,50"], ["-a", "-M"]):
+        r = pu.oracle_sam(c, extra=extra)
+        assert not pu.first_diff(r, pu.engine_sam(c, hostsim, extra=extra, env=pu.HOSTSIM_ENV)), extra
+
+
+@pytest.mark.skipif(not os.access(pu.ORACLE_BATCH, os.X_OK), reason="oracle/_ref/oracle_batch not built")
+def test_hostsim_absolute_read_index_and_int32_wrap(hostsim, workdir):
+    """results depend on the absolute index of a batch's first read, incl. the int32 wrap of `id<<8`."""
+    c = pu.make_case(workdir, "pe_repeat")
+    assert pu.check_first_read_offsets(c, hostsim, env=pu.HOSTSIM_ENV) > 100
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_hostsim_config0_full_size(hostsim, workdir):
+    """BASELINE.json configs[0] at its stated size (10 k x 100 bp single-end vs 5 Mbp), with the argv SparkBWA builds
+    for a single-end partition (Bwa.java:289-390): bwa mem <-w tokens> -f <out> <index> <fq>."""
+    c = pu.make_case(workdir, "cfg0_se100_5Mbp")
+    ref = pu.oracle_sam(c)
+    our = pu.engine_sam(c, hostsim, env=pu.HOSTSIM_ENV)
+    assert not pu.first_diff(ref, our)
+    assert len(pu.sam_body(our)) >= 10001
+
+
+def test_reducer_semantics(tmp_path):
+    """b200bwa_reduce_sam == the reducer of BwaInterpreter.java:342-376: files concatenated in order, lines starting with
+    '@' kept from the first file only, every line newline-terminated, inputs deleted."""
+    lib = ctypes.CDLL(LIB)
+    files = []
+    texts = [b"@SQ\tSN:c\tLN:9\n@PG\tID:bwa\nr1\t0\tc\t1\n@odd\t4\t*\n", b"@SQ\tSN:c\tLN:9\n@PG\tID:bwa\nr2\t0\tc\t2\nr3\t16\tc\t3",
+             b"", b"@SQ\tSN:c\tLN:9\n"]
+    for i, t in enumerate(texts):
+        p = tmp_path / f"part-{i}.sam"
+        p.write_bytes(t)
+        files.append(str(p).encode())
+    out = str(tmp_path / "FullOutput.sam")
+    arr = (ctypes.c_char_p * len(files))(*files)
+    assert lib.b200bwa_reduce_sam(len(files), arr, out.encode(), 1) == 0
+    # Java twin: for i, file: for line in file: if i == 0 or not line.startswith("@"): out.write(line + "\n")
+    want = b""
+    for i, t in enumerate(texts):
+        lines = t.split(b"\n")
+        if lines and lines[-1] == b"":
+            lines.pop()
+        want += b"".join(l + b"\n" for l in lines if i == 0 or not l.startswith(b"@"))
+    assert open(out, "rb").read() == want
+    assert not any(os.path.exists(f.decode()) for f in files)
+    assert lib.b200bwa_reduce_sam(1, (ctypes.c_char_p * 1)(b"/nonexistent.sam"), out.encode(), 0) == 1

@@ -268,3 +268,50 @@ def test_device_ingest_is_the_path_taken(tmp_path):
     assert r.returncode == 0, r.stderr[-2000:]
     assert b"device ingest" in r.stderr and b"host pack" not in r.stderr
     assert pu.sam_body(out) == pu.sam_body(os.path.join(GOLD, "pe.sam"))
+
+
+@pytest.mark.skipif(not os.access(pu.ORACLE_BATCH, os.X_OK), reason="oracle/_ref/oracle_batch not built")
+def test_absolute_read_index_and_int32_wrap(workdir):
+    """SURVEY.md H9 on the device: hash tie-breaks from the absolute read index, `id<<8` wrapping for pair indices >= 2^23
+    (what a 20 M-pair job reaches) -- against the reference's own mem_process_seqs called with that n_processed."""
+    c = pu.make_case(workdir, "pe_repeat")
+    assert pu.check_first_read_offsets(c, pu.CLI) > 100
+    c = pu.make_case(workdir, "pe_small")
+    assert pu.check_first_read_offsets(c, pu.CLI) > 10
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_partitions_map_and_reduce_like_sparkbwa(workdir, tmp_path):
+    """SparkBWA without Spark (BwaInterpreter.java:301-376): the reads split into partitions, one `mem` call per
+    partition, the reducer concatenating the partitions' SAM files (header of partition 0 only).  Expected: the
+    reference's `bwa mem` run on each partition file, merged the same way."""
+    c = pu.make_case(workdir, "pe_small")
+    parts = 3
+
+    def split(path, tag):
+        recs = open(path, "rb").read().split(b"\n")
+        n = (len(recs) - 1) // 4
+        out = []
+        for p in range(parts):
+            f = str(tmp_path / f"RDD{p}_{tag}")
+            with open(f, "wb") as fo:   # the shape BwaPairedAlignment writes: a blank line after every record
+                for k in range(p * n // parts, (p + 1) * n // parts):
+                    fo.write(b"\n".join(recs[4 * k:4 * k + 4]) + b"\n\n")
+            out.append(f)
+        return out
+    f1, f2 = split(c["fq"][0], 1), split(c["fq"][1], 2)
+    want = b""
+    for p in range(parts):
+        r = subprocess.run([pu.ORACLE, "mem", "-M", c["ref"], f1[p], f2[p]], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, check=True)
+        want += b"".join(l for l in r.stdout.splitlines(True) if not l.startswith(b"@PG") and (p == 0 or not l.startswith(b"@")))
+    lib = _lib()
+    opts = (ctypes.c_char_p * 1)(b"-M")
+    a1 = (ctypes.c_char_p * parts)(*[x.encode() for x in f1])
+    a2 = (ctypes.c_char_p * parts)(*[x.encode() for x in f2])
+    od = tmp_path / "out"
+    od.mkdir()
+    rc = lib.b200bwa_run_partitions(1, opts, c["ref"].encode(), parts, a1, a2, str(od).encode(), b"SparkBWA-app1", 1)
+    assert rc == 0, lib.b200bwa_last_error()
+    got = b"".join(l for l in open(od / "FullOutput.sam", "rb") if not l.startswith(b"@PG"))
+    assert got == want
+    assert sorted(os.listdir(od)) == ["FullOutput.sam"]
