@@ -58,23 +58,37 @@ B2_HD inline void b2_revseq_g(const B2Scratch& sc, int l, uint8_t* s) {
   for (int i = sc.lane; i < l >> 1; i += sc.gsize) { uint8_t t = s[i]; s[i] = s[l - 1 - i]; s[l - 1 - i] = t; }
 }
 
+// Dispatch of the three DP routines.  On the device every call runs a lane-group form: register-resident for whole
+// warps (b2_coopreg.cuh), memory-resident row-parallel otherwise (b2_coop.cuh) -- a "group" may be a single lane
+// (the lane-per-read kernels), its member mask is then the lane's own bit.  The host checker build (tests/hostsim)
+// substitutes the scalar forms of tests/hostsim/b2_scalar_dp.cuh, which are not part of the library.
+#if defined(__CUDA_ARCH__)
+__device__ inline B2G b2_group_of(const B2Scratch& sc) {
+  B2G g;
+  g.size = sc.gsize; g.lane = sc.lane;
+  g.mask = sc.gsize > 1 ? sc.gmask : (1u << (threadIdx.x & 31));
+  return g;
+}
+#endif
+
 B2_HD inline int b2_extend2_any(B2Scratch& sc, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
                                 const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int w, int end_bonus,
                                 int zdrop, int h0, int* qle, int* tle, int* gtle, int* gscore, int* max_off, B2EH* eh) {
   ++sc.ext_calls;
 #if defined(__CUDA_ARCH__)
-  if (sc.gsize > 1) {
-    B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
-    int s;
-    if (b2_extend2_reg_try(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle, gtle,
-                           gscore, max_off, &sc.ext_cells, &s))
-      return s;
-    return b2_extend2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle,
-                           gtle, gscore, max_off, eh, &sc.ext_cells);
-  }
-#endif
+  const B2G g = b2_group_of(sc);
+  int s;
+  if (sc.gsize > 1 && b2_extend2_reg_try(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle,
+                                         tle, gtle, gscore, max_off, &sc.ext_cells, &s))
+    return s;
+  return b2_extend2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle,
+                         gtle, gscore, max_off, eh, &sc.ext_cells);
+#elif defined(B2_HOSTSIM)
   return b2_extend2(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, qle, tle, gtle,
                     gscore, max_off, eh, &sc.ext_cells);
+#else
+  return 0;  // (host pass of the CUDA compiler: these functions only ever run on the device)
+#endif
 }
 
 B2_HD inline int b2_global2_any(B2Scratch& sc, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
@@ -82,45 +96,51 @@ B2_HD inline int b2_global2_any(B2Scratch& sc, int qlen, const uint8_t* query, i
                                 int* n_cigar_, uint32_t* cigar, int cigar_cap) {
   ++sc.glob_calls;
 #if defined(__CUDA_ARCH__)
-  if (sc.gsize > 1) {
-    B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
-    int s;
-    if (b2_global2_diag_try(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, z, n_cigar_, cigar, cigar_cap,
-                            &sc.glob_cells, &s))
-      return s;
-    return b2_global2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, eh, z, n_cigar_, cigar,
-                           cigar_cap, &sc.glob_cells);
-  }
-#endif
+  const B2G g = b2_group_of(sc);
+  int s;
+  if (sc.gsize > 1 && b2_global2_diag_try(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, z, n_cigar_, cigar,
+                                          cigar_cap, &sc.glob_cells, &s))
+    return s;
+  return b2_global2_coop(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, eh, z, n_cigar_, cigar,
+                         cigar_cap, &sc.glob_cells);
+#elif defined(B2_HOSTSIM)
   return b2_global2(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, w, eh, z, n_cigar_, cigar, cigar_cap,
                     &sc.glob_cells);
+#else
+  return 0;
+#endif
 }
 
+// work: 4 * npad + 32 int16 (npad = query length rounded up to the 16 / 8 SSE lanes of ksw_u8 / ksw_i16)
 B2_HD inline B2Kswr b2_align2_any(B2Scratch& sc, int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat,
                                   int o_del, int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf) {
   ++sc.sw_calls;
 #if defined(__CUDA_ARCH__)
-  if (sc.gsize >= 16) {
-    B2G g; g.mask = sc.gmask; g.lane = sc.lane; g.size = sc.gsize;
-    const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;
-    const bool reg_ok = size == 1 && sc.gsize == 16 && qlen <= 16 * B2_SW_SLMAX && mat[24] == mat[4] && mat[9] == mat[4];
-    B2Kswr r = reg_ok ? b2_sw_local_u8_reg(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, bbuf, &sc.sw_cells)
-                      : b2_sw_local_coop(g, size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
-    if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
-    // all lanes reverse the same private-to-the-group buffers: do it once
-    if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
-    g.sync();
-    B2Kswr rr = reg_ok ? b2_sw_local_u8_reg(g, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
-                                            B2_KSW_XSTOP | r.score, bbuf, &sc.sw_cells)
-                       : b2_sw_local_coop(g, size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
-                                          B2_KSW_XSTOP | r.score, work, bbuf, &sc.sw_cells);
-    if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
-    g.sync();
-    if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
-    return r;
-  }
-#endif
+  const B2G g = b2_group_of(sc);
+  const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;
+  // groups smaller than the SSE lane count (the 4-lane groups of the finalisation kernel, single lanes): blocks dealt
+  // over the lanes, exchange through memory
+  if (sc.gsize < 16) return b2_align2_g(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
+  const bool reg_ok = size == 1 && sc.gsize == 16 && qlen <= 16 * B2_SW_SLMAX && mat[24] == mat[4] && mat[9] == mat[4];
+  B2Kswr r = reg_ok ? b2_sw_local_u8_reg(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, bbuf, &sc.sw_cells)
+                    : b2_sw_local_coop(g, size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
+  if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
+  // all lanes reverse the same private-to-the-group buffers: do it once
+  if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
+  g.sync();
+  B2Kswr rr = reg_ok ? b2_sw_local_u8_reg(g, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
+                                          B2_KSW_XSTOP | r.score, bbuf, &sc.sw_cells)
+                     : b2_sw_local_coop(g, size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
+                                        B2_KSW_XSTOP | r.score, work, bbuf, &sc.sw_cells);
+  if (sc.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
+  g.sync();
+  if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+  return r;
+#elif defined(B2_HOSTSIM)
   return b2_align2(qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, &sc.sw_cells);
+#else
+  return B2Kswr();
+#endif
 }
 
 B2_HD inline int b2_get_pac(const uint8_t* pac, int64_t l) { return pac[l >> 2] >> ((~l & 3) << 1) & 3; }

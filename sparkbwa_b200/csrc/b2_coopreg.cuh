@@ -304,3 +304,154 @@ B2_UNROLL
   if (_max_off) *_max_off = max_off;
   return max;
 }
+
+// ---------------------------------------------------------------------------------------------
+// ksw_u8 / ksw_i16 (bwa/ksw.c:111-334) for a lane group of ANY size -- down to a single lane, i.e. fewer lanes than the
+// reference's 16 (byte) / 8 (word) SSE lanes.  This is the model of SURVEY.md Appendix A in query-column order: the
+// padded query (n = slen * lanes columns) is cut into `lanes` blocks of slen columns; block b is what SSE lane b of the
+// reference holds.  Per target row: (1) every block runs left to right with its F chain restarted at the block start
+// (first pass; the row maximum and the new E come from this pass only), (2) the F values leaving the blocks are
+// combined into the carry each block receives from its left -- x_b = max(F_b, x_{b-1} - slen*e_ins), what the lazy-F
+// loop converges to -- and decay into the block raising H (E is NOT revisited).  The blocks are dealt over the lanes
+// of the group (block b -> lane b mod G); the only exchange is the 2 x lanes values of step (2), through memory.
+// With o_ins or e_ins below 1 the reference's lazy-F early exit is observable: that case runs the
+// literal loop on one lane.  work: 4*n + 32 int16 (H0, H1, E, Hmax, exchange); bbuf: tlen+1 entries.
+template <class G>
+B2_HD inline B2Kswr b2_sw_local_g(const G& g, int size, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                  const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra, int16_t* work,
+                                  uint64_t* bbuf, unsigned long long* cells) {
+  const int lanes = size == 1 ? 16 : 8;
+  const int slen = (qlen + lanes - 1) / lanes;
+  const int n = slen * lanes;
+  int shift = 127, mx = 0;
+  for (int a = 0; a < 25; ++a) {
+    if (mat[a] < (int8_t)shift) shift = mat[a];
+    if (mat[a] > (int8_t)mx) mx = mat[a];
+  }
+  shift = (256 - shift) & 0xff;
+  const int oe_d = o_del + e_del, oe_i = o_ins + e_ins;
+  int16_t *H0 = work, *H1 = work + n, *E = work + 2 * n, *Hmax = work + 3 * n, *XF = work + 4 * n, *XM = work + 4 * n + 16;
+  B2Kswr r; r.score = 0; r.te = r.qe = r.score2 = r.te2 = r.tb = r.qb = -1;
+  const int minsc = (xtra & B2_KSW_XSUBO) ? xtra & 0xffff : 0x10000;
+  const int endsc = (xtra & B2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
+  const bool scan = o_ins >= 1 && e_ins >= 1 && !(xtra & B2_KSW_XLITERAL);
+  int n_b = 0, te = -1, gmax = 0, last_row = -2, last_sc = 0;
+  for (int p = g.lane; p < n; p += g.size) { H0[p] = 0; E[p] = 0; Hmax[p] = 0; }
+  g.sync();
+  for (int i = 0; i < tlen; ++i) {
+    const int8_t* srow = mat + target[i] * 5;
+    for (int b = g.lane; b < lanes; b += g.size) {  // (1) first pass over the blocks this lane owns
+      const int p0 = b * slen;
+      int f = 0, mxv = 0;
+      int h = b ? H0[p0 - 1] : 0;
+      for (int p = p0; p < p0 + slen; ++p) {
+        const int s = p < qlen ? srow[query[p]] : 0;
+        int e = E[p], t;
+        if (size == 1) { h += s + shift; h = h > 255 ? 255 : h; h -= shift; h = h < 0 ? 0 : h; }
+        else { h += s; h = h > 32767 ? 32767 : h; h = h < -32768 ? -32768 : h; }
+        h = h > e ? h : e;
+        h = h > f ? h : f;
+        mxv = mxv > h ? mxv : h;
+        H1[p] = (int16_t)h;
+        e -= e_del; e = e < 0 ? 0 : e;
+        t = h - oe_d; t = t < 0 ? 0 : t;
+        E[p] = (int16_t)(e > t ? e : t);
+        f -= e_ins; f = f < 0 ? 0 : f;
+        t = h - oe_i; t = t < 0 ? 0 : t;
+        f = f > t ? f : t;
+        h = H0[p];
+      }
+      XF[b] = (int16_t)f; XM[b] = (int16_t)mxv;
+    }
+    g.sync();
+    int imax = 0;
+    for (int b = 0; b < lanes; ++b) imax = imax > XM[b] ? imax : XM[b];
+    if (scan) {  // (2) carry into each block, then decay inside it
+      int x = 0;
+      for (int b = 1; b < lanes; ++b) {
+        int c = x - slen * e_ins; c = c < 0 ? 0 : c;
+        x = XF[b - 1] > c ? XF[b - 1] : c;           // x = carry leaving block b-1
+        if (b % g.size != g.lane) continue;
+        int f = x;
+        for (int p = b * slen; p < (b + 1) * slen && f > 0; ++p) {
+          if (H1[p] < f) H1[p] = (int16_t)f;
+          f -= e_ins;
+        }
+      }
+    } else if (g.lane == 0) {  // the reference's lazy-F loop as it is (vector element b of step j = column b*slen + j)
+      int fv[16];
+      for (int b = 0; b < lanes; ++b) fv[b] = XF[b];
+      for (int k = 0, done = 0; k < 16 && !done; ++k) {
+        for (int b = lanes - 1; b > 0; --b) fv[b] = fv[b - 1];
+        fv[0] = 0;
+        for (int j = 0; j < slen; ++j) {
+          int all = 1;
+          for (int b = 0; b < lanes; ++b) {
+            const int p = b * slen + j;
+            int h = H1[p];
+            h = h > fv[b] ? h : fv[b];
+            H1[p] = (int16_t)h;
+            h -= oe_i; h = h < 0 ? 0 : h;
+            int f = fv[b] - e_ins; f = f < 0 ? 0 : f;
+            fv[b] = f;
+            if (f > h) all = 0;
+          }
+          if (all) { done = 1; break; }
+        }
+      }
+    }
+    if (cells && g.lane == 0) *cells += (unsigned long long)qlen;
+    if (imax >= minsc) {  // sub-optimal list: consecutive rows merge into one entry (bwa/ksw.c:192-199)
+      if (n_b == 0 || last_row + 1 != i) { if (g.lane == 0) bbuf[n_b] = (uint64_t)imax << 32 | (uint32_t)i; ++n_b; last_row = i; last_sc = imax; }
+      else if (last_sc < imax) { if (g.lane == 0) bbuf[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i; last_row = i; last_sc = imax; }
+    }
+    g.sync();
+    int stop = 0;
+    if (imax > gmax) {
+      gmax = imax; te = i;
+      for (int p = g.lane; p < n; p += g.size) Hmax[p] = H1[p];
+      if ((size == 1 && gmax + shift >= 255) || gmax >= endsc) stop = 1;
+    }
+    if (stop) break;
+    { int16_t* t = H1; H1 = H0; H0 = t; }
+  }
+  g.sync();
+  r.score = size == 1 ? (gmax + shift < 255 ? gmax : 255) : gmax;
+  r.te = te;
+  if (size != 1 || r.score != 255) {
+    int max = -1;
+    if (size != 1) r.qe = -1;
+    for (int p = 0; p < n; ++p) {  // smallest query column holding the maximum of the saved row
+      const int v = size == 1 ? (Hmax[p] & 0xff) : (uint16_t)Hmax[p];
+      if (v > max) { max = v; r.qe = p; }
+    }
+    if (n_b) {
+      const int ii = (r.score + mx - 1) / mx;
+      const int low = te - ii, high = te + ii;
+      for (int k = 0; k < n_b; ++k) {
+        const int e = (int32_t)bbuf[k];
+        if ((e < low || e > high) && (int)(bbuf[k] >> 32) > r.score2) { r.score2 = (int)(bbuf[k] >> 32); r.te2 = e; }
+      }
+    }
+  }
+  g.sync();
+  return r;
+}
+
+// ksw_align2 (bwa/ksw.c:343-365) on top of it: end points and second best, then the start by a rerun on the reversed
+// prefixes (full tlen, KSW_XSTOP|score).  query/target are reversed in place and restored, by one lane.
+template <class G>
+B2_HD inline B2Kswr b2_align2_g(const G& g, int qlen, uint8_t* query, int tlen, uint8_t* target, const int8_t* mat, int o_del,
+                                int e_del, int o_ins, int e_ins, int xtra, int16_t* work, uint64_t* bbuf, unsigned long long* cells) {
+  const int size = (xtra & B2_KSW_XBYTE) ? 1 : 2;
+  B2Kswr r = b2_sw_local_g(g, size, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, work, bbuf, cells);
+  if ((xtra & B2_KSW_XSTART) == 0 || ((xtra & B2_KSW_XSUBO) && r.score < (xtra & 0xffff))) return r;
+  if (g.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
+  g.sync();
+  B2Kswr rr = b2_sw_local_g(g, size, r.qe + 1, query, tlen, target, mat, o_del, e_del, o_ins, e_ins,
+                            B2_KSW_XSTOP | r.score | (xtra & B2_KSW_XLITERAL), work, bbuf, cells);
+  if (g.lane == 0) { b2_revseq(r.qe + 1, query); b2_revseq(r.te + 1, target); }
+  g.sync();
+  if (r.score == rr.score) { r.tb = r.te - rr.te; r.qb = r.qe - rr.qe; }
+  return r;
+}

@@ -19,7 +19,9 @@ struct B2GalnStatsPrinter { ~B2GalnStatsPrinter() { fprintf(stderr, "[D::galn] r
 #endif
 
 #include <atomic>
+#include <chrono>
 #include <mutex>
+int b2_g_blocking_sync = 0;
 std::atomic<unsigned long long> b2_g_h2d_bytes{0}, b2_g_d2h_bytes{0}, b2_g_launches{0};
 
 namespace {
@@ -102,6 +104,7 @@ struct Worker {
   void* pin_in = nullptr; size_t pin_in_cap = 0;
   DBuf<uint8_t> raw_in; DBuf<int32_t> com_cnt;
   int ev_in0 = -1, ev_in1 = -1;
+  float stage_host_ms = 0;
 };
 
 }  // namespace
@@ -334,10 +337,12 @@ class B2EngineImpl {
       if (b2_host_alloc(&w.pin_in, w.pin_in_cap)) { w.pin_in_cap = 0; return fail("pinned host allocation failed"); }
     }
     uint8_t* st = (uint8_t*)w.pin_in;
+    const auto t_st0 = std::chrono::steady_clock::now();
     memcpy(st, in.base[0] + lo[0], sz[0]);
     if (in.n_files == 2) memcpy(st + o1, in.base[1] + lo[1], sz[1]);
     memcpy(st + orec0, in.recs[0], in.n_recs[0] * sizeof(B2Rec));
     if (in.n_files == 2) memcpy(st + orec1, in.recs[1], in.n_recs[1] * sizeof(B2Rec));
+    w.stage_host_ms = std::chrono::duration<float, std::milli>(std::chrono::steady_clock::now() - t_st0).count();
     const size_t nb = (size_t)in.n_bases;
     if (w.raw_in.ensure(total + 16) || w.seq.ensure(nb + 8) || w.qual.ensure(nb + 8) || w.has_qual.ensure(n + 1) ||
         w.names.ensure(tot_name + 8) || w.comments.ensure((in.copy_comment ? tot_com : 0) + 8) || w.seq_off.ensure(n + 2) ||
@@ -393,7 +398,7 @@ class B2EngineImpl {
     float t_h2d = w.times.h2d;
     w.times = B2StageTimes();
     w.times.h2d = t_h2d;
-    if (ingest) w.times.launches = 5;
+    if (ingest) { w.times.launches = 5; w.times.stage_host = w.stage_host_ms; }
     const int ev_in0 = w.ev_in0, ev_in1 = w.ev_in1;
     w.ev_in0 = w.ev_in1 = -1;
     if (n == 0) return 0;
@@ -420,11 +425,12 @@ class B2EngineImpl {
     // re-run with FEWER lanes rather than with that size for every lane -- the total stays within max_scratch_bytes
     int lane_grid = cfg.lane_grid;
     bool overflowed = false;
-    if (w.scratch_per_lane > cfg.scratch_per_lane && w.clean_batches >= w.decay_wait) {
-      // an outlier batch grew the per-lane size: try the smaller size again (and hand the memory back)
+    if (w.scratch_per_lane > cfg.scratch_per_lane && w.clean_batches >= w.decay_wait &&
+        cfg.max_scratch_bytes / w.scratch_per_lane / (size_t)cfg.lane_block < (size_t)cfg.lane_grid) {
+      // an outlier batch grew the per-lane size so far that the stages now run with fewer lanes than configured: try
+      // the smaller size again (the allocation itself is kept: freeing device memory stalls every stream)
       w.scratch_per_lane = std::max(cfg.scratch_per_lane, w.scratch_per_lane / 2);
       w.tried_decay = true;
-      if (w.scratch.cap > ((size_t)2 << 30)) w.scratch.release();
     }
     int flags = 0;
     int ev_begin = w.timer.mark();
@@ -577,7 +583,8 @@ class B2EngineImpl {
     }
     for (;;) {
       if (ensure_scratch()) return 1;
-      if (TC > 0) {
+      if (TC > 0 && cfg.no_ext_chain) b2_dev_memset(w.cand_ok.p, 0, (size_t)S + 1, w.stream);
+      if (TC > 0 && !cfg.no_ext_chain) {
         b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
         const int64_t blocks_needed = (TC * B2_G_EXT + cfg.lane_block - 1) / cfg.lane_block;
         B2_LAUNCH(k_ext_chain, (int)std::min<int64_t>(blocks_needed, lane_grid), cfg.lane_block, w.stream, c);
@@ -633,7 +640,7 @@ class B2EngineImpl {
     int ev_pes0 = w.timer.mark();
     // ---- mate-rescue attempts as independent SW tasks ------------------------------------------------
     c.resc_off = nullptr; c.n_resc = 0;
-    if (pe && !(opt.flag & B2_F_NO_RESCUE)) {
+    if (pe && !(opt.flag & B2_F_NO_RESCUE) && !cfg.no_resc_plan) {
       if (w.resc_cnt.ensure(n_items + 1) || w.resc_off.ensure(n_items + 2)) return fail("device allocation failed");
       c.resc_cnt = w.resc_cnt.p;
       B2_LAUNCH(k_resc_plan, (n_items + 127) / 128, 128, w.stream, c, 0);

@@ -59,6 +59,8 @@ struct B2EngineConfig {
   int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
   size_t scratch_per_lane = 48 << 10;
   int no_xext = 0;                             // 1: skip the inter-task seed extensions (B200BWA_NO_XEXT)
+  int no_ext_chain = 0;                        // 1: skip the per-chain extension kernel, the per-read pass computes in place (B200BWA_NO_EXT_CHAIN)
+  int no_resc_plan = 0;                        // 1: no planned mate-rescue SW tasks, the finalisation kernel runs them itself (B200BWA_NO_RESC_PLAN)
   int no_galn = 0;                             // 1: skip the speculative inter-task global alignments (B200BWA_NO_GALN)
   size_t max_scratch_bytes = (size_t)16 << 30;    // per stream/buffer set; a stage that needs more per lane runs with fewer lanes
   int n_workers = 6;                           // independent stream/buffer sets (batches in flight)
@@ -69,6 +71,7 @@ struct B2EngineConfig {
 
 struct B2StageTimes {  // milliseconds, device time (CUDA events) of the last batch
   float h2d = 0, seed = 0, sa = 0, chain = 0, extend = 0, pestat = 0, rescue = 0, final_ = 0, gather = 0, d2h = 0, total = 0;
+  float stage_host = 0;   // raw ingest: host copy of the file bytes into the pinned staging buffer (wall ms)
   int launches = 0;
   int64_t n_seed_tasks = 0, n_regs = 0, sam_bytes = 0, n_resc = 0;
 };
@@ -125,6 +128,7 @@ class B2Engine {
   B2EngineImpl* impl_;
 };
 
+extern int b2_g_blocking_sync;   // stream waits block instead of spinning (set per call by b2_mem_main)
 // number of usable CUDA devices (0 when there is none)
 int b2_device_count();
 

@@ -108,7 +108,7 @@ B2_HD inline int b2_seed_sw(const B2Opt& opt, const B2Index& ix, int l_query, co
   const int npad = ((ql + 7) / 8) * 8;
   uint8_t* q = (uint8_t*)sc.alloc((size_t)ql + 1, 1);
   uint8_t* ref = (uint8_t*)sc.alloc((size_t)tl + 1, 1);
-  int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
+  int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * (4 * (size_t)npad + 32), 8);
   uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
   if (sc.overflow) { sc.reset(mk); return -1; }
   sc.gsync();
@@ -658,7 +658,7 @@ B2_HD inline B2Kswr b2_rescue_sw(const B2Opt& opt, const B2Index& ix, const B2Re
   const int npad = ((l_ms + lanes - 1) / lanes) * lanes;
   uint8_t* seq = (uint8_t*)sc.alloc((size_t)l_ms + 1, 1);
   uint8_t* ref = (uint8_t*)sc.alloc((size_t)tl + 1, 1);
-  int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * 4 * (size_t)npad, 8);
+  int16_t* work = (int16_t*)sc.alloc(sizeof(int16_t) * (4 * (size_t)npad + 32), 8);
   uint64_t* bbuf = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)(tl + 1), 8);
   B2Kswr aln; aln.score = 0; aln.te = aln.qe = aln.score2 = aln.te2 = aln.tb = aln.qb = -1;
   if (sc.overflow) { sc.reset(mk); return aln; }

@@ -1169,6 +1169,8 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_SLOT"))) cfg->slot_per_read = atoi(s);
   if ((s = getenv("B200BWA_NO_GALN"))) cfg->no_galn = atoi(s);
   if ((s = getenv("B200BWA_NO_XEXT"))) cfg->no_xext = atoi(s);
+  if ((s = getenv("B200BWA_NO_EXT_CHAIN"))) cfg->no_ext_chain = atoi(s);
+  if ((s = getenv("B200BWA_NO_RESC_PLAN"))) cfg->no_resc_plan = atoi(s);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -1333,7 +1335,10 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     }
   }
   const bool smart = (opt.flag & B2_F_SMARTPE) != 0;  // interleaved input: pairs are adjacent reads with equal names
+  const bool times0 = getenv("B200BWA_TIMES") != 0;
+  if (times0) fprintf(stderr, "[T::b200bwa] inputs open at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   if (!get_engines()) return 1;
+  if (times0) fprintf(stderr, "[T::b200bwa] engines ready at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   // one aligning call at a time per index (the engines' stream/buffer sets and options are per index); calls on
   // other indices proceed concurrently
   std::lock_guard<std::mutex> run_lock(cached->run_mu);
@@ -1388,6 +1393,11 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
 
   const B2Pes* pes0 = m.has_pes0 ? m.pes0 : 0;
   const int n_workers = engs[0]->n_workers();
+  {  // stream waits block instead of spinning once the worker threads would occupy most host cores
+    const unsigned hw = std::thread::hardware_concurrency();
+    const char* bs = getenv("B200BWA_BLOCKING_SYNC");
+    b2_g_blocking_sync = bs ? atoi(bs) : (hw > 0 && (unsigned)(G * n_workers) * 2 > hw);
+  }
 
   // Pipeline (kt_pipeline's three ordered steps): reader thread (record boundaries only) -> GPU workers (pack,
   // upload, kernels, download, positioned write) -> this thread (ordered bookkeeping / ordered writer).
@@ -1416,6 +1426,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       n_processed += n;
       if (batch_index++ % shard_world != shard_rank) continue;
       if (m.verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)j->raw->n_bases);
+      if (times0) fprintf(stderr, "[T::b200bwa] batch %ld cut at %.1f ms\n", (long)j->index, (b2_realtime() - t_real) * 1e3);
       std::unique_lock<std::mutex> lk(mu);
       cv.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
       if (failed) break;
@@ -1437,7 +1448,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   const bool times = getenv("B200BWA_TIMES") != 0;
   std::vector<std::thread> writers;
   if (positioned) {
-    int n_writers = 2 * G;
+    int n_writers = 3 * G;
     if (const char* s = getenv("B200BWA_WRITERS")) n_writers = atoi(s);
     if (n_writers < 1) n_writers = 1;
     for (int t = 0; t < n_writers; ++t)
@@ -1463,6 +1474,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       });
   }
 
+  if (times0) fprintf(stderr, "[T::b200bwa] pipeline threads starting at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   std::vector<std::thread> gpu;
   for (int dv = 0; dv < G; ++dv)
    for (int wi = 0; wi < n_workers; ++wi)
@@ -1520,8 +1532,8 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           const B2StageTimes& t = eng->times(wi);
           fprintf(stderr, "[T::b200bwa] device %d worker %d batch %ld (%s): start %.1f ms, pack %.1f ms, upload+kernels+download %.1f ms (wall)\n", eng->device(), wi,
                   (long)j->index, raw_path ? "device ingest" : "host pack", (rt - t_real) * 1e3, (t_packed - rt) * 1e3, (t_gpu - t_packed) * 1e3);
-          fprintf(stderr, "[T::b200bwa] worker %d reads %d: h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f rescue %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
-                  wi, n_reads_job, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
+          fprintf(stderr, "[T::b200bwa] worker %d reads %d: stage %.2f h2d %.2f seed %.2f sa %.2f chain %.2f extend %.2f pestat %.2f rescue %.2f final %.2f gather %.2f d2h %.2f total %.2f ms; launches %d seeds %ld regs %ld sam %ld B\n",
+                  wi, n_reads_job, t.stage_host, t.h2d, t.seed, t.sa, t.chain, t.extend, t.pestat, t.rescue, t.final_, t.gather, t.d2h, t.total,
                   t.launches, (long)t.n_seed_tasks, (long)t.n_regs, (long)t.sam_bytes);
         }
         if (positioned && !rc) {

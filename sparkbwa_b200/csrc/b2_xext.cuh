@@ -44,7 +44,7 @@ B2_HD inline int b2_base_at(const uint8_t* pac, int64_t l_pac, int64_t p) {
   return 3 - (pac[k >> 2] >> ((~k & 3) << 1) & 3);
 }
 
-// Same results as b2_extend2 (b2_ksw.cuh) for matrices of bwa_fill_scmat's shape and h0 + qlen*max(mat) < 65536.
+// Same results as ksw_extend2 (fuzzed against its scalar form in tests/coop_fuzz.cpp) for matrices of bwa_fill_scmat's shape and h0 + qlen*max(mat) < 65536.
 B2_HD inline int b2_xext_one(const B2XMem& M, int qlen, int tlen, const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins,
                              int w, int end_bonus, int zdrop, int h0, int* _qle, int* _tle, int* _gtle, int* _gscore,
                              int* _max_off, unsigned long long* cells) {

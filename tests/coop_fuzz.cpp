@@ -5,6 +5,7 @@
 #include <stdlib.h>
 #include <string.h>
 #include <vector>
+#define B2_WITH_SCALAR_DP 1   // the scalar reference side: tests/hostsim/b2_scalar_dp.cuh
 #include "b2_ksw.cuh"
 #include "b2_coopreg.cuh"
 #include "b2_galn.cuh"

@@ -171,10 +171,12 @@ def test_striped_sw_scan_equals_lazy_f(tmp_path):
     """The mate-rescue SW replaces the reference's lazy-F loop (ksw.c:176-188) by a max-plus carry scan;
     fuzz it against a literal emulation of that loop (byte and word mode, random scorings)."""
     exe = str(tmp_path / "sw_fuzz")
-    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "sparkbwa_b200", "csrc"), "-o", exe,
-                    os.path.join(ROOT, "tests", "sw_fuzz.cpp")], check=True)
+    subprocess.run(["g++", "-O2", "-std=c++17", "-I" + os.path.join(ROOT, "sparkbwa_b200", "csrc"), "-I" + os.path.join(ROOT, "tests"),
+                    "-I" + os.path.join(ROOT, "tests", "hostsim"), "-o", exe, os.path.join(ROOT, "tests", "sw_fuzz.cpp")], check=True)
     r = subprocess.run([exe, "12000", "777"], stdout=subprocess.PIPE, check=False)
-    assert b"mismatches 0" in r.stdout, r.stdout
+    # second line: the generic-group form (groups of 1..16 lanes: what the device runs for groups smaller than the
+    # 16 / 8 SSE lanes) against the scalar form, including -O x,0 (literal lazy-F loop) and the cell counts
+    assert r.returncode == 0 and r.stdout.count(b"mismatches 0") == 2, r.stdout
 
 
 def test_register_resident_coop_dp_equals_scalar(tmp_path):
@@ -185,7 +187,8 @@ def test_register_resident_coop_dp_equals_scalar(tmp_path):
     of b2_galn.cuh (one alignment per lane, band in registers by diagonal) against ksw_global2's scalar form."""
     exe = str(tmp_path / "coop_fuzz")
     subprocess.run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", "-I" + os.path.join(ROOT, "sparkbwa_b200", "csrc"),
-                    "-I" + os.path.join(ROOT, "tests"), "-o", exe, os.path.join(ROOT, "tests", "coop_fuzz.cpp")], check=True)
+                    "-I" + os.path.join(ROOT, "tests"), "-I" + os.path.join(ROOT, "tests", "hostsim"), "-o", exe,
+                    os.path.join(ROOT, "tests", "coop_fuzz.cpp")], check=True)
     r = subprocess.run([exe, "1200", "31337"], stdout=subprocess.PIPE, check=False)
     assert r.returncode == 0 and r.stdout.count(b"mismatches 0") == 4, r.stdout
 

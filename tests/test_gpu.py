@@ -315,3 +315,17 @@ def test_partitions_map_and_reduce_like_sparkbwa(workdir, tmp_path):
     got = b"".join(l for l in open(od / "FullOutput.sam", "rb") if not l.startswith(b"@PG"))
     assert got == want
     assert sorted(os.listdir(od)) == ["FullOutput.sam"]
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["pe_repeat", "pe250", "se250", "pe_alt"])
+def test_in_kernel_dp_paths_match_oracle(workdir, name):
+    """The DP results that the consumers find missing are computed in place by the lane-group forms -- single lanes in the
+    per-read extension pass (b2_extend2_coop / b2_global2_coop with a one-lane group), 4-lane groups in the
+    finalisation kernel (b2_global2_*, and b2_align2_g: ksw_u8 / ksw_i16 with the SSE lanes dealt over 4 lanes).
+    With every run-ahead stage switched off ALL of the DP goes through those paths; the SAM must not change."""
+    c = pu.make_case(workdir, name)
+    ref = pu.oracle_sam(c)
+    env = {"B200BWA_NO_XEXT": "1", "B200BWA_NO_EXT_CHAIN": "1", "B200BWA_NO_GALN": "1", "B200BWA_NO_RESC_PLAN": "1"}
+    our = pu.engine_sam(c, pu.CLI, env=env)
+    assert not pu.first_diff(ref, our)
