@@ -8,6 +8,7 @@
  *                                              bound by java/com/github/sparkbwa/BwaJni.java:59
  *   b200bwa_main                               bwa/main.c:61 (`int main(int argc, char *argv[])`), `mem` only
  *   b200bwa_mem                                bwa/fastmap.c:115 (`int main_mem(int argc, char *argv[])`)
+ *   b200bwa_index_build                        bwa/bwtindex.c:210 (`int bwa_index(int argc, char *argv[])`)
  *   b200bwa_index_load / _align_batch / ...    bwa/bwa.c:252 (bwa_idx_load_from_disk) and
  *                                              bwa/bwamem.c:1172 (mem_process_seqs) -- the library-level
  *                                              calls a host program (bwa/example.c) would make
@@ -40,6 +41,12 @@ int b200bwa_main_to(int argc, char** argv, const char* out_path);
 
 /* argv as main_mem sees it: argv[0] = "mem". out_path may be NULL (stdout). */
 int b200bwa_mem(int argc, char** argv, const char* out_path);
+
+/* `bwa index` (bwa/bwtindex.c:210-324 bwa_index / bwa_idx_build; bwa/bntseq.c:275-328 bns_fasta2bntseq;
+ * bwa/bwt.c:62-84 bwt_cal_sa): argv[0] = "index", then [-p prefix] [-6] [-a algo] <in.fasta>.  Writes
+ * <prefix>.pac/.ann/.amb/.bwt/.sa byte-identical to the reference's, the suffix sorting done on the GPU
+ * (B200BWA_DEVICE selects it).  Also reachable as `b200bwa_main({"bwa", "index", ...})`. */
+int b200bwa_index_build(int argc, char** argv);
 
 /* The file-driven entry points keep the device image of an index cached across calls (keyed by prefix and the
  * size/mtime of <prefix>.bwt), the way `bwa shm` keeps it in host shared memory (bwa/bwashm.c:87-118).  This

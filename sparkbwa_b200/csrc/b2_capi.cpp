@@ -45,9 +45,10 @@ int b200bwa_main_to(int argc, char** argv, const char* out_path) {
       fprintf(stderr, "\nProgram: b200bwa (B200-native BWA-MEM behind the SparkBWA bridge)\nVersion: %s\n\nUsage:   bwa mem [options] <idxbase> <in1.fq> [in2.fq]\n\n", B200BWA_VERSION);
       return 1;
     }
+    if (strcmp(argv[1], "index") == 0) return b2_index_main(argc - 1, argv + 1);
     if (strcmp(argv[1], "mem") != 0) {
       fprintf(stderr, "[main] unrecognized command '%s'\n", argv[1]);
-      b2_tls_error = std::string("unrecognized command '") + argv[1] + "' (only `mem` is provided by b200bwa)";
+      b2_tls_error = std::string("unrecognized command '") + argv[1] + "' (`mem` and `index` are provided by b200bwa)";
       return 1;
     }
     std::string pg = make_pg(argc, argv);
@@ -62,6 +63,11 @@ int b200bwa_main_to(int argc, char** argv, const char* out_path) {
 int b200bwa_main(int argc, char** argv) { return b200bwa_main_to(argc, argv, 0); }
 
 int b200bwa_index_cache_evict(void) { return b2_index_cache_evict(); }
+
+int b200bwa_index_build(int argc, char** argv) {
+  try { b2_tls_error.clear(); return b2_index_main(argc, argv); }
+  catch (const std::exception& e) { b2_tls_error = e.what(); fprintf(stderr, "[E::b200bwa] %s\n", e.what()); return 1; }
+}
 
 int b200bwa_reduce_sam(int n_inputs, const char* const* inputs, const char* out_path, int delete_inputs) {
   try { b2_tls_error.clear(); return b2_reduce_sam(n_inputs, inputs, out_path, delete_inputs); }

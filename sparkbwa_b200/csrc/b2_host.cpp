@@ -1352,7 +1352,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   FILE* out = stdout;
   int out_fd = -1;
   if (out_path) {
-    out_fd = ::open(out_path, O_WRONLY | O_CREAT | O_TRUNC, 0666);
+    out_fd = ::open(out_path, O_RDWR | O_CREAT | O_TRUNC, 0666);
     if (out_fd < 0) { fprintf(stderr, "[E::main_mem] fail to open output `%s'.\n", out_path); return set_err("fail to open output `%s'", out_path); }
     struct stat st;
     if (fstat(out_fd, &st) != 0 || !S_ISREG(st.st_mode) || getenv("B200BWA_ORDERED_WRITER")) {
@@ -1442,6 +1442,44 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
 
   // Positioned mode: the file writes are done by a few writer threads, so that a GPU worker starts its next batch
   // as soon as the SAM text of the current one sits in its pinned buffer (each worker has two, used in turn).
+  // write()/pwrite() on ONE file are serialised by the kernel's inode lock (about 3 GB/s on tmpfs however many
+  // threads call it: 8 M reads/s of SAM, less than two GPUs produce), so the writers copy through a shared mapping
+  // of the output file instead, into pages an allocator thread has reserved ahead of them with fallocate() -- a full
+  // disk then shows up as ENOSPC from fallocate, never as SIGBUS inside the executor.  File systems without
+  // fallocate keep the positioned pwrite().
+  char* out_map = 0;
+  const size_t out_map_len = (size_t)1 << 38;
+  int64_t alloc_end = 0;        // bytes of the file reserved so far
+  bool alloc_stop = false;
+  std::thread allocator;
+  if (positioned && !getenv("B200BWA_NO_MMAP_OUT") && fallocate(out_fd, 0, 0, (off_t)(next_off > 0 ? next_off : 1)) == 0) {
+    void* mp = mmap(0, out_map_len, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, out_fd, 0);
+    if (mp != MAP_FAILED) {
+      out_map = (char*)mp;
+      alloc_end = next_off > 0 ? next_off : 1;
+      const int64_t look = ((int64_t)96 << 20) * G, step = (int64_t)32 << 20;
+      allocator = std::thread([&, look, step]() {
+        std::unique_lock<std::mutex> lk(mu);
+        for (;;) {
+          cv.wait(lk, [&] { return alloc_stop || failed || alloc_end < next_off + look; });
+          if (alloc_stop || failed) return;
+          const int64_t from = alloc_end;
+          lk.unlock();
+          int e = 0;
+          while (fallocate(out_fd, 0, (off_t)from, (off_t)step) != 0) { if (errno != EINTR) { e = errno; break; } }
+          lk.lock();
+          if (e) {
+            failed = true;
+            errmsg = std::string("cannot reserve space for the SAM output: ") + strerror(e);
+            cv.notify_all();
+            return;
+          }
+          alloc_end = from + step;
+          cv.notify_all();
+        }
+      });
+    }
+  }
   std::deque<std::shared_ptr<Job>> wq;                      // jobs with an assigned offset, waiting to be written
   std::vector<char> busy((size_t)G * n_workers * 2, 0);    // pinned buffer [device][worker][slot] still being written out
   int gpu_active = G * n_workers;
@@ -1462,8 +1500,15 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
             j = wq.front();
             wq.pop_front();
           }
+          bool wrote = true;
+          if (out_map) {
+            std::unique_lock<std::mutex> lk(mu);
+            cv.wait(lk, [&] { return failed || alloc_end >= j->offset + (int64_t)j->sam_size; });
+            if (failed) return;
+          }
           const double t_w0 = b2_realtime();
-          const bool wrote = pwrite_all(j->wdata, j->sam_size, j->offset);
+          if (out_map) memcpy(out_map + j->offset, j->wdata, j->sam_size);
+          else wrote = pwrite_all(j->wdata, j->sam_size, j->offset);
           if (times) fprintf(stderr, "[T::b200bwa] batch %ld: queued for writing %.1f ms, write %.1f ms, done at %.1f ms\n", (long)j->index, (t_w0 - j->t_gpu) * 1e3, (b2_realtime() - t_w0) * 1e3, (b2_realtime() - t_real) * 1e3);
           std::lock_guard<std::mutex> lk(mu);
           if (j->wslot >= 0) busy[j->wslot] = 0;
@@ -1585,6 +1630,14 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   reader.join();
   for (auto& t : gpu) t.join();
   for (auto& t : writers) t.join();
+  if (allocator.joinable()) {
+    { std::lock_guard<std::mutex> lk(mu); alloc_stop = true; cv.notify_all(); }
+    allocator.join();
+  }
+  if (out_map) {
+    munmap(out_map, out_map_len);
+    if (!rc && ftruncate(out_fd, (off_t)next_off) != 0) { rc = 1; errmsg = "cannot set the final size of the SAM output"; }
+  }
   if (rc) {
     std::string em = errmsg;
     for (B2Engine* e : engs) if (em.empty() && e->last_error()[0]) em = e->last_error();
@@ -1664,5 +1717,110 @@ int b2_run_partitions(int n_opts, char** opts, const char* idxbase, int n_parts,
     for (auto& o : outs) in.push_back(o.c_str());
     return b2_reduce_sam((int)in.size(), in.data(), (std::string(out_dir) + "/FullOutput.sam").c_str(), 1);
   }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// `bwa index` twin: bwa_index / bwa_idx_build (bwa/bwtindex.c:210-324) with the BWT, Occ and SA
+// built on the GPU (b2_index.cu).  .pac/.ann/.amb follow bns_fasta2bntseq + bns_dump (bwa/bntseq.c:66-96,228-328):
+// ambiguous bases become lrand48() & 3 with srand48(11) -- replayed here with the same 48-bit LCG so the packed
+// sequence, and with it every index file, is byte-identical -- and each run of one ambiguous letter is a "hole".
+int b2_build_fm(const uint8_t* fwd, int64_t l_pac, const char* prefix, int device, int64_t group_max, int sa_intv, int verbose,
+                std::string* err);
+
+int b2_index_main(int argc, char** argv) {
+  std::string prefix, fa;
+  bool is_64 = false;
+  for (int i = 1; i < argc; ++i) {
+    const std::string a = argv[i];
+    if (a == "-6") is_64 = true;
+    else if ((a == "-p" || a == "-a" || a == "-b") && i + 1 < argc) {
+      ++i;
+      if (a == "-p") prefix = argv[i];
+      else if (a == "-a" && strcmp(argv[i], "rb2") && strcmp(argv[i], "bwtsw") && strcmp(argv[i], "is"))
+        return set_err("unknown algorithm: '%s'.", argv[i]);   // (the three algorithms give the same files; so does this one)
+    } else if (a.size() > 1 && a[0] == '-') return set_err("index: invalid option '%s'", a.c_str());
+    else if (fa.empty()) fa = a;
+  }
+  if (fa.empty()) {
+    fprintf(stderr, "\nUsage:   bwa index [-p prefix] [-6] <in.fasta>\n\n");
+    return set_err("index: no input file");
+  }
+  if (prefix.empty()) prefix = fa + (is_64 ? ".64" : "");
+  const int verbose = 3;
+  double t0 = b2_realtime();
+  B2SeqReader ks;
+  if (ks.open(fa.c_str())) { fprintf(stderr, "[E::bwa_idx_build] fail to open file '%s'\n", fa.c_str()); return set_err("fail to open file '%s'", fa.c_str()); }
+  struct Ann { std::string name, anno; int64_t offset; int len, n_ambs; };
+  struct Amb { int64_t offset; int len; char amb; };
+  std::vector<Ann> anns;
+  std::vector<Amb> ambs;
+  std::vector<uint8_t> fwd;
+  uint64_t lcg = ((uint64_t)11 << 16) | 0x330E;   // srand48(11)
+  const unsigned char* nt4 = b2_nt4_table();
+  while (ks.next() >= 0) {
+    Ann p;
+    p.name = ks.name();
+    p.anno = ks.comment().empty() ? "(null)" : ks.comment();
+    p.len = (int)ks.seq().size();
+    p.offset = anns.empty() ? 0 : anns.back().offset + anns.back().len;
+    p.n_ambs = 0;
+    const std::string& sq = ks.seq();
+    int lasts = 0;
+    fwd.reserve(fwd.size() + sq.size());
+    for (size_t i = 0; i < sq.size(); ++i) {
+      int c = nt4[(unsigned char)sq[i]];
+      if (c >= 4) {
+        if (lasts == sq[i]) ++ambs.back().len;
+        else { Amb q; q.len = 1; q.offset = p.offset + (int64_t)i; q.amb = sq[i]; ambs.push_back(q); ++p.n_ambs; }
+        lcg = (lcg * 0x5DEECE66DULL + 0xB) & 0xFFFFFFFFFFFFULL;   // lrand48()
+        c = (int)((lcg >> 17) & 3);
+      }
+      lasts = sq[i];
+      fwd.push_back((uint8_t)c);
+    }
+    anns.push_back(p);
+  }
+  ks.close();
+  const int64_t l_pac = (int64_t)fwd.size();
+  if (l_pac == 0) return set_err("index: no sequence in '%s'", fa.c_str());
+  if (verbose >= 3) fprintf(stderr, "[bwa_index] Pack FASTA... %.2f sec\n", b2_realtime() - t0);
+  {  // .pac, forward strand only (the final state after bwa_idx_build's second packing pass)
+    std::vector<uint8_t> pac((size_t)(l_pac >> 2) + ((l_pac & 3) ? 1 : 0), 0);
+    for (int64_t l = 0; l < l_pac; ++l) pac[l >> 2] |= fwd[l] << ((~l & 3) << 1);
+    FILE* fp = fopen((prefix + ".pac").c_str(), "wb");
+    if (!fp) return set_err("cannot write %s.pac", prefix.c_str());
+    fwrite(pac.data(), 1, pac.size(), fp);
+    if (l_pac % 4 == 0) fputc(0, fp);
+    fputc((int)(l_pac % 4), fp);
+    if (fclose(fp) != 0) return set_err("write error on %s.pac", prefix.c_str());
+  }
+  {
+    FILE* fp = fopen((prefix + ".ann").c_str(), "w");
+    if (!fp) return set_err("cannot write %s.ann", prefix.c_str());
+    fprintf(fp, "%lld %d %u\n", (long long)l_pac, (int)anns.size(), 11u);
+    for (const Ann& p : anns) {
+      fprintf(fp, "%d %s", 0, p.name.c_str());
+      if (!p.anno.empty()) fprintf(fp, " %s\n", p.anno.c_str());
+      else fprintf(fp, "\n");
+      fprintf(fp, "%lld %d %d\n", (long long)p.offset, p.len, p.n_ambs);
+    }
+    if (fclose(fp) != 0) return set_err("write error on %s.ann", prefix.c_str());
+    fp = fopen((prefix + ".amb").c_str(), "w");
+    if (!fp) return set_err("cannot write %s.amb", prefix.c_str());
+    fprintf(fp, "%lld %d %u\n", (long long)l_pac, (int)anns.size(), (unsigned)ambs.size());
+    for (const Amb& q : ambs) fprintf(fp, "%lld %d %c\n", (long long)q.offset, q.len, q.amb);
+    if (fclose(fp) != 0) return set_err("write error on %s.amb", prefix.c_str());
+  }
+  t0 = b2_realtime();
+  if (verbose >= 3) fprintf(stderr, "[bwa_index] Construct BWT, Occ and SA for the packed sequence...\n");
+  int device = getenv("B200BWA_DEVICE") ? atoi(getenv("B200BWA_DEVICE")) : 0;
+  int64_t group_max = getenv("B200BWA_INDEX_GROUP") ? atoll(getenv("B200BWA_INDEX_GROUP")) : 0;
+  std::string err;
+  if (b2_build_fm(fwd.data(), l_pac, prefix.c_str(), device, group_max, 32, verbose, &err)) {
+    fprintf(stderr, "[E::b200bwa_index] %s\n", err.c_str());
+    return set_err("%s", err.c_str());
+  }
+  if (verbose >= 3) fprintf(stderr, "[bwa_index] %.2f seconds elapse.\n", b2_realtime() - t0);
   return 0;
 }

@@ -82,6 +82,7 @@ int b2_index_cache_evict();  // releases every cached device image no call is us
 // argv[0] = "mem"; out_path null = stdout; pg_cmdline = full @PG line or null
 int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdline);
 
+int b2_index_main(int argc, char** argv);   // argv[0] = "index": `bwa index` twin, BWT/Occ/SA built on the GPU
 int b2_reduce_sam(int n_inputs, const char* const* inputs, const char* out_path, int delete_inputs);
 int b2_run_partitions(int n_opts, char** opts, const char* idxbase, int n_parts, const char* const* fq1, const char* const* fq2,
                       const char* out_dir, const char* app, int reduce);

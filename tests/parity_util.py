@@ -206,3 +206,56 @@ def check_first_read_offsets(case, binary, env=None, offsets=(0, (1 << 24) + 2 *
         else:
             moved = max(moved, sum(1 for a, b in zip(ref, base) if a != b))
     return moved
+
+
+def index_cases():
+    """(tag, contigs, plant ambiguous bases?, builder env) for the index-construction parity tests: random genomes with
+    exact repeats (many refinement rounds), ambiguous bases (lrand48 replay, .amb holes incl. mixed letters and lower
+    case), several suffix groups, every text length around the 4 / 32 / 128 packing boundaries, homopolymers, tandem
+    repeats and a reverse-complement palindrome (forward and reverse strand suffixes tie until the very end)."""
+    import numpy as np
+    rng = np.random.default_rng(9)
+    out = [("rep", synth.make_reference(5000, n_contigs=2, seed=3, repeat_frac=0.3, rep_len=(100, 600), rep_copies=(2, 5), rep_div=0.0), False, {}),
+           ("mid", synth.make_reference(200_000, n_contigs=3, seed=4, repeat_frac=0.2, rep_len=(300, 3000), rep_copies=(2, 10), rep_div=0.01), False, {}),
+           ("groups", synth.make_reference(120_000, n_contigs=3, seed=5, repeat_frac=0.2, rep_len=(300, 3000), rep_copies=(2, 10), rep_div=0.01), True,
+            {"B200BWA_INDEX_GROUP": "30000"}),
+           ("withN", synth.make_reference(150_000, n_contigs=2, seed=6, repeat_frac=0.1), True, {})]
+    for L in (1, 2, 3, 5, 16, 31, 33, 64, 127, 129, 1000):
+        out.append((f"len{L}", [("c", rng.integers(0, 4, size=L, dtype=np.uint8))], False, {}))
+    tand = np.tile(rng.integers(0, 4, size=7, dtype=np.uint8), 400)
+    pal = rng.integers(0, 4, size=800, dtype=np.uint8)
+    out += [("polyA", [("a", np.zeros(3000, dtype=np.uint8)), ("b", rng.integers(0, 4, size=500, dtype=np.uint8))], False, {}),
+            ("polyTA", [("a", np.concatenate([np.full(700, 3, dtype=np.uint8), np.zeros(900, dtype=np.uint8)]))], False, {}),
+            ("tandem", [("t", np.concatenate([tand, rng.integers(0, 4, size=100, dtype=np.uint8), tand[:1500]]))], False, {}),
+            ("palindrome", [("p desc of p", np.concatenate([pal, (3 - pal[::-1]).astype(np.uint8)]))], False, {}),
+            ("polyA_groups", [("a", np.zeros(3000, dtype=np.uint8)), ("b", rng.integers(0, 4, size=5000, dtype=np.uint8))], False,
+             {"B200BWA_INDEX_GROUP": "1000"})]
+    return out
+
+
+def plant_ambiguous(fa, seed=5, runs=40):
+    import numpy as np
+    s = bytearray(open(fa, "rb").read())
+    rng = np.random.default_rng(seed)
+    for k in range(runs):
+        i = int(rng.integers(0, max(1, len(s) - 200)))
+        for j in range(i, min(len(s), i + int(rng.integers(1, 120)))):
+            if s[j] in b"ACGT":
+                s[j] = ord("N") if k % 3 else ord("R") if k % 2 else ord("n")
+    open(fa, "wb").write(bytes(s))
+
+
+def check_index_builder(binary, d, tag, contigs, with_n, env):
+    """`<binary> index` must write the five files `bwa index` writes, byte for byte."""
+    import filecmp
+    os.makedirs(d, exist_ok=True)
+    fa = os.path.join(d, tag + ".fa")
+    synth.write_fasta(fa, contigs)
+    if with_n:
+        plant_ambiguous(fa)
+    run([ORACLE, "index", "-p", os.path.join(d, tag + ".ref"), fa])
+    r = subprocess.run([binary, "index", "-p", os.path.join(d, tag + ".our"), fa], env=dict(os.environ, **env),
+                       stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert r.returncode == 0, r.stderr.decode()[-1500:]
+    for e in ("pac", "ann", "amb", "bwt", "sa"):
+        assert filecmp.cmp(os.path.join(d, tag + ".ref." + e), os.path.join(d, tag + ".our." + e), shallow=False), (tag, e)

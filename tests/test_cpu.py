@@ -111,8 +111,10 @@ def test_error_behaviour_without_exit(tmp_path):
         return lib.b200bwa_main_to(len(args), arr, out.encode() if out else None)
 
     assert call(["bwa"]) == 1
-    assert call(["bwa", "index", "x.fa"]) == 1                      # only `mem` is provided
+    assert call(["bwa", "aln", "x.fa", "r.fq"]) == 1                # `mem` and `index` are provided, nothing else
     assert b"unrecognized command" in lib.b200bwa_last_error()
+    assert call(["bwa", "index", "/nonexistent/x.fa"]) == 1
+    assert b"fail to open" in lib.b200bwa_last_error()
     assert call(["bwa", "mem"]) == 1                                 # usage
     assert call(["bwa", "mem", "-Z", "a", "b"]) == 1                 # unknown option
     assert call(["bwa", "mem", "-R", "RG\\tID:x", "a", "b"]) == 1    # bad read group
@@ -135,7 +137,7 @@ def test_no_cpu_fallback_without_cuda(tmp_path):
 def test_jni_symbol_through_fake_env(tmp_path):
     exe = str(tmp_path / "jni_fake")
     subprocess.run(["gcc", "-O1", "-o", exe, os.path.join(ROOT, "tests", "jni_fake.c"), "-ldl"], check=True)
-    r = subprocess.run([exe, LIB, "bwa", "index", "x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    r = subprocess.run([exe, LIB, "bwa", "aln", "x"], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
     assert b"rc=1 released=3" in r.stdout, (r.stdout, r.stderr)
     # "-f <out>" is consumed by the glue and not passed on as an aligner option
     r = subprocess.run([exe, LIB, "bwa", "mem", "-f", str(tmp_path / "x.sam"), "/nonexistent/idx", "r.fq"],
@@ -360,3 +362,12 @@ def test_reducer_semantics(tmp_path):
     assert open(out, "rb").read() == want
     assert not any(os.path.exists(f.decode()) for f in files)
     assert lib.b200bwa_reduce_sam(1, (ctypes.c_char_p * 1)(b"/nonexistent.sam"), out.encode(), 0) == 1
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_index_builder_matches_bwa_index(hostsim, workdir):
+    """the index builder (b2_index.cu: suffix groups, radix sort, tie refinement; b2_host.cpp: FASTA
+    packing with the lrand48 replay for ambiguous bases, .ann/.amb) against the reference's `bwa index`, byte for byte,
+    with the kernel bodies run by the host checker build."""
+    for tag, ctg, with_n, env in pu.index_cases():
+        pu.check_index_builder(hostsim, os.path.join(workdir, "index"), tag, ctg, with_n, env)

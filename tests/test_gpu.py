@@ -172,7 +172,7 @@ def _config_scale_index(tmp_path_factory, ref_len):
     prefix = os.path.join(d, "ref")
     ctg = synth.make_reference(ref_len, n_contigs=4, seed=1, repeat_frac=0.02)
     if not os.path.exists(prefix + ".sa"):
-        index.build_index(ctg, prefix + ".tmp")
+        index.build_index(ctg, prefix + ".tmp")   # the GPU builder; byte parity with `bwa index` has its own test
         for e in ("pac", "ann", "amb", "bwt", "sa"):
             os.replace(prefix + ".tmp." + e, prefix + "." + e)
     return d, prefix, ctg
@@ -329,3 +329,19 @@ def test_in_kernel_dp_paths_match_oracle(workdir, name):
     env = {"B200BWA_NO_XEXT": "1", "B200BWA_NO_EXT_CHAIN": "1", "B200BWA_NO_GALN": "1", "B200BWA_NO_RESC_PLAN": "1"}
     our = pu.engine_sam(c, pu.CLI, env=env)
     assert not pu.first_diff(ref, our)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_index_builder_matches_bwa_index(workdir):
+    """`b200bwa index` (suffix sort on the GPU) writes the files of `bwa index`, byte for byte: the small adversarial
+    cases, a 5 Mbp genome with ambiguous bases (BASELINE.json configs[0]'s reference size) and -- with
+    B200BWA_FULL_INDEX=1, about two minutes of single-threaded `bwa index` -- the 100 Mbp reference of configs[1]."""
+    from sparkbwa_b200 import synth
+    d = os.path.join(workdir, "index")
+    for tag, ctg, with_n, env in pu.index_cases():
+        pu.check_index_builder(pu.CLI, d, tag, ctg, with_n, env)
+    pu.check_index_builder(pu.CLI, d, "g5M", synth.make_reference(5_000_000, n_contigs=3, seed=11, repeat_frac=0.03), True, {})
+    pu.check_index_builder(pu.CLI, d, "g5M_groups", synth.make_reference(5_000_000, n_contigs=3, seed=12, repeat_frac=0.03), False,
+                           {"B200BWA_INDEX_GROUP": "1500000"})
+    if os.environ.get("B200BWA_FULL_INDEX") == "1":
+        pu.check_index_builder(pu.CLI, d, "g100M", synth.make_reference(100_000_000, n_contigs=4, seed=1, repeat_frac=0.02), True, {})
