@@ -728,23 +728,33 @@ B2_KERNEL k_scan(const int32_t* in, int64_t* out, int n) {
   for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
   out[n] = s;
 #else
-  __shared__ int64_t part[1024];
-  const int t = threadIdx.x, T = blockDim.x;
-  const int chunk = (n + T - 1) / T;
-  const int b = t * chunk, e = b + chunk < n ? b + chunk : n;
-  int64_t s = 0;
-  for (int i = b; i < e; ++i) s += in[i];
-  part[t] = s;
-  __syncthreads();
-  for (int d = 1; d < T; d <<= 1) {
-    int64_t v = t >= d ? part[t - d] : 0;
+  // one block; 1024 consecutive elements per trip (coalesced), scanned with warp shuffles, the running total carried on
+  __shared__ int64_t wsum[32];
+  __shared__ int64_t chunk_total;
+  const int t = threadIdx.x, T = blockDim.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
+  int64_t base = 0;
+  for (int c0 = 0; c0 < n; c0 += T) {
+    const int i = c0 + t;
+    const int64_t v = i < n ? (int64_t)in[i] : 0;
+    int64_t x = v;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
+    if (lane == 31) wsum[warp] = x;
     __syncthreads();
-    part[t] += v;
+    if (warp == 0) {
+      const int64_t wv = lane < n_warps ? wsum[lane] : 0;
+      int64_t w = wv;
+#pragma unroll
+      for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, w, d); if (lane >= d) w += y; }
+      wsum[lane] = w - wv;                 // exclusive prefix of the warp totals
+      if (lane == 31) chunk_total = w;
+    }
+    __syncthreads();
+    if (i < n) out[i] = base + wsum[warp] + x - v;
+    base += chunk_total;
     __syncthreads();
   }
-  int64_t base = t ? part[t - 1] : 0;
-  for (int i = b; i < e; ++i) { out[i] = base; base += in[i]; }
-  if (t == T - 1) out[n] = part[T - 1];
+  if (t == 0) out[n] = base;
 #endif
 }
 

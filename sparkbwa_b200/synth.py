@@ -251,9 +251,11 @@ def simulate_pairs_fast(contigs, n_pairs: int, read_len: int = 150, seed: int = 
 
 
 def write_fastq_fixed(path: str, seq_chunks, first_index: int = 0, suffix: bytes = b"/1"):
-    """Write fixed-width FASTQ records from (m, L) ASCII arrays; returns the number of reads."""
+    """Write fixed-width FASTQ records from (m, L) ASCII arrays (to a path, or appended to an open binary file);
+    returns the number of reads."""
+    import contextlib
     n = 0
-    with open(path, "wb") as f:
+    with (contextlib.nullcontext(path) if hasattr(path, "write") else open(path, "wb")) as f:
         for s in seq_chunks:
             m, L = s.shape
             ids = np.arange(first_index + n, first_index + n + m)
