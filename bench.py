@@ -98,7 +98,7 @@ class ClockSampler(threading.Thread):
 
 def workdir(args):
     base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    d = os.path.join(base, f"b2bench_L{args.ref_len}_P{args.pairs}_s{args.seed}")
+    d = os.path.join(base, f"b2bench_{args.workload}_L{args.ref_len}_P{args.pairs}_s{args.seed}")
     os.makedirs(d, exist_ok=True)
     return d
 
@@ -124,25 +124,32 @@ def prepare_reads(args, d, ctg, rank):
     f2 = os.path.join(d, "r_2.fq")
     s1, s2 = [], []
     t = time.time()
-    for a, b in synth.simulate_pairs_fast(ctg, args.pairs, 150, seed=args.seed * 1000 + 17, sub=0.01, indel=0.001):
+    if args.paired:
+        gen = synth.simulate_pairs_fast(ctg, args.pairs, 150, seed=args.seed * 1000 + 17, sub=0.01, indel=0.001)
+    else:  # single-end 250 bp: mate 1 of the same simulator, up to six single-base indels per read
+        gen = synth.simulate_pairs_fast(ctg, args.pairs, 250, seed=args.seed * 1000 + 19, sub=0.035, indel=0.015, indel_rounds=6,
+                                        ins_mean=600.0, ins_sd=60.0)
+    for a, b in gen:
         s1.append(a); s2.append(b)
-    if rank == 0 and not os.path.exists(f2):
-        synth.write_fastq_fixed(f1 + ".tmp", s1, 0, b"/1"); os.replace(f1 + ".tmp", f1)
-        synth.write_fastq_fixed(f2 + ".tmp", s2, 0, b"/2"); os.replace(f2 + ".tmp", f2)
-    sys.stderr.write(f"[bench] rank {rank}: {args.pairs} pairs simulated in {time.time() - t:.1f}s\n")
-    return np.concatenate(s1), np.concatenate(s2), f1, f2
+    if rank == 0 and not os.path.exists(f2 if args.paired else f1):
+        synth.write_fastq_fixed(f1 + ".tmp", s1, 0, b"/1" if args.paired else b""); os.replace(f1 + ".tmp", f1)
+        if args.paired:
+            synth.write_fastq_fixed(f2 + ".tmp", s2, 0, b"/2"); os.replace(f2 + ".tmp", f2)
+    sys.stderr.write(f"[bench] rank {rank}: {args.pairs} {'pairs' if args.paired else 'reads'} simulated in {time.time() - t:.1f}s\n")
+    return np.concatenate(s1), (np.concatenate(s2) if args.paired else None), f1, (f2 if args.paired else None)
 
 
 def cut_batches(n_reads, read_len, chunk):
-    """bseq_read (bwa.c:42-75): a batch ends once its bases reach `chunk` and the read count is even."""
+    """bseq_read (bwa.c:42-75): a batch ends once its bases reach `chunk` and the read count is even (reads are taken
+    two at a time from a pair of files, one at a time from a single file)."""
     out, first = [], 0
     per = read_len
     while first < n_reads:
         n = 0
         size = 0
         while first + n < n_reads:
-            n += 2; size += 2 * per
-            if size >= chunk:
+            n += 1; size += per
+            if size >= chunk and n % 2 == 0:
                 break
         out.append((first, n))
         first += n
@@ -152,25 +159,22 @@ def cut_batches(n_reads, read_len, chunk):
 def cpu_reference(args, prefix, f1, f2, sample_pairs, threads):
     """Times the reference's own bwa mem on the host cores over the first `sample_pairs` pairs."""
     d = os.path.dirname(f1)
-    h1, h2 = os.path.join(d, "cpu_1.fq"), os.path.join(d, "cpu_2.fq")
-    rec = 4  # lines per record
-    for src, dst in ((f1, h1), (f2, h2)):
+    files = [(f1, os.path.join(d, "cpu_1.fq"))] + ([(f2, os.path.join(d, "cpu_2.fq"))] if f2 else [])
+    for src, dst in files:
         with open(src, "rb") as fi, open(dst, "wb") as fo:
-            first = fi.readline()
+            l2 = sum(len(fi.readline()) for _ in range(4))   # fixed-width records: size of one record = 4 lines
             fi.seek(0)
-            # fixed-width records: size of one record = 4 lines
-            l2 = len(first) + 150 + 1 + 2 + 150 + 1
             fo.write(fi.read(l2 * sample_pairs))
     # index load warm-up is part of the reference run (as it is for a SparkBWA task); report wall time of the whole call
     t = time.time()
-    r = subprocess.run([ORACLE, "mem", "-t", str(threads), "-K", str(args.K), prefix, h1, h2], stdout=subprocess.DEVNULL,
+    r = subprocess.run([ORACLE, "mem", "-t", str(threads), "-K", str(args.K), prefix] + [x[1] for x in files], stdout=subprocess.DEVNULL,
                        stderr=subprocess.PIPE)
     dt = time.time() - t
     if r.returncode != 0:
         raise RuntimeError("oracle bwa failed: " + r.stderr.decode()[-500:])
     # subtract nothing: honest wall clock; parse bwa's own per-batch times for the note
     proc = [float(l.split(" in ")[1].split(" CPU")[0]) for l in r.stderr.decode().splitlines() if "Processed" in l]
-    return 2 * sample_pairs / dt, dt, sum(proc)
+    return (2 if f2 else 1) * sample_pairs / dt, dt, sum(proc)
 
 
 def main():
@@ -182,7 +186,10 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="engine")
-    ap.add_argument("--pairs", type=int, default=1_000_000)
+    ap.add_argument("--workload", default="pe150", choices=["pe150", "se250"],
+                    help="pe150: BASELINE.json configs[1]/[4] (2x150 bp pairs, 1 %% error); se250: configs[3] (single-end 250 bp, 3.5 %% "
+                         "substitutions + 1.5 %% indels: wide ksw_extend2 bands, band retries)")
+    ap.add_argument("--pairs", type=int, default=0, help="pairs (pe150; default 1,000,000) or reads (se250; default 400,000)")
     ap.add_argument("--ref-len", type=int, default=100_000_000)
     ap.add_argument("--K", type=int, default=10_000_000)
     ap.add_argument("--seed", type=int, default=1)
@@ -191,13 +198,24 @@ def main():
                     help="pairs timed by the CPU legs (0: the whole workload for --impl reference, 200000 for the engine arm's cpu_baseline)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-e2e-large", action="store_true", help="skip the N x pairs companion job of the multi-GPU e2e leg")
     args = ap.parse_args()
+    args.paired = args.workload == "pe150"
+    args.read_len = 150 if args.paired else 250
+    if args.pairs <= 0:
+        args.pairs = 1_000_000 if args.paired else 400_000
 
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     host_cores = os.cpu_count() or 1
-    workload = f"BWA-MEM paired-end {args.pairs} x 2x150bp vs {args.ref_len} bp synthetic reference (2% planted repeats), -K {args.K}"
+    if args.paired:
+        workload = f"BWA-MEM paired-end {args.pairs} x 2x150bp vs {args.ref_len} bp synthetic reference (2% planted repeats), -K {args.K}"
+        metric = "BWA-MEM reads/sec 2x150bp PE"
+    else:
+        workload = (f"BWA-MEM single-end {args.pairs} x 250bp at 3.5% substitutions + 1.5% indels vs {args.ref_len} bp synthetic reference "
+                    f"(2% planted repeats), -K {args.K}")
+        metric = "BWA-MEM reads/sec 250bp SE"
 
     if args.impl == "reference":
         if rank != 0:
@@ -222,7 +240,7 @@ def main():
         ms = float(np.mean([x[1] for x in vals])) * 1e3
         print(file=real_stdout, end="")
         real_stdout.write(json.dumps({
-            "impl": "reference", "metric": "BWA-MEM reads/sec 2x150bp PE", "value": v, "unit": "reads/s", "n_gpus": args.gpus,
+            "impl": "reference", "metric": metric, "value": v, "unit": "reads/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "strong",
             "vs_baseline": None, "dtype": "int32", "data": "synthetic",
             "config": {"workload": workload, "timing": "wall clock of the whole `bwa mem` call incl. its index load from the page cache "
@@ -272,21 +290,27 @@ def main():
     if not ix:
         raise SystemExit("index adopt failed: " + lib.b200bwa_last_error().decode())
     assert lib.b200bwa_set_options(ix, f"-K {args.K}".encode()) == 0
-    lib.b200bwa_set_paired(ix, 1)
+    lib.b200bwa_set_paired(ix, 1 if args.paired else 0)
 
     # ---- resident job ------------------------------------------------------------------------------
-    n_reads = 2 * args.pairs
-    inter = np.empty((n_reads, 150), dtype=np.uint8)
-    inter[0::2] = s1; inter[1::2] = s2
+    RL = args.read_len
+    if args.paired:
+        n_reads = 2 * args.pairs
+        inter = np.empty((n_reads, RL), dtype=np.uint8)
+        inter[0::2] = s1; inter[1::2] = s2
+        names = b"".join(b"r%09d\0r%09d\0" % (i, i) for i in range(args.pairs))
+    else:
+        n_reads = args.pairs
+        inter = s1
+        names = b"".join(b"r%09d\0" % i for i in range(args.pairs))
     del s1, s2
     seq = inter.tobytes()
     qual = b"I" * len(seq)
-    off = (np.arange(n_reads + 1, dtype=np.int64) * 150)
-    names = b"".join(b"r%09d\0r%09d\0" % (i, i) for i in range(args.pairs))
+    off = (np.arange(n_reads + 1, dtype=np.int64) * RL)
     if lib.b200bwa_upload_batch(ix, n_reads, seq, qual, off.ctypes.data, names, 0) != 0:
         raise SystemExit("upload failed: " + lib.b200bwa_last_error().decode())
     del inter
-    all_batches = cut_batches(n_reads, 150, args.K)
+    all_batches = cut_batches(n_reads, RL, args.K)
     batches = all_batches[rank::world]   # strong scaling: batch b of the one job -> rank b mod N
     lib.b200bwa_n_workers.argtypes = [ctypes.c_void_p]
     n_workers = max(1, min(args.workers, int(lib.b200bwa_n_workers(ix))))
@@ -304,7 +328,7 @@ def main():
                 if b >= len(batches) or err:
                     return
                 first, cnt = batches[b]
-                rc = lib.b200bwa_run_resident_range(ix, wi, first, cnt, 1, 0, None, None, ctypes.byref(t))
+                rc = lib.b200bwa_run_resident_range(ix, wi, first, cnt, 1 if args.paired else 0, 0, None, None, ctypes.byref(t))
                 if rc != 0:
                     err.append(lib.b200bwa_last_error().decode()); return
                 if collect is not None:
@@ -390,7 +414,7 @@ def main():
           "GCUPS_stage": cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else 0.0,
           "GCUPS_extend_stage": cnt[3] / (tot["extend"] / 1e3) / 1e9 if tot["extend"] > 0 else 0.0}
 
-    out = {"metric": "BWA-MEM reads/sec 2x150bp PE", "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
+    out = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
            "dtype": "int32", "data": "synthetic",
            "config": {"workload": workload, "batches_per_step": len(all_batches), "streams_per_gpu": n_workers,
@@ -417,7 +441,7 @@ def main():
     if not args.no_e2e and rank == 0:
         # ---- end to end through the reference-facing entry point (what the JNI symbol forwards to) ----
         sam = os.path.join(d, "e2e.sam")
-        argv = ["bwa", "mem", "-v", "1", "-K", str(args.K), prefix, f1, f2]
+        argv = ["bwa", "mem", "-v", "1", "-K", str(args.K), prefix, f1] + ([f2] if args.paired else [])
         arr = (ctypes.c_char_p * len(argv))(*[a.encode() for a in argv])
         os.environ["B200BWA_DEVICES"] = ",".join(str(g) for g in range(world))
         e2e_pairs = args.pairs
@@ -440,7 +464,7 @@ def main():
         # page-cache flush) would otherwise dominate the figure; every call's time is reported next to it
         dt = float(np.median(per_call))
         lib.b200bwa_process_counters(pc, 0)
-        out["e2e"] = {"value": 2 * e2e_pairs / dt, "unit": "reads/s", "h2d_bytes_per_step": int(pc[0] // n_e2e),
+        out["e2e"] = {"value": n_reads / dt, "unit": "reads/s", "h2d_bytes_per_step": int(pc[0] // n_e2e),
                       "d2h_bytes_per_step": int(pc[1] // n_e2e),
                       "path": f"one b200bwa_main_to call on {world} GPU(s): FASTQ files (tmpfs) -> one SAM file (tmpfs)",
                       "sam_bytes": os.path.getsize(sam), "seconds_per_step": dt,
@@ -449,6 +473,44 @@ def main():
             os.remove(sam)
         except OSError:
             pass
+        if world > 1 and not args.no_e2e_large:
+            # Companion figure: the same call on a job N times as long (N x pairs, distinct reads) -- what a
+            # configs[2]-sized job sees once start-up and drain are amortised over hundreds of batches.  Not the
+            # strong-scaling headline; reported next to it.
+            from sparkbwa_b200 import synth
+            ctg2 = synth.make_reference(args.ref_len, n_contigs=4 if args.ref_len >= 20_000_000 else 2, seed=args.seed, repeat_frac=0.02)
+            g1, g2 = os.path.join(d, "big_1.fq"), os.path.join(d, "big_2.fq")
+            big = world * args.pairs
+            with open(g1, "wb") as o1, open(g2, "wb") as o2:
+                base = 0
+                gen = synth.simulate_pairs_fast(ctg2, big, 150, seed=args.seed * 1000 + 23, sub=0.01, indel=0.001) if args.paired else \
+                    synth.simulate_pairs_fast(ctg2, big, 250, seed=args.seed * 1000 + 29, sub=0.035, indel=0.015, indel_rounds=6, ins_mean=600.0, ins_sd=60.0)
+                for a, b in gen:
+                    synth.write_fastq_fixed(o1, [a], base, b"/1" if args.paired else b"")
+                    if args.paired:
+                        synth.write_fastq_fixed(o2, [b], base, b"/2")
+                    base += len(a)
+            del ctg2
+            argv2 = ["bwa", "mem", "-v", "1", "-K", str(args.K), prefix, g1] + ([g2] if args.paired else [])
+            arr2 = (ctypes.c_char_p * len(argv2))(*[a.encode() for a in argv2])
+            calls = []
+            for _ in range(2):
+                try:
+                    os.remove(sam)
+                except OSError:
+                    pass
+                t0 = time.time()
+                if lib.b200bwa_main_to(len(argv2), arr2, sam.encode()) != 0:
+                    raise SystemExit("e2e (large job) failed: " + lib.b200bwa_last_error().decode())
+                calls.append(time.time() - t0)
+            nr = big * (2 if args.paired else 1)
+            out["e2e_large_job"] = {"value": nr / min(calls), "unit": "reads/s", "reads": nr, "seconds_per_call": [round(x, 4) for x in calls],
+                                    "sam_bytes": os.path.getsize(sam), "note": f"{world} x the job of `e2e`, one call on {world} GPUs"}
+            for p in (g1, g2, sam):
+                try:
+                    os.remove(p)
+                except OSError:
+                    pass
         if store is not None:
             store.set("b2_e2e_done", "1")
     if rank == 0:

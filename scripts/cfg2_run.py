@@ -41,6 +41,7 @@ def main():
     ap.add_argument("--out", default="gpurun_out/cfg2")
     ap.add_argument("--work", default="/dev/shm/b2cfg2")
     ap.add_argument("--keep", action="store_true")
+    ap.add_argument("--sim-procs", type=int, default=0, help="processes simulating reads (0: half the cores, at most 16)")
     a = ap.parse_args()
     os.makedirs(a.out, exist_ok=True)
     os.makedirs(a.work, exist_ok=True)
@@ -69,12 +70,37 @@ def main():
     # ---- 2. reads --------------------------------------------------------------------------------
     f1, f2 = os.path.join(a.work, "r_1.fq"), os.path.join(a.work, "r_2.fq")
     t = time.time()
-    with open(f1, "wb") as o1, open(f2, "wb") as o2:
-        base = 0
-        for s1, s2 in synth.simulate_pairs_fast(ctg, a.pairs, 150, seed=2024, sub=0.01, indel=0.001):
-            synth.write_fastq_fixed(o1, [s1], base, b"/1")
-            synth.write_fastq_fixed(o2, [s2], base, b"/2")
-            base += len(s1)
+    # simulated in slices by forked workers (each slice its own seed), concatenated in order
+    n_proc = max(1, min(a.sim_procs or (os.cpu_count() or 1) // 2, 16))
+    per = -(-a.pairs // n_proc)
+    pids = []
+    for k in range(n_proc):
+        lo, hi = k * per, min(a.pairs, (k + 1) * per)
+        if lo >= hi:
+            break
+        pid = os.fork()
+        if pid == 0:
+            with open(f"{f1}.{k}", "wb") as o1, open(f"{f2}.{k}", "wb") as o2:
+                base = lo
+                for s1, s2 in synth.simulate_pairs_fast(ctg, hi - lo, 150, seed=2024 + k, sub=0.01, indel=0.001):
+                    synth.write_fastq_fixed(o1, [s1], base, b"/1")
+                    synth.write_fastq_fixed(o2, [s2], base, b"/2")
+                    base += len(s1)
+            os._exit(0)
+        pids.append(pid)
+    for pid in pids:
+        if os.waitpid(pid, 0)[1] != 0:
+            raise SystemExit("read simulation worker failed")
+    for f in (f1, f2):
+        with open(f, "wb") as fo:
+            for k in range(len(pids)):
+                with open(f"{f}.{k}", "rb") as fi:
+                    while True:
+                        buf = fi.read(1 << 26)
+                        if not buf:
+                            break
+                        fo.write(buf)
+                os.remove(f"{f}.{k}")
     del ctg
     rep["simulate_reads_s"] = time.time() - t
     rep["fastq_bytes"] = os.path.getsize(f1) + os.path.getsize(f2)

@@ -590,7 +590,10 @@ struct B2SeqReader::Impl {
     if (!map || pre_on) return;
     if (const char* s = getenv("B200BWA_SCAN_CHUNK")) { long v = atol(s); if (v >= 64) chunk_bytes = (size_t)v; }
     const size_t n_chunks = (map_size + chunk_bytes - 1) / chunk_bytes;
-    int n_threads = 4;
+    // a quarter of the host cores per input file, between 2 and 8 (the scan runs at ~2 GB/s per thread; one job over
+    // 8 GPUs consumes FASTQ at 10+ GB/s)
+    int n_threads = (int)std::thread::hardware_concurrency() / 4;
+    n_threads = n_threads < 2 ? 2 : n_threads > 8 ? 8 : n_threads;
     if (const char* s = getenv("B200BWA_SCAN_THREADS")) n_threads = atoi(s);
     if (n_threads < 1) n_threads = 1;
     if ((size_t)n_threads > n_chunks) n_threads = (int)n_chunks;
@@ -1457,7 +1460,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     if (mp != MAP_FAILED) {
       out_map = (char*)mp;
       alloc_end = next_off > 0 ? next_off : 1;
-      const int64_t look = ((int64_t)96 << 20) * G, step = (int64_t)32 << 20;
+      const int64_t look = ((int64_t)48 << 20) * G + ((int64_t)32 << 20), step = (int64_t)16 << 20;
       allocator = std::thread([&, look, step]() {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
@@ -1766,18 +1769,22 @@ int b2_index_main(int argc, char** argv) {
     p.offset = anns.empty() ? 0 : anns.back().offset + anns.back().len;
     p.n_ambs = 0;
     const std::string& sq = ks.seq();
-    int lasts = 0;
-    fwd.reserve(fwd.size() + sq.size());
-    for (size_t i = 0; i < sq.size(); ++i) {
-      int c = nt4[(unsigned char)sq[i]];
-      if (c >= 4) {
-        if (lasts == sq[i]) ++ambs.back().len;
-        else { Amb q; q.len = 1; q.offset = p.offset + (int64_t)i; q.amb = sq[i]; ambs.push_back(q); ++p.n_ambs; }
-        lcg = (lcg * 0x5DEECE66DULL + 0xB) & 0xFFFFFFFFFFFFULL;   // lrand48()
-        c = (int)((lcg >> 17) & 3);
+    const size_t base = fwd.size();
+    fwd.resize(base + sq.size());
+    uint8_t* dst = fwd.data() + base;
+    unsigned any_amb = 0;
+    for (size_t i = 0; i < sq.size(); ++i) { const uint8_t c = nt4[(unsigned char)sq[i]]; dst[i] = c; any_amb |= c; }
+    if (any_amb & 4) {  // ambiguous bases present: holes + the lrand48 replay, in sequence order
+      int lasts = 0;
+      for (size_t i = 0; i < sq.size(); ++i) {
+        if (dst[i] >= 4) {
+          if (lasts == sq[i]) ++ambs.back().len;
+          else { Amb q; q.len = 1; q.offset = p.offset + (int64_t)i; q.amb = sq[i]; ambs.push_back(q); ++p.n_ambs; }
+          lcg = (lcg * 0x5DEECE66DULL + 0xB) & 0xFFFFFFFFFFFFULL;   // lrand48()
+          dst[i] = (uint8_t)((lcg >> 17) & 3);
+        }
+        lasts = sq[i];
       }
-      lasts = sq[i];
-      fwd.push_back((uint8_t)c);
     }
     anns.push_back(p);
   }

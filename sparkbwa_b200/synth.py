@@ -197,11 +197,13 @@ def write_fastq(path: str, reads):
 
 
 def simulate_pairs_fast(contigs, n_pairs: int, read_len: int = 150, seed: int = 7, sub: float = 0.01,
-                        indel: float = 0.001, ins_mean: float = 400.0, ins_sd: float = 40.0, chunk: int = 200_000):
+                        indel: float = 0.001, ins_mean: float = 400.0, ins_sd: float = 40.0, chunk: int = 200_000,
+                        indel_rounds: int = 1):
     """Vectorised paired-end simulator for the benchmark workloads (millions of pairs).
 
     Same model as simulate_reads (uniform start, 50/50 strand, per-base substitutions, FR pairs with
-    N(ins_mean, ins_sd) outer distance) with at most one single-base indel per read.  Yields chunks
+    N(ins_mean, ins_sd) outer distance) with at most `indel_rounds` single-base indels per read (each round plants one
+    with probability indel * read_len / indel_rounds; 1 for the 2x150 bp workloads, more for the 250 bp / 5 % one).  Yields chunks
     (seq1, seq2) of ASCII uint8 arrays shaped (m, read_len); names are r%09d by global pair index.
     """
     rng = np.random.default_rng(seed)
@@ -224,20 +226,24 @@ def simulate_pairs_fast(contigs, n_pairs: int, read_len: int = 150, seed: int = 
                 idx = st[:, None] + cols[None, :]
             else:
                 idx = (st + isz - 1)[:, None] - cols[None, :]
-            # one optional single-base indel per read: shift the source index after position p
-            ev = rng.random(m) < indel * L
-            p = rng.integers(10, L - 10, size=m)
-            is_del = rng.random(m) < 0.5
-            shift = (cols[None, :] >= p[:, None]) & ev[:, None]
-            step = np.where(is_del, 1, -1)[:, None] * (1 if which == 0 else -1)
-            idx = idx + shift * step
+            # optional single-base indels: shift the source index after position p
+            planted = []
+            for _ in range(indel_rounds):
+                ev = rng.random(m) < indel * L / indel_rounds
+                p = rng.integers(10, L - 10, size=m)
+                is_del = rng.random(m) < 0.5
+                shift = (cols[None, :] >= p[:, None]) & ev[:, None]
+                step = np.where(is_del, 1, -1)[:, None] * (1 if which == 0 else -1)
+                idx = idx + shift * step
+                planted.append((ev & ~is_del, p))
+            idx = np.clip(idx, 0, len(ref) - 1)
             r = ref[idx]
             if which == 1:
                 r = 3 - r
-            ins = ev & ~is_del
-            if ins.any():  # the inserted base itself is random
-                rows = np.nonzero(ins)[0]
-                r[rows, p[rows]] = rng.integers(0, 4, size=rows.size, dtype=np.uint8)
+            for ins, p in planted:
+                if ins.any():  # the inserted base itself is random
+                    rows = np.nonzero(ins)[0]
+                    r[rows, p[rows]] = rng.integers(0, 4, size=rows.size, dtype=np.uint8)
             if sub > 0:
                 msk = rng.random((m, L)) < sub
                 k = int(msk.sum())
