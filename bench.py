@@ -41,7 +41,8 @@ ORACLE = os.path.join(ROOT, "oracle", "_ref", "bwa")
 class Times(ctypes.Structure):
     _fields_ = [(n, ctypes.c_float) for n in ("h2d", "seed", "sa", "chain", "extend", "pestat", "finalize", "gather", "d2h", "total")] + \
                [("launches", ctypes.c_int), ("n_seed_tasks", ctypes.c_int64), ("n_regs", ctypes.c_int64), ("sam_bytes", ctypes.c_int64),
-                ("rescue", ctypes.c_float), ("n_rescue_tasks", ctypes.c_int64)]
+                ("rescue", ctypes.c_float), ("n_rescue_tasks", ctypes.c_int64),
+                ("k_xext", ctypes.c_float), ("k_resc_sw", ctypes.c_float), ("k_galn", ctypes.c_float)]
 
 
 def load_lib():
@@ -384,7 +385,8 @@ def main():
     lib.b200bwa_counters(ix, 0, cnt, 1)
     if rank != 0:
         stage = [{k: 0.0 for k, _ in Times._fields_}]
-    tot = {k: float(sum(s[k] for s in stage)) for k in ("seed", "sa", "chain", "extend", "pestat", "rescue", "finalize", "gather", "total")}
+    tot = {k: float(sum(s[k] for s in stage)) for k in ("seed", "sa", "chain", "extend", "pestat", "rescue", "finalize", "gather", "total",
+                                                        "k_xext", "k_resc_sw", "k_galn")}
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -410,9 +412,25 @@ def main():
                 "sa_kernel": {"bytes_per_read": sa_bytes / n_reads, "GB/s": sa_bytes / (tot["sa"] / 1e3) / 1e9 if tot["sa"] > 0 else 0.0}}
     cells = float(cnt[3] + cnt[5] + cnt[7])
     dp_ms = tot["extend"] + tot["rescue"] + tot["finalize"]
+    # SW kernels against the INT32 issue roofline: GCUPS of the kernel proper (its CUDA events) x the reference
+    # recurrence's integer operations per cell (ksw_extend2 14, ksw_global2 12, ksw_u8/i16 10) over the
+    # MEASURED full-rate integer issue peak (scripts/int_peak.cu on this box: profiles/r2/int_peaks.json, IADD3/IMNMX;
+    # DPX add-max / max3 forms issue at half that rate)
+    int_peak = None
+    try:
+        int_peak = float(json.load(open(os.path.join(ROOT, "profiles", "r2", "int_peaks.json")))["iadd3"]) * 1e12
+    except Exception:
+        pass
+
+    def sw_kernel(cells_k, ms, ops):
+        g = cells_k / (ms / 1e3) / 1e9 if ms > 0 else 0.0
+        return {"GCUPS": g, "ms_per_step": ms, "ops_per_cell": ops, "frac_of_int_peak": (g * 1e9 * ops / int_peak) if int_peak else None}
     sw = {"cells_per_read": {"extend": cnt[3] / n_reads, "global": cnt[5] / n_reads, "local": cnt[7] / n_reads},
           "GCUPS_stage": cells / (dp_ms / 1e3) / 1e9 if dp_ms > 0 else 0.0,
-          "GCUPS_extend_stage": cnt[3] / (tot["extend"] / 1e3) / 1e9 if tot["extend"] > 0 else 0.0}
+          "int_peak_lane_ops_per_s": int_peak, "int_peak_source": "measured: profiles/r2/int_peaks.json (scripts/int_peak.cu)",
+          "kernels": {"k_xext_run (ksw_extend2, first band try of every chain's best seed)": sw_kernel(cnt[9], tot["k_xext"], 14),
+                      "k_resc_sw (ksw_u8/i16 of mem_matesw)": sw_kernel(cnt[10], tot["k_resc_sw"], 10),
+                      "k_galn* (ksw_global2 of mem_reg2aln)": sw_kernel(cnt[11], tot["k_galn"], 12)}}
 
     out = {"metric": metric, "value": value, "unit": "reads/s", "n_gpus": world, "steps": args.steps,
            "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
@@ -437,7 +455,8 @@ def main():
     if not args.no_e2e and rank != 0:
         # rank 0's single call drives every GPU of the job; wait for it on the rendezvous store (a NCCL barrier would
         # keep a spinning kernel on this rank's GPU while the product call is being timed)
-        store.wait(["b2_e2e_done"])
+        import datetime
+        store.wait(["b2_e2e_done"], datetime.timedelta(minutes=30))
     if not args.no_e2e and rank == 0:
         # ---- end to end through the reference-facing entry point (what the JNI symbol forwards to) ----
         sam = os.path.join(d, "e2e.sam")
@@ -447,7 +466,8 @@ def main():
         e2e_pairs = args.pairs
         if lib.b200bwa_main_to(len(argv), arr, sam.encode()) != 0:  # warm-up: loads + caches the index in HBM (all devices)
             raise SystemExit("e2e failed: " + lib.b200bwa_last_error().decode())
-        lib.b200bwa_main_to(len(argv), arr, sam.encode())           # second warm-up: per-worker buffers at their steady size
+        for _ in range(2):                                          # more warm-ups: per-worker buffers at their steady size
+            lib.b200bwa_main_to(len(argv), arr, sam.encode())
         lib.b200bwa_process_counters(pc, 1)
         n_e2e = max(1, min(5, args.steps))
         per_call = []

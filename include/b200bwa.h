@@ -105,6 +105,7 @@ typedef struct {
   int64_t n_seed_tasks, n_regs, sam_bytes;
   float rescue;   /* planned mate-rescue SW tasks (between pestat and finalize) */
   int64_t n_rescue_tasks;
+  float k_xext, k_resc_sw, k_galn;  /* the DP kernels proper: inter-task ksw_extend2 (both sides), ksw_u8/i16, ksw_global2 */
 } b200bwa_times_t;
 int b200bwa_last_times(b200bwa_index_t* idx, b200bwa_times_t* t);
 
@@ -124,7 +125,8 @@ int b200bwa_n_workers(b200bwa_index_t* idx);
 
 /* Algorithmic-work counters accumulated by the kernels of one worker: [0] 64-byte occ-block touches of
  * SMEM seeding, [1] SA lookups, [2] SA walk steps, [3] ksw_extend2 cells, [4] calls, [5] ksw_global2
- * cells, [6] calls, [7] local-SW cells, [8] calls (definitions: SURVEY.md 8(d)). */
+ * cells, [6] calls, [7] local-SW cells, [8] calls (definitions: SURVEY.md 8(d)); [9] [10] [11] the cells of the kernels
+ * k_xext_run, k_resc_sw and k_galn* alone (subsets of [3], [7], [5]). */
 int b200bwa_counters(b200bwa_index_t* idx, int worker, unsigned long long out[16], int reset);
 /* Process-wide totals: [0] host->device bytes, [1] device->host bytes, [2] kernel launches. */
 int b200bwa_process_counters(unsigned long long out[3], int reset);

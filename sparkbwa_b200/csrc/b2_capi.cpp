@@ -256,6 +256,7 @@ int b200bwa_last_times(b200bwa_index_t* ix, b200bwa_times_t* t) {
   t->h2d = s.h2d; t->seed = s.seed; t->sa = s.sa; t->chain = s.chain; t->extend = s.extend; t->pestat = s.pestat;
   t->finalize = s.final_; t->gather = s.gather; t->d2h = s.d2h; t->total = s.total; t->launches = s.launches;
   t->n_seed_tasks = s.n_seed_tasks; t->n_regs = s.n_regs; t->sam_bytes = s.sam_bytes; t->rescue = s.rescue; t->n_rescue_tasks = s.n_resc;
+  t->k_xext = s.k_xext; t->k_resc_sw = s.k_resc_sw; t->k_galn = s.k_galn;
   return 0;
 }
 
@@ -305,6 +306,7 @@ int b200bwa_run_resident_range(b200bwa_index_t* ix, int worker, int first, int c
       t->h2d = s.h2d; t->seed = s.seed; t->sa = s.sa; t->chain = s.chain; t->extend = s.extend; t->pestat = s.pestat;
       t->finalize = s.final_; t->gather = s.gather; t->d2h = s.d2h; t->total = s.total; t->launches = s.launches;
       t->n_seed_tasks = s.n_seed_tasks; t->n_regs = s.n_regs; t->sam_bytes = s.sam_bytes; t->rescue = s.rescue; t->n_rescue_tasks = s.n_resc;
+      t->k_xext = s.k_xext; t->k_resc_sw = s.k_resc_sw; t->k_galn = s.k_galn;
     }
     (void)paired;
     if (want_sam && sam_out) { *sam_out = dup_out(sam, sam_len); return *sam_out ? 0 : 1; }

@@ -47,7 +47,7 @@ struct DBuf {
 
 struct Timer {
 #if !defined(B2_HOSTSIM)
-  cudaEvent_t e[16];
+  cudaEvent_t e[32];
   int n = 0;
   cudaStream_t s;
   void init(cudaStream_t st) { s = st; for (auto& x : e) cudaEventCreate(&x); }
@@ -555,6 +555,7 @@ class B2EngineImpl {
     if (b2_sync(w.stream)) return fail("device synchronisation failed");
     c.chain_off = w.chain_off.p; c.n_chain_tasks = TC; c.cand = w.cand.p; c.cand_ok = w.cand_ok.p;
     // inter-task extension of every chain's best seed, left then right, ahead of the group-cooperative kernel
+    int ev_x[4] = {-1, -1, -1, -1}, ev_r[2] = {-1, -1}, ev_g[2] = {-1, -1};   // CUDA events around the three DP kernels proper
     c.xext_res = nullptr; c.xext_tasks = nullptr;
     if (TC > 0 && !cfg.no_xext && b2_mat_simple(opt.mat) && S < (1 << 29)) {
       c.xext_qcap = w.max_len; c.xext_tcap = w.max_len + 2 * opt.w + 64;
@@ -576,7 +577,9 @@ class B2EngineImpl {
           B2_LAUNCH(k_xext_plan, pgrid, 128, w.stream, c, side);
           B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.xext_hist.p, w.xext_hoff.p, bins);
           B2_LAUNCH(k_xext_scatter, pgrid, 128, w.stream, c);
+          ev_x[2 * side] = w.timer.mark();
           B2_LAUNCH_SMEM(k_xext_run, xgrid, 32, smem, w.stream, c);
+          ev_x[2 * side + 1] = w.timer.mark();
           w.times.launches += 4;
         }
       }
@@ -660,7 +663,9 @@ class B2EngineImpl {
           b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
           const int64_t groups_needed = (T * B2_G_RESC + cfg.lane_block - 1) / cfg.lane_block;
           const int grid = (int)std::min<int64_t>(groups_needed, lane_grid);
+          ev_r[0] = w.timer.mark();
           B2_LAUNCH(k_resc_sw, grid, cfg.lane_block, w.stream, c);
+          ev_r[1] = w.timer.mark();
           ++w.times.launches;
           if (read_flags(w, &flags)) return 1;
           if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
@@ -702,10 +707,12 @@ class B2EngineImpl {
           // one-warp blocks: a batch has only a few hundred warps of these tasks, spread them over all SMs
           const int blk = std::min(cfg.lane_block, 32);
           auto grid_for = [&](int64_t cnt) { return (int)std::min<int64_t>((cnt + blk - 1) / blk, (int64_t)lane_grid * cfg.lane_block / blk); };
+          ev_g[0] = w.timer.mark();
           if (tot[0] > 0) { B2_LAUNCH(k_galn9, grid_for(tot[0]), blk, w.stream, c); ++w.times.launches; }
           if (tot[1] > 0) { B2_LAUNCH(k_galn17, grid_for(tot[1]), blk, w.stream, c); ++w.times.launches; }
           if (tot[2] > 0) { B2_LAUNCH(k_galn33, grid_for(tot[2]), blk, w.stream, c); ++w.times.launches; }
           if (tot[3] > 0) { B2_LAUNCH(k_galn65, grid_for(tot[3]), blk, w.stream, c); ++w.times.launches; }
+          ev_g[1] = w.timer.mark();
         }
       }
     }
@@ -812,6 +819,9 @@ class B2EngineImpl {
     w.times.d2h = w.timer.ms(ev_gat, ev_d2h);
     w.times.total = w.timer.ms(ev_begin, ev_d2h);
     if (ingest) w.times.h2d = w.timer.ms(ev_in0, ev_in1);
+    if (ev_x[1] >= 0) w.times.k_xext = w.timer.ms(ev_x[0], ev_x[1]) + (ev_x[3] >= 0 ? w.timer.ms(ev_x[2], ev_x[3]) : 0.f);
+    if (ev_r[1] >= 0) w.times.k_resc_sw = w.timer.ms(ev_r[0], ev_r[1]);
+    if (ev_g[1] >= 0) w.times.k_galn = w.timer.ms(ev_g[0], ev_g[1]);
     if (overflowed) {
       if (w.tried_decay) w.decay_wait = std::min(w.decay_wait * 4, 4096);  // the smaller size was not enough: ask less often
       w.clean_batches = 0;

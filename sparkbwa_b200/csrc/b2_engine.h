@@ -71,6 +71,7 @@ struct B2EngineConfig {
 
 struct B2StageTimes {  // milliseconds, device time (CUDA events) of the last batch
   float h2d = 0, seed = 0, sa = 0, chain = 0, extend = 0, pestat = 0, rescue = 0, final_ = 0, gather = 0, d2h = 0, total = 0;
+  float k_xext = 0, k_resc_sw = 0, k_galn = 0;   // the DP kernels proper (last launch of each in the batch)
   float stage_host = 0;   // raw ingest: host copy of the file bytes into the pinned staging buffer (wall ms)
   int launches = 0;
   int64_t n_seed_tasks = 0, n_regs = 0, sam_bytes = 0, n_resc = 0;

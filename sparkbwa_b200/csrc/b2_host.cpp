@@ -1452,24 +1452,33 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   // fallocate keep the positioned pwrite().
   char* out_map = 0;
   const size_t out_map_len = (size_t)1 << 38;
-  int64_t alloc_end = 0;        // bytes of the file reserved so far
-  bool alloc_stop = false;
+  int64_t alloc_end = 0;        // the allocator thread's frontier
+  int64_t file_size = 0;        // size the file has been extended to (offsets handed out never exceed it)
+  bool alloc_stop = false, populate_ok = false;
   std::thread allocator;
+#ifndef MADV_POPULATE_WRITE
+#define MADV_POPULATE_WRITE 23
+#endif
   if (positioned && !getenv("B200BWA_NO_MMAP_OUT") && fallocate(out_fd, 0, 0, (off_t)(next_off > 0 ? next_off : 1)) == 0) {
     void* mp = mmap(0, out_map_len, PROT_READ | PROT_WRITE, MAP_SHARED | MAP_NORESERVE, out_fd, 0);
     if (mp != MAP_FAILED) {
       out_map = (char*)mp;
-      alloc_end = next_off > 0 ? next_off : 1;
-      const int64_t look = ((int64_t)48 << 20) * G + ((int64_t)32 << 20), step = (int64_t)16 << 20;
+      alloc_end = file_size = next_off > 0 ? next_off : 1;
+      // Writers reserve their own range with MADV_POPULATE_WRITE (Linux >= 5.14: the page faults of a write, batched,
+      // with an error return where a store would raise SIGBUS) -- allocation then runs in parallel in every writer --
+      // while the allocator thread works ahead of the offsets handed out so far.  Without that madvise the writers
+      // wait for the allocator.
+      populate_ok = !getenv("B200BWA_NO_POPULATE") && madvise(out_map, 4096, MADV_POPULATE_WRITE) == 0;
+      const int64_t look = ((int64_t)16 << 20) * G + ((int64_t)64 << 20), step = (int64_t)16 << 20;
       allocator = std::thread([&, look, step]() {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
-          cv.wait(lk, [&] { return alloc_stop || failed || alloc_end < next_off + look; });
+          cv.wait(lk, [&] { return alloc_stop || failed || (populate_ok ? std::max(alloc_end, next_off) : alloc_end) < next_off + look; });
           if (alloc_stop || failed) return;
-          const int64_t from = alloc_end;
+          const int64_t from = populate_ok ? std::max(alloc_end, next_off) : alloc_end;
           lk.unlock();
           int e = 0;
-          while (fallocate(out_fd, 0, (off_t)from, (off_t)step) != 0) { if (errno != EINTR) { e = errno; break; } }
+          while (fallocate(out_fd, FALLOC_FL_KEEP_SIZE, (off_t)from, (off_t)step) != 0) { if (errno != EINTR) { e = errno; break; } }
           lk.lock();
           if (e) {
             failed = true;
@@ -1478,11 +1487,21 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
             return;
           }
           alloc_end = from + step;
+          if (!populate_ok && alloc_end > file_size) {   // writers wait for the allocator: the file has to cover what it reserved
+            file_size = alloc_end;
+            if (ftruncate(out_fd, (off_t)file_size) != 0) { failed = true; errmsg = "cannot extend the SAM output"; cv.notify_all(); return; }
+          }
           cv.notify_all();
         }
       });
     }
   }
+  // the file is extended (no allocation) ahead of the offsets handed out; called with `mu` held
+  auto grow_file = [&]() -> bool {
+    if (!out_map || next_off <= file_size) return true;
+    file_size = next_off + ((int64_t)1 << 30);
+    return ftruncate(out_fd, (off_t)file_size) == 0;
+  };
   std::deque<std::shared_ptr<Job>> wq;                      // jobs with an assigned offset, waiting to be written
   std::vector<char> busy((size_t)G * n_workers * 2, 0);    // pinned buffer [device][worker][slot] still being written out
   int gpu_active = G * n_workers;
@@ -1504,14 +1523,26 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
             wq.pop_front();
           }
           bool wrote = true;
-          if (out_map) {
+          if (out_map && !populate_ok) {
             std::unique_lock<std::mutex> lk(mu);
             cv.wait(lk, [&] { return failed || alloc_end >= j->offset + (int64_t)j->sam_size; });
             if (failed) return;
           }
           const double t_w0 = b2_realtime();
-          if (out_map) memcpy(out_map + j->offset, j->wdata, j->sam_size);
-          else wrote = pwrite_all(j->wdata, j->sam_size, j->offset);
+          if (out_map) {
+            if (populate_ok && j->sam_size) {
+              const int64_t a0 = j->offset & ~(int64_t)4095, a1 = (j->offset + (int64_t)j->sam_size + 4095) & ~(int64_t)4095;
+              if (madvise(out_map + a0, (size_t)(a1 - a0), MADV_POPULATE_WRITE) != 0) {
+                std::lock_guard<std::mutex> lk(mu);
+                failed = true;
+                errmsg = std::string("cannot reserve space for the SAM output: ") + strerror(errno == EFAULT ? ENOSPC : errno);
+                j->rc = 1;
+                cv.notify_all();
+                return;
+              }
+            }
+            memcpy(out_map + j->offset, j->wdata, j->sam_size);
+          } else wrote = pwrite_all(j->wdata, j->sam_size, j->offset);
           if (times) fprintf(stderr, "[T::b200bwa] batch %ld: queued for writing %.1f ms, write %.1f ms, done at %.1f ms\n", (long)j->index, (t_w0 - j->t_gpu) * 1e3, (b2_realtime() - t_w0) * 1e3, (b2_realtime() - t_real) * 1e3);
           std::lock_guard<std::mutex> lk(mu);
           if (j->wslot >= 0) busy[j->wslot] = 0;
@@ -1523,6 +1554,9 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   }
 
   if (times0) fprintf(stderr, "[T::b200bwa] pipeline threads starting at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
+  // A job of a device goes to its lowest-numbered idle worker: a device that never has more than three batches in
+  // flight keeps using the same three stream/buffer sets (their buffers are allocated once, and stay warm).
+  std::vector<unsigned> idle(G, 0u);
   std::vector<std::thread> gpu;
   for (int dv = 0; dv < G; ++dv)
    for (int wi = 0; wi < n_workers; ++wi)
@@ -1536,10 +1570,13 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
         int slot = -1;
         {
           std::unique_lock<std::mutex> lk(mu);
-          cv.wait(lk, [&] { return !q.empty() || read_done || failed; });
-          if (failed || (q.empty() && read_done)) return;
+          idle[dv] |= 1u << wi;
+          cv.wait(lk, [&] { return (!q.empty() && (idle[dv] & ((1u << wi) - 1)) == 0) || (q.empty() && read_done) || failed; });
+          idle[dv] &= ~(1u << wi);
+          if (failed || (q.empty() && read_done)) { cv.notify_all(); return; }
           j = q.front();
           q.pop_front();
+          cv.notify_all();   // (a higher-numbered worker may be the lowest idle one now)
           if (positioned && !smart) {  // the pinned buffer this batch's text will land in must have been written out
             slot = (dv * n_workers + wi) * 2 + eng->next_view_slot(wi);
             cv.wait(lk, [&] { return !busy[slot] || failed; });
@@ -1594,6 +1631,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
             wq.push_back(unassigned.front());
             unassigned.pop_front();
           }
+          if (!grow_file()) { failed = true; errmsg = "cannot extend the SAM output"; }
           cv.notify_all();
           continue;   // a writer thread marks the job done
         }

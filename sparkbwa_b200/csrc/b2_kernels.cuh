@@ -23,7 +23,11 @@
 #define B2_FLAG_OVF_REG 16
 
 enum { B2_CNT_OCC_BLOCKS = 0, B2_CNT_SA_CALLS, B2_CNT_SA_STEPS, B2_CNT_EXT_CELLS, B2_CNT_EXT_CALLS, B2_CNT_GLOB_CELLS,
-       B2_CNT_GLOB_CALLS, B2_CNT_SW_CELLS, B2_CNT_SW_CALLS, B2_CNT_N };
+       B2_CNT_GLOB_CALLS, B2_CNT_SW_CELLS, B2_CNT_SW_CALLS,
+       B2_CNT_XEXT_CELLS,    // cells of k_xext_run alone      } the three DP kernels proper, for their own GCUPS figures
+       B2_CNT_RESCSW_CELLS,  // cells of k_resc_sw alone       } (the category counters above include every in-kernel DP)
+       B2_CNT_GALN_CELLS,    // cells of k_galn* alone         }
+       B2_CNT_N };
 
 struct B2Batch {  // device-resident read batch
   int n_reads;
@@ -453,7 +457,10 @@ B2_KERNEL k_xext_run(B2Ctx c) {
     ++calls;
     c.xext_res[task.slot] = res;
   }
-  if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], calls); }
+  if (calls) {
+    B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], calls);
+    B2_ATOMIC_ADD(&c.counters[B2_CNT_XEXT_CELLS], cells);
+  }
 #if defined(B2_HOSTSIM)
   free(M.eh);
 #endif
@@ -565,6 +572,7 @@ B2_KERNEL k_resc_sw(B2Ctx c) {
     if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
     if (sc.lane == 0) c.resc_res[t] = r;
   }
+  if (sc.lane == 0 && sc.sw_cells) B2_ATOMIC_ADD(&c.counters[B2_CNT_RESCSW_CELLS], sc.sw_cells);
   b2_flush_counters(c, sc);
 }
 
@@ -635,7 +643,10 @@ B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
     b2_galn_one<ND>(qlen, q, tlen, tg, c.opt.mat, c.opt.o_del, c.opt.e_del, c.opt.o_ins, c.opt.e_ins, task.w, zw, LW, res, &cells);
     ++calls;
   }
-  if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CELLS], cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CALLS], calls); }
+  if (calls) {
+    B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CELLS], cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_GLOB_CALLS], calls);
+    B2_ATOMIC_ADD(&c.counters[B2_CNT_GALN_CELLS], cells);
+  }
 }
 B2_KERNEL k_galn9(B2Ctx c) { b2_galn_run<9>(c, 0); }
 B2_KERNEL k_galn17(B2Ctx c) { b2_galn_run<17>(c, 1); }
