@@ -19,6 +19,7 @@
 #include <sys/time.h>
 #include <zlib.h>
 
+#include <algorithm>
 #include <condition_variable>
 #include <deque>
 #include <map>
@@ -1040,7 +1041,12 @@ struct B2CachedIndex {
   bool ignore_alt = false;
   std::unique_ptr<B2IndexHost> host;
   std::vector<std::unique_ptr<B2Engine>> engines;  // one per device, in order of first use
-  std::mutex run_mu;
+  // Engines are leased to calls: a call takes every engine of its device list that is free (at least one, at most
+  // B200BWA_DEVICES_PER_CALL), so several tasks of one executor run side by side on different GPUs while a lone task
+  // spreads over all of them.
+  std::mutex lease_mu;
+  std::condition_variable lease_cv;
+  std::vector<B2Engine*> leased;
   // the ord-th engine on device d (a device listed twice in B200BWA_DEVICES gets two engines: that is how the
   // multi-engine path is exercised on a box with a single GPU)
   B2Engine* on_device(int d, int ord = 0) {
@@ -1146,8 +1152,9 @@ int b2_index_cache_evict() {
   std::lock_guard<std::mutex> lk(g_cache_mu);
   int n = 0;
   for (size_t i = 0; i < g_cache.size();) {
-    if (g_cache[i].use_count() == 1 && g_cache[i]->run_mu.try_lock()) {
-      g_cache[i]->run_mu.unlock();
+    bool idle = g_cache[i].use_count() == 1;
+    if (idle) { std::lock_guard<std::mutex> l2(g_cache[i]->lease_mu); idle = g_cache[i]->leased.empty(); }
+    if (idle) {
       g_cache.erase(g_cache.begin() + i);
       ++n;
     } else ++i;
@@ -1311,7 +1318,6 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     }
     if (devices.empty()) devices.push_back(0);
   }
-  const int G = (int)devices.size();
   // index first (same order of failure modes as the reference: index, then reads)
   std::vector<B2Engine*> engs;
   std::shared_ptr<B2CachedIndex> cached;
@@ -1342,9 +1348,28 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   if (times0) fprintf(stderr, "[T::b200bwa] inputs open at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   if (!get_engines()) return 1;
   if (times0) fprintf(stderr, "[T::b200bwa] engines ready at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
-  // one aligning call at a time per index (the engines' stream/buffer sets and options are per index); calls on
-  // other indices proceed concurrently
-  std::lock_guard<std::mutex> run_lock(cached->run_mu);
+  // Lease engines: every free one of the list (at least one: wait for it), at most B200BWA_DEVICES_PER_CALL.  Calls on
+  // other indices proceed independently; calls on this index that find no free engine take turns.
+  struct Lease {
+    B2CachedIndex* c; std::vector<B2Engine*> mine;
+    ~Lease() { std::lock_guard<std::mutex> lk(c->lease_mu); for (B2Engine* e : mine) c->leased.erase(std::find(c->leased.begin(), c->leased.end(), e)); c->lease_cv.notify_all(); }
+  } lease{cached.get(), {}};
+  {
+    size_t per_call = engs.size();
+    if (const char* pc = getenv("B200BWA_DEVICES_PER_CALL")) { long v = atol(pc); if (v >= 1 && (size_t)v < per_call) per_call = (size_t)v; }
+    std::unique_lock<std::mutex> lk(cached->lease_mu);
+    for (;;) {
+      for (B2Engine* e : engs)
+        if (lease.mine.size() < per_call && std::find(cached->leased.begin(), cached->leased.end(), e) == cached->leased.end() &&
+            std::find(lease.mine.begin(), lease.mine.end(), e) == lease.mine.end())
+          lease.mine.push_back(e);
+      if (!lease.mine.empty()) break;
+      cached->lease_cv.wait(lk);
+    }
+    for (B2Engine* e : lease.mine) cached->leased.push_back(e);
+    engs = lease.mine;
+  }
+  const int G = (int)engs.size();
   B2IndexHost* host = cached->host.get();
   for (B2Engine* e : engs) e->set_options(opt, m.rg_id.c_str(), m.verbose);
 

@@ -371,3 +371,19 @@ def test_index_builder_matches_bwa_index(hostsim, workdir):
     with the kernel bodies run by the host checker build."""
     for tag, ctg, with_n, env in pu.index_cases():
         pu.check_index_builder(hostsim, os.path.join(workdir, "index"), tag, ctg, with_n, env)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_hostsim_concurrent_calls_lease_engines(hostsim, workdir):
+    """Several task threads of one executor calling the entry point at once (the reference cannot: global state): each
+    call leases the free engines of its device list -- one each with B200BWA_DEVICES_PER_CALL=1, turns otherwise -- and
+    every call writes the reference's SAM."""
+    c = pu.make_case(workdir, "pe150")
+    ref = pu.oracle_sam(c)
+    out = os.path.join(c["dir"], "conc.sam")
+    for env in ({"B200BWA_DEVICES": "0,1,2", "B200BWA_DEVICES_PER_CALL": "1"}, {"B200BWA_DEVICES": "0,1"}, {"B200BWA_DEVICES": "0"}):
+        e = dict(os.environ, **pu.HOSTSIM_ENV, B200BWA_HOSTSIM_DEVICES="3", B200BWA_WORKERS="2", B200BWA_CLI_CONCURRENT="3", **env)
+        r = subprocess.run([hostsim, "mem"] + c["opts"] + ["-f", out, c["ref"]] + c["fq"], env=e, stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+        assert r.returncode == 0, r.stderr[-1000:]
+        for k in range(3):
+            assert not pu.first_diff(ref, out + f".{k}"), (env, k)

@@ -345,3 +345,22 @@ def test_index_builder_matches_bwa_index(workdir):
                            {"B200BWA_INDEX_GROUP": "1500000"})
     if os.environ.get("B200BWA_FULL_INDEX") == "1":
         pu.check_index_builder(pu.CLI, d, "g100M", synth.make_reference(100_000_000, n_contigs=4, seed=1, repeat_frac=0.02), True, {})
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_concurrent_calls_in_one_process(workdir, tmp_path):
+    """Three threads of one process call the C-ABI entry point at the same time (what `--executor-cores 3` does to the
+    JNI symbol); engines are leased per call, every output equals the reference's."""
+    import threading
+    c = pu.make_case(workdir, "pe150")
+    ref = pu.oracle_sam(c)
+    lib = _lib()
+    rcs = {}
+
+    def call(k):
+        rcs[k] = _main_to(lib, ["bwa", "mem", "-v", "1"] + c["opts"] + [c["ref"]] + c["fq"], str(tmp_path / f"o{k}.sam"))
+    th = [threading.Thread(target=call, args=(k,)) for k in range(3)]
+    [t.start() for t in th]; [t.join() for t in th]
+    assert rcs == {0: 0, 1: 0, 2: 0}
+    for k in range(3):
+        assert not pu.first_diff(ref, str(tmp_path / f"o{k}.sam"))
