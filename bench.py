@@ -493,6 +493,53 @@ def main():
             os.remove(sam)
         except OSError:
             pass
+        if world > 1:
+            # Companion figure: the job as SparkBWA itself would run it on this box -- N partitions, N concurrent calls
+            # of the entry point from N task threads (each leases one GPU: B200BWA_DEVICES_PER_CALL=1), N SAM files.
+            # Each partition's SAM equals the reference's on that partition; no single output file to funnel through.
+            import threading as _th
+            parts = []
+            for fsrc in [f1] + ([f2] if args.paired else []):
+                with open(fsrc, "rb") as fi:
+                    rec = sum(len(fi.readline()) for _ in range(4))
+                    per = -(-args.pairs // world)
+                    names_p = []
+                    for p_ in range(world):
+                        fi.seek(rec * p_ * per)
+                        fp_ = f"{fsrc}.part{p_}"
+                        with open(fp_, "wb") as fo:
+                            fo.write(fi.read(rec * max(0, min(per, args.pairs - p_ * per))))
+                        names_p.append(fp_)
+                    parts.append(names_p)
+            os.environ["B200BWA_DEVICES_PER_CALL"] = "1"
+            rcs = [0] * world
+
+            def run_part(p_):
+                av = ["bwa", "mem", "-v", "1", "-K", str(args.K), prefix] + [x[p_] for x in parts]
+                ar = (ctypes.c_char_p * len(av))(*[a.encode() for a in av])
+                rcs[p_] = lib.b200bwa_main_to(len(av), ar, f"{sam}.part{p_}".encode())
+            tcalls = []
+            for it in range(3):
+                for p_ in range(world):
+                    try:
+                        os.remove(f"{sam}.part{p_}")
+                    except OSError:
+                        pass
+                ths = [_th.Thread(target=run_part, args=(p_,)) for p_ in range(world)]
+                t0 = time.time()
+                [t.start() for t in ths]; [t.join() for t in ths]
+                tcalls.append(time.time() - t0)
+                if any(rcs):
+                    raise SystemExit("e2e (partitions) failed: " + lib.b200bwa_last_error().decode())
+            del os.environ["B200BWA_DEVICES_PER_CALL"]
+            out["e2e_partitions"] = {"value": n_reads / min(tcalls[1:]), "unit": "reads/s", "seconds_per_round": [round(x, 4) for x in tcalls],
+                                     "note": f"the same reads as {world} partitions, {world} concurrent calls (one GPU each), {world} SAM files"}
+            for p_ in range(world):
+                for fp_ in [f"{sam}.part{p_}"] + [x[p_] for x in parts]:
+                    try:
+                        os.remove(fp_)
+                    except OSError:
+                        pass
         if world > 1 and not args.no_e2e_large:
             # Companion figure: the same call on a job N times as long (N x pairs, distinct reads) -- what a
             # configs[2]-sized job sees once start-up and drain are amortised over hundreds of batches.  Not the

@@ -739,15 +739,19 @@ B2_KERNEL k_scan(const int32_t* in, int64_t* out, int n) {
   for (int i = 0; i < n; ++i) { out[i] = s; s += in[i]; }
   out[n] = s;
 #else
-  // one block; 1024 consecutive elements per trip (coalesced), scanned with warp shuffles, the running total carried on
+  // one block; 4 consecutive elements per thread and trip (4096 per trip, coalesced), thread-local prefix, then warp
+  // shuffles over the per-thread sums and one pass over the warp totals; the running total is carried on
   __shared__ int64_t wsum[32];
   __shared__ int64_t chunk_total;
   const int t = threadIdx.x, T = blockDim.x, lane = t & 31, warp = t >> 5, n_warps = T >> 5;
   int64_t base = 0;
-  for (int c0 = 0; c0 < n; c0 += T) {
-    const int i = c0 + t;
-    const int64_t v = i < n ? (int64_t)in[i] : 0;
-    int64_t x = v;
+  for (int c0 = 0; c0 < n; c0 += 4 * T) {
+    const int i = c0 + 4 * t;
+    int64_t v[4];
+#pragma unroll
+    for (int k = 0; k < 4; ++k) v[k] = i + k < n ? (int64_t)in[i + k] : 0;
+    const int64_t mine = v[0] + v[1] + v[2] + v[3];
+    int64_t x = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) { const int64_t y = __shfl_up_sync(0xffffffffu, x, d); if (lane >= d) x += y; }
     if (lane == 31) wsum[warp] = x;
@@ -761,7 +765,9 @@ B2_KERNEL k_scan(const int32_t* in, int64_t* out, int n) {
       if (lane == 31) chunk_total = w;
     }
     __syncthreads();
-    if (i < n) out[i] = base + wsum[warp] + x - v;
+    int64_t run = base + wsum[warp] + x - mine;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { if (i + k < n) out[i + k] = run; run += v[k]; }
     base += chunk_total;
     __syncthreads();
   }
