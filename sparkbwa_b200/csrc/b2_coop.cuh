@@ -283,11 +283,15 @@ B2_NOINLINE __device__ inline int b2_global2_coop(const B2G& g, int qlen, const 
 // -1 against N; bwa/bwa.c:99-108), so the inner loops touch no memory at all.  Same lane-for-lane arithmetic as
 // b2_sw_local_coop below (which remains the general path for word mode and longer reads).
 #define B2_SW_SLMAX 16
-__device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
-                                            const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra,
-                                            uint64_t* bbuf, unsigned long long* cells) {
-  const int lanes = 16;
-  const int slen = (qlen + lanes - 1) / lanes;
+// SL = columns per lane = ceil(qlen / 16), a compile-time constant: the register arrays have exactly that length, the
+// column loops are fully unrolled without predication, and the substitution score of a column is one compare + select
+// against per-column constants (the reference window comes from the 2-bit pac, so its codes are 0..3; rows with any
+// other target code take the general expression).
+template <int SL>
+__device__ __noinline__ B2Kswr b2_sw_local_u8_regT(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                                   const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra,
+                                                   uint64_t* bbuf, unsigned long long* cells) {
+  const int slen = SL;
   const int sa = mat[0], sb = mat[1], sn = mat[4];  // match, mismatch, ambiguous
   int shift = 127, mx = 0;
   for (int a = 0; a < 25; ++a) {
@@ -302,44 +306,60 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
   const int endsc = (xtra & B2_KSW_XSTOP) ? xtra & 0xffff : 0x10000;
   int n_b = 0, te = -1, gmax = 0;
   const int l = g.lane;
-  int H[B2_SW_SLMAX], E[B2_SW_SLMAX], Hm[B2_SW_SLMAX], H1[B2_SW_SLMAX], qc[B2_SW_SLMAX];
+  int H[SL], E[SL], Hm[SL], qc[SL], sms[SL];   // H/E/saved row, base code, (mismatch-or-fixed score) + shift of the column
 #pragma unroll
-  for (int j = 0; j < B2_SW_SLMAX; ++j) {
-    H[j] = E[j] = Hm[j] = H1[j] = 0;
+  for (int j = 0; j < SL; ++j) {
+    H[j] = E[j] = Hm[j] = 0;
     const int col = l * slen + j;
-    qc[j] = (j < slen && col < qlen) ? query[col] : 5;  // 5: pad column, score 0
+    qc[j] = col < qlen ? query[col] : 5;  // 5: pad column, score 0
+    sms[j] = shift + (qc[j] == 5 ? 0 : (qc[j] >= 4 ? sn : sb));
   }
+  const int sas = sa + shift, sns = sn + shift;
   int last_b_row = -2, last_b_sc = 0;  // mirror of bbuf[n_b-1] kept in registers
   for (int i = 0; i < tlen; ++i) {
     const int tb = target[i];
     int f = 0, mxv = 0;
-    int h;
-    {  // H[slen-1] of the left lane (the byte shift of the last striped vector)
-      int hl = 0;
+    int h = g.shfl_up(H[SL - 1], 1);   // H[slen-1] of the left lane (the byte shift of the last striped vector)
+    if (l == 0) h = 0;
+    if (tb < 4) {
 #pragma unroll
-      for (int j = 0; j < B2_SW_SLMAX; ++j) if (j == slen - 1) hl = H[j];
-      h = g.shfl_up(hl, 1);
-      if (l == 0) h = 0;
-    }
-#pragma unroll
-    for (int j = 0; j < B2_SW_SLMAX; ++j) {
-      if (j < slen) {
-        const int q = qc[j];
-        const int s = q == 5 ? 0 : ((q | tb) >= 4 ? sn : (q == tb ? sa : sb));
+      for (int j = 0; j < SL; ++j) {
+        const int sp = qc[j] == tb ? sas : sms[j];
         int e = E[j], t;
-        h = h + (s + shift); if (h > 255) h = 255;
-        h = h - shift; if (h < 0) h = 0;
+        h += sp; h = h > 255 ? 255 : h;
+        h -= shift; h = h < 0 ? 0 : h;
         h = h > e ? h : e;
         h = h > f ? h : f;
         mxv = mxv > h ? mxv : h;
-        H1[j] = h;
-        e = e - e_del; if (e < 0) e = 0;
-        t = h - oe_d; if (t < 0) t = 0;
+        const int hn = H[j];
+        H[j] = h;
+        e -= e_del; e = e < 0 ? 0 : e;
+        t = h - oe_d; t = t < 0 ? 0 : t;
         E[j] = e > t ? e : t;
-        f = f - e_ins; if (f < 0) f = 0;
-        t = h - oe_i; if (t < 0) t = 0;
+        f -= e_ins; f = f < 0 ? 0 : f;
+        t = h - oe_i; t = t < 0 ? 0 : t;
         f = f > t ? f : t;
-        h = H[j];
+        h = hn;
+      }
+    } else {
+#pragma unroll
+      for (int j = 0; j < SL; ++j) {
+        const int sp = qc[j] == 5 ? shift : sns;
+        int e = E[j], t;
+        h += sp; h = h > 255 ? 255 : h;
+        h -= shift; h = h < 0 ? 0 : h;
+        h = h > e ? h : e;
+        h = h > f ? h : f;
+        mxv = mxv > h ? mxv : h;
+        const int hn = H[j];
+        H[j] = h;
+        e -= e_del; e = e < 0 ? 0 : e;
+        t = h - oe_d; t = t < 0 ? 0 : t;
+        E[j] = e > t ? e : t;
+        f -= e_ins; f = f < 0 ? 0 : f;
+        t = h - oe_i; t = t < 0 ? 0 : t;
+        f = f > t ? f : t;
+        h = hn;
       }
     }
     if (use_scan) {  // carry of F across the lanes' column blocks (see b2_sw_local), then decay inside the block
@@ -353,22 +373,20 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
       f = g.shfl_up(x, 1);
       if (l == 0) f = 0;
 #pragma unroll
-      for (int j = 0; j < B2_SW_SLMAX; ++j) {
-        if (j < slen) {
-          H1[j] = H1[j] > f ? H1[j] : f;
-          f = f - e_ins; if (f < 0) f = 0;
-        }
+      for (int j = 0; j < SL; ++j) {
+        H[j] = H[j] > f ? H[j] : f;
+        f -= e_ins; f = f < 0 ? 0 : f;
       }
     } else
     for (int k = 0, done = 0; k < 16 && !done; ++k) {  // lazy-F, literally
       f = g.shfl_up(f, 1);
       if (l == 0) f = 0;
 #pragma unroll
-      for (int j = 0; j < B2_SW_SLMAX; ++j) {
-        if (j < slen && !done) {
-          int hh = H1[j];
+      for (int j = 0; j < SL; ++j) {
+        if (!done) {
+          int hh = H[j];
           hh = hh > f ? hh : f;
-          H1[j] = hh;
+          H[j] = hh;
           hh = hh - oe_i; if (hh < 0) hh = 0;
           f = f - e_ins; if (f < 0) f = 0;
           if (__all_sync(g.mask, !(f > hh))) done = 1;
@@ -380,16 +398,12 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
       if (n_b == 0 || last_b_row + 1 != i) { if (l == 0) bbuf[n_b] = (uint64_t)imax << 32 | (uint32_t)i; ++n_b; last_b_row = i; last_b_sc = imax; }
       else if (last_b_sc < imax) { if (l == 0) bbuf[n_b - 1] = (uint64_t)imax << 32 | (uint32_t)i; last_b_row = i; last_b_sc = imax; }
     }
-    int stop = 0;
     if (imax > gmax) {
       gmax = imax; te = i;
 #pragma unroll
-      for (int j = 0; j < B2_SW_SLMAX; ++j) Hm[j] = H1[j];
-      if (gmax + shift >= 255 || gmax >= endsc) stop = 1;
+      for (int j = 0; j < SL; ++j) Hm[j] = H[j];
+      if (gmax + shift >= 255 || gmax >= endsc) break;
     }
-#pragma unroll
-    for (int j = 0; j < B2_SW_SLMAX; ++j) H[j] = H1[j];
-    if (stop) break;
   }
   if (cells && l == 0) *cells += (unsigned long long)qlen * (unsigned long long)(te >= 0 && (gmax + shift >= 255 || gmax >= endsc) ? te + 1 : tlen);
   g.sync();
@@ -399,8 +413,7 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
     // qe: smallest query column holding the maximum of the saved row
     int best = -1, bcol = 1 << 30;
 #pragma unroll
-    for (int j = 0; j < B2_SW_SLMAX; ++j)
-      if (j < slen) { int v = Hm[j] & 0xff, col = l * slen + j; if (v > best) { best = v; bcol = col; } }
+    for (int j = 0; j < SL; ++j) { int v = Hm[j] & 0xff, col = l * slen + j; if (v > best) { best = v; bcol = col; } }
     // reduce (max value, then min column)
     long long key = ((long long)best << 32) | (unsigned)(0x7fffffff - bcol);
     key = g.max_all64(key);
@@ -416,6 +429,18 @@ __device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_
   }
   g.sync();
   return r;
+}
+
+__device__ inline B2Kswr b2_sw_local_u8_reg(const B2G& g, int qlen, const uint8_t* query, int tlen, const uint8_t* target,
+                                            const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins, int xtra,
+                                            uint64_t* bbuf, unsigned long long* cells) {
+#define B2_SWR(N) case N: return b2_sw_local_u8_regT<N>(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, bbuf, cells);
+  switch ((qlen + 15) / 16) {
+    B2_SWR(1) B2_SWR(2) B2_SWR(3) B2_SWR(4) B2_SWR(5) B2_SWR(6) B2_SWR(7) B2_SWR(8)
+    B2_SWR(9) B2_SWR(10) B2_SWR(11) B2_SWR(12) B2_SWR(13) B2_SWR(14) B2_SWR(15)
+    default: return b2_sw_local_u8_regT<16>(g, qlen, query, tlen, target, mat, o_del, e_del, o_ins, e_ins, xtra, bbuf, cells);
+  }
+#undef B2_SWR
 }
 
 // One GPU lane per SSE lane.  Lanes >= `lanes` of the group idle (16-bit mode uses 8 of 16).

@@ -559,7 +559,11 @@ class B2EngineImpl {
     c.xext_res = nullptr; c.xext_tasks = nullptr;
     if (TC > 0 && !cfg.no_xext && b2_mat_simple(opt.mat) && S < (1 << 29)) {
       c.xext_qcap = w.max_len; c.xext_tcap = w.max_len + 2 * opt.w + 64;
-      const size_t words = (size_t)32 * ((size_t)c.xext_qcap + 2 + c.xext_qcap / 8 + 1 + c.xext_tcap / 8 + 1);
+      // {h, e} cells of 8 + 8 bits when no score of the batch can reach 256 (an extension's scores are bounded by
+      // read length x match score), 16 + 16 bits otherwise
+      c.xext_cell8 = (opt.a * w.max_len <= 250 && !getenv("B200BWA_XEXT_CELL32")) ? 1 : 0;
+      const size_t ehw = (((size_t)c.xext_qcap + 2) * (c.xext_cell8 ? 2 : 4) + 3) / 4;
+      const size_t words = (size_t)32 * (ehw + c.xext_qcap / 8 + 1 + c.xext_tcap / 8 + 1);
       const size_t smem = words * sizeof(uint32_t);
       if (smem <= (size_t)227 * 1024) {
         const int bins = c.xext_qcap + 1;
@@ -569,7 +573,7 @@ class B2EngineImpl {
         c.xext_tasks = w.xext_tasks.p; c.xext_res = w.xext_res.p; c.xext_key = w.xext_key.p; c.xext_perm = w.xext_perm.p;
         c.xext_hist = w.xext_hist.p; c.xext_cur = w.xext_hist.p + bins + 1; c.xext_hoff = w.xext_hoff.p;
         b2_dev_memset(w.xext_res.p, 0xff, (2 * (size_t)S + 2) * sizeof(B2XextRes), w.stream);  // w = -1: no result
-        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(16, ((size_t)227 * 1024) / smem));
+        const int per_sm = (int)std::max<size_t>(1, std::min<size_t>(24, ((size_t)227 * 1024) / smem));
         const int xgrid = (int)std::min<int64_t>((TC + 31) / 32, (int64_t)148 * per_sm);
         const int pgrid = (int)std::min<int64_t>((TC + 127) / 128, 148 * 8);
         for (int side = 0; side < 2; ++side) {
@@ -708,10 +712,32 @@ class B2EngineImpl {
           const int blk = std::min(cfg.lane_block, 32);
           auto grid_for = [&](int64_t cnt) { return (int)std::min<int64_t>((cnt + blk - 1) / blk, (int64_t)lane_grid * cfg.lane_block / blk); };
           ev_g[0] = w.timer.mark();
-          if (tot[0] > 0) { B2_LAUNCH(k_galn9, grid_for(tot[0]), blk, w.stream, c); ++w.times.launches; }
-          if (tot[1] > 0) { B2_LAUNCH(k_galn17, grid_for(tot[1]), blk, w.stream, c); ++w.times.launches; }
-          if (tot[2] > 0) { B2_LAUNCH(k_galn33, grid_for(tot[2]), blk, w.stream, c); ++w.times.launches; }
-          if (tot[3] > 0) { B2_LAUNCH(k_galn65, grid_for(tot[3]), blk, w.stream, c); ++w.times.launches; }
+          {  // one launch for the four classes: each gets blocks in proportion to its tasks, within the scratch lanes
+            const int64_t budget = (int64_t)lane_grid * cfg.lane_block / blk;
+            int64_t want[B2_GALN_CLASSES], sum = 0;
+            int n_nonempty = 0;
+            for (int k = 0; k < B2_GALN_CLASSES; ++k) { want[k] = (tot[k] + blk - 1) / blk; sum += want[k]; n_nonempty += want[k] > 0; }
+            (void)grid_for;
+            if (budget >= n_nonempty) {
+              const int64_t spare = budget - n_nonempty, extra = sum - n_nonempty;
+              int nb = 0;
+              for (int k = 0; k < B2_GALN_CLASSES; ++k) {
+                c.galn_blk[k] = nb;
+                if (want[k] > 0) nb += (int)(1 + (extra <= spare ? want[k] - 1 : (want[k] - 1) * spare / extra));
+              }
+              c.galn_blk[B2_GALN_CLASSES] = nb;
+              B2_LAUNCH(k_galn, nb, blk, w.stream, c);
+              ++w.times.launches;
+            } else {  // fewer scratch lanes than classes (the host checker build's single lane): one class after the other
+              for (int k = 0; k < B2_GALN_CLASSES; ++k) {
+                if (want[k] == 0) continue;
+                const int g1 = (int)std::max<int64_t>(1, std::min<int64_t>(want[k], budget));
+                for (int j = 0; j <= B2_GALN_CLASSES; ++j) c.galn_blk[j] = j <= k ? 0 : g1;
+                B2_LAUNCH(k_galn, g1, blk, w.stream, c);
+                ++w.times.launches;
+              }
+            }
+          }
           ev_g[1] = w.timer.mark();
         }
       }

@@ -79,11 +79,13 @@ struct B2Ctx {
   // seed extensions computed ahead of the chain-extension kernel (b2_xext.cuh)
   B2XextTask* xext_tasks; B2XextRes* xext_res;  // one task per (read, chain) and side; two result slots per seed
   int xext_qcap, xext_tcap;                     // staging capacity per lane (bases)
+  int xext_cell8;                               // 1: {h, e} cells of 8 + 8 bits (scores of this batch stay below 256)
   int32_t *xext_key, *xext_hist, *xext_cur, *xext_perm;  // counting sort of the tasks by query length (longest first):
   const int64_t* xext_hoff;                              // the lanes of a warp then run extensions of similar size
   // global alignments computed ahead of the finalisation kernel (b2_galn.cuh)
   int32_t* galn_cnt; const int64_t* galn_off;   // [class][read] counts and their exclusive scans (row strides n+1, n+2)
   int64_t galn_base[B2_GALN_CLASSES], galn_n[B2_GALN_CLASSES];
+  int galn_blk[B2_GALN_CLASSES + 1];            // first block of each class in the combined k_galn launch
   B2GalnTask* galn_tasks; B2GalnRes* galn_res; int32_t* galn_table;
   B2GalnCache galn;
   // SAM
@@ -406,7 +408,7 @@ B2_KERNEL k_xext_plan(B2Ctx c, int side) {
         }
       }
       if (task.qlen >= 0 && (task.qlen < 1 || task.qlen > c.xext_qcap || task.tlen < 0 || task.tlen > c.xext_tcap ||
-                             task.h0 + task.qlen * c.opt.a >= 65000 || 2 * gidx + 1 > 0x7fffffff))
+                             task.h0 + task.qlen * c.opt.a >= (c.xext_cell8 ? 255 : 65000) || 2 * gidx + 1 > 0x7fffffff))
         task.qlen = -1;
     }
     c.xext_tasks[t] = task;
@@ -425,19 +427,22 @@ B2_KERNEL k_xext_scatter(B2Ctx c) {
 }
 
 // one extension per lane; the warp's shared-memory block holds, lane-interleaved, eh[] and the two staged sequences
-B2_KERNEL k_xext_run(B2Ctx c) {
+template <class Cell>
+B2_D inline void b2_xext_run_body(const B2Ctx& c) {
   const int qw = c.xext_qcap / 8 + 1, tw = c.xext_tcap / 8 + 1;
-  B2XMem M;
+  const int ehw = (int)(((size_t)(c.xext_qcap + 2) * sizeof(Cell) + 3) / 4);   // 32-bit words of one lane's eh[]
+  B2XMemT<Cell> M;
 #if defined(B2_HOSTSIM)
   M.stride = 1;
-  M.eh = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(c.xext_qcap + 2 + qw + tw));
-  M.q = M.eh + c.xext_qcap + 2; M.t = M.q + qw;
+  uint32_t* hbase = (uint32_t*)malloc(sizeof(uint32_t) * (size_t)(ehw + qw + tw));
+  M.eh = (Cell*)hbase;
+  M.q = hbase + ehw; M.t = M.q + qw;
 #else
   extern __shared__ uint32_t b2_xext_smem[];
   const int lane = threadIdx.x & 31;
-  uint32_t* base = b2_xext_smem + (size_t)(threadIdx.x >> 5) * 32 * (size_t)(c.xext_qcap + 2 + qw + tw);
+  uint32_t* base = b2_xext_smem + (size_t)(threadIdx.x >> 5) * 32 * (size_t)(ehw + qw + tw);
   M.stride = 32;
-  M.eh = base + lane; M.q = base + (size_t)32 * (c.xext_qcap + 2) + lane; M.t = M.q + (size_t)32 * qw;
+  M.eh = (Cell*)base + lane; M.q = base + (size_t)32 * ehw + lane; M.t = M.q + (size_t)32 * qw;
 #endif
   unsigned long long cells = 0, calls = 0;
   const int64_t n_valid = c.xext_hoff[c.xext_qcap];  // the invalid tasks sit in the last bin
@@ -462,8 +467,13 @@ B2_KERNEL k_xext_run(B2Ctx c) {
     B2_ATOMIC_ADD(&c.counters[B2_CNT_XEXT_CELLS], cells);
   }
 #if defined(B2_HOSTSIM)
-  free(M.eh);
+  free(hbase);
 #endif
+}
+
+B2_KERNEL k_xext_run(B2Ctx c) {
+  if (c.xext_cell8) b2_xext_run_body<uint16_t>(c);
+  else b2_xext_run_body<uint32_t>(c);
 }
 
 // One task group per (read, kept chain): extends the chain's seeds against a chain-local region list and
@@ -616,8 +626,11 @@ B2_KERNEL k_galn_plan(B2Ctx c, int mode) {
 
 // one alignment per lane; the lanes of a warp share a pool made of their scratch regions: per-lane staging of the
 // two sequences, then the lane-interleaved direction words.
+// The four band classes run as ONE launch: blocks [galn_blk[k], galn_blk[k+1]) of the grid serve class k (a class
+// alone is a few hundred warps, one or two per SM; side by side they overlap each other's latency).  tid0 / tsize:
+// the lane's index and the lane count inside its class's share of the grid.
 template <int ND>
-B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
+B2_D inline void b2_galn_run(const B2Ctx& c, int cls, int tid0, int tsize) {
   const int LW = B2_WARP_LANES;
   const int lane = B2_GTID() & (LW - 1);
   uint8_t* pool = c.scratch + (size_t)(B2_GTID() - lane) * c.scratch_per_lane;
@@ -627,7 +640,7 @@ B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
   uint32_t* zw = (uint32_t*)(pool + (size_t)LW * 2 * half) + lane;
   const int64_t first = c.galn_base[cls], last = first + c.galn_n[cls];
   unsigned long long cells = 0, calls = 0;
-  for (int64_t t = first + B2_GTID(); t < last; t += B2_GSIZE()) {
+  for (int64_t t = first + tid0; t < last; t += tsize) {
     const B2GalnTask task = c.galn_tasks[t];
     B2GalnRes* res = &c.galn_res[t];
     const int qlen = task.qe - task.qb, tlen = (int)(task.re - task.rb);
@@ -648,10 +661,20 @@ B2_D inline void b2_galn_run(const B2Ctx& c, int cls) {
     B2_ATOMIC_ADD(&c.counters[B2_CNT_GALN_CELLS], cells);
   }
 }
-B2_KERNEL k_galn9(B2Ctx c) { b2_galn_run<9>(c, 0); }
-B2_KERNEL k_galn17(B2Ctx c) { b2_galn_run<17>(c, 1); }
-B2_KERNEL k_galn33(B2Ctx c) { b2_galn_run<33>(c, 2); }
-B2_KERNEL k_galn65(B2Ctx c) { b2_galn_run<65>(c, 3); }
+B2_KERNEL k_galn(B2Ctx c) {
+#if defined(B2_HOSTSIM)
+  const int blk = B2_GTID() / b2_dim.block, bdim = b2_dim.block, tin = B2_GTID() % b2_dim.block;
+#else
+  const int blk = (int)blockIdx.x, bdim = (int)blockDim.x, tin = (int)threadIdx.x;
+#endif
+  int cls = 0;
+  while (cls < B2_GALN_CLASSES - 1 && blk >= c.galn_blk[cls + 1]) ++cls;
+  const int tid0 = (blk - c.galn_blk[cls]) * bdim + tin, tsize = (c.galn_blk[cls + 1] - c.galn_blk[cls]) * bdim;
+  if (cls == 0) b2_galn_run<9>(c, 0, tid0, tsize);
+  else if (cls == 1) b2_galn_run<17>(c, 1, tid0, tsize);
+  else if (cls == 2) b2_galn_run<33>(c, 2, tid0, tsize);
+  else b2_galn_run<65>(c, 3, tid0, tsize);
+}
 
 B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
   int gid, n_groups;

@@ -29,13 +29,17 @@ struct B2XextRes {
   int32_t score, qle, tle, gtle, gscore, max_off;
 };
 
-// element k of a lane-strided array
-struct B2XMem {
-  uint32_t* eh;  // qlen+1 words: h | e << 16
+// element k of a lane-strided array.  Cell = uint32_t: {h, e} as 16 + 16 bits; Cell = uint16_t: 8 + 8 bits, for batches
+// whose scores stay below 256 (read length x match score <= 250: every 2x150 bp and 250 bp workload at -A 1) -- half
+// the shared memory per extension, i.e. nearly twice the warps per SM for a kernel that is latency-bound.
+template <class Cell>
+struct B2XMemT {
+  Cell* eh;      // qlen+1 cells: h | e << (4 * sizeof(Cell))
   uint32_t* q;   // 4-bit codes, 8 per word
   uint32_t* t;
   int stride;
 };
+typedef B2XMemT<uint32_t> B2XMem;
 
 // base code at bidirectional position p (forward strand [0, l_pac), reverse complement [l_pac, 2 l_pac))
 B2_HD inline int b2_base_at(const uint8_t* pac, int64_t l_pac, int64_t p) {
@@ -45,17 +49,20 @@ B2_HD inline int b2_base_at(const uint8_t* pac, int64_t l_pac, int64_t p) {
 }
 
 // Same results as ksw_extend2 (fuzzed against its scalar form in tests/coop_fuzz.cpp) for matrices of bwa_fill_scmat's shape and h0 + qlen*max(mat) < 65536.
-B2_HD inline int b2_xext_one(const B2XMem& M, int qlen, int tlen, const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins,
+template <class Cell>
+B2_HD inline int b2_xext_one(const B2XMemT<Cell>& M, int qlen, int tlen, const int8_t* mat, int o_del, int e_del, int o_ins, int e_ins,
                              int w, int end_bonus, int zdrop, int h0, int* _qle, int* _tle, int* _gtle, int* _gscore,
                              int* _max_off, unsigned long long* cells) {
   const int oe_del = o_del + e_del, oe_ins = o_ins + e_ins;
   const int sa = mat[0], sb = mat[1], sn = mat[4];
   const int st = M.stride;
+  constexpr int ESH = 4 * (int)sizeof(Cell);            // bit position of e inside a cell
+  constexpr uint32_t HMASK = (1u << ESH) - 1;
   int i, j, beg, end, max, max_i, max_j, max_ins, max_del, max_ie, gscore, max_off;
   {
     const int a1 = h0 > oe_ins ? h0 - oe_ins : 0;
-    M.eh[0] = (uint32_t)h0;
-    for (j = 1; j <= qlen; ++j) { int h = a1 - (j - 1) * e_ins; M.eh[(size_t)j * st] = (uint32_t)(h > 0 ? h : 0); }
+    M.eh[0] = (Cell)h0;
+    for (j = 1; j <= qlen; ++j) { int h = a1 - (j - 1) * e_ins; M.eh[(size_t)j * st] = (Cell)(h > 0 ? h : 0); }
   }
   max = 0;
   for (i = 0; i < 25; ++i) max = max > mat[i] ? max : mat[i];
@@ -82,7 +89,7 @@ B2_HD inline int b2_xext_one(const B2XMem& M, int qlen, int tlen, const int8_t* 
       const int q = (int)(qw >> ((j & 7) << 2)) & 15;
       const int s = (q | t) >= 4 ? sn : (q == t ? sa : sb);
       const uint32_t p = M.eh[(size_t)j * st];
-      int Mv = (int)(p & 0xffffu), e = (int)(p >> 16);
+      int Mv = (int)(p & HMASK), e = (int)(p >> ESH);
       Mv = Mv ? Mv + s : 0;
       int h = Mv > e ? Mv : e;
       h = h > f ? h : f;
@@ -92,11 +99,11 @@ B2_HD inline int b2_xext_one(const B2XMem& M, int qlen, int tlen, const int8_t* 
       m = m > h ? m : h;
       int t2 = Mv - oe_del; t2 = t2 > 0 ? t2 : 0;
       e -= e_del; e = e > t2 ? e : t2;
-      M.eh[(size_t)j * st] = (uint32_t)hprev | (uint32_t)e << 16;
+      M.eh[(size_t)j * st] = (Cell)((uint32_t)hprev | (uint32_t)e << ESH);
       t2 = Mv - oe_ins; t2 = t2 > 0 ? t2 : 0;
       f -= e_ins; f = f > t2 ? f : t2;
     }
-    M.eh[(size_t)end * st] = (uint32_t)h1;  // {h1, e = 0}
+    M.eh[(size_t)end * st] = (Cell)h1;  // {h1, e = 0}
     if (j == qlen) {
       max_ie = gscore > h1 ? max_ie : i;
       gscore = gscore > h1 ? gscore : h1;

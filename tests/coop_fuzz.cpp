@@ -112,6 +112,16 @@ int main(int argc, char** argv) {
         if (s2 != s0 || memcmp(r0, r2, sizeof(r0)) || c2 != c0) {
           if (++bad_x <= 5) fprintf(stderr, "XEXT mismatch trial %d qlen %d tlen %d w %d h0 %d: %d vs %d\n", tr, qlen, tlen, w, h0, s0, s2);
         }
+        if (h0 + qlen * a < 255) {  // the 8 + 8 bit cell form (batches whose scores stay below 256)
+          std::vector<uint16_t> eh8((size_t)(qlen + 2) * zs + 8);
+          B2XMemT<uint16_t> M8; M8.eh = eh8.data(); M8.q = qv.data(); M8.t = tv.data(); M8.stride = zs;
+          int r3[5]; unsigned long long c3 = 0;
+          int s3 = b2_xext_one(M8, qlen, tlen, mat, o_del, e_del, o_ins, e_ins, w, end_bonus, zdrop, h0, &r3[0], &r3[1], &r3[2], &r3[3], &r3[4], &c3);
+          ++n_x;
+          if (s3 != s0 || memcmp(r0, r3, sizeof(r0)) || c3 != c0) {
+            if (++bad_x <= 5) fprintf(stderr, "XEXT8 mismatch trial %d qlen %d tlen %d w %d h0 %d: %d vs %d\n", tr, qlen, tlen, w, h0, s0, s3);
+          }
+        }
       }
       if (s0 != s1 || memcmp(r0, r1, sizeof(r0)) || c0 != c1) {
         if (++bad_e <= 5)
