@@ -1,6 +1,6 @@
 #!/bin/bash
 # Round-2 visit I (1 GPU): parity after the rescue-SW / scan / output-path changes + bench.
-O=gpurun_out/r2i
+O=gpurun_out/${OUTDIR:-r2i}
 mkdir -p $O
 python -m pytest tests -m gpu -x -q > $O/pytest_gpu.log 2>&1; echo "pytest rc $?" >> $O/pytest_gpu.log
 tail -3 $O/pytest_gpu.log

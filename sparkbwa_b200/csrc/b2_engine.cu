@@ -498,7 +498,8 @@ class B2EngineImpl {
     c.raw = w.raw.p; c.raw_rid = w.raw_rid.p; c.chains = w.chains.p; c.cseeds = w.cseeds.p;
     c.n_chain = w.n_chain.p; c.reg_cap = w.reg_cap.p; c.n_regs = w.n_regs.p;
     if (S > 0) {
-      int grid = (int)std::min<int64_t>((S + 127) / 128, 148 * 16);
+      int grid = (int)std::min<int64_t>((S + 127) / 128, 148 * 8);   // resident lanes only: each takes lookup after lookup
+      b2_dev_memset(w.flags.p + 3, 0, sizeof(int), w.stream);   // the lookups are dealt from this cursor (c.work[2])
       B2_LAUNCH(k_sa, grid, 128, w.stream, c);
       ++w.times.launches;
     }

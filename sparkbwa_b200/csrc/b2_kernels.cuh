@@ -223,32 +223,66 @@ B2_KERNEL k_seed_fin(B2Ctx c) {
 }
 
 B2_KERNEL k_sa(B2Ctx c) {
+  // One suffix-array lookup per lane at a time: an LF walk to the next sampled row, geometric in length (mean 31 steps,
+  // the longest of 32 about four times that).  A lane that finishes takes the next lookup from the stage's cursor right
+  // away instead of idling until the warp's longest walk ends; every trip of the loop is ONE LF step for all lanes
+  // that hold a lookup.
   unsigned long long steps_total = 0, calls = 0;
-  for (int64_t t = B2_GTID(); t < c.n_seed_tasks; t += B2_GSIZE()) {
-    int lo = 0, hi = c.b.n_reads;  // last r with seed_off[r] <= t
-    while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.seed_off[mid] <= t) lo = mid; else hi = mid; }
-    const int r = lo;
-    long idx = (long)(t - c.seed_off[r]);
-    const B2Intv* iv = c.intv + (size_t)r * c.cap_intv;
-    const int n = c.n_intv[r];
-    int i = 0;
-    for (; i < n; ++i) {
-      long cnt = iv[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)iv[i].x[2];
-      if (idx < cnt) break;
-      idx -= cnt;
+  const uint64_t mask = (uint64_t)c.ix.sa_intv - 1;
+  int64_t t = 0;
+  uint64_t k = 0;
+  unsigned steps = 0;
+  int32_t qbeg = 0, slen = 0;
+  bool have = false, alive = true;
+  for (;;) {
+    if (!have && alive) {
+#if defined(__CUDA_ARCH__)
+      t = (int64_t)atomicAdd(c.work + 2, 1);
+#else
+      t = (int64_t)c.work[2]++;
+#endif
+      if (t >= c.n_seed_tasks) alive = false;
+      else {
+        int lo = 0, hi = c.b.n_reads;  // last r with seed_off[r] <= t
+        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.seed_off[mid] <= t) lo = mid; else hi = mid; }
+        const int r = lo;
+        long idx = (long)(t - c.seed_off[r]);
+        const B2Intv* iv = c.intv + (size_t)r * c.cap_intv;
+        const int n = c.n_intv[r];
+        int i = 0;
+        for (; i < n; ++i) {
+          long cnt = iv[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)iv[i].x[2];
+          if (idx < cnt) break;
+          idx -= cnt;
+        }
+        const B2Intv& p = iv[i];
+        const long step = p.x[2] > (uint64_t)c.opt.max_occ ? (long)(p.x[2] / c.opt.max_occ) : 1;
+        slen = (int32_t)((uint32_t)p.info - (uint32_t)(p.info >> 32));
+        qbeg = (int32_t)(p.info >> 32);
+        k = p.x[0] + (uint64_t)(idx * step);
+        steps = 0;
+        have = true;
+      }
     }
-    const B2Intv& p = iv[i];
-    const long step = p.x[2] > (uint64_t)c.opt.max_occ ? (long)(p.x[2] / c.opt.max_occ) : 1;
-    const int slen = (int)((uint32_t)p.info - (uint32_t)(p.info >> 32));
-    B2Seed s;
-    unsigned n_steps = 0;
-    s.rbeg = (int64_t)b2_sa(c.ix, p.x[0] + (uint64_t)(idx * step), &n_steps);
-    steps_total += n_steps; ++calls;
-    s.qbeg = (int32_t)(p.info >> 32);
-    s.len = s.score = slen;
-    s.next = -1;
-    c.raw[t] = s;
-    c.raw_rid[t] = b2_intv2rid(c.ix, s.rbeg, s.rbeg + s.len);
+#if defined(__CUDA_ARCH__)
+    if (__ballot_sync(0xffffffffu, have) == 0) break;
+#else
+    if (!have) break;
+#endif
+    if (have) {
+      if (k & mask) { ++steps; k = b2_inv_psi(c.ix, k); }
+      else {
+        B2Seed s;
+        s.rbeg = (int64_t)(steps + c.ix.sa[k >> c.ix.sa_shift]);
+        s.qbeg = qbeg;
+        s.len = s.score = slen;
+        s.next = -1;
+        c.raw[t] = s;
+        c.raw_rid[t] = b2_intv2rid(c.ix, s.rbeg, s.rbeg + s.len);
+        steps_total += steps; ++calls;
+        have = false;
+      }
+    }
   }
   if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_CALLS], calls); B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_STEPS], steps_total); }
 }
