@@ -275,7 +275,8 @@ B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, c
     { extern long b2_galn_stats[16]; const int wb = b2_cigar_band(opt, qe - qb, (int)(re - rb), w2);
       const bool nodp = (qe - qb == re - rb && w2 == 0);
       ++b2_galn_stats[nodp ? 0 : (pre ? 1 : (i > 0 ? 2 : (b2_galn_class(wb) < 0 ? 3 : 4)))];
-      if (!nodp && !pre) b2_galn_stats[8] += (long)(2 * wb + 1 < qe - qb ? 2 * wb + 1 : qe - qb) * (re - rb); }
+      if (!nodp && !pre) b2_galn_stats[8] += (long)(2 * wb + 1 < qe - qb ? 2 * wb + 1 : qe - qb) * (re - rb);
+      if (!nodp && !pre && i == 0 && getenv("B200BWA_DEBUG_GALN_MISS")) fprintf(stderr, "[D::miss] q %d-%d r %ld-%ld w2 %d wb %d truesc %d score %d arw %d sec %d\n", qb, qe, (long)rb, (long)re, w2, wb, ar->truesc, ar->score, ar->w, ar->secondary); }
 #endif
     b2_gen_cigar2(opt, ix, w2, qe - qb, query + qb, rb, re, &score, &cg, sc, pre);
     if (score == last_sc || w2 == opt.w << 2) break;

@@ -623,6 +623,31 @@ B2_KERNEL k_resc_sw(B2Ctx c) {
 // ---- speculative global alignments (b2_galn.cuh) ----------------------------------------------------------------
 // mode 0: count the alignments worth computing ahead, per band class; mode 1: write them (class-major task ids) and
 // enter them into the hash table.  One lane per read; mirrors the entry conditions of mem_reg2aln / bwa_gen_cigar2.
+B2_D inline void b2_galn_admit(const B2Ctx& c, int r, const B2Reg* ar, int mode, int* cnt) {
+  const int n = c.b.n_reads;
+  const int64_t l_pac = c.ix.l_pac;
+  if (ar->rb < 0 || ar->re < 0) return;
+  const int qb = ar->qb, qe = ar->qe, l_query = qe - qb;
+  const int64_t rb = ar->rb, re = ar->re;
+  if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac) || re - rb > l_query + 64) return;
+  const int w_in = b2_reg2aln_w0(c.opt, ar);
+  if (l_query == re - rb && w_in == 0) return;  // gap-free: no DP (bwa/bwa.c:131)
+  const int w = b2_cigar_band(c.opt, l_query, (int)(re - rb), w_in);
+  const int cls = b2_galn_class(w);
+  const int dl = l_query > (int)(re - rb) ? l_query - (int)(re - rb) : (int)(re - rb) - l_query;
+  if (cls < 0 || dl > w) return;
+  if (mode) {
+    const int64_t id = c.galn_base[cls] + c.galn_off[(size_t)cls * (n + 2) + r] + cnt[cls];
+    B2GalnTask t;
+    t.seq_off = c.b.seq_off[r]; t.rb = rb; t.re = re; t.read = r; t.qb = qb; t.qe = qe; t.w_in = w_in; t.w = w;
+    c.galn_tasks[id] = t;
+    c.galn_res[id].n_cigar = -1;
+    uint32_t h = b2_galn_hash(t.seq_off, qb, qe, rb, re, w_in) & c.galn.mask;
+    while (B2_ATOMIC_CAS(&c.galn_table[h], -1, (int32_t)id) != -1) h = (h + 1) & c.galn.mask;
+  }
+  ++cnt[cls];
+}
+
 B2_KERNEL k_galn_plan(B2Ctx c, int mode) {
   const int n = c.b.n_reads;
   const int64_t l_pac = c.ix.l_pac;
@@ -631,28 +656,39 @@ B2_KERNEL k_galn_plan(B2Ctx c, int mode) {
     for (int k = 0; k < B2_GALN_CLASSES; ++k) cnt[k] = 0;
     const B2Reg* a = c.regs + c.reg_off[r];
     const int nr = c.n_regs[r];
-    for (int k = 0; k < nr && k < B2_GALN_MAXREGS; ++k) {
-      const B2Reg* ar = &a[k];
-      if (ar->rb < 0 || ar->re < 0) continue;
-      const int qb = ar->qb, qe = ar->qe, l_query = qe - qb;
-      const int64_t rb = ar->rb, re = ar->re;
-      if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac) || re - rb > l_query + 64) continue;
-      const int w_in = b2_reg2aln_w0(c.opt, ar);
-      if (l_query == re - rb && w_in == 0) continue;  // gap-free: no DP (bwa/bwa.c:131)
-      const int w = b2_cigar_band(c.opt, l_query, (int)(re - rb), w_in);
-      const int cls = b2_galn_class(w);
-      const int dl = l_query > (int)(re - rb) ? l_query - (int)(re - rb) : (int)(re - rb) - l_query;
-      if (cls < 0 || dl > w) continue;
-      if (mode) {
-        const int64_t id = c.galn_base[cls] + c.galn_off[(size_t)cls * (n + 2) + r] + cnt[cls];
-        B2GalnTask t;
-        t.seq_off = c.b.seq_off[r]; t.rb = rb; t.re = re; t.read = r; t.qb = qb; t.qe = qe; t.w_in = w_in; t.w = w;
-        c.galn_tasks[id] = t;
-        c.galn_res[id].n_cigar = -1;
-        uint32_t h = b2_galn_hash(t.seq_off, qb, qe, rb, re, w_in) & c.galn.mask;
-        while (B2_ATOMIC_CAS(&c.galn_table[h], -1, (int32_t)id) != -1) h = (h + 1) & c.galn.mask;
+    // the two best regions (primary / supplementary candidates), and -- when few enough regions score within
+    // XA_drop_ratio of the best for an XA tag to be written at all (mem_gen_alt, bwa/bwamem_extra.c:98-140) -- those too
+    int n_plan = nr < B2_GALN_MAXREGS ? nr : B2_GALN_MAXREGS;
+    if (nr > B2_GALN_MAXREGS && !(c.opt.flag & B2_F_ALL)) {
+      int m = 0;
+      while (m < nr && m <= c.opt.max_XA_hits + 1 && (double)a[m].score >= (double)a[0].score * (double)c.opt.XA_drop_ratio) ++m;
+      if (m <= c.opt.max_XA_hits + 1 && m > n_plan) n_plan = m;
+    }
+    for (int k = 0; k < n_plan; ++k) b2_galn_admit(c, r, &a[k], mode, cnt);
+    // regions that mate rescue is going to add to this read: the local SW of every planned attempt has run
+    // (k_resc_sw), so the region mem_matesw builds from a hit (bwa/bwamem_pair.c:152-172) is known here
+    if ((c.opt.flag & B2_F_PE) && c.resc_off && c.n_resc > 0) {
+      const int item = r >> 1;
+      int planned = 0;
+      for (int64_t ti = c.resc_off[item]; ti < c.resc_off[item + 1] && planned < B2_GALN_MAXREGS; ++ti) {
+        const B2RescTask t = c.resc_tasks[ti];
+        if (2 * t.item + (t.end_i ? 0 : 1) != r) continue;
+        const B2Kswr aln = c.resc_res[ti];
+        if (!(aln.score >= c.opt.min_seed_len && aln.qb >= 0)) continue;
+        const int is_rev = (t.r >> 1 != (t.r & 1));
+        const int l_ms = t.l_ms;
+        B2Reg b = B2Reg();
+        b.qb = is_rev ? l_ms - (aln.qe + 1) : aln.qb;
+        b.qe = is_rev ? l_ms - aln.qb : aln.qe + 1;
+        b.rb = is_rev ? (l_pac << 1) - (t.rb + aln.te + 1) : t.rb + aln.tb;
+        b.re = is_rev ? (l_pac << 1) - (t.rb + aln.tb) : t.rb + aln.te + 1;
+        b.score = aln.score;
+        b.csub = aln.score2;
+        b.secondary = -1;
+        b.seedcov = (int)((b.re - b.rb < b.qe - b.qb ? b.re - b.rb : b.qe - b.qb) >> 1);
+        b2_galn_admit(c, r, &b, mode, cnt);
+        ++planned;
       }
-      ++cnt[cls];
     }
     if (!mode) for (int k = 0; k < B2_GALN_CLASSES; ++k) c.galn_cnt[(size_t)k * (n + 1) + r] = cnt[k];
   }
