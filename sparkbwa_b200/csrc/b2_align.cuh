@@ -582,11 +582,42 @@ struct B2RegScLt {
   }
 };
 
+// Sorting the 96-byte region records of a repeat-rich read moves a lot of memory (the reads with dozens of regions are
+// the tail of the finalisation kernel).  The permutation ks_introsort produces depends only on the outcomes of its
+// comparisons, so the same algorithm run over 24-byte (key, index) records with the same predicate gives the same
+// permutation; the records are then moved once.  One lane of the group sorts, all lanes copy.
+struct B2SortKey { int64_t a; uint64_t b; int32_t c; int32_t idx; };
+struct B2KeyRe { B2_HD B2SortKey operator()(const B2Reg& r) const { B2SortKey k; k.a = r.re; k.b = 0; k.c = 0; k.idx = 0; return k; } };
+struct B2KeyReLt { B2_HD bool operator()(const B2SortKey& x, const B2SortKey& y) const { return x.a < y.a; } };
+struct B2KeySc { B2_HD B2SortKey operator()(const B2Reg& r) const { B2SortKey k; k.a = r.rb; k.b = (uint64_t)(int64_t)r.qb; k.c = r.score; k.idx = 0; return k; } };
+struct B2KeyScLt {
+  B2_HD bool operator()(const B2SortKey& x, const B2SortKey& y) const {
+    return x.c > y.c || (x.c == y.c && (x.a < y.a || (x.a == y.a && (int64_t)x.b < (int64_t)y.b)));
+  }
+};
+#define B2_SORT_KEYS_MIN 5
+template <class RegLt, class MakeKey, class KeyLt>
+B2_HD inline void b2_sort_regs(B2Reg* a, int n, B2Scratch& sc, RegLt rlt, MakeKey mk, KeyLt klt) {
+  const size_t need = (size_t)n * (sizeof(B2SortKey) + sizeof(B2Reg)) + 32;
+  if (n < B2_SORT_KEYS_MIN || sc.used + need > sc.cap) { b2_introsort(a, (long)n, rlt); return; }
+  const size_t mk0 = sc.mark();
+  B2SortKey* keys = (B2SortKey*)sc.alloc(sizeof(B2SortKey) * (size_t)n, 8);
+  B2Reg* tmp = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)n, 8);
+  sc.gsync();
+  for (int i = sc.lane; i < n; i += sc.gsize) { B2SortKey k = mk(a[i]); k.idx = i; keys[i] = k; tmp[i] = a[i]; }
+  sc.gsync();
+  if (sc.lane == 0) b2_introsort(keys, (long)n, klt);
+  sc.gsync();
+  for (int i = sc.lane; i < n; i += sc.gsize) a[i] = tmp[keys[i].idx];
+  sc.gsync();
+  sc.reset(mk0);
+}
+
 B2_NOINLINE B2_HD inline int b2_sort_dedup_patch(const B2Opt& opt, const B2Index& ix, int have_ref, uint8_t* query, int n,
                                      B2Reg* a, B2Scratch& sc) {
   int m, i, j;
   if (n <= 1) return n;
-  b2_introsort(a, (long)n, B2RegReLt());
+  b2_sort_regs(a, n, sc, B2RegReLt(), B2KeyRe(), B2KeyReLt());
   for (i = 0; i < n; ++i) a[i].n_comp = 1;
   for (i = 1; i < n; ++i) {
     B2Reg* p = &a[i];
@@ -618,7 +649,7 @@ B2_NOINLINE B2_HD inline int b2_sort_dedup_patch(const B2Opt& opt, const B2Index
   for (i = 0, m = 0; i < n; ++i)
     if (a[i].qe > a[i].qb) { if (m != i) a[m++] = a[i]; else ++m; }
   n = m;
-  b2_introsort(a, (long)n, B2RegScLt());
+  b2_sort_regs(a, n, sc, B2RegScLt(), B2KeySc(), B2KeyScLt());
   for (i = 1; i < n; ++i)
     if (a[i].score == a[i - 1].score && a[i].rb == a[i - 1].rb && a[i].qb == a[i - 1].qb) a[i].qe = a[i].qb;
   for (i = 1, m = 1; i < n; ++i)

@@ -130,6 +130,17 @@ struct B2RegHash2Lt {
     return a.is_alt < b.is_alt || (a.is_alt == b.is_alt && (a.score > b.score || (a.score == b.score && a.hash < b.hash)));
   }
 };
+struct B2KeyHash { B2_HD B2SortKey operator()(const B2Reg& r) const { B2SortKey k; k.a = r.is_alt; k.b = r.hash; k.c = r.score; k.idx = 0; return k; } };
+struct B2KeyHashLt {
+  B2_HD bool operator()(const B2SortKey& x, const B2SortKey& y) const {
+    return x.c > y.c || (x.c == y.c && (x.a < y.a || (x.a == y.a && x.b < y.b)));
+  }
+};
+struct B2KeyHash2Lt {
+  B2_HD bool operator()(const B2SortKey& x, const B2SortKey& y) const {
+    return x.a < y.a || (x.a == y.a && (x.c > y.c || (x.c == y.c && x.b < y.b)));
+  }
+};
 
 // z: int scratch of n entries
 B2_HD inline void b2_mark_primary_core(const B2Opt& opt, int n, B2Reg* a, int* z) {
@@ -157,7 +168,7 @@ B2_HD inline void b2_mark_primary_core(const B2Opt& opt, int n, B2Reg* a, int* z
   }
 }
 
-B2_NOINLINE B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* a, int64_t id, int* z) {
+B2_NOINLINE B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* a, int64_t id, int* z, B2Scratch& sc) {
   int i, n_pri;
   if (n == 0) return 0;
   for (i = n_pri = 0; i < n; ++i) {
@@ -165,7 +176,7 @@ B2_NOINLINE B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* 
     a[i].hash = b2_hash64((uint64_t)(id + i));
     if (!a[i].is_alt) ++n_pri;
   }
-  b2_introsort(a, (long)n, B2RegHashLt());
+  b2_sort_regs(a, n, sc, B2RegHashLt(), B2KeyHash(), B2KeyHashLt());
   b2_mark_primary_core(opt, n, a, z);
   for (i = 0; i < n; ++i) {
     B2Reg* p = &a[i];
@@ -173,7 +184,7 @@ B2_NOINLINE B2_HD inline int b2_mark_primary_se(const B2Opt& opt, int n, B2Reg* 
     if (!p->is_alt && p->secondary >= 0 && a[p->secondary].is_alt) p->alt_sc = a[p->secondary].score;
   }
   if (n_pri >= 0 && n_pri < n) {
-    if (n_pri > 0) b2_introsort(a, (long)n, B2RegHash2Lt());
+    if (n_pri > 0) b2_sort_regs(a, n, sc, B2RegHash2Lt(), B2KeyHash(), B2KeyHash2Lt());
     for (i = 0; i < n; ++i) z[a[i].secondary_all] = i;
     for (i = 0; i < n; ++i) {
       if (a[i].secondary >= 0) {
@@ -844,8 +855,8 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
   int zn = (n[0] > n[1] ? n[0] : n[1]) + 1;
   int* zbuf = (int*)sc.alloc(sizeof(int) * (size_t)zn, 4);
   if (sc.overflow) { sc.reset(mk0); return; }
-  n_pri[0] = b2_mark_primary_se(opt, n[0], a[0], (int64_t)(id << 1 | 0), zbuf);
-  n_pri[1] = b2_mark_primary_se(opt, n[1], a[1], (int64_t)(id << 1 | 1), zbuf);
+  n_pri[0] = b2_mark_primary_se(opt, n[0], a[0], (int64_t)(id << 1 | 0), zbuf, sc);
+  n_pri[1] = b2_mark_primary_se(opt, n[1], a[1], (int64_t)(id << 1 | 1), zbuf, sc);
   int no_pairing = 0;
   if (opt.flag & B2_F_NOPAIRING) no_pairing = 1;
   if (!no_pairing && n_pri[0] && n_pri[1] &&

@@ -762,7 +762,7 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
     if (!sc.overflow) {
       for (int i = 0; i < n; ++i) a[i] = c.regs[c.reg_off[r] + i];
       B2Read s = b2_make_read(c.b, r, 1);
-      b2_mark_primary_se(c.opt, n, a, c.n_processed + r, z);
+      b2_mark_primary_se(c.opt, n, a, c.n_processed + r, z, sc);
       b2_reg2sam(c.opt, c.ix, c.tb, c.fmt, out, s, n, a, 0, 0, sc, &err);
     }
     if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
