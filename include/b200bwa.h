@@ -115,8 +115,8 @@ int b200bwa_upload_batch(b200bwa_index_t* idx, int n_reads, const char* seq, con
 int b200bwa_run_resident(b200bwa_index_t* idx, int paired, int want_sam, char** sam_out, size_t* sam_len);
 
 /* Runs reads [first, first+count) of the batch uploaded by b200bwa_upload_batch on stream/buffer set
- * `worker` (0 .. b200bwa_n_workers()-1, else rc 1; sets may run concurrently from different host threads).  Pairing mode comes from
- * b200bwa_set_paired.  `t` (may be NULL) receives the device stage times of this call. */
+ * `worker` (0 .. b200bwa_n_workers()-1, else rc 1; sets may run concurrently from different host threads).  `paired` non-zero:
+ * the range is paired-end (interleaved mates, even count).  `t` (may be NULL) receives the device stage times of this call. */
 int b200bwa_run_resident_range(b200bwa_index_t* idx, int worker, int first, int count, int paired, int want_sam,
                                char** sam_out, size_t* sam_len, b200bwa_times_t* t);
 int b200bwa_set_paired(b200bwa_index_t* idx, int paired);

@@ -297,7 +297,7 @@ int b200bwa_run_resident_range(b200bwa_index_t* ix, int worker, int first, int c
     }
     // options are set once by the caller (b200bwa_set_options / b200bwa_set_paired); concurrent workers share them
     std::string sam;
-    if (ix->engine->run_resident_range(ix->args.has_pes0 ? ix->args.pes0 : 0, want_sam ? &sam : 0, worker, 0, first, count)) {
+    if (ix->engine->run_resident_range(ix->args.has_pes0 ? ix->args.pes0 : 0, want_sam ? &sam : 0, worker, 0, first, count, paired ? 1 : 0)) {
       b2_tls_error = ix->engine->last_error();
       return 1;
     }
@@ -308,7 +308,6 @@ int b200bwa_run_resident_range(b200bwa_index_t* ix, int worker, int first, int c
       t->n_seed_tasks = s.n_seed_tasks; t->n_regs = s.n_regs; t->sam_bytes = s.sam_bytes; t->rescue = s.rescue; t->n_rescue_tasks = s.n_resc;
       t->k_xext = s.k_xext; t->k_resc_sw = s.k_resc_sw; t->k_galn = s.k_galn;
     }
-    (void)paired;
     if (want_sam && sam_out) { *sam_out = dup_out(sam, sam_len); return *sam_out ? 0 : 1; }
     return 0;
   } catch (const std::exception& e) { b2_tls_error = e.what(); return 1; }

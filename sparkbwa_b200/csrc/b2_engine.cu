@@ -978,8 +978,8 @@ int B2Engine::upload(const B2HostBatch& b, int worker) { return impl_->upload(im
 int B2Engine::run_resident(const B2Pes* pes0, std::string* sam, int worker) {
   return impl_->run(impl_->workers[worker], pes0, sam);
 }
-int B2Engine::run_resident_range(const B2Pes* pes0, std::string* sam, int worker, int src_worker, int first, int count) {
-  return impl_->run(impl_->workers[worker], pes0, sam, &impl_->workers[src_worker], first, count);
+int B2Engine::run_resident_range(const B2Pes* pes0, std::string* sam, int worker, int src_worker, int first, int count, int paired) {
+  return impl_->run(impl_->workers[worker], pes0, sam, &impl_->workers[src_worker], first, count, false, paired < 0 ? -1 : (paired ? 1 : 0));
 }
 void B2Engine::set_options(const B2Opt& opt, const char* rg_id, int verbose) {
   impl_->bind_device();

@@ -110,7 +110,8 @@ class B2Engine {
   int upload(const B2HostBatch& b, int worker = 0);
   int run_resident(const B2Pes* pes0, std::string* sam, int worker = 0);
   // reads [first, first+count) of the batch resident on src_worker, run on `worker`'s stream/buffers
-  int run_resident_range(const B2Pes* pes0, std::string* sam, int worker, int src_worker, int first, int count);
+  // paired: 0 / 1 = this range single-end / paired-end, -1 = as the options say
+  int run_resident_range(const B2Pes* pes0, std::string* sam, int worker, int src_worker, int first, int count, int paired = -1);
   // per-call options (a cached index serves successive calls with different bwa-mem options)
   void set_options(const B2Opt& opt, const char* rg_id, int verbose);
   const B2Opt& options() const;

@@ -1438,6 +1438,11 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   std::string errmsg;
   const size_t max_inflight = (size_t)G * ((size_t)n_workers + 2);
 
+  // One mutex, one condition variable per role (reader, each device's workers, writers, allocator, the ordering loop
+  // below): with 48 workers and 24 writers on 8 GPUs a single notify_all would wake ~80 threads for every event.
+  std::condition_variable cv_r, cv_w, cv_a, cv_m;
+  std::vector<std::condition_variable> cv_dev(G);
+  auto wake_all = [&]() { cv.notify_all(); cv_r.notify_all(); cv_w.notify_all(); cv_a.notify_all(); cv_m.notify_all(); for (auto& x : cv_dev) x.notify_all(); };
   std::thread reader([&]() {
     // B200BWA_FIRST_READ: absolute index of this input's first read within a larger run (a partition of a job that
     // was split upstream); it enters the hash tie-breaks exactly like n_processed of bwa/fastmap.c:85
@@ -1456,16 +1461,17 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       if (m.verbose >= 3) fprintf(stderr, "[M::process] read %d sequences (%ld bp)...\n", n, (long)j->raw->n_bases);
       if (times0) fprintf(stderr, "[T::b200bwa] batch %ld cut at %.1f ms\n", (long)j->index, (b2_realtime() - t_real) * 1e3);
       std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
+      cv_r.wait(lk, [&] { return inorder.size() < max_inflight || failed; });
       if (failed) break;
-      todo[dealt++ % G].push_back(j);
+      const int to_dev = (int)(dealt++ % G);
+      todo[to_dev].push_back(j);
       inorder.push_back(j);
       if (positioned) unassigned.push_back(j);
-      cv.notify_all();
+      cv_dev[to_dev].notify_all();
     }
     std::lock_guard<std::mutex> lk(mu);
     read_done = true;
-    cv.notify_all();
+    wake_all();
   });
 
   // Positioned mode: the file writes are done by a few writer threads, so that a GPU worker starts its next batch
@@ -1498,7 +1504,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       allocator = std::thread([&, look, step]() {
         std::unique_lock<std::mutex> lk(mu);
         for (;;) {
-          cv.wait(lk, [&] { return alloc_stop || failed || (populate_ok ? std::max(alloc_end, next_off) : alloc_end) < next_off + look; });
+          cv_a.wait(lk, [&] { return alloc_stop || failed || (populate_ok ? std::max(alloc_end, next_off) : alloc_end) < next_off + look; });
           if (alloc_stop || failed) return;
           const int64_t from = populate_ok ? std::max(alloc_end, next_off) : alloc_end;
           lk.unlock();
@@ -1508,15 +1514,15 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           if (e) {
             failed = true;
             errmsg = std::string("cannot reserve space for the SAM output: ") + strerror(e);
-            cv.notify_all();
+            wake_all();
             return;
           }
           alloc_end = from + step;
           if (!populate_ok && alloc_end > file_size) {   // writers wait for the allocator: the file has to cover what it reserved
             file_size = alloc_end;
-            if (ftruncate(out_fd, (off_t)file_size) != 0) { failed = true; errmsg = "cannot extend the SAM output"; cv.notify_all(); return; }
+            if (ftruncate(out_fd, (off_t)file_size) != 0) { failed = true; errmsg = "cannot extend the SAM output"; wake_all(); return; }
           }
-          cv.notify_all();
+          cv_w.notify_all();
         }
       });
     }
@@ -1542,7 +1548,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           std::shared_ptr<Job> j;
           {
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return !wq.empty() || failed || gpu_active == 0; });
+            cv_w.wait(lk, [&] { return !wq.empty() || failed || gpu_active == 0; });
             if (failed || wq.empty()) return;
             j = wq.front();
             wq.pop_front();
@@ -1550,7 +1556,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           bool wrote = true;
           if (out_map && !populate_ok) {
             std::unique_lock<std::mutex> lk(mu);
-            cv.wait(lk, [&] { return failed || alloc_end >= j->offset + (int64_t)j->sam_size; });
+            cv_w.wait(lk, [&] { return failed || alloc_end >= j->offset + (int64_t)j->sam_size; });
             if (failed) return;
           }
           const double t_w0 = b2_realtime();
@@ -1562,7 +1568,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
                 failed = true;
                 errmsg = std::string("cannot reserve space for the SAM output: ") + strerror(errno == EFAULT ? ENOSPC : errno);
                 j->rc = 1;
-                cv.notify_all();
+                wake_all();
                 return;
               }
             }
@@ -1570,10 +1576,10 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
           } else wrote = pwrite_all(j->wdata, j->sam_size, j->offset);
           if (times) fprintf(stderr, "[T::b200bwa] batch %ld: queued for writing %.1f ms, write %.1f ms, done at %.1f ms\n", (long)j->index, (t_w0 - j->t_gpu) * 1e3, (b2_realtime() - t_w0) * 1e3, (b2_realtime() - t_real) * 1e3);
           std::lock_guard<std::mutex> lk(mu);
-          if (j->wslot >= 0) busy[j->wslot] = 0;
-          if (!wrote) { j->rc = 1; failed = true; errmsg = "write error on SAM output"; }
+          if (j->wslot >= 0) { busy[j->wslot] = 0; cv_dev[j->wslot / (2 * n_workers)].notify_all(); }
+          if (!wrote) { j->rc = 1; failed = true; errmsg = "write error on SAM output"; wake_all(); }
           j->done = true;
-          cv.notify_all();
+          cv_m.notify_all();
         }
       });
   }
@@ -1589,22 +1595,22 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       B2HostBatch hb;
       B2Engine* eng = engs[dv];
       std::deque<std::shared_ptr<Job>>& q = todo[dv];
-      struct Leave { std::mutex& m; std::condition_variable& c; int& n; ~Leave() { std::lock_guard<std::mutex> lk(m); --n; c.notify_all(); } } leave{mu, cv, gpu_active};
+      struct Leave { std::mutex& m; std::condition_variable& c; int& n; ~Leave() { std::lock_guard<std::mutex> lk(m); --n; c.notify_all(); } } leave{mu, cv_w, gpu_active};
       for (;;) {
         std::shared_ptr<Job> j;
         int slot = -1;
         {
           std::unique_lock<std::mutex> lk(mu);
           idle[dv] |= 1u << wi;
-          cv.wait(lk, [&] { return (!q.empty() && (idle[dv] & ((1u << wi) - 1)) == 0) || (q.empty() && read_done) || failed; });
+          cv_dev[dv].wait(lk, [&] { return (!q.empty() && (idle[dv] & ((1u << wi) - 1)) == 0) || (q.empty() && read_done) || failed; });
           idle[dv] &= ~(1u << wi);
-          if (failed || (q.empty() && read_done)) { cv.notify_all(); return; }
+          if (failed || (q.empty() && read_done)) { cv_dev[dv].notify_all(); return; }
           j = q.front();
           q.pop_front();
-          cv.notify_all();   // (a higher-numbered worker may be the lowest idle one now)
+          cv_dev[dv].notify_all();   // (a higher-numbered worker may be the lowest idle one now)
           if (positioned && !smart) {  // the pinned buffer this batch's text will land in must have been written out
             slot = (dv * n_workers + wi) * 2 + eng->next_view_slot(wi);
-            cv.wait(lk, [&] { return !busy[slot] || failed; });
+            cv_dev[dv].wait(lk, [&] { return !busy[slot] || failed; });
             if (failed) return;
           }
         }
@@ -1656,14 +1662,14 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
             wq.push_back(unassigned.front());
             unassigned.pop_front();
           }
-          if (!grow_file()) { failed = true; errmsg = "cannot extend the SAM output"; }
-          cv.notify_all();
+          if (!grow_file()) { failed = true; errmsg = "cannot extend the SAM output"; wake_all(); }
+          cv_w.notify_all(); cv_a.notify_all();
           continue;   // a writer thread marks the job done
         }
         std::lock_guard<std::mutex> lk(mu);
         j->rc = rc; j->done = true;
-        if (rc) failed = true;
-        cv.notify_all();
+        if (rc) { failed = true; wake_all(); }
+        cv_m.notify_all();
       }
     });
 
@@ -1673,31 +1679,31 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     std::shared_ptr<Job> j;
     {
       std::unique_lock<std::mutex> lk(mu);
-      cv.wait(lk, [&] { return failed || (!inorder.empty() && inorder.front()->done) || (inorder.empty() && read_done); });
+      cv_m.wait(lk, [&] { return failed || (!inorder.empty() && inorder.front()->done) || (inorder.empty() && read_done); });
       if (failed) { rc = 1; break; }
       if (inorder.empty()) break;
       j = inorder.front();
       inorder.pop_front();
-      cv.notify_all();
+      cv_r.notify_all();
     }
     if (fidx) fprintf(fidx, "%ld\t%d\t%zu\n", (long)j->index, j->n_reads, positioned ? j->sam_size : j->sam.size());
     if (!positioned && fwrite(j->sam.data(), 1, j->sam.size(), out) != j->sam.size()) {
       std::lock_guard<std::mutex> lk(mu);
       failed = true; rc = 1; errmsg = "write error on SAM output";
-      cv.notify_all();
+      wake_all();
       break;
     }
   }
   {
     std::lock_guard<std::mutex> lk(mu);
     if (rc) failed = true;
-    cv.notify_all();
+    wake_all();
   }
   reader.join();
   for (auto& t : gpu) t.join();
   for (auto& t : writers) t.join();
   if (allocator.joinable()) {
-    { std::lock_guard<std::mutex> lk(mu); alloc_stop = true; cv.notify_all(); }
+    { std::lock_guard<std::mutex> lk(mu); alloc_stop = true; wake_all(); }
     allocator.join();
   }
   if (out_map) {
