@@ -2,7 +2,7 @@
 # Round-2 visit G (N GPUs, default 8): strong-scaling bench at N + configs[2] (3.1 Gbp, 20 M pairs) as ONE job over N GPUs.
 N=${1:-8}
 mkdir -p gpurun_out/r2g
-O=gpurun_out/r2g
+O=gpurun_out/${OUTDIR:-r2g}
 nvidia-smi -L > $O/gpus_n$N.txt; nproc >> $O/gpus_n$N.txt; free -g >> $O/gpus_n$N.txt
 B200BWA_TIMES=1 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus $N --steps 3 --warmup 3 > $O/bench_n$N.json 2> $O/bench_n$N.err; echo "bench rc $?"
 python -c "

@@ -24,6 +24,17 @@ struct B2Scratch {
   int lane = 0, gsize = 1;
   unsigned gmask = 0;
   const B2GalnCache* galn = 0;  // global alignments computed ahead of the finalisation kernel (b2_galn.cuh)
+  long long* prof = 0;          // B200BWA_DEBUG_TIMES: cycles per phase of the finalisation, summed over the tasks
+  long long prof_t = 0;
+  B2_HD inline void tick(int k) {   // k < 0: start the clock
+#if defined(__CUDA_ARCH__)
+    if (prof) {
+      const long long t = clock64();
+      if (k >= 0 && lane == 0) atomicAdd((unsigned long long*)&prof[k], (unsigned long long)(t - prof_t));
+      prof_t = t;
+    }
+#endif
+  }
   B2_HD inline void gsync() const {
 #if defined(__CUDA_ARCH__)
     if (gsize > 1) __syncwarp(gmask);

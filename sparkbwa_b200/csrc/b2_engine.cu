@@ -756,8 +756,8 @@ class B2EngineImpl {
       if (w.slots.ensure((size_t)n_items * w.slot_size)) return fail("device allocation failed (SAM slots)");
       c.slots = w.slots.p; c.slot_size = w.slot_size;
       if (getenv("B200BWA_DEBUG_TIMES")) {
-        if (w.dbg.ensure((size_t)n_items * 4 + 4)) return fail("device allocation failed");
-        b2_dev_memset(w.dbg.p, 0, (size_t)n_items * 4 * sizeof(long long), w.stream);
+        if (w.dbg.ensure((size_t)n_items * 4 + 16)) return fail("device allocation failed");
+        b2_dev_memset(w.dbg.p, 0, ((size_t)n_items * 4 + 16) * sizeof(long long), w.stream);
         c.dbg = w.dbg.p;
       }
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
@@ -775,9 +775,23 @@ class B2EngineImpl {
     }
     int ev_fin = w.timer.mark();
     if (c.dbg) {
-      std::vector<long long> h((size_t)n_items * 4);
+      std::vector<long long> h((size_t)n_items * 4 + 16);
       b2_d2h(h.data(), w.dbg.p, h.size() * sizeof(long long), w.stream);
       b2_sync(w.stream);
+      {
+        const long long* ph = h.data() + (size_t)n_items * 4;
+        fprintf(stderr, "[D::final] phase cycles: load %lld rescue %lld mark_primary %lld pair+mapq %lld xa %lld reg2aln %lld aln2sam %lld reg2sam(unpaired) %lld\n",
+                ph[7], ph[0], ph[1], ph[2], ph[3], ph[4], ph[5], ph[6]);
+        std::vector<long long> cyc(n_items);
+        for (int i = 0; i < n_items; ++i) cyc[i] = h[4 * (size_t)i];
+        std::sort(cyc.begin(), cyc.end());
+        long long all = 0, top1 = 0;
+        for (int i = 0; i < n_items; ++i) { all += cyc[i]; if (i >= n_items - n_items / 100) top1 += cyc[i]; }
+        auto pct = [&](double f) { return cyc[std::min<size_t>((size_t)n_items - 1, (size_t)(f * n_items))]; };
+        if (n_items > 0)
+          fprintf(stderr, "[D::final] cycles per item: p10 %lld p50 %lld p90 %lld p99 %lld p99.9 %lld max %lld; slowest 1%% of the items hold %.1f%% of the cycles\n",
+                  pct(.10), pct(.50), pct(.90), pct(.99), pct(.999), cyc[n_items - 1], all ? 100.0 * top1 / all : 0.);
+      }
       std::vector<int> ord(n_items);
       for (int i = 0; i < n_items; ++i) ord[i] = i;
       std::sort(ord.begin(), ord.end(), [&](int a, int b) { return h[4 * a] > h[4 * b]; });
@@ -862,57 +876,93 @@ class B2EngineImpl {
 };
 
 // ---------------------------------------------------------------------------------------------
-void b2_pestat_host(const B2Opt& opt, int n_pairs, const int8_t* dir, const int64_t* is, B2Pes pes[4], int verbose) {
-  std::vector<uint64_t> isize[4];
-  memset(pes, 0, 4 * sizeof(B2Pes));
-  (void)opt;
-  for (int i = 0; i < n_pairs; ++i)
-    if (dir[i] >= 0) isize[dir[i]].push_back((uint64_t)is[i]);
-  if (verbose >= 3)
-    fprintf(stderr, "[M::mem_pestat] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n",
-            (long)isize[0].size(), (long)isize[1].size(), (long)isize[2].size(), (long)isize[3].size());
-  for (int d = 0; d < 4; ++d) {
-    B2Pes* r = &pes[d];
-    std::vector<uint64_t>& q = isize[d];
-    int p25, p50, p75, x;
-    if (q.size() < 10) {
-      if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] skip orientation %c%c as there are not enough pairs\n", "FR"[d >> 1 & 1], "FR"[d & 1]);
-      r->failed = 1;
-      continue;
-    } else if (verbose >= 3)
-      fprintf(stderr, "[M::mem_pestat] analyzing insert size distribution for orientation %c%c...\n", "FR"[d >> 1 & 1], "FR"[d & 1]);
-    std::sort(q.begin(), q.end());
-    p25 = (int)q[(int)(.25 * q.size() + .499)];
-    p50 = (int)q[(int)(.50 * q.size() + .499)];
-    p75 = (int)q[(int)(.75 * q.size() + .499)];
-    r->low = (int)(p25 - 2.0 * (p75 - p25) + .499);
-    if (r->low < 1) r->low = 1;
-    r->high = (int)(p75 + 2.0 * (p75 - p25) + .499);
-    if (verbose >= 3) {
-      fprintf(stderr, "[M::mem_pestat] (25, 50, 75) percentile: (%d, %d, %d)\n", p25, p50, p75);
-      fprintf(stderr, "[M::mem_pestat] low and high boundaries for computing mean and std.dev: (%d, %d)\n", r->low, r->high);
+// Insert-size statistics of one batch (what mem_pestat computes, bwa/bwamem_pair.c:46-109), from the per-pair candidates
+// k_pestat left: each orientation's sizes are reduced to ascending (value, multiplicity) runs; quartiles are read off the
+// cumulative multiplicities, the mean from exact integer sums, and the variance by adding each run's squared deviation
+// `multiplicity` times in ascending order -- the same sequence of double additions as a pass over the sorted list, which
+// is what keeps avg/std (and the low/high bounds derived from them) bit-identical.
+namespace {
+struct B2IsRun { uint64_t v; size_t cnt; };
+struct B2IsDist {
+  std::vector<B2IsRun> runs;
+  size_t total = 0;
+  void build(std::vector<uint64_t>& vals) {
+    std::sort(vals.begin(), vals.end());
+    total = vals.size();
+    for (size_t i = 0; i < vals.size();) {
+      size_t j = i;
+      while (j < vals.size() && vals[j] == vals[i]) ++j;
+      runs.push_back(B2IsRun{vals[i], j - i});
+      i = j;
     }
-    size_t i;
-    for (i = 0, x = 0, r->avg = 0; i < q.size(); ++i)
-      if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) { r->avg += q[i]; ++x; }
-    r->avg /= x;
-    for (i = 0, r->std = 0; i < q.size(); ++i)
-      if (q[i] >= (uint64_t)r->low && q[i] <= (uint64_t)r->high) r->std += (q[i] - r->avg) * (q[i] - r->avg);
-    r->std = sqrt(r->std / x);
-    if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] mean and std.dev: (%.2f, %.2f)\n", r->avg, r->std);
-    r->low = (int)(p25 - 3.0 * (p75 - p25) + .499);
-    r->high = (int)(p75 + 3.0 * (p75 - p25) + .499);
-    if (r->low > r->avg - 4.0 * r->std) r->low = (int)(r->avg - 4.0 * r->std + .499);
-    if (r->high < r->avg + 4.0 * r->std) r->high = (int)(r->avg + 4.0 * r->std + .499);
-    if (r->low < 1) r->low = 1;
-    if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] low and high boundaries for proper pairs: (%d, %d)\n", r->low, r->high);
   }
-  size_t max = 0;
-  for (int d = 0; d < 4; ++d) max = std::max(max, isize[d].size());
-  for (int d = 0; d < 4; ++d)
-    if (pes[d].failed == 0 && isize[d].size() < max * 0.05) {
+  uint64_t at_rank(size_t k) const {  // k-th smallest (0-based)
+    for (const B2IsRun& r : runs) { if (k < r.cnt) return r.v; k -= r.cnt; }
+    return runs.empty() ? 0 : runs.back().v;
+  }
+  int quantile(double f) const { return (int)at_rank((size_t)(int)(f * total + .499)); }
+};
+const char* b2_orient_name(int d) { static const char* nm[4] = {"FF", "FR", "RF", "RR"}; return nm[d]; }
+}  // namespace
+
+void b2_pestat_host(const B2Opt& opt, int n_pairs, const int8_t* dir, const int64_t* is, B2Pes pes[4], int verbose) {
+  (void)opt;
+  const bool say = verbose >= 3;
+  B2IsDist dist[4];
+  {
+    std::vector<uint64_t> vals[4];
+    for (int i = 0; i < n_pairs; ++i)
+      if (dir[i] >= 0) vals[dir[i]].push_back((uint64_t)is[i]);
+    for (int d = 0; d < 4; ++d) dist[d].build(vals[d]);
+  }
+  if (say)
+    fprintf(stderr, "[M::mem_pestat] # candidate unique pairs for (FF, FR, RF, RR): (%ld, %ld, %ld, %ld)\n",
+            (long)dist[0].total, (long)dist[1].total, (long)dist[2].total, (long)dist[3].total);
+  size_t most = 0;
+  for (int d = 0; d < 4; ++d) {
+    const B2IsDist& D = dist[d];
+    B2Pes& out = pes[d];
+    memset(&out, 0, sizeof(B2Pes));
+    most = std::max(most, D.total);
+    if (D.total < 10) {
+      if (say) fprintf(stderr, "[M::mem_pestat] skip orientation %s as there are not enough pairs\n", b2_orient_name(d));
+      out.failed = 1;
+      continue;
+    }
+    if (say) fprintf(stderr, "[M::mem_pestat] analyzing insert size distribution for orientation %s...\n", b2_orient_name(d));
+    const int q1 = D.quantile(.25), q2 = D.quantile(.50), q3 = D.quantile(.75), iqr = q3 - q1;
+    // inliers for the moments: within 2 IQR of the quartiles
+    int in_lo = (int)(q1 - 2.0 * iqr + .499), in_hi = (int)(q3 + 2.0 * iqr + .499);
+    if (in_lo < 1) in_lo = 1;
+    if (say) {
+      fprintf(stderr, "[M::mem_pestat] (25, 50, 75) percentile: (%d, %d, %d)\n", q1, q2, q3);
+      fprintf(stderr, "[M::mem_pestat] low and high boundaries for computing mean and std.dev: (%d, %d)\n", in_lo, in_hi);
+    }
+    double sum = 0;   // integers below 2^53: exact whatever the grouping
+    size_t n_in = 0;
+    for (const B2IsRun& r : D.runs)
+      if (r.v >= (uint64_t)in_lo && r.v <= (uint64_t)in_hi) { sum += (double)r.v * (double)r.cnt; n_in += r.cnt; }
+    const double mean = sum / (int)n_in;
+    double ss = 0;
+    for (const B2IsRun& r : D.runs)
+      if (r.v >= (uint64_t)in_lo && r.v <= (uint64_t)in_hi) {
+        const double dev2 = ((double)r.v - mean) * ((double)r.v - mean);
+        for (size_t k = 0; k < r.cnt; ++k) ss += dev2;   // one addition per pair, in ascending order
+      }
+    const double sd = sqrt(ss / (int)n_in);
+    if (say) fprintf(stderr, "[M::mem_pestat] mean and std.dev: (%.2f, %.2f)\n", mean, sd);
+    // proper-pair window: 3 IQR around the quartiles, widened to mean +- 4 sd
+    int lo = (int)(q1 - 3.0 * iqr + .499), hi = (int)(q3 + 3.0 * iqr + .499);
+    if (lo > mean - 4.0 * sd) lo = (int)(mean - 4.0 * sd + .499);
+    if (hi < mean + 4.0 * sd) hi = (int)(mean + 4.0 * sd + .499);
+    if (lo < 1) lo = 1;
+    if (say) fprintf(stderr, "[M::mem_pestat] low and high boundaries for proper pairs: (%d, %d)\n", lo, hi);
+    out.low = lo; out.high = hi; out.avg = mean; out.std = sd;
+  }
+  for (int d = 0; d < 4; ++d)   // an orientation with under 5 % of the commonest one's pairs is not trusted
+    if (!pes[d].failed && dist[d].total < most * 0.05) {
       pes[d].failed = 1;
-      if (verbose >= 3) fprintf(stderr, "[M::mem_pestat] skip orientation %c%c\n", "FR"[d >> 1 & 1], "FR"[d & 1]);
+      if (say) fprintf(stderr, "[M::mem_pestat] skip orientation %s\n", b2_orient_name(d));
     }
 }
 

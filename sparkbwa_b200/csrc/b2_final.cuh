@@ -838,6 +838,7 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
   int i, j, z[2] = {0, 0}, o, subo = 0, n_sub = 0, extra_flag = 1, n_pri[2];
   B2Aln h[2];
   const size_t mk0 = sc.mark();
+  sc.tick(-1);
   if (!(opt.flag & B2_F_NO_RESCUE)) {
     B2Reg* b[2];
     int nb[2] = {0, 0};
@@ -852,11 +853,13 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
         b2_matesw(opt, ix, pes, &b[i][j], s[!i].l_seq, s[!i].seq, a[!i], &n[!i], cap[!i], sc, i, j, cache);
     sc.reset(mk0);
   }
+  sc.tick(0);
   int zn = (n[0] > n[1] ? n[0] : n[1]) + 1;
   int* zbuf = (int*)sc.alloc(sizeof(int) * (size_t)zn, 4);
   if (sc.overflow) { sc.reset(mk0); return; }
   n_pri[0] = b2_mark_primary_se(opt, n[0], a[0], (int64_t)(id << 1 | 0), zbuf, sc);
   n_pri[1] = b2_mark_primary_se(opt, n[1], a[1], (int64_t)(id << 1 | 1), zbuf, sc);
+  sc.tick(1);
   int no_pairing = 0;
   if (opt.flag & B2_F_NOPAIRING) no_pairing = 1;
   if (!no_pairing && n_pri[0] && n_pri[1] &&
@@ -902,8 +905,10 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
         }
       }
       char** XA[2] = {0, 0};
+      sc.tick(2);
       if (!(opt.flag & B2_F_ALL))
         for (i = 0; i < 2; ++i) XA[i] = b2_gen_alt(opt, ix, tb, n[i], a[i], s[i].l_seq, s[i].seq, sc, err);
+      sc.tick(3);
       B2Aln g[2], aa[2][2];
       int n_aa[2] = {0, 0};
       for (i = 0; i < 2; ++i) {
@@ -921,13 +926,16 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
           aa[i][n_aa[i]++] = g[i];
         }
       }
+      sc.tick(4);
       for (i = 0; i < n_aa[0]; ++i) b2_aln2sam(opt, ix, fmt, out, s[0], n_aa[0], aa[0], i, &h[1]);
       for (i = 0; i < n_aa[1]; ++i) b2_aln2sam(opt, ix, fmt, out, s[1], n_aa[1], aa[1], i, &h[0]);
+      sc.tick(5);
       sc.reset(mk0);
       return;
     }
   }
   // no_pairing
+  sc.tick(2);
   for (i = 0; i < 2; ++i) {
     int which = -1;
     if (n[i]) {
@@ -942,7 +950,9 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
     int d = b2_infer_dir(ix.l_pac, a[0][0].rb, a[1][0].rb, &dist);
     if (!pes[d].failed && dist >= pes[d].low && dist <= pes[d].high) extra_flag |= 2;
   }
+  sc.tick(4);
   b2_reg2sam(opt, ix, tb, fmt, out, s[0], n[0], a[0], 0x41 | extra_flag, &h[1], sc, err);
   b2_reg2sam(opt, ix, tb, fmt, out, s[1], n[1], a[1], 0x81 | extra_flag, &h[0], sc, err);
+  sc.tick(6);
   sc.reset(mk0);
 }

@@ -778,9 +778,11 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) {
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
   sc.galn = &c.galn;
   const int n_pairs = c.b.n_reads >> 1;
+  sc.prof = c.dbg ? c.dbg + 4 * (size_t)n_pairs : 0;
   for (int i = b2_next_task(c, sc); i < n_pairs; i = b2_next_task(c, sc)) {
     sc.gsync();
     sc.reset(0);
+    sc.tick(-1);
 #if defined(__CUDA_ARCH__)
     const long long t0 = clock64();
     const unsigned sw0 = sc.sw_calls, gl0 = sc.glob_calls;
@@ -808,6 +810,7 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) {
         cache.tasks = c.resc_tasks + c.resc_off[i];
         cache.res = c.resc_res + c.resc_off[i];
       }
+      sc.tick(7);
       b2_sam_pe(c.opt, c.ix, c.tb, c.fmt, c.pes, (uint64_t)((c.n_processed >> 1) + i), s, a, n, cap, out, sc, &err, &cache);
     }
     if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
