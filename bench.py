@@ -362,11 +362,16 @@ def main():
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    one_pass(batches=dealt(args.steps))
+    trace = [] if os.environ.get("B200BWA_BENCH_TRACE") else None
+    one_pass(trace, batches=dealt(args.steps))
     torch.cuda.synchronize()
     e1.record(); e1.synchronize()
     ms_total = e0.elapsed_time(e1)
     sampler.stop_ev.set(); sampler.join()
+    if trace:   # per-batch stage times of the concurrent passes (each batch's own CUDA events): mean / max over the batches
+        for k in ("seed", "sa", "chain", "extend", "pestat", "rescue", "finalize", "gather", "total"):
+            v = [t[k] for t in trace]
+            sys.stderr.write(f"[bench trace] {k:9s} mean {np.mean(v):8.2f} ms  max {np.max(v):8.2f} ms  ({len(v)} batches)\n")
     lib.b200bwa_process_counters(pc, 0)
     launches = int(pc[2])
     tt = torch.tensor([ms_total], dtype=torch.float64, device="cuda")

@@ -60,13 +60,43 @@ struct B2Scratch {
     used = o + bytes;
     return base + o;
   }
-  B2_HD inline size_t mark() const { return used; }
-  B2_HD inline void reset(size_t m) { used = m; }
+  // Small second arena in shared memory (the finalisation kernels give every task group a few hundred bytes): the
+  // private copy of the read and the reference window of an alignment are walked base by base several times (score,
+  // NM/MD, reversal), and a round trip to L2 per step is what those loops otherwise cost.  Falls back to the global
+  // arena when absent or full; marks cover both arenas.
+  uint8_t* fast = 0;
+  unsigned fast_cap = 0, fast_used = 0;
+  B2_HD inline void* alloc_fast(size_t bytes, size_t align = 8) {
+    const size_t o = ((size_t)fast_used + align - 1) & ~(align - 1);
+    if (fast && o + bytes <= fast_cap) { fast_used = (unsigned)(o + bytes); return fast + o; }
+    return alloc(bytes, align);
+  }
+  B2_HD inline size_t mark() const { return used | (size_t)fast_used << 48; }
+  B2_HD inline void reset(size_t m) { used = m & (((size_t)1 << 48) - 1); fast_used = (unsigned)(m >> 48); }
 };
+
+// dst[i] = get(i) for i = lane, lane + gsize, ... < n: four elements in flight per lane -- the loads of a trip are issued
+// before its stores (byte stores may alias anything as far as the compiler knows, which would otherwise serialise the
+// loop at one memory round trip per element)
+template <class F>
+B2_HD inline void b2_gfill(uint8_t* dst, int n, int lane, int gsize, F get) {
+  int i = lane;
+  for (; i + 3 * gsize < n; i += 4 * gsize) {
+    const uint8_t v0 = get(i), v1 = get(i + gsize), v2 = get(i + 2 * gsize), v3 = get(i + 3 * gsize);
+    dst[i] = v0; dst[i + gsize] = v1; dst[i + 2 * gsize] = v2; dst[i + 3 * gsize] = v3;
+  }
+  for (; i < n; i += gsize) dst[i] = get(i);
+}
 
 // in-place reversal split over the lanes of the group (each lane swaps its own pairs)
 B2_HD inline void b2_revseq_g(const B2Scratch& sc, int l, uint8_t* s) {
-  for (int i = sc.lane; i < l >> 1; i += sc.gsize) { uint8_t t = s[i]; s[i] = s[l - 1 - i]; s[l - 1 - i] = t; }
+  const int h = l >> 1, g = sc.gsize;
+  int i = sc.lane;
+  for (; i + g < h; i += 2 * g) {   // two swaps in flight per lane
+    const uint8_t a0 = s[i], b0 = s[l - 1 - i], a1 = s[i + g], b1 = s[l - 1 - i - g];
+    s[i] = b0; s[l - 1 - i] = a0; s[i + g] = b1; s[l - 1 - i - g] = a1;
+  }
+  for (; i < h; i += g) { uint8_t t = s[i]; s[i] = s[l - 1 - i]; s[l - 1 - i] = t; }
 }
 
 // Dispatch of the three DP routines.  On the device every call runs a lane-group form: register-resident for whole
@@ -236,9 +266,9 @@ B2_NOINLINE B2_HD inline int64_t b2_get_seq_g(B2Scratch& sc, int64_t l_pac, cons
     sc.gsync();
     if (beg >= l_pac) {
       const int64_t end_f = (l_pac << 1) - 1 - beg;
-      for (int64_t l = sc.lane; l < n; l += sc.gsize) seq[l] = 3 - b2_get_pac(pac, end_f - l);
+      b2_gfill(seq, (int)n, sc.lane, sc.gsize, [&](int l) { return (uint8_t)(3 - b2_get_pac(pac, end_f - l)); });
     } else {
-      for (int64_t l = sc.lane; l < n; l += sc.gsize) seq[l] = b2_get_pac(pac, beg + l);
+      b2_gfill(seq, (int)n, sc.lane, sc.gsize, [&](int l) { return (uint8_t)b2_get_pac(pac, beg + l); });
     }
     sc.gsync();
     return n;
@@ -466,7 +496,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
   if (out) { out->n_cigar = 0; out->NM = -1; out->l_md = 0; if (out->md_cap > 0) out->md[0] = 0; }
   if (l_query <= 0 || rb >= re || (rb < l_pac && re > l_pac)) return 0;
   const size_t mk = sc.mark();
-  uint8_t* rseq = (uint8_t*)sc.alloc((size_t)(re - rb) + 1, 1);
+  uint8_t* rseq = (uint8_t*)sc.alloc_fast((size_t)(re - rb) + 1, 1);
   if (sc.overflow) { sc.reset(mk); return 0; }
   int64_t rlen = b2_get_seq_g(sc, l_pac, ix.pac, rb, re, rseq);
   if (re - rb != rlen) { sc.reset(mk); return 0; }

@@ -40,6 +40,7 @@ inline T b2_host_fetch_add(T* p, V v) { T o = *p; *p += (T)v; return o; }
 #define B2_TASK_GROUP 1
 #define B2_G_EXT 1
 #define B2_G_FINAL 1
+#define B2_G_HEAVY 1
 #define B2_G_RESC 1
 #define B2_LB_EXT 1
 #define B2_LB_FINAL 1
@@ -76,6 +77,9 @@ inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_G_FINAL 4   // measured on the B200 (profiles/r1d/variants_group_size.jsonl): 32: 5.20, 16: 5.38, 8: 5.69, 4: 5.83, 2: 5.34, 1: 5.36 M reads/s
 #endif
 #define B2_G_RESC 16
+#ifndef B2_G_HEAVY
+#define B2_G_HEAVY 32  // pairs with many regions (k_final_pe_heavy): a warp each
+#endif
 #ifndef B2_LB_EXT
 #define B2_LB_EXT 4
 #endif

@@ -179,6 +179,39 @@ __device__ inline void b2_rank4(const B2Blk& b, int n, uint64_t r[4]) {
   r[3] = ((uint64_t)b.c23.w << 32 | b.c23.z) + T;
 }
 
+// One LF step (bwt_invPsi, bwa/bwt.c:53-59) for a lane of k_sa.  The 64-byte block that holds row k gives both the BWT
+// symbol at k and the rank of that symbol up to and including k, so the step is ONE fetch (two 32-byte loads issued
+// together) where symbol-then-count would be two dependent round trips to L2/HBM; and the rank is taken for that one
+// symbol only, branch-free, so that the 32 lanes of a warp -- each at its own row -- run the same instructions:
+// the block's words are XORed with the symbol replicated into every 2-bit field, after which the wanted symbol reads 11
+// and one AND of the two bit planes per word pair marks it.
+__device__ inline uint32_t b2_cnt1_pair(uint32_t wa, uint32_t wb, int n2) {
+  const int ma2 = __vimin_s32_relu(n2, 32), mb2 = __vimin_s32_relu(n2 - 32, 32);
+  const uint32_t sa = ~__funnelshift_rc(0xFFFFFFFFu, 0u, ma2), sb = ~__funnelshift_rc(0xFFFFFFFFu, 0u, mb2);
+  const uint32_t ta = wa & (wa >> 1) & sa;   // marker on the low bit of a field of word a ...
+  const uint32_t tb = wb & (wb << 1) & sb;   // ... and on the high bit of a field of word b
+  return __popc((ta & 0x55555555u) | (tb & 0xAAAAAAAAu));
+}
+
+__device__ inline uint64_t b2_inv_psi_lane(const B2Index& ix, uint64_t k) {
+  if (k == ix.primary) return 0;
+  const uint64_t x = k - (k > ix.primary);   // row in the $-less BWT string
+  B2Blk b;
+  b2_ld_blk(ix.bwt + ((x >> 7) << 4), b);
+  const int off = (int)(x & 127), wi = off >> 4;
+  const uint32_t lo4 = (wi & 2) ? ((wi & 1) ? b.w03.w : b.w03.z) : ((wi & 1) ? b.w03.y : b.w03.x);
+  const uint32_t hi4 = (wi & 2) ? ((wi & 1) ? b.w47.w : b.w47.z) : ((wi & 1) ? b.w47.y : b.w47.x);
+  const uint32_t w = (wi & 4) ? hi4 : lo4;
+  const int c = (int)(w >> ((~off & 15) << 1)) & 3;
+  const uint32_t flip = ~((uint32_t)c * 0x55555555u);
+  const int n2 = 2 * (off + 1);
+  const uint32_t cnt = b2_cnt1_pair(b.w03.x ^ flip, b.w03.y ^ flip, n2) + b2_cnt1_pair(b.w03.z ^ flip, b.w03.w ^ flip, n2 - 64) +
+                       b2_cnt1_pair(b.w47.x ^ flip, b.w47.y ^ flip, n2 - 128) + b2_cnt1_pair(b.w47.z ^ flip, b.w47.w ^ flip, n2 - 192);
+  const uint32_t n_lo = (c & 2) ? ((c & 1) ? b.c23.z : b.c23.x) : ((c & 1) ? b.c01.z : b.c01.x);
+  const uint32_t n_hi = (c & 2) ? ((c & 1) ? b.c23.w : b.c23.y) : ((c & 1) ? b.c01.w : b.c01.y);
+  return ix.L2[c] + ((uint64_t)n_hi << 32 | n_lo) + cnt;
+}
+
 struct B2OccLane {
   unsigned long long n_blk = 0;
   __device__ inline void child(const B2Index& ix, const B2Intv& ik, int c, int back, B2Intv& out) {

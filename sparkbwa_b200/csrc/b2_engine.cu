@@ -77,6 +77,7 @@ struct Worker {
   DBuf<uint8_t> scratch; DBuf<int8_t> pe_dir; DBuf<int64_t> pe_is; DBuf<double> pairtab;
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
+  DBuf<uint8_t> fin_heavy; DBuf<int32_t> fin_list;
   DBuf<long long> dbg;
   DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
@@ -169,7 +170,7 @@ class B2EngineImpl {
       w.timer.init(w.stream);
       w.scratch_per_lane = cfg.scratch_per_lane;
       w.cap_intv = cfg.cap_intv;
-      if (w.flags.ensure(4) || w.counters.ensure(16)) return fail("device allocation failed");
+      if (w.flags.ensure(8) || w.counters.ensure(16)) return fail("device allocation failed");
       b2_dev_memset(w.counters.p, 0, 16 * sizeof(unsigned long long), w.stream);
     }
     return 0;
@@ -244,7 +245,7 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release(); w.counters.release(); w.dbg.release();
+      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
@@ -751,6 +752,16 @@ class B2EngineImpl {
       int per_read = cfg.slot_per_read ? cfg.slot_per_read : 3 * w.max_len + 384;
       w.slot_size = pe ? 2 * per_read : per_read;
     }
+    // pairs with many regions are listed once and finalised by their own launch, a warp each (see k_final_plan)
+    const bool split = pe && cfg.final_heavy_regs > 0;
+    c.fin_mode = 0;
+    if (split) {
+      if (w.fin_heavy.ensure(n_items + 1) || w.fin_list.ensure(n_items + 1)) return fail("device allocation failed");
+      c.fin_heavy = w.fin_heavy.p; c.fin_list = w.fin_list.p; c.fin_heavy_min = cfg.final_heavy_regs;
+      b2_dev_memset(w.flags.p + 4, 0, sizeof(int), w.stream);   // number of listed pairs (c.work[3])
+      B2_LAUNCH(k_final_plan, (n_items + 127) / 128, 128, w.stream, c);
+      ++w.times.launches;
+    }
     for (;;) {
       if (ensure_scratch()) return 1;
       if (w.slots.ensure((size_t)n_items * w.slot_size)) return fail("device allocation failed (SAM slots)");
@@ -761,7 +772,16 @@ class B2EngineImpl {
         c.dbg = w.dbg.p;
       }
       b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
-      if (pe) B2_LAUNCH(k_final_pe, lane_grid, cfg.lane_block, w.stream, c);
+      if (split) {
+        c.fin_mode = 2;
+        c.fin_fast = 2048;
+        B2_LAUNCH_SMEM(k_final_pe_heavy, std::min(lane_grid, 148 * B2_LB_FINAL), cfg.lane_block, (size_t)(cfg.lane_block / B2_G_HEAVY) * c.fin_fast, w.stream, c);
+        b2_dev_memset(w.flags.p + 1, 0, sizeof(int), w.stream);   // the cursor; the flags word keeps what the first launch raised
+        c.fin_mode = 1;
+        ++w.times.launches;
+      }
+      c.fin_fast = cfg.final_fast_bytes;
+      if (pe) B2_LAUNCH_SMEM(k_final_pe, lane_grid, cfg.lane_block, (size_t)(cfg.lane_block / B2_G_FINAL) * c.fin_fast, w.stream, c);
       else B2_LAUNCH(k_final_se, lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;

@@ -56,6 +56,8 @@ struct B2EngineConfig {
   int seed_grid = 148 * 16, seed_block = 128;  // seeding: one task per lane; grid = min(tasks, SMs x blocks per SM, seed_grid)
   int seed_blocks_per_sm = 4;                  // shared memory is split for this many resident seeding blocks per SM
   int seed3_blocks_per_sm = 8;                 // forward-only pass: no stack, fewer registers
+  int final_fast_bytes = 512;                  // shared memory per task group of k_final_pe: read copy + reference window of an alignment
+  int final_heavy_regs = 4;                    // pairs with at least this many regions (both mates) are finalised a warp each, in their own launch (0: no split)
   int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
   size_t scratch_per_lane = 48 << 10;
   int no_xext = 0;                             // 1: skip the inter-task seed extensions (B200BWA_NO_XEXT)

@@ -37,12 +37,18 @@ struct B2Out {
   long cap, len;
   int lane = 0, gsize = 1;  // task group writing this record: bulk fields are written lane-strided
   // n characters tab[codes[i]] for i = from, from+step, ... (step = +1 or -1)
-  B2_HD inline void put_codes(const uint8_t* codes, int from, int step, int n, const char* tab) {
-    for (int i = lane; i < n; i += gsize) if (len + i < cap) p[len + i] = tab[codes[from + i * step]];
+#define B2_BASES_FWD ((uint64_t)'A' | (uint64_t)'C' << 8 | (uint64_t)'G' << 16 | (uint64_t)'T' << 24 | (uint64_t)'N' << 32)
+#define B2_BASES_REV ((uint64_t)'T' | (uint64_t)'G' << 8 | (uint64_t)'C' << 16 | (uint64_t)'A' << 24 | (uint64_t)'N' << 32)
+  // (four characters in flight per lane: loads first, then the stores -- see b2_gfill)
+  // tab: the five characters for codes 0..4 packed into one word (B2_BASES_FWD / B2_BASES_REV), no table in memory
+  B2_HD inline void put_codes(const uint8_t* codes, int from, int step, int n, uint64_t tab) {
+    const int m = (long)n < cap - len ? n : (int)(cap - len > 0 ? cap - len : 0);   // characters that fit
+    b2_gfill((uint8_t*)p + len, m, lane, gsize, [&](int i) { return (uint8_t)(tab >> (8 * codes[from + i * step])); });
     len += n;
   }
   B2_HD inline void put_chars(const char* s, int from, int step, int n) {
-    for (int i = lane; i < n; i += gsize) if (len + i < cap) p[len + i] = s[from + i * step];
+    const int m = (long)n < cap - len ? n : (int)(cap - len > 0 ? cap - len : 0);
+    b2_gfill((uint8_t*)p + len, m, lane, gsize, [&](int i) { return (uint8_t)s[from + i * step]; });
     len += n;
   }
   B2_HD inline void putc_(int c) { if (len < cap) p[len] = (char)c; ++len; }
@@ -272,10 +278,10 @@ B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, c
   cg.cigar = (uint32_t*)sc.alloc(sizeof(uint32_t) * (size_t)cg.cap, 4);
   cg.md_cap = 2 * (int)(re - rb) + (qe - qb) + 32;
   cg.md = (char*)sc.alloc((size_t)cg.md_cap, 1);
-  uint8_t* query = (uint8_t*)sc.alloc((size_t)l_query + 1, 1);
+  uint8_t* query = (uint8_t*)sc.alloc_fast((size_t)l_query + 1, 1);
   if (sc.overflow) { a.rid = -1; a.pos = -1; a.flag |= 0x4; return a; }
   sc.gsync();
-  for (i = sc.lane; i < l_query; i += sc.gsize) query[i] = query_[i];
+  b2_gfill(query, l_query, sc.lane, sc.gsize, [&](int k) { return query_[k]; });
   sc.gsync();
   cg.n_cigar = 0; cg.NM = -1; cg.l_md = 0; cg.md[0] = 0;
   i = 0;
@@ -461,7 +467,7 @@ B2_NOINLINE B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, co
       if ((p->cigar[0] & 0xf) == 4 || (p->cigar[0] & 0xf) == 3) qb += p->cigar[0] >> 4;
       if ((p->cigar[p->n_cigar - 1] & 0xf) == 4 || (p->cigar[p->n_cigar - 1] & 0xf) == 3) qe -= p->cigar[p->n_cigar - 1] >> 4;
     }
-    str.put_codes(s.seq, qb, 1, qe - qb, "ACGTN");
+    str.put_codes(s.seq, qb, 1, qe - qb, B2_BASES_FWD);
     str.putc_('\t');
     if (s.qual) str.put_chars(s.qual, qb, 1, qe - qb);
     else str.putc_('*');
@@ -471,7 +477,7 @@ B2_NOINLINE B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, co
       if ((p->cigar[0] & 0xf) == 4 || (p->cigar[0] & 0xf) == 3) qe -= p->cigar[0] >> 4;
       if ((p->cigar[p->n_cigar - 1] & 0xf) == 4 || (p->cigar[p->n_cigar - 1] & 0xf) == 3) qb += p->cigar[p->n_cigar - 1] >> 4;
     }
-    str.put_codes(s.seq, qe - 1, -1, qe - qb, "TGCAN");
+    str.put_codes(s.seq, qe - 1, -1, qe - qb, B2_BASES_REV);
     str.putc_('\t');
     if (s.qual) str.put_chars(s.qual, qe - 1, -1, qe - qb);
     else str.putc_('*');

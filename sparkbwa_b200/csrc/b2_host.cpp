@@ -1171,6 +1171,8 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_SEED_ENTRIES"))) cfg->seed_smem_entries = atoi(s);
   if ((s = getenv("B200BWA_SEED_BPS"))) cfg->seed_blocks_per_sm = atoi(s);
   if ((s = getenv("B200BWA_SEED3_BPS"))) cfg->seed3_blocks_per_sm = atoi(s);
+  if ((s = getenv("B200BWA_FINAL_HEAVY"))) cfg->final_heavy_regs = atoi(s);
+  if ((s = getenv("B200BWA_FINAL_FAST"))) cfg->final_fast_bytes = atoi(s);
   if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
   if ((s = getenv("B200BWA_MAX_SCRATCH"))) cfg->max_scratch_bytes = (size_t)atoll(s);
   if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
@@ -1699,6 +1701,7 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     if (rc) failed = true;
     wake_all();
   }
+  if (times0) fprintf(stderr, "[T::b200bwa] last batch delivered at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   reader.join();
   for (auto& t : gpu) t.join();
   for (auto& t : writers) t.join();
@@ -1706,9 +1709,12 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     { std::lock_guard<std::mutex> lk(mu); alloc_stop = true; wake_all(); }
     allocator.join();
   }
+  if (times0) fprintf(stderr, "[T::b200bwa] threads joined at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   if (out_map) {
     munmap(out_map, out_map_len);
+    if (times0) fprintf(stderr, "[T::b200bwa] output unmapped at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
     if (!rc && ftruncate(out_fd, (off_t)next_off) != 0) { rc = 1; errmsg = "cannot set the final size of the SAM output"; }
+    if (times0) fprintf(stderr, "[T::b200bwa] output truncated to size at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   }
   if (rc) {
     std::string em = errmsg;

@@ -88,6 +88,9 @@ struct B2Ctx {
   int galn_blk[B2_GALN_CLASSES + 1];            // first block of each class in the combined k_galn launch
   B2GalnTask* galn_tasks; B2GalnRes* galn_res; int32_t* galn_table;
   B2GalnCache galn;
+  // finalisation in two launches: pairs with many regions first, a warp each (k_final_plan)
+  uint8_t* fin_heavy; int32_t* fin_list; int fin_heavy_min, fin_mode;
+  int fin_fast;           // bytes of shared memory per task group of the pair finalisation (B2Scratch::alloc_fast)
   // SAM
   char* slots; int slot_size; int32_t* sam_len; const int64_t* sam_off; char* sam_out;
 };
@@ -270,7 +273,11 @@ B2_KERNEL k_sa(B2Ctx c) {
     if (!have) break;
 #endif
     if (have) {
+#if defined(__CUDA_ARCH__)
+      if (k & mask) { ++steps; k = b2_inv_psi_lane(c.ix, k); }
+#else
       if (k & mask) { ++steps; k = b2_inv_psi(c.ix, k); }
+#endif
       else {
         B2Seed s;
         s.rbeg = (int64_t)(steps + c.ix.sa[k >> c.ix.sa_shift]);
@@ -773,13 +780,39 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
   b2_flush_counters(c, sc);
 }
 
-B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) {
-  int gid, n_groups;
-  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
-  sc.galn = &c.galn;
+// Pairs are finalised in two launches (c.fin_mode).  The few pairs with many candidate regions -- reads in repeats:
+// dozens of rescue attempts, region lists re-sorted after each, XA alignments -- take 10-20x the time of an ordinary
+// pair; inside a warp of sub-warp groups the other groups wait for such a pair at the end of every trip of the task
+// loop.  k_final_plan lists them (fin_list, flags in fin_heavy); k_final_pe_heavy gives each a whole warp
+// (B2_G_HEAVY lanes for its DP, sorts' data movement and text), k_final_pe then runs the ordinary pairs in
+// B2_G_FINAL-lane groups, skipping the flagged ones.  fin_mode 0: one launch over all pairs (single-end batches,
+// splitting disabled).
+B2_KERNEL k_final_plan(B2Ctx c) {
   const int n_pairs = c.b.n_reads >> 1;
+  for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
+    const int heavy = c.n_regs[2 * i] + c.n_regs[2 * i + 1] >= c.fin_heavy_min;
+    c.fin_heavy[i] = (uint8_t)heavy;
+    if (heavy) c.fin_list[B2_ATOMIC_ADD(c.work + 3, 1)] = i;
+  }
+}
+
+template <int G>
+B2_D inline void b2_final_pe_body(const B2Ctx& c) {
+  int gid, n_groups;
+  B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, G);
+  sc.galn = &c.galn;
+#if defined(__CUDA_ARCH__)
+  extern __shared__ uint4 b2_fin_smem[];   // c.fin_fast bytes per task group (B2Scratch::alloc_fast)
+  sc.fast = (uint8_t*)b2_fin_smem + (size_t)(threadIdx.x / G) * (size_t)c.fin_fast;
+  sc.fast_cap = (unsigned)c.fin_fast;
+#endif
+  const int n_pairs = c.b.n_reads >> 1;
+  const int n_tasks = c.fin_mode == 2 ? c.work[3] : n_pairs;
   sc.prof = c.dbg ? c.dbg + 4 * (size_t)n_pairs : 0;
-  for (int i = b2_next_task(c, sc); i < n_pairs; i = b2_next_task(c, sc)) {
+  for (int t = b2_next_task(c, sc); t < n_tasks; t = b2_next_task(c, sc)) {
+    int i = t;
+    if (c.fin_mode == 2) i = c.fin_list[t];
+    else if (c.fin_mode == 1 && c.fin_heavy[t]) continue;
     sc.gsync();
     sc.reset(0);
     sc.tick(-1);
@@ -826,6 +859,9 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) {
   }
   b2_flush_counters(c, sc);
 }
+
+B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe(B2Ctx c) { b2_final_pe_body<B2_G_FINAL>(c); }
+B2_KERNEL_LB(128, B2_LB_FINAL) k_final_pe_heavy(B2Ctx c) { b2_final_pe_body<B2_G_HEAVY>(c); }
 
 // exclusive scan int32 -> int64, out[n] = total.  One block.
 B2_KERNEL k_scan(const int32_t* in, int64_t* out, int n) {
