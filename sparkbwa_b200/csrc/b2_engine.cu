@@ -78,6 +78,7 @@ struct Worker {
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
   DBuf<uint8_t> fin_heavy; DBuf<int32_t> fin_list;
+  DBuf<int32_t> sa_task_r; DBuf<uint32_t> sa_task_iv;
   DBuf<long long> dbg;
   DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
@@ -122,6 +123,8 @@ class B2EngineImpl {
   int n_log = 1 << 16;
   B2Fmt fmt{};
   std::vector<Worker> workers;
+  std::atomic<size_t> grown_scratch{0};            // sizes some worker had to grow to, taken over by the others (run())
+  std::atomic<int> grown_cap_intv{0}, grown_slot{0};
   std::string err;
   mutable std::mutex err_mu;  // fail() is called from every GPU worker thread
 
@@ -245,7 +248,7 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release();
+      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
@@ -426,12 +429,21 @@ class B2EngineImpl {
     // re-run with FEWER lanes rather than with that size for every lane -- the total stays within max_scratch_bytes
     int lane_grid = cfg.lane_grid;
     bool overflowed = false;
+    // sizes another stream/buffer set of this engine had to grow to (an outlier read or pair) are taken over at the next
+    // batch boundary: every set meets such input sooner or later, and a growth in mid-batch costs a re-run of the stage
+    // plus a device-wide allocation
+    w.scratch_per_lane = std::max(w.scratch_per_lane, grown_scratch.load());
+    w.cap_intv = std::max(w.cap_intv, grown_cap_intv.load());
+    if (w.slot_size) w.slot_size = std::max(w.slot_size, grown_slot.load());
+    const size_t scratch_in = w.scratch_per_lane;
+    const int cap_intv_in = w.cap_intv;
     if (w.scratch_per_lane > cfg.scratch_per_lane && w.clean_batches >= w.decay_wait &&
         cfg.max_scratch_bytes / w.scratch_per_lane / (size_t)cfg.lane_block < (size_t)cfg.lane_grid) {
       // an outlier batch grew the per-lane size so far that the stages now run with fewer lanes than configured: try
       // the smaller size again (the allocation itself is kept: freeing device memory stalls every stream)
       w.scratch_per_lane = std::max(cfg.scratch_per_lane, w.scratch_per_lane / 2);
       w.tried_decay = true;
+      grown_scratch.store(w.scratch_per_lane);
     }
     int flags = 0;
     int ev_begin = w.timer.mark();
@@ -498,11 +510,19 @@ class B2EngineImpl {
       return fail("device allocation failed (seeds)");
     c.raw = w.raw.p; c.raw_rid = w.raw_rid.p; c.chains = w.chains.p; c.cseeds = w.cseeds.p;
     c.n_chain = w.n_chain.p; c.reg_cap = w.reg_cap.p; c.n_regs = w.n_regs.p;
+    c.sa_task_r = nullptr; c.sa_task_iv = nullptr;
+    if (S > 0 && opt.max_occ <= 0xffff && w.cap_intv <= 0xffff) {
+      if (w.sa_task_r.ensure(S + 1) || w.sa_task_iv.ensure(S + 1)) return fail("device allocation failed (seeds)");
+      c.sa_task_r = w.sa_task_r.p; c.sa_task_iv = w.sa_task_iv.p;
+      B2_LAUNCH(k_sa_plan, (n + 127) / 128, 128, w.stream, c);
+      ++w.times.launches;
+    }
     if (S > 0) {
-      int grid = (int)std::min<int64_t>((S + 127) / 128, 148 * 8);   // resident lanes only: each takes lookup after lookup
+      int grid = (int)std::min<int64_t>((S + 127) / 128, 148 * 16);   // resident lanes only (all 64 warps of an SM: the walk is a chain of dependent fetches); each takes lookup after lookup
       b2_dev_memset(w.flags.p + 3, 0, sizeof(int), w.stream);   // the lookups are dealt from this cursor (c.work[2])
       B2_LAUNCH(k_sa, grid, 128, w.stream, c);
-      ++w.times.launches;
+      B2_LAUNCH(k_sa_rid, (int)std::min<int64_t>((S + 255) / 256, 148 * 16), 256, w.stream, c);
+      w.times.launches += 2;
     }
     int ev_sa = w.timer.mark();
 
@@ -750,8 +770,9 @@ class B2EngineImpl {
     c.sam_len = w.sam_len.p;
     if (w.slot_size == 0) {
       int per_read = cfg.slot_per_read ? cfg.slot_per_read : 3 * w.max_len + 384;
-      w.slot_size = pe ? 2 * per_read : per_read;
+      w.slot_size = std::max(pe ? 2 * per_read : per_read, grown_slot.load());
     }
+    const int slot_in = w.slot_size;
     // pairs with many regions are listed once and finalised by their own launch, a warp each (see k_final_plan)
     const bool split = pe && cfg.final_heavy_regs > 0;
     c.fin_mode = 0;
@@ -883,6 +904,12 @@ class B2EngineImpl {
     if (ev_x[1] >= 0) w.times.k_xext = w.timer.ms(ev_x[0], ev_x[1]) + (ev_x[3] >= 0 ? w.timer.ms(ev_x[2], ev_x[3]) : 0.f);
     if (ev_r[1] >= 0) w.times.k_resc_sw = w.timer.ms(ev_r[0], ev_r[1]);
     if (ev_g[1] >= 0) w.times.k_galn = w.timer.ms(ev_g[0], ev_g[1]);
+    {  // publish what grew during this batch
+      auto raise = [](auto& shared, auto v) { auto cur = shared.load(); while (cur < v && !shared.compare_exchange_weak(cur, v)) {} };
+      if (w.scratch_per_lane > scratch_in) raise(grown_scratch, w.scratch_per_lane);
+      if (w.cap_intv > cap_intv_in) raise(grown_cap_intv, w.cap_intv);
+      if (w.slot_size > slot_in && slot_in) raise(grown_slot, w.slot_size);
+    }
     if (overflowed) {
       if (w.tried_decay) w.decay_wait = std::min(w.decay_wait * 4, 4096);  // the smaller size was not enough: ask less often
       w.clean_batches = 0;

@@ -287,7 +287,8 @@ B2_NOINLINE B2_HD inline B2Aln b2_reg2aln(const B2Opt& opt, const B2Index& ix, c
   i = 0;
   do {
     w2 = w2 < opt.w << 2 ? w2 : opt.w << 2;
-    const B2GalnRes* pre = i == 0 ? b2_galn_lookup(sc.galn, query_, qb, qe, rb, re, w2) : 0;
+    // (a gap-free region of band 0 runs no DP, bwa/bwa.c:131: nothing to look up)
+    const B2GalnRes* pre = i == 0 && !(qe - qb == re - rb && w2 == 0) ? b2_galn_lookup(sc.galn, query_, qb, qe, rb, re, w2) : 0;
 #if defined(B2_HOSTSIM) && defined(B2_GALN_STATS)
     { extern long b2_galn_stats[16]; const int wb = b2_cigar_band(opt, qe - qb, (int)(re - rb), w2);
       const bool nodp = (qe - qb == re - rb && w2 == 0);

@@ -64,6 +64,7 @@ struct B2Ctx {
   int seed_E, seed_QW, seed_RS;  // per lane in shared memory: stack entries, words of 4-bit base codes, re-seed candidates
   // SA / chaining
   const int64_t* seed_off; int64_t n_seed_tasks;
+  int32_t* sa_task_r; uint32_t* sa_task_iv;   // per lookup: read, interval << 16 | rank (k_sa_plan); null: k_sa searches
   B2Seed* raw; int32_t* raw_rid;
   B2Chain* chains; B2Seed* cseeds; int32_t* n_chain; int32_t* reg_cap;
   // extension
@@ -225,6 +226,22 @@ B2_KERNEL k_seed_fin(B2Ctx c) {
   }
 }
 
+// (read, interval, rank inside the interval) of every suffix-array lookup, written by the read's own lane once the
+// offsets are known: k_sa then fetches a lookup's description with two coalesced loads where a search for the read
+// (17 dependent probes of seed_off) and a scan of its intervals would sit on the path of the lane's refill -- and a
+// refill is executed by the few lanes of a warp that finished a walk in the same trip.
+B2_KERNEL k_sa_plan(B2Ctx c) {
+  for (int r = B2_GTID(); r < c.b.n_reads; r += B2_GSIZE()) {
+    int64_t t = c.seed_off[r];
+    const B2Intv* iv = c.intv + (size_t)r * c.cap_intv;
+    const int n = c.n_intv[r];
+    for (int i = 0; i < n; ++i) {
+      const int cnt = iv[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (int)iv[i].x[2];
+      for (int idx = 0; idx < cnt; ++idx, ++t) { c.sa_task_r[t] = r; c.sa_task_iv[t] = (uint32_t)i << 16 | (uint32_t)idx; }
+    }
+  }
+}
+
 B2_KERNEL k_sa(B2Ctx c) {
   // One suffix-array lookup per lane at a time: an LF walk to the next sampled row, geometric in length (mean 31 steps,
   // the longest of 32 about four times that).  A lane that finishes takes the next lookup from the stage's cursor right
@@ -246,18 +263,26 @@ B2_KERNEL k_sa(B2Ctx c) {
 #endif
       if (t >= c.n_seed_tasks) alive = false;
       else {
-        int lo = 0, hi = c.b.n_reads;  // last r with seed_off[r] <= t
-        while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.seed_off[mid] <= t) lo = mid; else hi = mid; }
-        const int r = lo;
-        long idx = (long)(t - c.seed_off[r]);
-        const B2Intv* iv = c.intv + (size_t)r * c.cap_intv;
-        const int n = c.n_intv[r];
-        int i = 0;
-        for (; i < n; ++i) {
-          long cnt = iv[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)iv[i].x[2];
-          if (idx < cnt) break;
-          idx -= cnt;
+        int r, i;
+        long idx;
+        if (c.sa_task_r) {   // planned (k_sa_plan)
+          r = c.sa_task_r[t];
+          const uint32_t pk = c.sa_task_iv[t];
+          i = (int)(pk >> 16); idx = (long)(pk & 0xffff);
+        } else {
+          int lo = 0, hi = c.b.n_reads;  // last r with seed_off[r] <= t
+          while (hi - lo > 1) { int mid = (lo + hi) >> 1; if (c.seed_off[mid] <= t) lo = mid; else hi = mid; }
+          r = lo;
+          idx = (long)(t - c.seed_off[r]);
+          const B2Intv* iv0 = c.intv + (size_t)r * c.cap_intv;
+          const int n = c.n_intv[r];
+          for (i = 0; i < n; ++i) {
+            long cnt = iv0[i].x[2] > (uint64_t)c.opt.max_occ ? c.opt.max_occ : (long)iv0[i].x[2];
+            if (idx < cnt) break;
+            idx -= cnt;
+          }
         }
+        const B2Intv* iv = c.intv + (size_t)r * c.cap_intv;
         const B2Intv& p = iv[i];
         const long step = p.x[2] > (uint64_t)c.opt.max_occ ? (long)(p.x[2] / c.opt.max_occ) : 1;
         slen = (int32_t)((uint32_t)p.info - (uint32_t)(p.info >> 32));
@@ -284,14 +309,22 @@ B2_KERNEL k_sa(B2Ctx c) {
         s.qbeg = qbeg;
         s.len = s.score = slen;
         s.next = -1;
-        c.raw[t] = s;
-        c.raw_rid[t] = b2_intv2rid(c.ix, s.rbeg, s.rbeg + s.len);
+        c.raw[t] = s;   // (its contig id: k_sa_rid, all lanes together)
         steps_total += steps; ++calls;
         have = false;
       }
     }
   }
   if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_CALLS], calls); B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_STEPS], steps_total); }
+}
+
+// contig of every seed (bns_intv2rid, bwa/bntseq.c:343-359; negative: the seed bridges two contigs or the strands and
+// mem_chain skips it): two searches of the contig table per seed, kept out of k_sa's end-of-walk path
+B2_KERNEL k_sa_rid(B2Ctx c) {
+  for (int64_t t = B2_GTID(); t < c.n_seed_tasks; t += B2_GSIZE()) {
+    const int64_t rb = c.raw[t].rbeg;
+    c.raw_rid[t] = b2_intv2rid(c.ix, rb, rb + c.raw[t].len);
+  }
 }
 
 B2_HD inline B2Scratch b2_lane_scratch(const B2Ctx& c, int lane) {

@@ -83,25 +83,35 @@ B2_HD inline int b2_xext_one(const B2XMemT<Cell>& M, int qlen, int tlen, const i
     if (end > qlen) end = qlen;
     ncell += (unsigned long long)(end > beg ? end - beg : 0);
     if (beg == 0) { h1 = h0 - (o_del + e_del * (i + 1)); if (h1 < 0) h1 = 0; } else h1 = 0;
-    uint32_t qw = beg < end ? M.q[(size_t)(beg >> 3) * st] : 0;
-    for (j = beg; j < end; ++j) {
-      if ((j & 7) == 0) qw = M.q[(size_t)(j >> 3) * st];
-      const int q = (int)(qw >> ((j & 7) << 2)) & 15;
-      const int s = (q | t) >= 4 ? sn : (q == t ? sa : sb);
-      const uint32_t p = M.eh[(size_t)j * st];
-      int Mv = (int)(p & HMASK), e = (int)(p >> ESH);
-      Mv = Mv ? Mv + s : 0;
-      int h = Mv > e ? Mv : e;
-      h = h > f ? h : f;
-      const int hprev = h1;
-      h1 = h;
-      mj = m > h ? mj : j;
-      m = m > h ? m : h;
-      int t2 = Mv - oe_del; t2 = t2 > 0 ? t2 : 0;
-      e -= e_del; e = e > t2 ? e : t2;
-      M.eh[(size_t)j * st] = (Cell)((uint32_t)hprev | (uint32_t)e << ESH);
-      t2 = Mv - oe_ins; t2 = t2 > 0 ? t2 : 0;
-      f -= e_ins; f = f > t2 ? f : t2;
+    // The band is walked in runs of up to eight columns that share one word of query codes: the word is fetched once per
+    // run (and the next run's while this one computes), the codes come off it by shifting, and the cell of the next
+    // column is read before this column's is written back, so neither load sits on the dependent path h -> f -> h.
+    j = beg;
+    uint32_t qnext = beg < end ? M.q[(size_t)(beg >> 3) * st] : 0;
+    uint32_t p = beg < end ? M.eh[(size_t)beg * st] : 0;
+    while (j < end) {
+      uint32_t qs = qnext >> ((j & 7) << 2);
+      const int jrun = (j | 7) + 1 < end ? (j | 7) + 1 : end;
+      if (jrun < end) qnext = M.q[(size_t)(jrun >> 3) * st];
+      for (; j < jrun; ++j, qs >>= 4) {
+        const uint32_t pn = M.eh[(size_t)(j + 1) * st];   // (j + 1 <= end <= qlen: inside the array)
+        const int q = (int)(qs & 15);
+        const int s = (q | t) >= 4 ? sn : (q == t ? sa : sb);
+        int Mv = (int)(p & HMASK), e = (int)(p >> ESH);
+        Mv = Mv ? Mv + s : 0;
+        int h = Mv > e ? Mv : e;
+        h = h > f ? h : f;
+        const int hprev = h1;
+        h1 = h;
+        mj = m > h ? mj : j;
+        m = m > h ? m : h;
+        int t2 = Mv - oe_del; t2 = t2 > 0 ? t2 : 0;
+        e -= e_del; e = e > t2 ? e : t2;
+        M.eh[(size_t)j * st] = (Cell)((uint32_t)hprev | (uint32_t)e << ESH);
+        t2 = Mv - oe_ins; t2 = t2 > 0 ? t2 : 0;
+        f -= e_ins; f = f > t2 ? f : t2;
+        p = pn;
+      }
     }
     M.eh[(size_t)end * st] = (Cell)h1;  // {h1, e = 0}
     if (j == qlen) {
