@@ -66,6 +66,10 @@ struct B2Scratch {
   // arena when absent or full; marks cover both arenas.
   uint8_t* fast = 0;
   unsigned fast_cap = 0, fast_used = 0;
+  // a task that does not fit the lane's (group's) own region is run again in a slot of the outlier pool (b2_retry_big)
+  int big = 0;
+  uint8_t* small_base = 0;
+  size_t small_cap = 0;
   B2_HD inline void* alloc_fast(size_t bytes, size_t align = 8) {
     const size_t o = ((size_t)fast_used + align - 1) & ~(align - 1);
     if (fast && o + bytes <= fast_cap) { fast_used = (unsigned)(o + bytes); return fast + o; }

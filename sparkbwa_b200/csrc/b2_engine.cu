@@ -87,7 +87,8 @@ struct Worker {
   DBuf<unsigned long long> counters;
   unsigned long long h_counters[16] = {0};
   unsigned long long h2d_bytes = 0, d2h_bytes = 0;
-  size_t scratch_per_lane = 0;
+  size_t scratch_per_lane = 0, big_slot = 0;
+  DBuf<uint8_t> big;   // outlier pool
   int clean_batches = 0, decay_wait = 4;   // batches without a scratch overflow / how many of them before the size is halved again
   bool tried_decay = false;
   int cap_intv = 0, slot_size = 0;
@@ -123,6 +124,7 @@ class B2EngineImpl {
   int n_log = 1 << 16;
   B2Fmt fmt{};
   std::vector<Worker> workers;
+  std::atomic<size_t> grown_big_slot{0};
   std::atomic<size_t> grown_scratch{0};            // sizes some worker had to grow to, taken over by the others (run())
   std::atomic<int> grown_cap_intv{0}, grown_slot{0};
   std::string err;
@@ -172,6 +174,7 @@ class B2EngineImpl {
 #endif
       w.timer.init(w.stream);
       w.scratch_per_lane = cfg.scratch_per_lane;
+      w.big_slot = std::min(cfg.big_slot_bytes, std::min(cfg.big_pool_bytes ? cfg.big_pool_bytes : cfg.big_slot_bytes, cfg.max_scratch_bytes));
       w.cap_intv = cfg.cap_intv;
       if (w.flags.ensure(8) || w.counters.ensure(16)) return fail("device allocation failed");
       b2_dev_memset(w.counters.p, 0, 16 * sizeof(unsigned long long), w.stream);
@@ -248,7 +251,7 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release();
+      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release(); w.big.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
@@ -433,9 +436,10 @@ class B2EngineImpl {
     // batch boundary: every set meets such input sooner or later, and a growth in mid-batch costs a re-run of the stage
     // plus a device-wide allocation
     w.scratch_per_lane = std::max(w.scratch_per_lane, grown_scratch.load());
+    w.big_slot = std::max(w.big_slot, grown_big_slot.load());
     w.cap_intv = std::max(w.cap_intv, grown_cap_intv.load());
     if (w.slot_size) w.slot_size = std::max(w.slot_size, grown_slot.load());
-    const size_t scratch_in = w.scratch_per_lane;
+    const size_t scratch_in = w.scratch_per_lane, big_slot_in = w.big_slot;
     const int cap_intv_in = w.cap_intv;
     if (w.scratch_per_lane > cfg.scratch_per_lane && w.clean_batches >= w.decay_wait &&
         cfg.max_scratch_bytes / w.scratch_per_lane / (size_t)cfg.lane_block < (size_t)cfg.lane_grid) {
@@ -533,29 +537,44 @@ class B2EngineImpl {
       lane_grid = (int)std::min<size_t>((size_t)cfg.lane_grid, fit);
       if (w.scratch.ensure((size_t)lane_grid * cfg.lane_block * w.scratch_per_lane, true)) return fail("device allocation failed (scratch)");
       c.scratch = w.scratch.p; c.scratch_per_lane = w.scratch_per_lane;
+      c.big_pool = nullptr; c.big_n = 0; c.big_slot = 0; c.big_count = w.flags.p + 2;
+      if (cfg.big_pool_bytes > 0) {   // outlier pool (see B2Ctx::big_pool)
+        if (w.big_slot > cfg.max_scratch_bytes) return fail("per-lane scratch limit exceeded (a single read needs more than B200BWA_MAX_SCRATCH)");
+        const size_t bytes = std::max(std::min(cfg.big_pool_bytes, cfg.max_scratch_bytes), w.big_slot);
+        if (w.big.ensure(bytes, true)) return fail("device allocation failed (scratch pool)");
+        c.big_pool = w.big.p; c.big_slot = w.big_slot; c.big_n = (int)std::min<size_t>(w.big.cap / w.big_slot, (size_t)1 << 30);
+      }
       return 0;
     };
+    // a stage flagged an overflow: inside a pool slot -> larger slots; more outliers than slots (or no pool) -> larger
+    // regions for every lane (then fewer lanes, within max_scratch_bytes)
+    auto grow_scratch = [&](int fl) {
+      overflowed = true;
+      if (fl & B2_FLAG_OVF_BIGN) w.scratch_per_lane *= 2;
+      if (fl & B2_FLAG_OVF_SCRATCH) { if (c.big_pool) w.big_slot *= 2; else w.scratch_per_lane *= 2; }
+    };
+    const int OVF_ANY = B2_FLAG_OVF_SCRATCH | B2_FLAG_OVF_BIGN;
     for (;;) {
       if (ensure_scratch()) return 1;
-      b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+      b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);   // flags, task cursor, pool slots handed out
       B2_LAUNCH(k_chain, lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
-      if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-      { w.scratch_per_lane *= 2; overflowed = true; }
+      if (!(flags & OVF_ANY)) break;
+      grow_scratch(flags);
     }
     {  // mem_flt_chained_seeds acts only on long reads (5.5 ln l <= 0.05 l: l >= 725 with the default options)
       const double min_l = opt.min_chain_weight ? (double)(1.1f * (float)opt.min_chain_weight) : 5.5 * log((double)w.max_len);
       if (!(min_l > (double)(0.05f * (float)w.max_len)) && !getenv("B200BWA_DEBUG_NO_SEED_FILTER")) {  // (the switch exists to show the filter matters)
         for (;;) {
           if (ensure_scratch()) return 1;
-          b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+          b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);   // flags, task cursor, pool slots handed out
           B2_LAUNCH(k_flt_seeds, lane_grid, cfg.lane_block, w.stream, c);
           ++w.times.launches;
           if (read_flags(w, &flags)) return 1;
           if (flags & B2_FLAG_ERR_TABLE) return fail("log table index out of range (read too long)");
-          if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-          { w.scratch_per_lane *= 2; overflowed = true; }
+          if (!(flags & OVF_ANY)) break;
+          grow_scratch(flags);
         }
       }
     }
@@ -614,19 +633,19 @@ class B2EngineImpl {
       if (ensure_scratch()) return 1;
       if (TC > 0 && cfg.no_ext_chain) b2_dev_memset(w.cand_ok.p, 0, (size_t)S + 1, w.stream);
       if (TC > 0 && !cfg.no_ext_chain) {
-        b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+        b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);   // flags, task cursor, pool slots handed out
         const int64_t blocks_needed = (TC * B2_G_EXT + cfg.lane_block - 1) / cfg.lane_block;
         B2_LAUNCH(k_ext_chain, (int)std::min<int64_t>(blocks_needed, lane_grid), cfg.lane_block, w.stream, c);
         ++w.times.launches;
         if (read_flags(w, &flags)) return 1;
-        if (flags & B2_FLAG_OVF_SCRATCH) { { w.scratch_per_lane *= 2; overflowed = true; } continue; }
+        if (flags & OVF_ANY) { grow_scratch(flags); continue; }
       }
-      b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+      b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);   // flags, task cursor, pool slots handed out
       B2_LAUNCH(k_extend, lane_grid, cfg.lane_block, w.stream, c);
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
-      if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-      { w.scratch_per_lane *= 2; overflowed = true; }
+      if (!(flags & OVF_ANY)) break;
+      grow_scratch(flags);
     }
     int ev_ext = w.timer.mark();
 
@@ -686,7 +705,7 @@ class B2EngineImpl {
         ++w.times.launches;
         for (;;) {
           if (ensure_scratch()) return 1;
-          b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+          b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);   // flags, task cursor, pool slots handed out
           const int64_t groups_needed = (T * B2_G_RESC + cfg.lane_block - 1) / cfg.lane_block;
           const int grid = (int)std::min<int64_t>(groups_needed, lane_grid);
           ev_r[0] = w.timer.mark();
@@ -694,8 +713,8 @@ class B2EngineImpl {
           ev_r[1] = w.timer.mark();
           ++w.times.launches;
           if (read_flags(w, &flags)) return 1;
-          if (!(flags & B2_FLAG_OVF_SCRATCH)) break;
-          { w.scratch_per_lane *= 2; overflowed = true; }
+          if (!(flags & OVF_ANY)) break;
+          grow_scratch(flags);
         }
       }
     }
@@ -792,7 +811,7 @@ class B2EngineImpl {
         b2_dev_memset(w.dbg.p, 0, ((size_t)n_items * 4 + 16) * sizeof(long long), w.stream);
         c.dbg = w.dbg.p;
       }
-      b2_dev_memset(w.flags.p, 0, 2 * sizeof(int), w.stream);
+      b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);   // flags, task cursor, pool slots handed out
       if (split) {
         c.fin_mode = 2;
         c.fin_fast = 2048;
@@ -807,8 +826,8 @@ class B2EngineImpl {
       ++w.times.launches;
       if (read_flags(w, &flags)) return 1;
       if (flags & B2_FLAG_ERR_TABLE) return fail("log/pairing table index out of range");
-      if (!(flags & (B2_FLAG_OVF_SCRATCH | B2_FLAG_OVF_SLOT))) break;
-      if (flags & B2_FLAG_OVF_SCRATCH) { w.scratch_per_lane *= 2; overflowed = true; }
+      if (!(flags & (OVF_ANY | B2_FLAG_OVF_SLOT))) break;
+      if (flags & OVF_ANY) grow_scratch(flags);
       if (flags & B2_FLAG_OVF_SLOT) {
         if (w.slot_size > (1 << 24)) return fail("SAM slot limit exceeded");
         w.slot_size *= 2;
@@ -907,6 +926,7 @@ class B2EngineImpl {
     {  // publish what grew during this batch
       auto raise = [](auto& shared, auto v) { auto cur = shared.load(); while (cur < v && !shared.compare_exchange_weak(cur, v)) {} };
       if (w.scratch_per_lane > scratch_in) raise(grown_scratch, w.scratch_per_lane);
+      if (w.big_slot > big_slot_in) raise(grown_big_slot, w.big_slot);
       if (w.cap_intv > cap_intv_in) raise(grown_cap_intv, w.cap_intv);
       if (w.slot_size > slot_in && slot_in) raise(grown_slot, w.slot_size);
     }

@@ -1174,6 +1174,8 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_FINAL_HEAVY"))) cfg->final_heavy_regs = atoi(s);
   if ((s = getenv("B200BWA_FINAL_FAST"))) cfg->final_fast_bytes = atoi(s);
   if ((s = getenv("B200BWA_SCRATCH"))) cfg->scratch_per_lane = (size_t)atol(s);
+  if ((s = getenv("B200BWA_BIG_POOL"))) cfg->big_pool_bytes = (size_t)atoll(s);
+  if ((s = getenv("B200BWA_BIG_SLOT"))) cfg->big_slot_bytes = (size_t)atoll(s);
   if ((s = getenv("B200BWA_MAX_SCRATCH"))) cfg->max_scratch_bytes = (size_t)atoll(s);
   if ((s = getenv("B200BWA_DEVICE"))) cfg->device = atoi(s);
   if ((s = getenv("B200BWA_WORKERS"))) cfg->n_workers = atoi(s);

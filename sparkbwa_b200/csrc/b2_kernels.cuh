@@ -18,6 +18,7 @@
 
 #define B2_FLAG_OVF_INTV 1
 #define B2_FLAG_OVF_SCRATCH 2
+#define B2_FLAG_OVF_BIGN 32     // more tasks needed a slot of the outlier pool than it has
 #define B2_FLAG_OVF_SLOT 4
 #define B2_FLAG_ERR_TABLE 8
 #define B2_FLAG_OVF_REG 16
@@ -73,6 +74,10 @@ struct B2Ctx {
   B2Reg* cand; uint8_t* cand_ok;                     // per seed: region computed ahead of the serial pass
   // per-lane scratch for the lane-per-read kernels
   uint8_t* scratch; size_t scratch_per_lane;
+  // Outlier pool: big_n slots of big_slot bytes.  The per-lane regions above are sized for the ordinary read / pair; the
+  // rare task that needs more (a read with thousands of seeds, a pair with dozens of regions, a wide traceback) takes a
+  // slot (big_count: slots handed out in this launch) and runs again there, instead of every lane's region growing.
+  uint8_t* big_pool; size_t big_slot; int big_n; int* big_count;
   // pestat
   int8_t* pe_dir; int64_t* pe_is;
   // planned mate-rescue attempts
@@ -360,6 +365,32 @@ B2_D inline int b2_next_task(const B2Ctx& c, const B2Scratch& sc) {
 #endif
 }
 
+// After a task body: true if it overflowed the lane's own region and now holds a slot of the outlier pool to run again in.
+B2_D inline bool b2_retry_big(const B2Ctx& c, B2Scratch& sc) {
+  if (!sc.overflow || sc.big || !c.big_pool) return false;
+  int slot = 0;
+#if defined(__CUDA_ARCH__)
+  if (sc.lane == 0) slot = atomicAdd(c.big_count, 1);
+  if (sc.gsize > 1) slot = __shfl_sync(sc.gmask, slot, 0, sc.gsize);
+#else
+  slot = (*c.big_count)++;
+#endif
+  if (slot >= c.big_n) return false;
+  sc.small_base = sc.base; sc.small_cap = sc.cap;
+  sc.base = c.big_pool + (size_t)slot * c.big_slot; sc.cap = c.big_slot;
+  sc.big = 1; sc.overflow = 0;
+  return true;
+}
+// End of a task: reports an overflow that remains (inside a slot: the slots are too small; outside: no slot was left) and
+// returns to the lane's own region.  Returns 1 if the task's results are void.
+B2_D inline int b2_end_task(const B2Ctx& c, B2Scratch& sc) {
+  const int ovf = sc.overflow;
+  if (ovf) B2_ATOMIC_OR(c.flags, (sc.big || !c.big_pool) ? B2_FLAG_OVF_SCRATCH : B2_FLAG_OVF_BIGN);
+  if (sc.big) { sc.base = sc.small_base; sc.cap = sc.small_cap; sc.big = 0; }
+  sc.overflow = 0;
+  return ovf;
+}
+
 B2_D inline void b2_flush_counters(const B2Ctx& c, const B2Scratch& sc) {
   if (sc.lane != 0) return;
   if (sc.ext_calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CELLS], sc.ext_cells); B2_ATOMIC_ADD(&c.counters[B2_CNT_EXT_CALLS], (unsigned long long)sc.ext_calls); }
@@ -374,21 +405,24 @@ B2_KERNEL k_chain(B2Ctx c) {
     const int n_raw = (int)(c.seed_off[r + 1] - off);
     int kept = 0, cap = 0;
     if (n_raw > 0) {
-      sc.reset(0);
-      const int node_cap = n_raw / 3 + 4;
-      B2Seed* raw = (B2Seed*)sc.alloc(sizeof(B2Seed) * (size_t)n_raw, 8);
-      B2Chain* tree_ch = (B2Chain*)sc.alloc(sizeof(B2Chain) * (size_t)n_raw, 8);
-      int* order = (int*)sc.alloc(sizeof(int) * (size_t)n_raw, 4);
-      B2BtNode* nodes = (B2BtNode*)sc.alloc(sizeof(B2BtNode) * (size_t)node_cap, 4);
-      if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
-      else {
-        for (int i = 0; i < n_raw; ++i) { raw[i] = c.raw[off + i]; raw[i].next = c.raw_rid[off + i]; }
-        int ovf = 0;
-        kept = b2_chain_read(c.opt, c.ix.l_pac, c.ix.anns, c.b.l_seq[r], c.intv + (size_t)r * c.cap_intv, c.n_intv[r],
-                             raw, n_raw, tree_ch, c.chains + off, c.cseeds + off, order, nodes, node_cap, &ovf);
-        if (ovf) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH);
-        for (int i = 0; i < kept; ++i) cap += c.chains[off + i].n;
-      }
+      do {
+        sc.reset(0);
+        kept = cap = 0;
+        const int node_cap = n_raw / 3 + 4;
+        B2Seed* raw = (B2Seed*)sc.alloc(sizeof(B2Seed) * (size_t)n_raw, 8);
+        B2Chain* tree_ch = (B2Chain*)sc.alloc(sizeof(B2Chain) * (size_t)n_raw, 8);
+        int* order = (int*)sc.alloc(sizeof(int) * (size_t)n_raw, 4);
+        B2BtNode* nodes = (B2BtNode*)sc.alloc(sizeof(B2BtNode) * (size_t)node_cap, 4);
+        if (!sc.overflow) {
+          for (int i = 0; i < n_raw; ++i) { raw[i] = c.raw[off + i]; raw[i].next = c.raw_rid[off + i]; }
+          int ovf = 0;
+          kept = b2_chain_read(c.opt, c.ix.l_pac, c.ix.anns, c.b.l_seq[r], c.intv + (size_t)r * c.cap_intv, c.n_intv[r],
+                               raw, n_raw, tree_ch, c.chains + off, c.cseeds + off, order, nodes, node_cap, &ovf);
+          if (ovf) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH);
+          for (int i = 0; i < kept; ++i) cap += c.chains[off + i].n;
+        }
+      } while (b2_retry_big(c, sc));
+      if (b2_end_task(c, sc)) kept = cap = 0;
     }
     c.n_chain[r] = kept;
     c.reg_cap[r] = cap;
@@ -432,7 +466,7 @@ B2_KERNEL k_flt_seeds(B2Ctx c) {
       sc.gsync();
       cap += k;
     }
-    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; continue; }
+    if (b2_end_task(c, sc)) continue;   // (no second run in a pool slot here: the compaction is in place)
     if (sc.lane == 0) c.reg_cap[r] = cap;
   }
   b2_flush_counters(c, sc);
@@ -565,15 +599,19 @@ B2_KERNEL_LB(128, B2_LB_EXT) k_ext_chain(B2Ctx c) {
     const int64_t off = c.seed_off[r];
     const B2Chain& ch = c.chains[off + (t - c.chain_off[r])];
     const int l_seq = c.b.l_seq[r];
-    uint64_t* srt = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)ch.n, 8);
-    B2Reg* av = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)ch.n, 8);
-    if (!sc.overflow) {
-      int n_av = 0;
-      b2_chain2aln(c.opt, c.ix, l_seq, c.b.seq + c.b.seq_off[r], ch, c.cseeds + off + ch.seed_head, av, &n_av, ch.n, srt, sc, 1,
-                   c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head,
-                   c.xext_res ? c.xext_res + 2 * (off + ch.seed_head) : 0);
-    }
-    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+    do {
+      sc.gsync();
+      sc.reset(0);
+      uint64_t* srt = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)ch.n, 8);
+      B2Reg* av = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)ch.n, 8);
+      if (!sc.overflow) {
+        int n_av = 0;
+        b2_chain2aln(c.opt, c.ix, l_seq, c.b.seq + c.b.seq_off[r], ch, c.cseeds + off + ch.seed_head, av, &n_av, ch.n, srt, sc, 1,
+                     c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head,
+                     c.xext_res ? c.xext_res + 2 * (off + ch.seed_head) : 0);
+      }
+    } while (b2_retry_big(c, sc));
+    b2_end_task(c, sc);
   }
   b2_flush_counters(c, sc);
 }
@@ -589,27 +627,30 @@ B2_KERNEL_LB(128, 4) k_extend(B2Ctx c) {
     B2Reg* av = c.regs + c.reg_off[r];
     const int cap = (int)(c.reg_off[r + 1] - c.reg_off[r]);
     int n_av = 0;
-    sc.reset(0);
     if (nch > 0) {
       int max_n = 0;
       for (int i = 0; i < nch; ++i) max_n = max_n > c.chains[off + i].n ? max_n : c.chains[off + i].n;
-      uint64_t* srt = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)max_n, 8);
-      uint8_t* query = (uint8_t*)sc.alloc((size_t)l_seq + 1, 1);
-      if (!sc.overflow) {
-        const uint8_t* q0 = c.b.seq + c.b.seq_off[r];
-        for (int i = 0; i < nch && !sc.overflow; ++i) {
-          const B2Chain& ch = c.chains[off + i];
-          b2_chain2aln(c.opt, c.ix, l_seq, q0, ch, c.cseeds + off + ch.seed_head, av, &n_av, cap, srt, sc, 2,
-                       c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head);
+      do {
+        sc.reset(0);
+        n_av = 0;
+        uint64_t* srt = (uint64_t*)sc.alloc(sizeof(uint64_t) * (size_t)max_n, 8);
+        uint8_t* query = (uint8_t*)sc.alloc((size_t)l_seq + 1, 1);
+        if (!sc.overflow) {
+          const uint8_t* q0 = c.b.seq + c.b.seq_off[r];
+          for (int i = 0; i < nch && !sc.overflow; ++i) {
+            const B2Chain& ch = c.chains[off + i];
+            b2_chain2aln(c.opt, c.ix, l_seq, q0, ch, c.cseeds + off + ch.seed_head, av, &n_av, cap, srt, sc, 2,
+                         c.cand + off + ch.seed_head, c.cand_ok + off + ch.seed_head);
+          }
+          if (!sc.overflow && n_av > 1) {
+            for (int i = 0; i < l_seq; ++i) query[i] = q0[i];  // patching may reverse the read in place
+            n_av = b2_sort_dedup_patch(c.opt, c.ix, 1, query, n_av, av, sc);
+          }
+          for (int i = 0; i < n_av; ++i)
+            if (av[i].rid >= 0 && c.ix.anns[av[i].rid].is_alt) av[i].is_alt = 1;
         }
-        if (!sc.overflow && n_av > 1) {
-          for (int i = 0; i < l_seq; ++i) query[i] = q0[i];  // patching may reverse the read in place
-          n_av = b2_sort_dedup_patch(c.opt, c.ix, 1, query, n_av, av, sc);
-        }
-        for (int i = 0; i < n_av; ++i)
-          if (av[i].rid >= 0 && c.ix.anns[av[i].rid].is_alt) av[i].is_alt = 1;
-      }
-      if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; n_av = 0; }
+      } while (b2_retry_big(c, sc));
+      if (b2_end_task(c, sc)) n_av = 0;
     }
     c.n_regs[r] = n_av;
   }
@@ -648,12 +689,15 @@ B2_KERNEL k_resc_sw(B2Ctx c) {
   int gid, n_groups;
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_RESC);
   for (int t = b2_next_task(c, sc); t < c.n_resc; t = b2_next_task(c, sc)) {
-    sc.gsync();
-    sc.reset(0);
     const B2RescTask task = c.resc_tasks[t];
     const int mate = 2 * task.item + (task.end_i ? 0 : 1);
-    B2Kswr r = b2_rescue_sw(c.opt, c.ix, task, c.b.seq + c.b.seq_off[mate], sc);
-    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+    B2Kswr r;
+    do {
+      sc.gsync();
+      sc.reset(0);
+      r = b2_rescue_sw(c.opt, c.ix, task, c.b.seq + c.b.seq_off[mate], sc);
+    } while (b2_retry_big(c, sc));
+    b2_end_task(c, sc);
     if (sc.lane == 0) c.resc_res[t] = r;
   }
   if (sc.lane == 0 && sc.sw_cells) B2_ATOMIC_ADD(&c.counters[B2_CNT_RESCSW_CELLS], sc.sw_cells);
@@ -791,21 +835,25 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
   B2Scratch sc = b2_group_scratch(c, &gid, &n_groups, B2_G_FINAL);
   sc.galn = &c.galn;
   for (int r = b2_next_task(c, sc); r < c.b.n_reads; r = b2_next_task(c, sc)) {
-    sc.gsync();
-    sc.reset(0);
     int err = 0;
     const int n = c.n_regs[r];
-    B2Reg* a = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)(n > 0 ? n : 1), 8);
-    int* z = (int*)sc.alloc(sizeof(int) * (size_t)(n + 1), 4);
-    B2Out out; out.p = c.slots + (size_t)r * c.slot_size; out.cap = c.slot_size; out.len = 0;
-    out.lane = sc.lane; out.gsize = sc.gsize;
-    if (!sc.overflow) {
-      for (int i = 0; i < n; ++i) a[i] = c.regs[c.reg_off[r] + i];
-      B2Read s = b2_make_read(c.b, r, 1);
-      b2_mark_primary_se(c.opt, n, a, c.n_processed + r, z, sc);
-      b2_reg2sam(c.opt, c.ix, c.tb, c.fmt, out, s, n, a, 0, 0, sc, &err);
-    }
-    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+    B2Out out;
+    do {
+      sc.gsync();
+      sc.reset(0);
+      err = 0;
+      B2Reg* a = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)(n > 0 ? n : 1), 8);
+      int* z = (int*)sc.alloc(sizeof(int) * (size_t)(n + 1), 4);
+      out.p = c.slots + (size_t)r * c.slot_size; out.cap = c.slot_size; out.len = 0;
+      out.lane = sc.lane; out.gsize = sc.gsize;
+      if (!sc.overflow) {
+        for (int i = 0; i < n; ++i) a[i] = c.regs[c.reg_off[r] + i];
+        B2Read s = b2_make_read(c.b, r, 1);
+        b2_mark_primary_se(c.opt, n, a, c.n_processed + r, z, sc);
+        b2_reg2sam(c.opt, c.ix, c.tb, c.fmt, out, s, n, a, 0, 0, sc, &err);
+      }
+    } while (b2_retry_big(c, sc));
+    b2_end_task(c, sc);
     if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE);
     if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
     c.sam_len[r] = (int32_t)out.len;
@@ -846,47 +894,51 @@ B2_D inline void b2_final_pe_body(const B2Ctx& c) {
     int i = t;
     if (c.fin_mode == 2) i = c.fin_list[t];
     else if (c.fin_mode == 1 && c.fin_heavy[t]) continue;
-    sc.gsync();
-    sc.reset(0);
-    sc.tick(-1);
 #if defined(__CUDA_ARCH__)
     const long long t0 = clock64();
     const unsigned sw0 = sc.sw_calls, gl0 = sc.glob_calls;
 #endif
     int err = 0;
     int n[2], cap[2];
-    B2Reg* a[2];
-    B2Read s[2];
-    n[0] = c.n_regs[2 * i]; n[1] = c.n_regs[2 * i + 1];
-    for (int k = 0; k < 2; ++k) {
-      int other = n[!k] < c.opt.max_matesw ? n[!k] : c.opt.max_matesw;
-      cap[k] = n[k] + ((c.opt.flag & B2_F_NO_RESCUE) ? 0 : 4 * other) + 1;
-      a[k] = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)cap[k], 8);
-      s[k] = b2_make_read(c.b, 2 * i + k, 1);
-    }
-    B2Out out; out.p = c.slots + (size_t)i * c.slot_size; out.cap = c.slot_size; out.len = 0;
-    out.lane = sc.lane; out.gsize = sc.gsize;
-    if (!sc.overflow) {
-      for (int k = 0; k < 2; ++k)
-        for (int j = 0; j < n[k]; ++j) a[k][j] = c.regs[c.reg_off[2 * i + k] + j];
-      B2RescCache cache;
-      cache.n = 0; cache.tasks = 0; cache.res = 0;
-      if (c.resc_off) {
-        cache.n = (int)(c.resc_off[i + 1] - c.resc_off[i]);
-        cache.tasks = c.resc_tasks + c.resc_off[i];
-        cache.res = c.resc_res + c.resc_off[i];
+    B2Out out;
+    do {   // (a second time in a slot of the outlier pool if the group's own region is too small for this pair)
+      sc.gsync();
+      sc.reset(0);
+      sc.tick(-1);
+      err = 0;
+      B2Reg* a[2];
+      B2Read s[2];
+      n[0] = c.n_regs[2 * i]; n[1] = c.n_regs[2 * i + 1];
+      for (int k = 0; k < 2; ++k) {
+        int other = n[!k] < c.opt.max_matesw ? n[!k] : c.opt.max_matesw;
+        cap[k] = n[k] + ((c.opt.flag & B2_F_NO_RESCUE) ? 0 : 4 * other) + 1;
+        a[k] = (B2Reg*)sc.alloc(sizeof(B2Reg) * (size_t)cap[k], 8);
+        s[k] = b2_make_read(c.b, 2 * i + k, 1);
       }
-      sc.tick(7);
-      b2_sam_pe(c.opt, c.ix, c.tb, c.fmt, c.pes, (uint64_t)((c.n_processed >> 1) + i), s, a, n, cap, out, sc, &err, &cache);
-    }
-    if (sc.overflow) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SCRATCH); sc.overflow = 0; }
+      out.p = c.slots + (size_t)i * c.slot_size; out.cap = c.slot_size; out.len = 0;
+      out.lane = sc.lane; out.gsize = sc.gsize;
+      if (!sc.overflow) {
+        for (int k = 0; k < 2; ++k)
+          for (int j = 0; j < n[k]; ++j) a[k][j] = c.regs[c.reg_off[2 * i + k] + j];
+        B2RescCache cache;
+        cache.n = 0; cache.tasks = 0; cache.res = 0;
+        if (c.resc_off) {
+          cache.n = (int)(c.resc_off[i + 1] - c.resc_off[i]);
+          cache.tasks = c.resc_tasks + c.resc_off[i];
+          cache.res = c.resc_res + c.resc_off[i];
+        }
+        sc.tick(7);
+        b2_sam_pe(c.opt, c.ix, c.tb, c.fmt, c.pes, (uint64_t)((c.n_processed >> 1) + i), s, a, n, cap, out, sc, &err, &cache);
+      }
+    } while (b2_retry_big(c, sc));
+    b2_end_task(c, sc);
     if (err) B2_ATOMIC_OR(c.flags, B2_FLAG_ERR_TABLE);
     if (out.len > out.cap) B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_SLOT);
     c.sam_len[i] = (int32_t)out.len;
 #if defined(__CUDA_ARCH__)
     if (c.dbg && sc.lane == 0) {
       c.dbg[4 * i] = clock64() - t0; c.dbg[4 * i + 1] = sc.sw_calls - sw0; c.dbg[4 * i + 2] = sc.glob_calls - gl0;
-      c.dbg[4 * i + 3] = (long long)n[0] << 32 | (unsigned)n[1];
+      c.dbg[4 * i + 3] = (long long)c.n_regs[2 * i] << 32 | (unsigned)c.n_regs[2 * i + 1];
     }
 #endif
   }

@@ -169,6 +169,21 @@ def test_capacity_retry_paths(hostsim, workdir):
         pu.engine_sam(c, hostsim, env=dict(env, B200BWA_MAX_SCRATCH="4096"))
 
 
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_pair_finalisation_split_host_logic(hostsim, workdir):
+    """k_final_plan / k_final_pe_heavy / k_final_pe: whichever pairs are listed for the first launch (none, all, those with
+    >= 2 or >= 4 regions), each pair is finalised exactly once and the SAM equals the reference's; a retry after a slot /
+    scratch overflow in either launch re-runs both.  (Host build: one lane per group; the GPU test repeats this on device.)"""
+    for name in ("pe_small", "pe_repeat"):
+        c = pu.make_case(workdir, name)
+        ref = pu.oracle_sam(c)
+        for heavy in ("0", "2", "4", "1000"):
+            env = dict(pu.HOSTSIM_ENV, B200BWA_FINAL_HEAVY=heavy)
+            assert not pu.first_diff(ref, pu.engine_sam(c, hostsim, env=env)), (name, heavy)
+        env = dict(pu.HOSTSIM_ENV, B200BWA_FINAL_HEAVY="2", B200BWA_SCRATCH="512", B200BWA_SLOT="64")
+        assert not pu.first_diff(ref, pu.engine_sam(c, hostsim, env=env)), name
+
+
 def test_striped_sw_scan_equals_lazy_f(tmp_path):
     """The mate-rescue SW replaces the reference's lazy-F loop (ksw.c:176-188) by a max-plus carry scan;
     fuzz it against a literal emulation of that loop (byte and word mode, random scorings)."""

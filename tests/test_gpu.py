@@ -332,6 +332,19 @@ def test_in_kernel_dp_paths_match_oracle(workdir, name):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("env", [{"B200BWA_FINAL_HEAVY": "0"}, {"B200BWA_FINAL_HEAVY": "2"}, {"B200BWA_FINAL_HEAVY": "1000"},
+                                 {"B200BWA_FINAL_FAST": "0"}, {"B200BWA_FINAL_FAST": "64"}],
+                         ids=["one-launch", "every-pair-a-warp", "no-pair-listed", "no-shared-arena", "tiny-shared-arena"])
+def test_pair_finalisation_split_does_not_change_the_sam(workdir, env):
+    """Pairs with many regions are finalised by k_final_pe_heavy (a warp each), the others by k_final_pe (4-lane groups);
+    which pair goes where, and whether the read copy / reference window live in shared memory, must not show in the
+    output: repeat-rich pairs (dozens of regions, rescue, XA), 250 bp pairs and ALT contigs against the reference."""
+    for name in ("pe_repeat", "pe250", "pe_alt"):
+        c = pu.make_case(workdir, name)
+        assert not pu.first_diff(pu.oracle_sam(c), pu.engine_sam(c, pu.CLI, env=env)), (name, env)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_index_builder_matches_bwa_index(workdir):
     """`b200bwa index` (suffix sort on the GPU) writes the files of `bwa index`, byte for byte: the small adversarial
     cases, a 5 Mbp genome with ambiguous bases (BASELINE.json configs[0]'s reference size) and -- with
