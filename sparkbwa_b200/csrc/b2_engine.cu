@@ -515,7 +515,7 @@ class B2EngineImpl {
     c.raw = w.raw.p; c.raw_rid = w.raw_rid.p; c.chains = w.chains.p; c.cseeds = w.cseeds.p;
     c.n_chain = w.n_chain.p; c.reg_cap = w.reg_cap.p; c.n_regs = w.n_regs.p;
     c.sa_task_r = nullptr; c.sa_task_iv = nullptr;
-    if (S > 0 && opt.max_occ <= 0xffff && w.cap_intv <= 0xffff) {
+    if (S > 0 && !cfg.no_sa_plan && opt.max_occ <= 0xffff && w.cap_intv <= 0xffff) {
       if (w.sa_task_r.ensure(S + 1) || w.sa_task_iv.ensure(S + 1)) return fail("device allocation failed (seeds)");
       c.sa_task_r = w.sa_task_r.p; c.sa_task_iv = w.sa_task_iv.p;
       B2_LAUNCH(k_sa_plan, (n + 127) / 128, 128, w.stream, c);
@@ -524,7 +524,8 @@ class B2EngineImpl {
     if (S > 0) {
       int grid = (int)std::min<int64_t>((S + 127) / 128, 148 * 16);   // resident lanes only (all 64 warps of an SM: the walk is a chain of dependent fetches); each takes lookup after lookup
       b2_dev_memset(w.flags.p + 3, 0, sizeof(int), w.stream);   // the lookups are dealt from this cursor (c.work[2])
-      B2_LAUNCH(k_sa, grid, 128, w.stream, c);
+      if (c.sa_task_r) B2_LAUNCH(k_sa, grid, 128, w.stream, c);
+      else B2_LAUNCH(k_sa_search, grid, 128, w.stream, c);
       B2_LAUNCH(k_sa_rid, (int)std::min<int64_t>((S + 255) / 256, 148 * 16), 256, w.stream, c);
       w.times.launches += 2;
     }

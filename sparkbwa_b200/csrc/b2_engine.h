@@ -59,12 +59,13 @@ struct B2EngineConfig {
   int final_fast_bytes = 512;                  // shared memory per task group of k_final_pe: read copy + reference window of an alignment
   int final_heavy_regs = 4;                    // pairs with at least this many regions (both mates) are finalised a warp each, in their own launch (0: no split)
   int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
-  size_t scratch_per_lane = 48 << 10;          // every lane's (task group's) own scratch region: sized for the ordinary read / pair
+  size_t scratch_per_lane = 16 << 10;          // every lane's (task group's) own scratch region: sized for the ordinary read / pair
   size_t big_pool_bytes = (size_t)1 << 30;     // outlier pool per stream set: tasks that overflow their region run again in one of its slots (0: none)
   size_t big_slot_bytes = 256 << 10;           // initial slot size of the pool
   int no_xext = 0;                             // 1: skip the inter-task seed extensions (B200BWA_NO_XEXT)
   int no_ext_chain = 0;                        // 1: skip the per-chain extension kernel, the per-read pass computes in place (B200BWA_NO_EXT_CHAIN)
   int no_resc_plan = 0;                        // 1: no planned mate-rescue SW tasks, the finalisation kernel runs them itself (B200BWA_NO_RESC_PLAN)
+  int no_sa_plan = 0;                          // 1: k_sa_search instead of k_sa_plan + k_sa (B200BWA_NO_SA_PLAN)
   int no_galn = 0;                             // 1: skip the speculative inter-task global alignments (B200BWA_NO_GALN)
   size_t max_scratch_bytes = (size_t)16 << 30;    // per stream/buffer set; a stage that needs more per lane runs with fewer lanes
   int n_workers = 6;                           // independent stream/buffer sets (batches in flight)

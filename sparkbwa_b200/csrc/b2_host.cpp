@@ -1182,6 +1182,7 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_CAP_INTV"))) cfg->cap_intv = atoi(s);
   if ((s = getenv("B200BWA_SLOT"))) cfg->slot_per_read = atoi(s);
   if ((s = getenv("B200BWA_NO_GALN"))) cfg->no_galn = atoi(s);
+  if ((s = getenv("B200BWA_NO_SA_PLAN"))) cfg->no_sa_plan = atoi(s);
   if ((s = getenv("B200BWA_NO_XEXT"))) cfg->no_xext = atoi(s);
   if ((s = getenv("B200BWA_NO_EXT_CHAIN"))) cfg->no_ext_chain = atoi(s);
   if ((s = getenv("B200BWA_NO_RESC_PLAN"))) cfg->no_resc_plan = atoi(s);

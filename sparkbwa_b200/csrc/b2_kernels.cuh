@@ -247,7 +247,9 @@ B2_KERNEL k_sa_plan(B2Ctx c) {
   }
 }
 
-B2_KERNEL k_sa(B2Ctx c) {
+// Form without k_sa_plan's tables (max_occ or the interval capacity beyond 16 bits): the lane finds its lookup's read by
+// searching seed_off.
+B2_KERNEL k_sa_search(B2Ctx c) {
   // One suffix-array lookup per lane at a time: an LF walk to the next sampled row, geometric in length (mean 31 steps,
   // the longest of 32 about four times that).  A lane that finishes takes the next lookup from the stage's cursor right
   // away instead of idling until the warp's longest walk ends; every trip of the loop is ONE LF step for all lanes
@@ -315,6 +317,92 @@ B2_KERNEL k_sa(B2Ctx c) {
         s.len = s.score = slen;
         s.next = -1;
         c.raw[t] = s;   // (its contig id: k_sa_rid, all lanes together)
+        steps_total += steps; ++calls;
+        have = false;
+      }
+    }
+  }
+  if (calls) { B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_CALLS], calls); B2_ATOMIC_ADD(&c.counters[B2_CNT_SA_STEPS], steps_total); }
+}
+
+// One suffix-array lookup per lane at a time: an LF walk to the next sampled row, geometric in length (mean 31 steps, the
+// longest of 32 about four times that); every trip of the loop is ONE LF step -- one dependent block fetch -- for all lanes
+// that hold a lookup.  What surrounds a walk is kept off that path by two small per-lane pipelines that advance one stage
+// per trip, each stage consuming what the previous trip requested:
+//   next lookup:  index from the stage's cursor -> its description (k_sa_plan's tables) -> its interval -> ready;
+//   finished one: the sampled SA entry is requested when the walk ends, the seed is written a trip later.
+// A lane that finishes a walk therefore continues with the next one in the same trip, and no trip waits for more than one
+// memory round trip (a refill done in place is a chain of four, executed by the few lanes that finished together).
+B2_KERNEL k_sa(B2Ctx c) {
+  unsigned long long steps_total = 0, calls = 0;
+  const uint64_t mask = (uint64_t)c.ix.sa_intv - 1;
+  int64_t t = 0;
+  uint64_t k = 0;
+  unsigned steps = 0;
+  int32_t qbeg = 0, slen = 0;
+  bool have = false;
+  int pf = 0;   // next lookup: 0 nothing requested, 1 index, 2 description, 3 interval requested, 4 ready, 5 no lookups left
+  int64_t pf_t = 0;
+  int pf_r = 0;
+  uint32_t pf_pk = 0;
+  uint64_t pf_x0 = 0, pf_x2 = 0, pf_info = 0;
+  bool fin = false;   // finished lookup whose seed is still to be written
+  int64_t fin_t = 0;
+  uint64_t fin_sa = 0;
+  unsigned fin_steps = 0;
+  int32_t fin_qbeg = 0, fin_slen = 0;
+  for (;;) {
+    if (fin) {
+      B2Seed s;
+      s.rbeg = (int64_t)(fin_steps + fin_sa);
+      s.qbeg = fin_qbeg;
+      s.len = s.score = fin_slen;
+      s.next = -1;
+      c.raw[fin_t] = s;   // (its contig id: k_sa_rid, all lanes together)
+      fin = false;
+    }
+    if (pf == 3) pf = 4;
+    else if (pf == 2) {
+      const B2Intv* p = c.intv + (size_t)pf_r * c.cap_intv + (pf_pk >> 16);
+      pf_x0 = p->x[0]; pf_x2 = p->x[2]; pf_info = p->info;
+      pf = 3;
+    } else if (pf == 1) {
+      if (pf_t >= c.n_seed_tasks) pf = 5;
+      else { pf_r = c.sa_task_r[pf_t]; pf_pk = c.sa_task_iv[pf_t]; pf = 2; }
+    } else if (pf == 0) {
+#if defined(__CUDA_ARCH__)
+      pf_t = (int64_t)atomicAdd(c.work + 2, 1);
+#else
+      pf_t = (int64_t)c.work[2]++;
+#endif
+      pf = 1;
+    }
+    if (!have && pf == 4) {
+      const long idx = (long)(pf_pk & 0xffff);
+      const long step = pf_x2 > (uint64_t)c.opt.max_occ ? (long)(pf_x2 / c.opt.max_occ) : 1;
+      slen = (int32_t)((uint32_t)pf_info - (uint32_t)(pf_info >> 32));
+      qbeg = (int32_t)(pf_info >> 32);
+      k = pf_x0 + (uint64_t)(idx * step);
+      t = pf_t;
+      steps = 0;
+      have = true;
+      pf = 0;
+    }
+#if defined(__CUDA_ARCH__)
+    if (__ballot_sync(0xffffffffu, have || fin || pf != 5) == 0) break;
+#else
+    if (!(have || fin || pf != 5)) break;
+#endif
+    if (have) {
+#if defined(__CUDA_ARCH__)
+      if (k & mask) { ++steps; k = b2_inv_psi_lane(c.ix, k); }
+#else
+      if (k & mask) { ++steps; k = b2_inv_psi(c.ix, k); }
+#endif
+      else {
+        fin_sa = c.ix.sa[k >> c.ix.sa_shift];
+        fin_t = t; fin_steps = steps; fin_qbeg = qbeg; fin_slen = slen;
+        fin = true;
         steps_total += steps; ++calls;
         have = false;
       }
@@ -868,10 +956,31 @@ B2_KERNEL_LB(128, B2_LB_FINAL) k_final_se(B2Ctx c) {
 // (B2_G_HEAVY lanes for its DP, sorts' data movement and text), k_final_pe then runs the ordinary pairs in
 // B2_G_FINAL-lane groups, skipping the flagged ones.  fin_mode 0: one launch over all pairs (single-end batches,
 // splitting disabled).
+// 1 iff mem_reg2aln of this region is going to run a global alignment inside the finalisation kernel: the region is not
+// gap-free and either no alignment was computed ahead for it (band wider than k_galn's classes, lengths too different) or
+// the one that was scores below truesc - a, so that the band is doubled and the DP repeated (bwa/bwamem.c:1072-1086)
+B2_D inline int b2_final_needs_dp(const B2Ctx& c, int r, const B2Reg* ar) {
+  if (ar->rb < 0 || ar->re < 0) return 0;
+  const int qb = ar->qb, qe = ar->qe;
+  const int64_t rb = ar->rb, re = ar->re;
+  if (qe - qb <= 0 || rb >= re || (rb < c.ix.l_pac && re > c.ix.l_pac)) return 0;
+  const int w2 = b2_reg2aln_w0(c.opt, ar);
+  if (qe - qb == re - rb && w2 == 0) return 0;
+  const B2GalnRes* pre = b2_galn_lookup(&c.galn, c.b.seq + c.b.seq_off[r], qb, qe, rb, re, w2);
+  if (pre == 0) return 1;
+  return w2 != c.opt.w << 2 && pre->score < ar->truesc - c.opt.a;
+}
+
 B2_KERNEL k_final_plan(B2Ctx c) {
   const int n_pairs = c.b.n_reads >> 1;
   for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
-    const int heavy = c.n_regs[2 * i] + c.n_regs[2 * i + 1] >= c.fin_heavy_min;
+    int heavy = c.n_regs[2 * i] + c.n_regs[2 * i + 1] >= c.fin_heavy_min;
+    // a pair whose leading regions need a DP in the kernel also gets a warp: 32 lanes for the alignment, and the other
+    // pairs of a 4-lane-group warp do not wait for it
+    for (int k = 0; k < 2 && !heavy; ++k) {
+      const int r = 2 * i + k, n = c.n_regs[r] < 2 ? c.n_regs[r] : 2;
+      for (int j = 0; j < n && !heavy; ++j) heavy = b2_final_needs_dp(c, r, c.regs + c.reg_off[r] + j);
+    }
     c.fin_heavy[i] = (uint8_t)heavy;
     if (heavy) c.fin_list[B2_ATOMIC_ADD(c.work + 3, 1)] = i;
   }

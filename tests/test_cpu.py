@@ -184,6 +184,17 @@ def test_pair_finalisation_split_host_logic(hostsim, workdir):
         assert not pu.first_diff(ref, pu.engine_sam(c, hostsim, env=env)), name
 
 
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_sa_lookup_forms(hostsim, workdir):
+    """k_sa takes each lookup's (read, interval, rank) from k_sa_plan's tables; k_sa_search -- used when max_occ or the
+    interval capacity does not fit 16 bits -- finds them by searching seed_off.  Same seeds either way."""
+    c = pu.make_case(workdir, "pe_repeat")
+    ref = pu.oracle_sam(c)
+    assert not pu.first_diff(ref, pu.engine_sam(c, hostsim, env=dict(pu.HOSTSIM_ENV, B200BWA_NO_SA_PLAN="1")))
+    c2 = dict(c, opts=c["opts"] + ["-c", "70000"])
+    assert not pu.first_diff(pu.oracle_sam(c2), pu.engine_sam(c2, hostsim, env=pu.HOSTSIM_ENV))
+
+
 def test_striped_sw_scan_equals_lazy_f(tmp_path):
     """The mate-rescue SW replaces the reference's lazy-F loop (ksw.c:176-188) by a max-plus carry scan;
     fuzz it against a literal emulation of that loop (byte and word mode, random scorings)."""

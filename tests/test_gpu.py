@@ -345,6 +345,16 @@ def test_pair_finalisation_split_does_not_change_the_sam(workdir, env):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_sa_lookup_forms(workdir):
+    """k_sa (lookups described by k_sa_plan, next lookup prefetched stage by stage) and k_sa_search (no tables) leave the
+    same seeds: repeat-rich pairs, where a read has thousands of lookups, against the reference."""
+    c = pu.make_case(workdir, "pe_repeat")
+    ref = pu.oracle_sam(c)
+    assert not pu.first_diff(ref, pu.engine_sam(c, pu.CLI, env={"B200BWA_NO_SA_PLAN": "1"}))
+    assert not pu.first_diff(ref, pu.engine_sam(c, pu.CLI))
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_index_builder_matches_bwa_index(workdir):
     """`b200bwa index` (suffix sort on the GPU) writes the files of `bwa index`, byte for byte: the small adversarial
     cases, a 5 Mbp genome with ambiguous bases (BASELINE.json configs[0]'s reference size) and -- with
