@@ -48,6 +48,13 @@ struct B2Scratch {
     return v;
   }
   // bit i set iff lane i of the group passed a true predicate
+  // OR of v over the lanes of the group (every lane gets the result)
+  B2_HD inline unsigned gor(unsigned v) const {
+#if defined(__CUDA_ARCH__)
+    for (int d = gsize >> 1; d; d >>= 1) v |= __shfl_xor_sync(gmask, v, d, gsize);
+#endif
+    return v;
+  }
   B2_HD inline unsigned gballot(int pred) const {
 #if defined(__CUDA_ARCH__)
     if (gsize > 1) return (__ballot_sync(gmask, pred) & gmask) >> (__ffs(gmask) - 1);
@@ -78,6 +85,10 @@ struct B2Scratch {
   B2_HD inline size_t mark() const { return used | (size_t)fast_used << 48; }
   B2_HD inline void reset(size_t m) { used = m & (((size_t)1 << 48) - 1); fast_used = (unsigned)(m >> 48); }
 };
+
+// the five characters of base codes 0..4 packed into one word: a shift instead of a table in memory
+#define B2_BASES_FWD ((uint64_t)'A' | (uint64_t)'C' << 8 | (uint64_t)'G' << 16 | (uint64_t)'T' << 24 | (uint64_t)'N' << 32)
+#define B2_BASES_REV ((uint64_t)'T' | (uint64_t)'G' << 8 | (uint64_t)'C' << 16 | (uint64_t)'A' << 24 | (uint64_t)'N' << 32)
 
 // dst[i] = get(i) for i = lane, lane + gsize, ... < n: four elements in flight per lane -- the loads of a trip are issued
 // before its stores (byte stores may alias anything as far as the compiler knows, which would otherwise serialise the
@@ -480,9 +491,16 @@ struct B2Cigar {
 };
 
 B2_HD inline int b2_put_int(char* s, int l, int cap, long c) {
+  if (c >= 0 && c < 1000000000l) {   // MD run lengths: digits written in place
+    const unsigned v = (unsigned)c;
+    const int n = v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 :
+                  v < 10000000u ? 7 : v < 100000000u ? 8 : 9;
+    unsigned y = v;
+    for (int k = n - 1; k >= 0; --k, y /= 10u) if (l + k < cap) s[l + k] = (char)('0' + y % 10u);
+    return l + n;
+  }
   char buf[24];
   int n = 0;
-  if (c == 0) { if (l < cap) s[l] = '0'; return l + 1; }
   unsigned long x = c < 0 ? (unsigned long)(-c) : (unsigned long)c;
   for (; x > 0; x /= 10) buf[n++] = (char)('0' + x % 10);
   if (c < 0) buf[n++] = '-';
@@ -545,16 +563,27 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
   }
   if (out) {  // NM and MD
     int k, x, y, u, n_mm = 0, n_gap = 0, l = 0;
-    const char* int2base = rb < l_pac ? "ACGTN" : "TGCAN";
+    const uint64_t int2base = rb < l_pac ? B2_BASES_FWD : B2_BASES_REV;
     char* md = out->md;
+    // mismatches of a match run: a lane compares P consecutive positions, the group's results are ORed into one word
+    // (small groups; whole warps vote instead), and the mismatches are then emitted in order
+    const int P = sc.gsize <= 8 ? 4 : 1, chunk = P * sc.gsize;
     const int cap = out->md_cap - 1;
     for (k = 0, x = y = u = 0; k < out->n_cigar; ++k) {
       int op = out->cigar[k] & 0xf, len = (int)(out->cigar[k] >> 4);
       if (op == 0) {  // the lanes compare gsize positions at a time; mismatches are then emitted in order
         int cur = 0;
-        for (int i0 = 0; i0 < len; i0 += sc.gsize) {
-          const int i = i0 + sc.lane;
-          unsigned bits = sc.gballot(i < len && query[x + i] != rseq[y + i]);
+        for (int i0 = 0; i0 < len; i0 += chunk) {
+          unsigned bits;
+          if (P == 1) {
+            const int i = i0 + sc.lane;
+            bits = sc.gballot(i < len && query[x + i] != rseq[y + i]);
+          } else {
+            unsigned mine = 0;
+            const int i1 = i0 + sc.lane * 4;
+            for (int k = 0; k < 4; ++k) mine |= (unsigned)(i1 + k < len && query[x + i1 + k] != rseq[y + i1 + k]) << k;
+            bits = sc.gor(mine << (sc.lane * 4));
+          }
           while (bits) {
             int b = 0;
             while (!(bits >> b & 1)) ++b;
@@ -562,7 +591,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
             const int p = i0 + b;
             u += p - cur;
             l = b2_put_int(md, l, cap, u);
-            if (l < cap) md[l] = int2base[rseq[y + p]];
+            if (l < cap) md[l] = (char)(int2base >> (8 * rseq[y + p]));
             ++l; ++n_mm; u = 0;
             cur = p + 1;
           }
@@ -574,7 +603,7 @@ B2_NOINLINE B2_HD inline int b2_gen_cigar2(const B2Opt& opt, const B2Index& ix, 
           l = b2_put_int(md, l, cap, u);
           if (l < cap) md[l] = '^';
           ++l;
-          for (int i = 0; i < len; ++i) { if (l < cap) md[l] = int2base[rseq[y + i]]; ++l; }
+          for (int i = 0; i < len; ++i) { if (l < cap) md[l] = (char)(int2base >> (8 * rseq[y + i])); ++l; }
           u = 0; n_gap += len;
         }
         y += len;

@@ -78,7 +78,7 @@ struct Worker {
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
   DBuf<uint8_t> fin_heavy; DBuf<int32_t> fin_list;
-  DBuf<int32_t> sa_task_r; DBuf<uint32_t> sa_task_iv;
+  DBuf<int32_t> sa_task_r; DBuf<uint32_t> sa_task_iv; DBuf<int32_t> dbg_seed;
   DBuf<long long> dbg;
   DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
@@ -251,7 +251,7 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release(); w.big.release();
+      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release(); w.big.release(); w.dbg_seed.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
@@ -490,6 +490,12 @@ class B2EngineImpl {
       c.seed_scratch = w.seed_scratch.p; c.seed_spill = w.seed_spill.p;
       c.seed_E = seed_E; c.seed_QW = seed_QW; c.seed_RS = seed_RS;
       b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);
+      c.dbg_seed = nullptr;
+      if (getenv("B200BWA_DEBUG_TIMES")) {
+        if (w.dbg_seed.ensure(n + 1)) return fail("device allocation failed");
+        b2_dev_memset(w.dbg_seed.p, 0, (size_t)n * sizeof(int32_t), w.stream);
+        c.dbg_seed = w.dbg_seed.p;
+      }
       B2_LAUNCH_SMEM(k_seed, seed_grid, seed_block, seed_smem, w.stream, c);
       B2_LAUNCH_SMEM(k_seed3, seed3_grid, seed_block, seed3_smem, w.stream, c);
       B2_LAUNCH(k_seed_fin, (n + 127) / 128, 128, w.stream, c);
@@ -498,6 +504,20 @@ class B2EngineImpl {
       if (!(flags & B2_FLAG_OVF_INTV)) break;
       if (w.cap_intv >= 8192) return fail("seed interval capacity exceeded");
       w.cap_intv *= 2;
+    }
+    if (c.dbg_seed) {   // extension steps per read: how uneven the lanes' work is (one read per lane)
+      std::vector<int32_t> h(n);
+      b2_d2h(h.data(), w.dbg_seed.p, (size_t)n * sizeof(int32_t), w.stream);
+      b2_sync(w.stream);
+      double sum = 0, wmax = 0, bmax = 0;
+      for (int i = 0; i < n; ++i) sum += h[i];
+      for (int i = 0; i + 32 <= n; i += 32) wmax += *std::max_element(h.begin() + i, h.begin() + i + 32);
+      for (int i = 0; i + 128 <= n; i += 128) bmax += *std::max_element(h.begin() + i, h.begin() + i + 128);
+      std::vector<int32_t> srt(h);
+      std::sort(srt.begin(), srt.end());
+      auto pct = [&](double f) { return srt[std::min<size_t>((size_t)n - 1, (size_t)(f * n))]; };
+      fprintf(stderr, "[D::seed] steps per read (passes 1+2): mean %.1f p10 %d p50 %d p90 %d p99 %d p99.9 %d max %d; mean / (mean of the maxima of 32 consecutive reads) %.3f, of 128 %.3f\n",
+              sum / n, pct(.1), pct(.5), pct(.9), pct(.99), pct(.999), srt[n - 1], sum / n / (wmax / (n / 32)), sum / n / (bmax / (n / 128)));
     }
     int ev_seed = w.timer.mark();
     B2_LAUNCH(k_scan, 1, 1024, w.stream, (const int32_t*)w.n_tasks.p, w.seed_off.p, n);

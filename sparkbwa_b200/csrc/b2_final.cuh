@@ -37,8 +37,6 @@ struct B2Out {
   long cap, len;
   int lane = 0, gsize = 1;  // task group writing this record: bulk fields are written lane-strided
   // n characters tab[codes[i]] for i = from, from+step, ... (step = +1 or -1)
-#define B2_BASES_FWD ((uint64_t)'A' | (uint64_t)'C' << 8 | (uint64_t)'G' << 16 | (uint64_t)'T' << 24 | (uint64_t)'N' << 32)
-#define B2_BASES_REV ((uint64_t)'T' | (uint64_t)'G' << 8 | (uint64_t)'C' << 16 | (uint64_t)'A' << 24 | (uint64_t)'N' << 32)
   // (four characters in flight per lane: loads first, then the stores -- see b2_gfill)
   // tab: the five characters for codes 0..4 packed into one word (B2_BASES_FWD / B2_BASES_REV), no table in memory
   B2_HD inline void put_codes(const uint8_t* codes, int from, int step, int n, uint64_t tab) {
@@ -55,12 +53,20 @@ struct B2Out {
   B2_HD inline void putsn(const char* s, int l) { for (int i = 0; i < l; ++i) putc_(s[i]); }
   B2_HD inline void puts_(const char* s) { for (; *s; ++s) putc_(*s); }
   B2_HD inline void putl(long c) {
+    if (c < 0) { putc_('-'); c = -c; }   // (LONG_MIN does not occur: positions, lengths, scores)
+    unsigned long x = (unsigned long)c;
+    if (x < 1000000000ul) {   // the common case in 32-bit arithmetic, digits written in place (no staging array)
+      const unsigned v = (unsigned)x;
+      const int n = v < 10u ? 1 : v < 100u ? 2 : v < 1000u ? 3 : v < 10000u ? 4 : v < 100000u ? 5 : v < 1000000u ? 6 :
+                    v < 10000000u ? 7 : v < 100000000u ? 8 : 9;
+      unsigned y = v;
+      for (int k = n - 1; k >= 0; --k, y /= 10u) if (len + k < cap) p[len + k] = (char)('0' + y % 10u);
+      len += n;
+      return;
+    }
     char buf[24];
     int n = 0;
-    if (c == 0) { putc_('0'); return; }
-    unsigned long x = c < 0 ? (unsigned long)(-c) : (unsigned long)c;
     for (; x > 0; x /= 10) buf[n++] = (char)('0' + x % 10);
-    if (c < 0) buf[n++] = '-';
     for (int i = n - 1; i >= 0; --i) putc_(buf[i]);
   }
 };

@@ -58,6 +58,7 @@ struct B2Ctx {
   unsigned long long* counters;  // [B2_CNT_*], algorithmic work
   int* work;                     // dynamic work-distribution cursor of the running stage
   long long* dbg;                // optional per-item profile: [4*i] = {cycles, sw calls, glob calls, n regs}
+  int32_t* dbg_seed;             // optional (B200BWA_DEBUG_TIMES): extension steps of every read in k_seed
   // seeding
   B2Intv* intv; int cap_intv; int32_t* n_intv; int32_t* n_tasks;
   B2Intv* seed_scratch;   // host checker build: per lane max_len+1 stack entries
@@ -142,7 +143,7 @@ B2_D inline void b2_seed_body(const B2Ctx& c) {
   }
 #endif
   m.phase = B2S_IDLE;
-  int r = -1, need = 0;
+  int r = -1, need = 0, trips = 0;
   bool alive = true;
   int32_t* n_out = MODE ? c.n_tasks : c.n_intv;  // (n_tasks holds the pass-3 count until k_seed_fin)
   for (;;) {
@@ -157,6 +158,7 @@ B2_D inline void b2_seed_body(const B2Ctx& c) {
       n_out[r] = 0;
       if (len < c.opt.min_seed_len) continue;
       need = m.begin(c.opt, c.ix, c.b.seq + c.b.seq_off[r], len, c.intv + (size_t)r * c.cap_intv, c.cap_intv);
+      trips = 0;
     }
     // the warp-wide vote is also the reconvergence point: every lane with a pending request runs the extension
     // below in the same pass
@@ -174,6 +176,7 @@ B2_D inline void b2_seed_body(const B2Ctx& c) {
       static long steps[4]; static int steps_read = -1;
       if (dump_steps) { if (steps_read != r) { steps_read = r; steps[0] = steps[1] = steps[2] = steps[3] = 0; } ++steps[m.phase]; }
 #endif
+      ++trips;
       need = m.consume(c.opt, c.ix, okc);
 #if defined(B2_HOSTSIM)
       if (dump_steps && !need) fprintf(stderr, "[D::seed_steps] %d fwd %ld bwd %ld s3 %ld n %d\n", r, steps[B2S_FWD], steps[B2S_BWD], steps[B2S_S3], m.n);
@@ -182,6 +185,7 @@ B2_D inline void b2_seed_body(const B2Ctx& c) {
         int n = m.n;
         if (n > c.cap_intv) { B2_ATOMIC_OR(c.flags, B2_FLAG_OVF_INTV); n = c.cap_intv; }
         n_out[r] = n;
+        if (MODE == 0 && c.dbg_seed) c.dbg_seed[r] = trips;
 #if defined(B2_HOSTSIM)
         if (MODE && c.n_intv[r] + n <= c.cap_intv) {  // cross-check against the plain nested-loop form (x[1] aside)
           B2OccScalar occ2;
