@@ -142,7 +142,7 @@ class B2EngineImpl {
 #if !defined(B2_HOSTSIM)
     if (cudaSetDevice(cfg.device) != cudaSuccess) return fail("cudaSetDevice failed (no usable CUDA device)");
     // a per-device function attribute, the same value from every engine of the process
-    if (cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
+    if (cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess)   // (it has a static word: the compaction count)
       return fail("cudaFuncSetAttribute(k_seed) failed");
     if (cudaFuncSetAttribute(k_xext_run, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail("cudaFuncSetAttribute(k_xext_run) failed");
@@ -482,7 +482,7 @@ class B2EngineImpl {
 #else
     if (w.seed_spill.ensure(seed_lanes * 5 * (size_t)(w.max_len + 1) + 8)) return fail("device allocation failed (seeding)");
     if (cfg.seed_span > 0 && w.seed_xfer.ensure((size_t)seed_grid * seed_block * B2_SEED_XFER_BYTES + 256)) return fail("device allocation failed (seeding)");
-    if (seed_smem > (size_t)227 * 1024) return fail("seeding shared-memory configuration exceeds 227 KB per block");
+    if (seed_smem > (size_t)227 * 1024 - 64) return fail("seeding shared-memory configuration exceeds 227 KB per block");
 #endif
     if (w.n_intv.ensure(n + 1) || w.n_tasks.ensure(n + 1) || w.seed_off.ensure(n + 2)) return fail("device allocation failed (seeding)");
     for (;;) {
