@@ -78,7 +78,7 @@ struct Worker {
   DBuf<char> slots, sam_out; DBuf<int32_t> sam_len; DBuf<int64_t> sam_off;
   DBuf<int> flags;
   DBuf<uint8_t> fin_heavy; DBuf<int32_t> fin_list;
-  DBuf<int32_t> sa_task_r; DBuf<uint32_t> sa_task_iv; DBuf<int32_t> dbg_seed; DBuf<uint8_t> seed_xfer;
+  DBuf<int32_t> sa_task_r; DBuf<uint32_t> sa_task_iv; DBuf<int32_t> dbg_seed;
   DBuf<long long> dbg;
   DBuf<int64_t> chain_off; DBuf<B2Reg> cand; DBuf<uint8_t> cand_ok;
   DBuf<int32_t> resc_cnt; DBuf<int64_t> resc_off; DBuf<B2RescTask> resc_tasks; DBuf<B2Kswr> resc_res;
@@ -142,7 +142,7 @@ class B2EngineImpl {
 #if !defined(B2_HOSTSIM)
     if (cudaSetDevice(cfg.device) != cudaSuccess) return fail("cudaSetDevice failed (no usable CUDA device)");
     // a per-device function attribute, the same value from every engine of the process
-    if (cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024 - 64) != cudaSuccess)   // (it has a static word: the compaction count)
+    if (cudaFuncSetAttribute(k_seed, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail("cudaFuncSetAttribute(k_seed) failed");
     if (cudaFuncSetAttribute(k_xext_run, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail("cudaFuncSetAttribute(k_xext_run) failed");
@@ -251,7 +251,7 @@ class B2EngineImpl {
       w.cseeds.release(); w.raw_rid.release(); w.chains.release(); w.n_chain.release(); w.reg_cap.release();
       w.reg_off.release(); w.regs.release(); w.n_regs.release(); w.pe_dir.release(); w.pe_is.release();
       w.pairtab.release(); w.slots.release(); w.sam_out.release(); w.sam_len.release(); w.sam_off.release();
-      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release(); w.big.release(); w.dbg_seed.release(); w.seed_xfer.release();
+      w.flags.release(); w.counters.release(); w.dbg.release(); w.fin_heavy.release(); w.fin_list.release(); w.sa_task_r.release(); w.sa_task_iv.release(); w.big.release(); w.dbg_seed.release();
       w.chain_off.release(); w.cand.release(); w.cand_ok.release();
       w.resc_cnt.release(); w.resc_off.release(); w.resc_tasks.release(); w.resc_res.release();
       w.xext_tasks.release(); w.xext_res.release(); w.xext_key.release(); w.xext_hist.release(); w.xext_perm.release(); w.xext_hoff.release();
@@ -481,8 +481,7 @@ class B2EngineImpl {
     (void)seed_smem; (void)seed3_smem;
 #else
     if (w.seed_spill.ensure(seed_lanes * 5 * (size_t)(w.max_len + 1) + 8)) return fail("device allocation failed (seeding)");
-    if (cfg.seed_span > 0 && w.seed_xfer.ensure((size_t)seed_grid * seed_block * B2_SEED_XFER_BYTES + 256)) return fail("device allocation failed (seeding)");
-    if (seed_smem > (size_t)227 * 1024 - 64) return fail("seeding shared-memory configuration exceeds 227 KB per block");
+    if (seed_smem > (size_t)227 * 1024) return fail("seeding shared-memory configuration exceeds 227 KB per block");
 #endif
     if (w.n_intv.ensure(n + 1) || w.n_tasks.ensure(n + 1) || w.seed_off.ensure(n + 2)) return fail("device allocation failed (seeding)");
     for (;;) {
@@ -490,7 +489,6 @@ class B2EngineImpl {
       c.intv = w.intv.p; c.cap_intv = w.cap_intv; c.n_intv = w.n_intv.p; c.n_tasks = w.n_tasks.p;
       c.seed_scratch = w.seed_scratch.p; c.seed_spill = w.seed_spill.p;
       c.seed_E = seed_E; c.seed_QW = seed_QW; c.seed_RS = seed_RS;
-      c.seed_xfer = cfg.seed_span > 0 ? w.seed_xfer.p : nullptr; c.seed_span = cfg.seed_span;
       b2_dev_memset(w.flags.p, 0, 3 * sizeof(int), w.stream);
       c.dbg_seed = nullptr;
       if (getenv("B200BWA_DEBUG_TIMES")) {

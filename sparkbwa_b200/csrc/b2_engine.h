@@ -58,7 +58,6 @@ struct B2EngineConfig {
   int seed3_blocks_per_sm = 8;                 // forward-only pass: no stack, fewer registers
   int final_fast_bytes = 512;                  // shared memory per task group of k_final_pe: read copy + reference window of an alignment
   int final_heavy_regs = 4;                    // pairs with at least this many regions (both mates) are finalised a warp each, in their own launch (0: no split)
-  int seed_span = 128;                         // k_seed packs its unfinished searches into full warps every this many trips (0: never)
   int seed_smem_entries = 0;                   // interval-stack entries per lane in shared memory (0: what fits)
   size_t scratch_per_lane = 16 << 10;          // every lane's (task group's) own scratch region: sized for the ordinary read / pair
   size_t big_pool_bytes = (size_t)1 << 30;     // outlier pool per stream set: tasks that overflow their region run again in one of its slots (0: none)

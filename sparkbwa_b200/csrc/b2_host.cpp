@@ -1169,7 +1169,6 @@ void b2_engine_config_from_env(B2EngineConfig* cfg) {
   if ((s = getenv("B200BWA_SEED_GRID"))) cfg->seed_grid = atoi(s);
   if ((s = getenv("B200BWA_SEED_BLOCK"))) cfg->seed_block = atoi(s);
   if ((s = getenv("B200BWA_SEED_ENTRIES"))) cfg->seed_smem_entries = atoi(s);
-  if ((s = getenv("B200BWA_SEED_SPAN"))) cfg->seed_span = atoi(s);
   if ((s = getenv("B200BWA_SEED_BPS"))) cfg->seed_blocks_per_sm = atoi(s);
   if ((s = getenv("B200BWA_SEED3_BPS"))) cfg->seed3_blocks_per_sm = atoi(s);
   if ((s = getenv("B200BWA_FINAL_HEAVY"))) cfg->final_heavy_regs = atoi(s);

@@ -17,7 +17,6 @@
 #include "b2_final.cuh"
 
 #define B2_FLAG_OVF_INTV 1
-#define B2_SEED_XFER_BYTES 320   // >= sizeof(B2SeedXfer) of b2_seed_body (checked there)
 #define B2_FLAG_OVF_SCRATCH 2
 #define B2_FLAG_OVF_BIGN 32     // more tasks needed a slot of the outlier pool than it has
 #define B2_FLAG_OVF_SLOT 4
@@ -65,7 +64,6 @@ struct B2Ctx {
   B2Intv* seed_scratch;   // host checker build: per lane max_len+1 stack entries
   uint32_t* seed_spill;   // device: per lane 5*(max_len+1) words for what does not fit the shared-memory part
   int seed_E, seed_QW, seed_RS;  // per lane in shared memory: stack entries, words of 4-bit base codes, re-seed candidates
-  uint8_t* seed_xfer; int seed_span;   // lane compaction of k_seed: hand-over area (B2_SEED_XFER_BYTES per lane), trips between two compactions
   // SA / chaining
   const int64_t* seed_off; int64_t n_seed_tasks;
   int32_t* sa_task_r; uint32_t* sa_task_iv;   // per lookup: read, interval << 16 | rank (k_sa_plan); null: k_sa searches
@@ -148,20 +146,6 @@ B2_D inline void b2_seed_body(const B2Ctx& c) {
   int r = -1, need = 0, trips = 0;
   bool alive = true;
   int32_t* n_out = MODE ? c.n_tasks : c.n_intv;  // (n_tasks holds the pass-3 count until k_seed_fin)
-#if defined(__CUDA_ARCH__)
-  // Lane compaction (passes 1+2).  A batch has about as many reads as the chip has seeding lanes, so a lane gets ONE read,
-  // and reads differ 4x in extension steps (p10 261, p50 582, p99 1 183 at 2x150 bp): a warp lives until its longest
-  // search ends, with half its lanes idle on average -- and a trip costs the same issue slots whatever the number of
-  // lanes in it.  Every c.seed_span trips the block therefore packs its unfinished searches into its first warps: a
-  // search is the B2SeedFsm object (its shared-memory column and spill area are reached through pointers inside it, so
-  // they move with it), handed over through global memory; warps left without a search wait at the next barrier.
-  struct B2SeedXfer { B2SeedFsm<B2SeedMemDev, MODE> m; int r, trips; };
-  static_assert(sizeof(B2SeedXfer) <= B2_SEED_XFER_BYTES, "B2_SEED_XFER_BYTES too small");
-  __shared__ int b2_seed_live;
-  const bool compact = MODE == 0 && c.seed_xfer != 0 && c.seed_span > 0;
-  for (;;) {
-  int span = 0;
-#endif
   for (;;) {
     while (alive && !need) {  // next task of this lane
 #if defined(__CUDA_ARCH__)
@@ -224,29 +208,7 @@ B2_D inline void b2_seed_body(const B2Ctx& c) {
 #endif
       }
     }
-#if defined(__CUDA_ARCH__)
-    if (compact && ++span >= c.seed_span) break;
-#endif
   }
-#if defined(__CUDA_ARCH__)
-  if (!compact) break;
-  __syncthreads();
-  if (threadIdx.x == 0) b2_seed_live = 0;
-  __syncthreads();
-  B2SeedXfer* xb = (B2SeedXfer*)(c.seed_xfer + (size_t)blockIdx.x * blockDim.x * B2_SEED_XFER_BYTES);
-  if (need) {
-    B2SeedXfer& x = xb[atomicAdd(&b2_seed_live, 1)];
-    x.m = m; x.r = r; x.trips = trips;
-  }
-  __syncthreads();
-  const int n_live = b2_seed_live;
-  if (n_live == 0) break;
-  need = 0;
-  alive = (int)threadIdx.x < n_live;   // (a lane without a search has no shared-memory column of its own any more)
-  if (alive) { const B2SeedXfer& x = xb[threadIdx.x]; m = x.m; r = x.r; trips = x.trips; need = 1; }
-  __syncthreads();
-  }
-#endif
   if (occ.n_blk) B2_ATOMIC_ADD(&c.counters[B2_CNT_OCC_BLOCKS], occ.n_blk);
 #if defined(B2_HOSTSIM)
   free(chk); free(m.mem.rsv);
