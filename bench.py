@@ -314,9 +314,13 @@ def main():
     all_batches = cut_batches(n_reads, RL, args.K)
     # strong scaling: the passes of one measurement are queued back to back (like the steps of a training loop: no drain
     # between them), batch b of pass p -> rank (p * n_batches + b) mod N, each with its absolute n_processed
+    deal_rank, deal_world = rank, world
+    if os.environ.get("B200BWA_BENCH_DEAL"):   # "r/w": run, on this one GPU, the share rank r of w ranks would get (debugging aid)
+        deal_rank, deal_world = (int(x) for x in os.environ["B200BWA_BENCH_DEAL"].split("/"))
+
     def dealt(n_pass):
         seq = [bt for _ in range(n_pass) for bt in all_batches]
-        return seq[rank::world]
+        return seq[deal_rank::deal_world]
     batches = all_batches[rank::world]
     stagger_s = float(os.environ.get("B200BWA_BENCH_STAGGER_MS", "0")) / 1e3
     lib.b200bwa_n_workers.argtypes = [ctypes.c_void_p]

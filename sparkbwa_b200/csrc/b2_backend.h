@@ -50,8 +50,16 @@ inline T b2_host_fetch_add(T* p, V v) { T o = *p; *p += (T)v; return o; }
 #define B2_KERNEL_LB(threads, blocks_per_sm) static __global__ void __launch_bounds__(threads, blocks_per_sm)
 #define B2_GTID() ((int)(blockIdx.x * blockDim.x + threadIdx.x))
 #define B2_GSIZE() ((int)(gridDim.x * blockDim.x))
-#define B2_LAUNCH(kern, _g, _b, stream, ...) kern<<<(_g), (_b), 0, (stream)>>>(__VA_ARGS__)
-#define B2_LAUNCH_SMEM(kern, _g, _b, _smem, stream, ...) kern<<<(_g), (_b), (_smem), (stream)>>>(__VA_ARGS__)
+// B200BWA_SYNC_DEBUG=1: wait for every kernel and name the one that faults (diagnosis only: serialises the stream)
+inline void b2_launch_check(const char* name, cudaStream_t s) {
+  static const int dbg = getenv("B200BWA_SYNC_DEBUG") ? atoi(getenv("B200BWA_SYNC_DEBUG")) : 0;
+  if (!dbg) return;
+  cudaError_t e = cudaGetLastError();
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  if (e != cudaSuccess) fprintf(stderr, "[E::b200bwa] kernel %s: %s\n", name, cudaGetErrorString(e));
+}
+#define B2_LAUNCH(kern, _g, _b, stream, ...) do { kern<<<(_g), (_b), 0, (stream)>>>(__VA_ARGS__); b2_launch_check(#kern, (stream)); } while (0)
+#define B2_LAUNCH_SMEM(kern, _g, _b, _smem, stream, ...) do { kern<<<(_g), (_b), (_smem), (stream)>>>(__VA_ARGS__); b2_launch_check(#kern, (stream)); } while (0)
 typedef cudaStream_t b2_stream_t;
 inline int b2_dev_malloc(void** p, size_t n) { return cudaMalloc(p, n ? n : 1) != cudaSuccess; }
 inline void b2_dev_free(void* p) { if (p) cudaFree(p); }

@@ -382,7 +382,13 @@ class B2EngineImpl {
 
   int read_flags(Worker& w, int* f) {
     b2_d2h(f, w.flags.p, sizeof(int), w.stream);
-    if (b2_sync(w.stream)) return fail("device synchronisation failed (kernel fault?)");
+    if (b2_sync(w.stream)) {
+#if !defined(B2_HOSTSIM)
+      return fail(std::string("device synchronisation failed: ") + cudaGetErrorString(cudaGetLastError()));
+#else
+      return fail("device synchronisation failed");
+#endif
+    }
     return check_cuda("kernel");
   }
 
