@@ -377,6 +377,7 @@ B2_NOINLINE B2_HD inline char** b2_gen_alt(const B2Opt& opt, const B2Index& ix, 
     if (cnt[r] > opt.max_XA_hits_alt || (!has_alt[r] && cnt[r] > opt.max_XA_hits)) continue;
     const size_t mk = sc.mark();
     B2Aln t = b2_reg2aln(opt, ix, tb, l_query, query, &a[i], sc, err);
+    if (sc.overflow || t.rid < 0) { sc.overflow = 1; sc.reset(mk); return 0; }   // (no alignment: nothing below may index with it)
     B2Out o; o.p = XA[r] + xlen[r]; o.cap = (long)cnt[r] * per_hit - xlen[r]; o.len = 0;
     const B2Ann& an = ix.anns[t.rid];
     o.putsn(ix.names + an.name_off, an.name_len);
@@ -504,7 +505,7 @@ B2_NOINLINE B2_HD inline void b2_aln2sam(const B2Opt& opt, const B2Index& ix, co
       str.putsn("\tSA:Z:", 6);
       for (i = 0; i < n; ++i) {
         const B2Aln* r = &list[i];
-        if (i == which || (r->flag & 0x100)) continue;
+        if (i == which || (r->flag & 0x100) || r->rid < 0) continue;
         const B2Ann& an = ix.anns[r->rid];
         str.putsn(ix.names + an.name_off, an.name_len); str.putc_(',');
         str.putl(r->pos + 1); str.putc_(',');
@@ -550,6 +551,7 @@ B2_NOINLINE B2_HD inline void b2_reg2sam(const B2Opt& opt, const B2Index& ix, co
     if (l && !p->is_alt && q->mapq > aa[0].mapq) q->mapq = aa[0].mapq;
     ++l;
   }
+  if (sc.overflow) { sc.reset(mk); return; }   // an alignment above is missing (the task runs again with more scratch): no text from it
   if (n_aa == 0) {
     B2Aln t = b2_reg2aln(opt, ix, tb, s.l_seq, s.seq, 0, sc, err);
     t.flag |= extra_flag;
@@ -940,6 +942,7 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
         }
       }
       sc.tick(4);
+      if (sc.overflow) { sc.reset(mk0); return; }   // an alignment above is missing: the task runs again with more scratch
       for (i = 0; i < n_aa[0]; ++i) b2_aln2sam(opt, ix, fmt, out, s[0], n_aa[0], aa[0], i, &h[1]);
       for (i = 0; i < n_aa[1]; ++i) b2_aln2sam(opt, ix, fmt, out, s[1], n_aa[1], aa[1], i, &h[0]);
       sc.tick(5);
@@ -958,6 +961,7 @@ B2_HD inline void b2_sam_pe(const B2Opt& opt, const B2Index& ix, const B2Tables&
     if (which >= 0) h[i] = b2_reg2aln(opt, ix, tb, s[i].l_seq, s[i].seq, &a[i][which], sc, err);
     else h[i] = b2_reg2aln(opt, ix, tb, s[i].l_seq, s[i].seq, 0, sc, err);
   }
+  if (sc.overflow) { sc.reset(mk0); return; }
   if (!(opt.flag & B2_F_NOPAIRING) && h[0].rid == h[1].rid && h[0].rid >= 0) {
     int64_t dist;
     int d = b2_infer_dir(ix.l_pac, a[0][0].rb, a[1][0].rb, &dist);
