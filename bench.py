@@ -16,8 +16,9 @@ Reported on one JSON line:
   sw         DP work: cells of ksw_extend2 + ksw_global2 + local SW over the DP stages' device time
   cpu_baseline  the reference's own `bwa mem -t <host cores>` (oracle/_ref) on a bounded sample
 Multi-GPU (torchrun, one rank per GPU): STRONG scaling of the same job at every N.  `value`: the job's -K
-batches are dealt over the ranks (batch b -> rank b mod N, each with its absolute n_processed), the index image is
-broadcast once over NCCL, no collective on the data path; time = max over ranks.  `e2e`: ONE call of the product entry
+batches are dealt over the ranks (the K passes of the timed region are queued back to back, pass p batch b -> rank
+(p * n_batches + b) mod N, each with its absolute n_processed; no drain between passes, like the steps of a training
+loop), the index image is broadcast once over NCCL, no collective on the data path; time = max over ranks.  `e2e`: ONE call of the product entry
 point on rank 0 drives all N GPUs (one reader, N engines, one ordered SAM file -- what a Spark executor's JNI call
 does); the other ranks wait on the rendezvous store without touching their GPUs.
 """
