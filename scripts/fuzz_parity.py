@@ -1,0 +1,174 @@
+#!/usr/bin/env python
+"""Differential fuzzing of the engine against the oracle (test infrastructure, CPU only).
+
+Every trial draws a reference, a read set and a `bwa mem` option string from a seeded generator, runs the unmodified
+reference (`oracle/_ref/bwa`) and the host build of the kernel bodies (`tests/hostsim/_build/b200bwa_hostsim`, the same
+.cuh code as libbwa.so compiled for the CPU) on the same files and compares the SAM bodies line by line.  A mismatch
+keeps its directory and is appended to the report; the findings of a campaign go into tests/ as fixed cases.
+
+  python scripts/fuzz_parity.py --first 1000 --count 200 --jobs 6 --out /tmp/b2fuzz
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import shutil
+import subprocess
+import sys
+import time
+from concurrent.futures import ProcessPoolExecutor
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+import parity_util as pu  # noqa: E402
+from sparkbwa_b200 import synth  # noqa: E402
+
+
+def draw(seed: int):
+    """(reference kwargs, reads kwargs, option list, interleaved?) of trial `seed`."""
+    r = np.random.default_rng(seed)
+    pick = lambda xs: xs[int(r.integers(0, len(xs)))]  # noqa: E731
+    rep = float(pick([0.0, 0.02, 0.05, 0.2, 0.5, 0.7]))
+    ref_kw = dict(total_len=int(pick([60_000, 150_000, 300_000])), n_contigs=int(pick([1, 2, 3, 5])), seed=seed * 7 + 1,
+                  repeat_frac=rep)
+    if rep >= 0.2:
+        ref_kw.update(rep_len=(int(pick([50, 100, 300])), int(pick([400, 1500, 3000]))), rep_copies=(2, int(pick([6, 20, 60]))),
+                      rep_div=float(pick([0.0, 0.01, 0.04, 0.08])))
+    if r.random() < 0.2:
+        ref_kw["alt"] = dict(n_alt=int(pick([2, 6, 12])), alt_len=(800, 3000), div=float(pick([0.005, 0.02, 0.05])), seed=seed * 7 + 2)
+    read_len = int(pick([30, 36, 50, 76, 100, 125, 150, 150, 200, 250, 300, 500, 800]))
+    paired = bool(r.random() < 0.6)
+    n = int(pick([150, 300, 600])) if read_len <= 250 else int(pick([40, 80, 120]))
+    reads_kw = dict(n=n, read_len=read_len, paired=paired, seed=seed * 7 + 3, sub=float(pick([0.0, 0.005, 0.01, 0.02, 0.05, 0.09])),
+                    indel=float(pick([0.0, 0.001, 0.004, 0.015, 0.03])), n_frac=float(pick([0.0, 0.0, 0.002, 0.02])),
+                    junk_frac=float(pick([0.0, 0.01, 0.05])), chimeric_frac=float(pick([0.0, 0.0, 0.1, 0.3])) if read_len >= 70 else 0.0,
+                    ragged=bool(r.random() < 0.15))
+    if paired:
+        reads_kw.update(ins_mean=float(pick([read_len + 20, 250, 400, 700])), ins_sd=float(pick([5, 40, 120])))
+        if r.random() < 0.4:
+            reads_kw["mate2_sub"] = float(pick([0.05, 0.1, 0.15]))
+    opts = []
+    pool = [
+        (0.25, lambda: ["-a"]), (0.15, lambda: ["-M"]), (0.15, lambda: ["-Y"]), (0.1, lambda: ["-S"]), (0.1, lambda: ["-P"]),
+        (0.1, lambda: ["-j"]), (0.1, lambda: ["-C"]), (0.1, lambda: ["-V"]), (0.1, lambda: ["-1"]),
+        (0.25, lambda: ["-K", str(int(pick([20_000, 50_000, 200_000])))]),
+        (0.15, lambda: ["-k", str(int(pick([10, 15, 17, 23, 30])))]),
+        (0.15, lambda: ["-w", str(int(pick([5, 20, 40, 200])))]),
+        (0.15, lambda: ["-d", str(int(pick([20, 50, 200])))]),
+        (0.15, lambda: ["-r", pick(["1.0", "1.2", "2.5", "10"])]),
+        (0.1, lambda: ["-y", str(int(pick([0, 4, 8, 50])))]),
+        (0.15, lambda: ["-c", str(int(pick([5, 20, 100, 2000])))]),
+        (0.1, lambda: ["-D", pick(["0.1", "0.3", "0.8"])]),
+        (0.1, lambda: ["-W", str(int(pick([10, 30, 40])))]),
+        (0.1, lambda: ["-m", str(int(pick([0, 3, 10, 100])))]),
+        (0.15, lambda: ["-A", str(int(pick([1, 2, 3])))]),
+        (0.15, lambda: ["-B", str(int(pick([1, 2, 4, 6, 9])))]),
+        (0.15, lambda: ["-O", pick(["0", "1", "4", "6,8", "10,3"])]),
+        (0.15, lambda: ["-E", pick(["1", "2", "1,3", "3,1"])]),
+        (0.15, lambda: ["-L", pick(["0", "3", "5,9", "12,0", "40"])]),
+        (0.15, lambda: ["-U", str(int(pick([0, 5, 9, 17, 40])))]),
+        (0.2, lambda: ["-T", str(int(pick([0, 10, 20, 30, 45])))]),
+        (0.1, lambda: ["-h", pick(["1", "3", "5,300", "20"])]),
+        (0.1, lambda: ["-Q", str(int(pick([0, 10, 30])))]),
+        (0.1, lambda: ["-G", str(int(pick([50, 1000, 100000])))]),
+        (0.1, lambda: ["-N", str(int(pick([1, 5, 25])))]),
+        (0.1, lambda: ["-s", str(int(pick([1, 5, 30])))]),
+        (0.1, lambda: ["-X", pick(["0.3", "0.7", "0.95"])]),
+        (0.1, lambda: ["-R", r"@RG\tID:fz\tSM:s\tPL:x"]),
+        (0.1, lambda: ["-I", pick(["300", "400,40", "350,60,900", "300,30,700,100"])]),
+        (0.08, lambda: ["-x", pick(["pacbio", "ont2d", "intractg"])]),
+    ]
+    for p, mk in pool:
+        if r.random() < p:
+            opts += mk()
+    inter = paired and r.random() < 0.15
+    return ref_kw, reads_kw, opts, inter
+
+
+def trial(args):
+    seed, outdir, keep = args
+    ref_kw, reads_kw, opts, inter = draw(seed)
+    d = os.path.join(outdir, f"t{seed}")
+    shutil.rmtree(d, ignore_errors=True)
+    os.makedirs(d)
+    rec = dict(seed=seed, ref=ref_kw, reads=reads_kw, opts=opts, interleaved=inter)
+    t0 = time.time()
+    try:
+        kw = dict(ref_kw)
+        alt_kw = kw.pop("alt", None)
+        ctg = synth.make_reference(**kw)
+        alt = []
+        if alt_kw:
+            ctg, alt = synth.add_alt_contigs(ctg, **alt_kw)
+        fa = os.path.join(d, "ref.fa")
+        synth.write_fasta(fa, ctg)
+        if alt:
+            with open(fa + ".alt", "w") as f:
+                f.write("@SQ\tSN:chr1\tLN:1\n")
+                for nm in alt:
+                    f.write(f"{nm}\t0\tchr1\t1\t60\t100M\t*\t0\t0\t*\t*\n")
+        pu.run([pu.ORACLE, "index", fa])
+        r1, r2 = synth.simulate_reads(ctg, **reads_kw)
+        fq = [os.path.join(d, "r_1.fq")]
+        synth.write_fastq(fq[0], r1)
+        if r2 is not None:
+            fq.append(os.path.join(d, "r_2.fq"))
+            synth.write_fastq(fq[1], r2)
+        case = dict(dir=d, ref=fa, opts=opts, paired=reads_kw["paired"], fq=fq)
+        if inter:
+            case["fq"] = [pu.make_interleaved(case)]
+            case["opts"] = opts + ["-p"]
+        ro = subprocess.run([pu.ORACLE, "mem"] + case["opts"] + [fa] + case["fq"], stdout=open(os.path.join(d, "oracle.sam"), "wb"),
+                            stderr=subprocess.PIPE, timeout=1200)
+        env = dict(os.environ, **pu.HOSTSIM_ENV)
+        re_ = subprocess.run([pu.HOSTSIM, "mem"] + case["opts"] + ["-f", os.path.join(d, "engine.sam"), fa] + case["fq"],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=2400)
+        rec["rc_oracle"], rec["rc_engine"] = ro.returncode, re_.returncode
+        if ro.returncode != 0 or re_.returncode != 0:
+            # both refusing the same option string is agreement; one side alone is a finding
+            rec["ok"] = (ro.returncode != 0) == (re_.returncode != 0)
+            rec["stderr_engine"] = re_.stderr.decode(errors="replace")[-600:]
+            rec["stderr_oracle"] = ro.stderr.decode(errors="replace")[-300:]
+        else:
+            diff = pu.first_diff(os.path.join(d, "oracle.sam"), os.path.join(d, "engine.sam"))
+            rec["ok"] = not diff
+            rec["lines"] = len(pu.sam_body(os.path.join(d, "oracle.sam")))
+            if diff:
+                rec["diff"] = diff
+    except Exception as e:  # noqa: BLE001
+        rec["ok"] = False
+        rec["error"] = repr(e)[:600]
+    rec["seconds"] = round(time.time() - t0, 1)
+    if rec["ok"] and not keep:
+        shutil.rmtree(d, ignore_errors=True)
+    return rec
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--first", type=int, default=1000)
+    ap.add_argument("--count", type=int, default=100)
+    ap.add_argument("--jobs", type=int, default=4)
+    ap.add_argument("--out", default="/tmp/b2fuzz")
+    ap.add_argument("--keep", action="store_true")
+    a = ap.parse_args()
+    assert pu.have_oracle() and os.access(pu.HOSTSIM, os.X_OK), "build oracle/_ref and tests/hostsim first"
+    os.makedirs(a.out, exist_ok=True)
+    rep = os.path.join(a.out, "report.jsonl")
+    n_ok = n_bad = 0
+    with ProcessPoolExecutor(a.jobs) as ex, open(rep, "a") as f:
+        for rec in ex.map(trial, [(s, a.out, a.keep) for s in range(a.first, a.first + a.count)]):
+            f.write(json.dumps(rec) + "\n")
+            f.flush()
+            n_ok += rec["ok"]
+            n_bad += not rec["ok"]
+            if not rec["ok"]:
+                print("MISMATCH", json.dumps(rec)[:1500], flush=True)
+    print(f"trials {n_ok + n_bad}: {n_ok} identical, {n_bad} findings; report {rep}")
+
+
+if __name__ == "__main__":
+    main()
