@@ -414,8 +414,9 @@ struct B2SeedMemHost {  // plain arrays (host checker build)
 };
 
 #if defined(__CUDACC__)
-// Device: per lane E stack entries of three words {x0.lo, x2.lo, x0.hi | x2.hi << 8 | info << 16} (the engine refuses
-// indexes of 2^40 symbols or more and runs reads of 65 536 bases or more through the spill path only), QW words of
+// Device: per lane E stack entries of three words {x0.lo, x2.lo, x0.hi | x2.hi << 4 | info << 8}: four high bits for each
+// interval bound and 24 bits for the query end (the engine refuses indexes of 2^36 symbols or more -- a 34 Gbp
+// reference -- and reads of 2^24 bases or more), QW words of
 // 4-bit base codes and RS candidate pairs, all word-transposed over the block's lanes (bank-conflict free).
 // Deeper stack entries, longer reads and further candidates spill to a per-lane global array.
 // x[1] -- the interval of the reverse complement -- is not kept on the stack: backward extension only passes it
@@ -451,13 +452,13 @@ struct B2SeedMemDev {
     uint32_t w[3];
     if (i < E) { const uint32_t* a = s + (size_t)i * 3 * stride; w[0] = a[0]; w[1] = a[stride]; w[2] = a[2 * stride]; }
     else b2_spill_get3(g + (size_t)(i - E) * 3, w);
-    v.x[0] = (uint64_t)(w[2] & 0xff) << 32 | w[0];
+    v.x[0] = (uint64_t)(w[2] & 0xf) << 32 | w[0];
     v.x[1] = 0;
-    v.x[2] = (uint64_t)(w[2] >> 8 & 0xff) << 32 | w[1];
-    v.info = w[2] >> 16;
+    v.x[2] = (uint64_t)(w[2] >> 4 & 0xf) << 32 | w[1];
+    v.info = w[2] >> 8;
   }
   __device__ inline void put(int i, const B2Intv& v) {
-    const uint32_t w2 = (uint32_t)(v.x[0] >> 32) | (uint32_t)(v.x[2] >> 32) << 8 | (uint32_t)v.info << 16;
+    const uint32_t w2 = (uint32_t)(v.x[0] >> 32) | (uint32_t)(v.x[2] >> 32) << 4 | (uint32_t)v.info << 8;
     if (i < E) { uint32_t* a = s + (size_t)i * 3 * stride; a[0] = (uint32_t)v.x[0]; a[stride] = (uint32_t)v.x[2]; a[2 * stride] = w2; }
     else b2_spill_put3(g + (size_t)(i - E) * 3, (uint32_t)v.x[0], (uint32_t)v.x[2], w2);
   }

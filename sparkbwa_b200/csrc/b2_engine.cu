@@ -121,7 +121,7 @@ class B2EngineImpl {
   DBuf<double> d_logtab; DBuf<char> d_rg;
   bool owns_index = true;
   size_t bwt_bytes = 0, sa_bytes = 0, pac_bytes = 0;
-  int n_log = 1 << 16;
+  int n_log = 1 << 21;   // log(i) for every length a read of up to ~1 Mbp can produce (region spans reach twice the read length)
   B2Fmt fmt{};
   std::vector<Worker> workers;
   std::atomic<size_t> grown_big_slot{0};
@@ -147,7 +147,7 @@ class B2EngineImpl {
     if (cudaFuncSetAttribute(k_xext_run, cudaFuncAttributeMaxDynamicSharedMemorySize, 227 * 1024) != cudaSuccess)
       return fail("cudaFuncSetAttribute(k_xext_run) failed");
 #endif
-    if (h.seq_len >= (1ull << 40)) return fail("index too large: the seeding kernel packs interval bounds into 40 bits");
+    if (h.seq_len >= (1ull << 36)) return fail("index too large: the seeding kernel packs interval bounds into 36 bits");
     ix.primary = h.primary; ix.seq_len = h.seq_len;
     for (int i = 0; i < 5; ++i) ix.L2[i] = h.L2[i];
     ix.bwt_size = h.bwt_words ? h.bwt_words : h.bwt.size(); ix.n_sa = h.n_sa ? h.n_sa : h.sa.size();
@@ -461,6 +461,7 @@ class B2EngineImpl {
     // ---- seeding ----
     // one read per lane; the lane count is what fits on the chip at once (shared-memory interval stacks), the
     // lanes pull reads from a cursor
+    if (w.max_len >= (1 << 24)) return fail("read of 16 777 216 bases or more (the seeding kernel keeps query positions in 24 bits)");
     const int seed_block = cfg.seed_block;
     int seed_QW = std::min((w.max_len + 7) / 8, 32), seed_RS = 4, seed_E;
     {  // split the per-lane share of the SM's shared memory: bases, candidates, the rest for the interval stack
@@ -508,7 +509,10 @@ class B2EngineImpl {
       w.times.launches += 3;
       if (read_flags(w, &flags)) return 1;
       if (!(flags & B2_FLAG_OVF_INTV)) break;
-      if (w.cap_intv >= 8192) return fail("seed interval capacity exceeded");
+      // a long read seeded with a short -k has more intervals than bases (re-seeding, bwamem.c:131-144): past 8 192
+      // entries per read the table keeps doubling for as long as the whole batch's stays within 4 GB
+      if (w.cap_intv >= 8192 && (size_t)n * (size_t)w.cap_intv * 2 * sizeof(B2Intv) > ((size_t)4 << 30))
+        return fail("seed interval capacity exceeded");
       w.cap_intv *= 2;
     }
     if (c.dbg_seed) {   // extension steps per read: how uneven the lanes' work is (one read per lane)
@@ -856,7 +860,10 @@ class B2EngineImpl {
       if (!(flags & (OVF_ANY | B2_FLAG_OVF_SLOT))) break;
       if (flags & OVF_ANY) grow_scratch(flags);
       if (flags & B2_FLAG_OVF_SLOT) {
-        if (w.slot_size > (1 << 24)) return fail("SAM slot limit exceeded");
+        // (a long read printed with -a -Y repeats its full sequence in every record: past 16 MB per read the slots keep
+        // doubling while the batch's stay within 8 GB)
+        if (w.slot_size > (1 << 24) && (w.slot_size >= (1 << 29) || (size_t)n_items * (size_t)w.slot_size * 2 > ((size_t)8 << 30)))
+          return fail("SAM slot limit exceeded");
         w.slot_size *= 2;
       }
     }

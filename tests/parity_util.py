@@ -65,6 +65,14 @@ CASES = {
                      dict(n=80, read_len=1200, paired=False, seed=95, sub=0.10, indel=0.05, chimeric_frac=0.2), ["-x", "ont2d"]),
     "se_intractg2000": (dict(total_len=300_000, n_contigs=2, seed=97, repeat_frac=0.3, rep_len=(100, 800), rep_copies=(3, 20), rep_div=0.05),
                         dict(n=80, read_len=2000, paired=False, seed=99, sub=0.01, indel=0.002, chimeric_frac=0.3), ["-x", "intractg"]),
+    # found by scripts/fuzz_parity.py: 2.5 kb reads seeded with -k 5 on a repeat-rich reference have more than 8 192 seed
+    # intervals per read (re-seeding, bwamem.c:131-144), which the interval table once refused to grow to
+    "se_k5_long2500": (dict(total_len=80_000, n_contigs=2, seed=7005482, repeat_frac=0.8, rep_len=(60, 250), rep_copies=(2, 10), rep_div=0.02),
+                       dict(n=20, read_len=2500, paired=False, seed=7005484, sub=0.2, indel=0.0, junk_frac=0.1, chimeric_frac=0.6),
+                       ["-a", "-S", "-k", "5"]),
+    # reads beyond 65 535 bases (query positions no longer fit 16 bits; lengths beyond the first 2^16 log-table entries)
+    "se_ont2d_70k": (dict(total_len=600_000, n_contigs=2, seed=5, repeat_frac=0.1, rep_len=(100, 800), rep_copies=(2, 10), rep_div=0.05),
+                     dict(n=3, read_len=70_000, paired=False, seed=9, sub=0.08, indel=0.03, chimeric_frac=0.5), ["-x", "ont2d"]),
     "pe_small": (dict(total_len=200_000, n_contigs=2, seed=41, repeat_frac=0.20, rep_len=(200, 1500), rep_copies=(2, 12)),
                  dict(n=400, read_len=125, paired=True, seed=43, sub=0.015, indel=0.002, mate2_sub=0.05, chimeric_frac=0.05), []),
 }

@@ -64,7 +64,7 @@ def test_hostsim_matches_golden(hostsim, tmp_path, args, gold):
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("name", ["se100", "pe150", "se250", "pe_rescue", "pe_repeat", "pe250", "pe_chimeric", "se_short", "se_long900",
-                                  "se_pacbio1500", "pe_alt", "se_alt", "se_ont2d1200", "se_intractg2000"])
+                                  "se_pacbio1500", "pe_alt", "se_alt", "se_ont2d1200", "se_intractg2000", "se_k5_long2500", "se_ont2d_70k"])
 def test_hostsim_matches_oracle(hostsim, workdir, name):
     c = pu.make_case(workdir, name)
     ref = pu.oracle_sam(c)
