@@ -88,7 +88,8 @@ int b200bwa_set_options(b200bwa_index_t* idx, const char* mem_options);
  *   seq_off[n+1]     start of read i in seq/qual (seq_off[n] = total)
  *   names            NUL-separated read names, one per read (the /1 /2 suffix already trimmed)
  *   n_processed      absolute index of the first read of this batch within the whole run
- *   paired           non-zero: paired-end
+ *   paired           non-zero: paired-end; the two reads of a pair must then carry the same name, as in the reference
+ *                    (bwa/bwamem_pair.c:355,385: "paired reads have different names" ends its run) -- rc 1 otherwise
  * Returns 0 on success. */
 int b200bwa_align_batch(b200bwa_index_t* idx, int n_reads, const char* seq, const char* qual,
                         const int64_t* seq_off, const char* names, int64_t n_processed, int paired,

@@ -94,7 +94,7 @@ def draw_extreme(seed: int):
 
 def draw(seed: int):
     """(reference kwargs, reads kwargs, option list, interleaved?) of trial `seed` (seeds >= 1 000 000: draw_extreme)."""
-    if seed >= 1_000_000:
+    if 1_000_000 <= seed < 3_000_000:
         return draw_extreme(seed)
     r = np.random.default_rng(seed)
     pick = lambda xs: xs[int(r.integers(0, len(xs)))]  # noqa: E731
@@ -155,6 +155,52 @@ def draw(seed: int):
     return ref_kw, reads_kw, opts, inter
 
 
+def write_mangled(path: str, reads, r, style):
+    """FASTQ / FASTA text the way real files vary (kseq semantics, bwa/kseq.h:175-215): CR/LF, blank lines, '+name' lines,
+    comments after the name, lower case and ambiguity codes, empty records, FASTA records, a missing final newline, gzip.
+    (No '-' in reads: nst_nt4_table gives it code 5, with which the reference indexes past a row of its 5x5 scoring matrix
+    and prints a NUL byte into SEQ -- undefined input, not reproduced.)"""
+    import gzip
+    eol = b"\r\n" if style["crlf"] else b"\n"
+    out = bytearray()
+    for k, (name, seq, qual) in enumerate(reads):
+        if style["comment"] and r.random() < 0.5:
+            name = name + (b" " if r.random() < 0.7 else b"\t") + b"BC:Z:ACGT%d" % k
+        if style["lower"] and r.random() < 0.3:
+            seq = seq.lower()
+        if style["iupac"] and len(seq) > 3 and r.random() < 0.2:
+            b = bytearray(seq); b[int(r.integers(0, len(b)))] = ord(str(r.choice(list("RYKMSW.nX*")))); seq = bytes(b)
+        if style["empty"] and r.random() < 0.03:
+            seq, qual = b"", b""
+        if style["fasta"] == 2 or (style["fasta"] == 1 and k % 3 == 1):
+            out += b">" + name + eol
+            w = style["fold"]
+            for p in range(0, max(len(seq), 1), w):
+                out += seq[p:p + w] + eol
+        else:
+            out += b"@" + name + eol + seq + eol + (b"+" + (name.split()[0] if style["plusname"] else b"")) + eol + qual + eol
+        if style["blank"] and r.random() < 0.1:
+            out += eol
+    if style["no_final_eol"] and out.endswith(eol):
+        del out[-len(eol):]
+    if style.get("truncate") and len(out) > 400:   # a file cut off in mid-record (kseq returns -2 / EOF: the reader stops there)
+        del out[len(out) - int(r.integers(1, 400)):]
+    if style["gz"]:
+        path += ".gz"
+        with gzip.open(path, "wb", compresslevel=1) as f:
+            f.write(bytes(out))
+    else:
+        with open(path, "wb") as f:
+            f.write(bytes(out))
+    return path
+
+
+def draw_style(r):
+    pr = lambda p: bool(r.random() < p)  # noqa: E731
+    return dict(crlf=pr(0.2), comment=pr(0.3), lower=pr(0.2), iupac=pr(0.2), empty=pr(0.15), fasta=int(r.choice([0, 0, 0, 1, 2])),
+                fold=int(r.choice([60, 7, 100000])), plusname=pr(0.2), blank=pr(0.3), no_final_eol=pr(0.25), gz=pr(0.15), truncate=pr(0.2))
+
+
 def trial(args):
     seed, outdir, keep, engine = args
     ref_kw, reads_kw, opts, inter = draw(seed)
@@ -185,12 +231,26 @@ def trial(args):
             shutil.rmtree(d, ignore_errors=True)
             return rec
         fq = [os.path.join(d, "r_1.fq")]
-        synth.write_fastq(fq[0], r1)
-        if r2 is not None:
-            fq.append(os.path.join(d, "r_2.fq"))
-            synth.write_fastq(fq[1], r2)
+        if 3_000_000 <= seed < 4_000_000:   # "format" trials: the content of a regular trial in irregular files
+            fr = np.random.default_rng(seed + 17)
+            style = draw_style(fr)
+            rec["style"] = [dict(style)]
+            fq[0] = write_mangled(fq[0], r1, fr, style)
+            if r2 is not None:
+                if fr.random() < 0.5:   # the mates' files need not be written alike
+                    style = draw_style(fr)
+                    style["empty"] = False
+                rec["style"].append(dict(style))
+                if fr.random() < 0.1:
+                    r2 = r2[:max(1, len(r2) - int(fr.integers(1, 4)))]   # the 2nd file has fewer sequences (bwa/bwa.c:66-69)
+                fq.append(write_mangled(os.path.join(d, "r_2.fq"), r2, fr, style))
+        else:
+            synth.write_fastq(fq[0], r1)
+            if r2 is not None:
+                fq.append(os.path.join(d, "r_2.fq"))
+                synth.write_fastq(fq[1], r2)
         case = dict(dir=d, ref=fa, opts=opts, paired=reads_kw["paired"], fq=fq)
-        if inter:
+        if inter and not (3_000_000 <= seed < 4_000_000):
             case["fq"] = [pu.make_interleaved(case)]
             case["opts"] = opts + ["-p"]
         ro = subprocess.run([pu.ORACLE, "mem"] + case["opts"] + [fa] + case["fq"], stdout=open(os.path.join(d, "oracle.sam"), "wb"),

@@ -36,6 +36,7 @@ template <class T, class V>
 inline T b2_host_fetch_add(T* p, V v) { T o = *p; *p += (T)v; return o; }
 #define B2_ATOMIC_ADD(p, v) b2_host_fetch_add((p), (v))
 #define B2_ATOMIC_CAS(p, cmp, val) (*(p) == (cmp) ? (*(p) = (val), (cmp)) : *(p))
+#define B2_ATOMIC_MIN(p, v) (*(p) = *(p) < (v) ? *(p) : (v))
 #define B2_WARP_LANES 1
 #define B2_TASK_GROUP 1
 #define B2_G_EXT 1
@@ -72,6 +73,7 @@ inline void b2_host_free(void* p) { if (p) cudaFreeHost(p); }
 #define B2_ATOMIC_OR(p, v) atomicOr((p), (v))
 #define B2_ATOMIC_ADD(p, v) atomicAdd((p), (v))
 #define B2_ATOMIC_CAS(p, cmp, val) atomicCAS((p), (cmp), (val))
+#define B2_ATOMIC_MIN(p, v) atomicMin((p), (v))
 #define B2_WARP_LANES 32
 #define B2_TASK_GROUP B2_TASK_LANES
 // Lanes per task of the group-cooperative kernels.  The chain-extension kernel runs the register-resident row-parallel

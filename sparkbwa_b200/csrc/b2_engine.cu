@@ -682,7 +682,12 @@ class B2EngineImpl {
 
     // ---- insert-size statistics (batch-wide barrier) ----
     const int n_items = pe ? n >> 1 : n;
+    int bad_pair = 0x7f7f7f7f;
     if (pe) {
+      b2_dev_memset(w.flags.p + 6, 0x7f, sizeof(int), w.stream);
+      B2_LAUNCH(k_pair_names, (n_items + 255) / 256, 256, w.stream, c, w.flags.p + 6);
+      ++w.times.launches;
+      b2_d2h(&bad_pair, w.flags.p + 6, sizeof(int), w.stream);   // (read after the stage's closing synchronisation below)
       if (pes0) memcpy(c.pes, pes0, sizeof(B2Pes) * 4);
       else {
         if (w.pe_dir.ensure(n_items + 1) || w.pe_is.ensure(n_items + 1)) return fail("device allocation failed");
@@ -715,6 +720,18 @@ class B2EngineImpl {
       if (!tab.empty()) b2_h2d(w.pairtab.p, tab.data(), tab.size() * sizeof(double), w.stream);
       for (int d = 0; d < 4; ++d) c.tb.pairtab[d] = w.pairtab.p + offs[d];
       b2_sync(w.stream);
+      if (bad_pair != 0x7f7f7f7f) {   // as the reference: the run ends here (it exits; this call returns 1)
+        std::string nm[2];
+        for (int k = 0; k < 2; ++k) {
+          int64_t off = 0; int32_t len = 0;
+          b2_d2h(&off, c.b.name_off + 2 * bad_pair + k, sizeof(off), w.stream);
+          b2_d2h(&len, c.b.l_name + 2 * bad_pair + k, sizeof(len), w.stream);
+          b2_sync(w.stream);
+          nm[k].resize((size_t)(len > 0 ? len : 0));
+          if (len > 0) { b2_d2h(&nm[k][0], c.b.names + off, (size_t)len, w.stream); b2_sync(w.stream); }
+        }
+        return fail("[mem_sam_pe] paired reads have different names: \"" + nm[0] + "\", \"" + nm[1] + "\"");
+      }
     }
     int ev_pes0 = w.timer.mark();
     // ---- mate-rescue attempts as independent SW tasks ------------------------------------------------

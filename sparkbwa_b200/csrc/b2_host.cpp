@@ -1418,9 +1418,10 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   if (shard_world > 1 && out_path) fidx = fopen((std::string(out_path) + ".batches").c_str(), "w");
   std::string hdr = b2_sam_header(*host, m.hdr_line, pg_cmdline ? pg_cmdline : "");
   int64_t next_off = 0;  // positioned mode: where the next unassigned batch goes
+  int64_t hdr_bytes = 0; // length of the header: what a failed run leaves behind
   bool write_failed = false;
   if (shard_rank == 0) {
-    if (positioned) { if (!pwrite_all(hdr.data(), hdr.size(), 0)) write_failed = true; next_off = (int64_t)hdr.size(); }
+    if (positioned) { if (!pwrite_all(hdr.data(), hdr.size(), 0)) write_failed = true; next_off = hdr_bytes = (int64_t)hdr.size(); }
     else fwrite(hdr.data(), 1, hdr.size(), out);
   }
 
@@ -1724,6 +1725,9 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     if (!rc && ftruncate(out_fd, (off_t)next_off) != 0) { rc = 1; errmsg = "cannot set the final size of the SAM output"; }
     if (times0) fprintf(stderr, "[T::b200bwa] output truncated to size at %.1f ms\n", (b2_realtime() - t_real) * 1e3);
   }
+  // a failed run leaves the header alone: the batches behind it were written at their final offsets as they finished, so
+  // the reserved range has holes (and, mapped, its fallocate()d length)
+  if (rc && positioned && ftruncate(out_fd, (off_t)hdr_bytes) != 0) {}
   if (rc) {
     std::string em = errmsg;
     for (B2Engine* e : engs) if (em.empty() && e->last_error()[0]) em = e->last_error();

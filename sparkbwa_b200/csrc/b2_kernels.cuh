@@ -760,6 +760,20 @@ B2_KERNEL k_pestat(B2Ctx c) {
   }
 }
 
+// The two reads of a pair must carry the same name (after bseq_read's /1 /2 trimming): mem_sam_pe stops the reference's
+// run on the first pair that does not (bwa/bwamem_pair.c:355,385) -- the sign of mate files that are out of step.
+// *first_bad = lowest such pair of the batch.
+B2_KERNEL k_pair_names(B2Ctx c, int* first_bad) {
+  const int n_pairs = c.b.n_reads >> 1;
+  for (int i = B2_GTID(); i < n_pairs; i += B2_GSIZE()) {
+    const int la = c.b.l_name[2 * i];
+    bool same = la == c.b.l_name[2 * i + 1];
+    const char *a = c.b.names + c.b.name_off[2 * i], *b = c.b.names + c.b.name_off[2 * i + 1];
+    for (int k = 0; same && k < la; ++k) same = a[k] == b[k];
+    if (!same) B2_ATOMIC_MIN(first_bad, i);
+  }
+}
+
 // mode 0: count the planned rescue attempts of every pair; mode 1: write them at resc_off[pair]
 B2_KERNEL k_resc_plan(B2Ctx c, int mode) {
   const int n_pairs = c.b.n_reads >> 1;

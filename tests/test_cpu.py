@@ -222,6 +222,26 @@ def test_register_resident_coop_dp_equals_scalar(tmp_path):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_paired_names_must_match(hostsim, workdir):
+    """Mate files that are out of step: mem_sam_pe ends the reference's run on the first pair whose reads carry different
+    names (bwa/bwamem_pair.c:355,385; it exits with status 1).  The engine returns 1 with the same message instead of
+    aligning the wrong reads to each other, and leaves a well-formed (header-only) file.  Found by scripts/fuzz_parity.py."""
+    c = pu.make_case(workdir, "pe_small")
+    bad = os.path.join(c["dir"], "r_2_shifted.fq")
+    recs = open(c["fq"][1], "rb").read().split(b"\n")
+    with open(bad, "wb") as f:   # drop the 11th record of mate 2: every later pair is mismatched
+        f.write(b"\n".join(recs[:40] + recs[44:]))
+    r = subprocess.run([pu.ORACLE, "mem", c["ref"], c["fq"][0], bad], stdout=subprocess.DEVNULL, stderr=subprocess.PIPE)
+    assert r.returncode == 1 and b"paired reads have different names" in r.stderr
+    out = os.path.join(c["dir"], "shifted.sam")
+    e = subprocess.run([hostsim, "mem", "-f", out, c["ref"], c["fq"][0], bad], stdout=subprocess.PIPE, stderr=subprocess.PIPE,
+                       env=dict(os.environ, **pu.HOSTSIM_ENV))
+    assert e.returncode == 1
+    assert b'paired reads have different names: "r10", "r11"' in e.stderr, e.stderr[-500:]
+    assert all(l.startswith(b"@") for l in open(out, "rb").read().splitlines())
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_hostsim_smart_pairing(hostsim, workdir):
     """-p (bwa/fastmap.c:64-83): interleaved input with single-end reads mixed in, several -K batches."""
     c = pu.make_case(workdir, "pe_small")

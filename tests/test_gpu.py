@@ -161,6 +161,21 @@ def test_smart_pairing(workdir):
     assert not pu.first_diff(ref, our)
 
 
+def test_paired_names_must_match(workdir):
+    """Out-of-step mate files end the run with the reference's message and status 1 (bwa/bwamem_pair.c:355,385), in the
+    middle of a multi-batch job too; the output file is cut back to its header."""
+    c = pu.make_case(workdir, "pe_small")
+    bad = os.path.join(c["dir"], "r_2_shifted.fq")
+    recs = open(c["fq"][1], "rb").read().split(b"\n")
+    with open(bad, "wb") as f:   # drop record 300 of mate 2: with -K 30000 the first batches are still in step
+        f.write(b"\n".join(recs[:1200] + recs[1204:]))
+    out = os.path.join(c["dir"], "shifted.sam")
+    e = subprocess.run([pu.CLI, "mem", "-K", "30000", "-f", out, c["ref"], c["fq"][0], bad], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert e.returncode == 1
+    assert b"paired reads have different names" in e.stderr, e.stderr[-500:]   # (which batch reports first is a race)
+    assert all(l.startswith(b"@") for l in open(out, "rb").read().splitlines())  # a failed run leaves the header alone
+
+
 def _config_scale_index(tmp_path_factory, ref_len):
     """100 Mbp-class synthetic reference + index files written by the GPU builder, cached in /dev/shm."""
     import sys
