@@ -259,6 +259,8 @@ def trial(args):
             binary, env = pu.CLI, dict(os.environ, B200BWA_WORKERS=os.environ.get("B200BWA_WORKERS", "2"))
         else:
             binary, env = pu.HOSTSIM, dict(os.environ, **pu.HOSTSIM_ENV)
+        for kv in filter(None, os.environ.get("FUZZ_ENGINE_ENV", "").split(",")):   # e.g. tiny capacities: every overflow / retry path
+            env[kv.split("=", 1)[0]] = kv.split("=", 1)[1]
         re_ = subprocess.run([binary, "mem"] + case["opts"] + ["-f", os.path.join(d, "engine.sam"), fa] + case["fq"],
                              stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env, timeout=120 if engine == "gpu" else 2400)
         rec["rc_oracle"], rec["rc_engine"] = ro.returncode, re_.returncode
