@@ -347,6 +347,19 @@ def test_in_kernel_dp_paths_match_oracle(workdir, name):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+@pytest.mark.parametrize("name", ["pe_small", "pe_repeat", "se_long900"])
+def test_capacity_retry_paths_on_device(workdir, name):
+    """Deliberately tiny per-lane regions, outlier-pool slots, interval tables and SAM slots: on the device too every
+    stage must notice the overflow, run the task again in a pool slot or grow the buffer and re-run, and still produce
+    the reference's SAM (the host-build twin is test_capacity_retry_paths; round 2's only device fault sat on such a path)."""
+    c = pu.make_case(workdir, name)
+    ref = pu.oracle_sam(c)
+    env = {"B200BWA_SCRATCH": "1024", "B200BWA_BIG_SLOT": "4096", "B200BWA_BIG_POOL": str(1 << 20), "B200BWA_CAP_INTV": "2",
+           "B200BWA_SLOT": "64", "B200BWA_WORKERS": "2"}
+    assert not pu.first_diff(ref, pu.engine_sam(c, pu.CLI, env=env))
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 @pytest.mark.parametrize("env", [{"B200BWA_FINAL_HEAVY": "0"}, {"B200BWA_FINAL_HEAVY": "2"}, {"B200BWA_FINAL_HEAVY": "1000"},
                                  {"B200BWA_FINAL_FAST": "0"}, {"B200BWA_FINAL_FAST": "64"}],
                          ids=["one-launch", "every-pair-a-warp", "no-pair-listed", "no-shared-arena", "tiny-shared-arena"])
