@@ -27,7 +27,6 @@ inline void b2_dev_free(void* p) { free(p); }
 inline int b2_h2d(void* d, const void* h, size_t n, b2_stream_t) { memcpy(d, h, n); return 0; }
 inline int b2_d2h(void* h, const void* d, size_t n, b2_stream_t) { memcpy(h, d, n); return 0; }
 inline int b2_dev_memset(void* d, int v, size_t n, b2_stream_t) { memset(d, v, n); return 0; }
-extern int b2_g_blocking_sync;
 inline int b2_sync(b2_stream_t) { return 0; }
 inline int b2_host_alloc(void** p, size_t n) { *p = malloc(n ? n : 1); return *p ? 0 : 1; }
 inline void b2_host_free(void* p) { free(p); }

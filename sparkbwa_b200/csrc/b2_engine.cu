@@ -21,7 +21,6 @@ struct B2GalnStatsPrinter { ~B2GalnStatsPrinter() { fprintf(stderr, "[D::galn] r
 #include <atomic>
 #include <chrono>
 #include <mutex>
-int b2_g_blocking_sync = 0;
 std::atomic<unsigned long long> b2_g_h2d_bytes{0}, b2_g_d2h_bytes{0}, b2_g_launches{0};
 
 namespace {

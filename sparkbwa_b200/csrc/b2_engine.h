@@ -135,7 +135,6 @@ class B2Engine {
   B2EngineImpl* impl_;
 };
 
-extern int b2_g_blocking_sync;   // stream waits block instead of spinning (set per call by b2_mem_main)
 // number of usable CUDA devices (0 when there is none)
 int b2_device_count();
 

@@ -1427,11 +1427,6 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
 
   const B2Pes* pes0 = m.has_pes0 ? m.pes0 : 0;
   const int n_workers = engs[0]->n_workers();
-  {  // stream waits block instead of spinning once the worker threads would occupy most host cores
-    const unsigned hw = std::thread::hardware_concurrency();
-    const char* bs = getenv("B200BWA_BLOCKING_SYNC");
-    b2_g_blocking_sync = bs ? atoi(bs) : (hw > 0 && (unsigned)(G * n_workers) * 2 > hw);
-  }
 
   // Pipeline (kt_pipeline's three ordered steps): reader thread (record boundaries only) -> GPU workers (pack,
   // upload, kernels, download, positioned write) -> this thread (ordered bookkeeping / ordered writer).
