@@ -223,6 +223,19 @@ def trial(args):
                 f.write("@SQ\tSN:chr1\tLN:1\n")
                 for nm in alt:
                     f.write(f"{nm}\t0\tchr1\t1\t60\t100M\t*\t0\t0\t*\t*\n")
+        if 1_000_000 <= seed < 3_000_000 and seed % 4 == 0:   # ambiguity codes / lower case in the REFERENCE (.amb holes, random fill)
+            mr = np.random.default_rng(seed + 5)
+            lines = open(fa, "rb").read().split(b"\n")
+            for k, ln in enumerate(lines):
+                if ln and not ln.startswith(b">") and mr.random() < 0.02:
+                    b = bytearray(ln)
+                    a0 = int(mr.integers(0, len(b))); m = int(mr.choice([1, 3, 60]))
+                    b[a0:a0 + m] = bytes([ord(str(mr.choice(list("NNNRYn"))))]) * len(b[a0:a0 + m])
+                    lines[k] = bytes(b)
+                elif ln and not ln.startswith(b">") and mr.random() < 0.05:
+                    lines[k] = ln.lower()
+            open(fa, "wb").write(b"\n".join(lines))
+            rec["ref_mangled"] = True
         pu.run([pu.ORACLE, "index", fa])
         try:
             r1, r2 = synth.simulate_reads(ctg, **reads_kw)
