@@ -328,6 +328,15 @@ int b2_load_index(const char* hint, B2IndexHost* ix, int verbose, int meta_only)
     for (int i = 0; i < 4; ++i) ix->L2[i + 1] = hdr[i + 1];
     ix->seq_len = ix->L2[4];
     size_t words = (size_t)(sz - 40) >> 2;
+    {  // a .bwt cut short (a partial copy to the executor's disk) would send the rank queries past the image: the file
+       // must hold the 2-bit string plus one 32-byte count record per 128 symbols (bwt_bwtupdate_core, bwa/bwtindex.c:151-173)
+      const uint64_t L = ix->seq_len;
+      const uint64_t need = ((L + 15) >> 4) + ((L + 127) / 128 + 1) * 8;
+      if (L == 0 || ix->primary > L || ix->L2[1] > ix->L2[2] || ix->L2[2] > ix->L2[3] || ix->L2[3] > L || (uint64_t)words < need) {
+        fclose(fp);
+        return set_err("truncated or corrupt %s.bwt (%zu words for %llu symbols)", prefix.c_str(), words, (unsigned long long)L);
+      }
+    }
     ix->bwt.resize(meta_only ? 0 : words);
     if (!meta_only && fread(ix->bwt.data(), 4, words, fp) != words) { fclose(fp); return set_err("truncated %s.bwt", prefix.c_str()); }
     ix->bwt_words = words;
@@ -340,6 +349,7 @@ int b2_load_index(const char* hint, B2IndexHost* ix, int verbose, int meta_only)
     if (fread(hdr, 8, 7, fp) != 7) { fclose(fp); return set_err("truncated %s.sa", prefix.c_str()); }
     if (hdr[0] != ix->primary) { fclose(fp); return set_err("SA-BWT inconsistency: primary is not the same."); }
     ix->sa_intv = (int)hdr[5];
+    if (hdr[5] == 0 || hdr[5] > (1u << 20) || (hdr[5] & (hdr[5] - 1))) { fclose(fp); return set_err("corrupt %s.sa (sampling interval %llu)", prefix.c_str(), (unsigned long long)hdr[5]); }
     if (hdr[6] != ix->seq_len) { fclose(fp); return set_err("SA-BWT inconsistency: seq_len is not the same."); }
     size_t n_sa = (ix->seq_len + ix->sa_intv) / ix->sa_intv;
     ix->n_sa = n_sa;
@@ -393,6 +403,11 @@ int b2_load_index(const char* hint, B2IndexHost* ix, int verbose, int meta_only)
     if (fscanf(fp, "%lld%d%d", &xx, &n_seqs, &ix->n_holes) != 3) { fclose(fp); return set_err("Parse error reading %s.amb", prefix.c_str()); }
     fclose(fp);
     if (xx != ix->l_pac || n_seqs != ix->n_seqs) return set_err("inconsistent .ann and .amb files.");
+    if ((uint64_t)ix->l_pac * 2 != ix->seq_len) return set_err("inconsistent .ann and .bwt files (%lld bases packed, %llu symbols indexed)", (long long)ix->l_pac, (unsigned long long)ix->seq_len);
+    for (int i = 0; i < ix->n_seqs; ++i)   // contigs must tile [0, l_pac) (bns_pos2rid's binary search relies on it)
+      if (ix->anns[i].offset < 0 || ix->anns[i].len < 0 || ix->anns[i].offset + ix->anns[i].len > ix->l_pac ||
+          (i > 0 && ix->anns[i].offset < ix->anns[i - 1].offset + ix->anns[i - 1].len))
+        return set_err("corrupt %s.ann (contig %d out of range)", prefix.c_str(), i);
   }
   if (!meta_only) {  // .pac
     FILE* fp = fopen((prefix + ".pac").c_str(), "rb");
@@ -1328,6 +1343,10 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   std::shared_ptr<B2CachedIndex> cached;
   auto get_engines = [&]() -> bool {
     cached = b2_get_engines(m.positional[0].c_str(), devices, m.ignore_alt, m.verbose, &engs);
+    // (a missing index has had its reference-style message already; a truncated or inconsistent one -- where the reference
+    // aborts or crashes -- is named here)
+    if (!cached && m.verbose >= 1 && b2_tls_error.find("fail to locate") == std::string::npos)
+      fprintf(stderr, "[E::b200bwa] %s\n", b2_tls_error.c_str());
     return cached != nullptr;
   };
   if (ks.open(m.positional[1].c_str())) {

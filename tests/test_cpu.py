@@ -222,6 +222,62 @@ def test_register_resident_coop_dp_equals_scalar(tmp_path):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_damaged_index_files_are_refused(hostsim, workdir, tmp_path):
+    """An index cut short or mixed up on its way to the executor's disk: the reference aborts (`inconsistent .ann and
+    .amb files`, bwa/bntseq.c:146) or simply crashes (a truncated .bwt: SIGSEGV in the first rank query); inside a JVM
+    neither may happen -- every such file set is refused with status 1 and a message before anything is uploaded."""
+    import shutil
+    c = pu.make_case(workdir, "pe_small")
+    env = dict(os.environ, **pu.HOSTSIM_ENV)
+
+    def attempt(damage):
+        d = str(tmp_path / damage.__name__)
+        os.makedirs(d)
+        for e in ("", ".bwt", ".sa", ".pac", ".ann", ".amb"):
+            shutil.copy(c["ref"] + e, os.path.join(d, "ref.fa" + e))
+        damage(os.path.join(d, "ref.fa"))
+        r = subprocess.run([hostsim, "mem", "-f", os.path.join(d, "out.sam"), os.path.join(d, "ref.fa"), c["fq"][0]],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        assert r.returncode == 1, (damage.__name__, r.returncode, r.stderr[-300:])
+        assert b"[E::" in r.stderr, damage.__name__
+        return r.stderr
+
+    def short_bwt(p):
+        with open(p + ".bwt", "r+b") as f:
+            f.truncate(5000)
+
+    def short_sa(p):
+        with open(p + ".sa", "r+b") as f:
+            f.truncate(os.path.getsize(p + ".sa") // 2)
+
+    def short_pac(p):
+        with open(p + ".pac", "r+b") as f:
+            f.truncate(100)
+
+    def foreign_amb(p):
+        txt = open(p + ".amb").read().split("\n")
+        txt[0] = "12345 " + txt[0].split(" ", 1)[1]
+        open(p + ".amb", "w").write("\n".join(txt))
+
+    def foreign_bwt(p):   # a .bwt/.sa pair of another (shorter) reference next to this .ann/.pac
+        other = pu.make_case(workdir, "se250")
+        shutil.copy(other["ref"] + ".bwt", p + ".bwt")
+        shutil.copy(other["ref"] + ".sa", p + ".sa")
+
+    def zero_sa_interval(p):
+        with open(p + ".sa", "r+b") as f:
+            f.seek(40)
+            f.write(b"\0" * 8)
+
+    assert b"bwt" in attempt(short_bwt)
+    assert b".sa" in attempt(short_sa)
+    assert b".pac" in attempt(short_pac)
+    assert b"inconsistent .ann and .amb" in attempt(foreign_amb)
+    assert b"inconsistent .ann and .bwt" in attempt(foreign_bwt)
+    assert b"sampling interval" in attempt(zero_sa_interval)
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_paired_names_must_match(hostsim, workdir):
     """Mate files that are out of step: mem_sam_pe ends the reference's run on the first pair whose reads carry different
     names (bwa/bwamem_pair.c:355,385; it exits with status 1).  The engine returns 1 with the same message instead of
