@@ -172,6 +172,8 @@ def write_mangled(path: str, reads, r, style):
             b = bytearray(seq); b[int(r.integers(0, len(b)))] = ord(str(r.choice(list("RYKMSW.nX*")))); seq = bytes(b)
         if style["empty"] and r.random() < 0.03:
             seq, qual = b"", b""
+        if style.get("badqual") and len(qual) > 8 and r.random() < 0.03:   # kseq_read returns -2: the batch ends, reading resumes behind it
+            qual = qual + b"IIIII" if r.random() < 0.5 else qual[:-3]
         if style["fasta"] == 2 or (style["fasta"] == 1 and k % 3 == 1):
             out += b">" + name + eol
             w = style["fold"]
@@ -198,7 +200,7 @@ def write_mangled(path: str, reads, r, style):
 def draw_style(r):
     pr = lambda p: bool(r.random() < p)  # noqa: E731
     return dict(crlf=pr(0.2), comment=pr(0.3), lower=pr(0.2), iupac=pr(0.2), empty=pr(0.15), fasta=int(r.choice([0, 0, 0, 1, 2])),
-                fold=int(r.choice([60, 7, 100000])), plusname=pr(0.2), blank=pr(0.3), no_final_eol=pr(0.25), gz=pr(0.15), truncate=pr(0.2))
+                fold=int(r.choice([60, 7, 100000])), plusname=pr(0.2), blank=pr(0.3), no_final_eol=pr(0.25), gz=pr(0.15), truncate=pr(0.2), badqual=pr(0.2))
 
 
 def trial(args):

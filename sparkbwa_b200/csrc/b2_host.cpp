@@ -115,7 +115,7 @@ int b2_parse_mem_args(int argc, char** argv, B2MemArgs* m) {
   B2Opt opt0;
   b2_opt_init(opt);
   memset(&opt0, 0, sizeof(opt0));
-  m->verbose = 3; m->copy_comment = 0; m->fixed_chunk_size = -1; m->ignore_alt = 0; m->has_pes0 = 0;
+  m->verbose = 3; m->copy_comment = 0; m->fixed_chunk_size = -1; m->ignore_alt = 0; m->has_pes0 = 0; m->no_mt_io = 0;
   m->rg_id.clear(); m->hdr_line.clear(); m->positional.clear();
   memset(m->pes0, 0, sizeof(m->pes0));
   for (int i = 0; i < 4; ++i) m->pes0[i].failed = 1;
@@ -137,7 +137,7 @@ int b2_parse_mem_args(int argc, char** argv, B2MemArgs* m) {
         else { fprintf(stderr, "%s: option requires an argument -- '%c'\n", argv[0], c); return 1; }
       }
       if (c == 'k') opt->min_seed_len = atoi(optarg), opt0.min_seed_len = 1;
-      else if (c == '1') {}
+      else if (c == '1') m->no_mt_io = 1;
       else if (c == 'x') mode = optarg;
       else if (c == 'w') opt->w = atoi(optarg), opt0.w = 1;
       else if (c == 'A') opt->a = atoi(optarg), opt0.a = 1;
@@ -1468,11 +1468,18 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
     // was split upstream); it enters the hash tie-breaks exactly like n_processed of bwa/fastmap.c:85
     int64_t n_processed = getenv("B200BWA_FIRST_READ") ? atoll(getenv("B200BWA_FIRST_READ")) : 0;
     int64_t batch_index = 0, dealt = 0;
+    // The reference's pipeline has two threads that take turns at the reading step (one with -1), and each leaves when a
+    // read attempt of its own returns no sequences (bwa/kthread.c:92-102, bwa/fastmap.c:44-47): the input is at its end
+    // after the SECOND empty attempt.  Normally both happen at EOF; but a malformed record (kseq_read returns -2: a
+    // quality string longer or shorter than its sequence) ends the batch being read, and when it is the first record of
+    // an attempt that attempt is empty -- the reference then carries on behind it once (bseq_read resumes at the next
+    // '@' or '>'), and stops for good at the second such record or at EOF.
+    int empty_attempts_left = m.no_mt_io ? 1 : 2;
     for (;;) {
       std::shared_ptr<Job> j(new Job);
       j->raw.reset(new B2RawBatch);
       int n = b2_read_raw_batch(chunk, &ks, have2 ? &ks2 : 0, j->raw.get());
-      if (n == 0) break;
+      if (n == 0) { if (--empty_attempts_left == 0) break; continue; }
       j->raw->n_processed = n_processed;
       j->index = batch_index;
       j->n_reads = n;

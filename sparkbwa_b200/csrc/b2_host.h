@@ -10,6 +10,7 @@
 struct B2MemArgs {
   B2Opt opt;
   int verbose, copy_comment, fixed_chunk_size, ignore_alt, has_pes0;
+  int no_mt_io;   // -1: one I/O thread in the reference's pipeline (decides how a malformed record ends the input, b2_mem_main)
   B2Pes pes0[4];
   std::string rg_id, hdr_line;
   std::vector<std::string> positional;  // idxbase, in1 [, in2]

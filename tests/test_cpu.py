@@ -278,6 +278,32 @@ def test_damaged_index_files_are_refused(hostsim, workdir, tmp_path):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_malformed_records_end_the_input_like_the_reference(hostsim, workdir):
+    """A quality string longer than its sequence makes kseq_read return -2: bseq_read ends the batch there and the next
+    attempt resumes at the next '@'.  The reference's pipeline has two threads taking turns at the reading step (one
+    with -1) and each leaves at its first empty attempt (bwa/kthread.c:92-102, bwa/fastmap.c:44-47), so the input ends at
+    the second (first) malformed record that opens an attempt, or at EOF.  Four bad records: after 7 reads, two in a row
+    after 22 more (the second of them opens an attempt), one further on."""
+    c = pu.make_case(workdir, "pe_small")
+    recs = open(c["fq"][0], "rb").read().split(b"\n")
+    bad = os.path.join(c["dir"], "midbad.fq")
+    with open(bad, "wb") as f:
+        for k in range(60):
+            r = recs[4 * k:4 * k + 4]
+            if k in (7, 30, 31, 45):
+                r = r[:3] + [r[3] + b"IIIIII"]
+            f.write(b"\n".join(r) + b"\n")
+    n_lines = {}
+    for opts in ([], ["-1"], ["-K", "1000"], ["-K", "1000", "-1"]):
+        c1 = dict(c, fq=[bad], opts=opts)
+        ref = pu.oracle_sam(c1)
+        for env in (pu.HOSTSIM_ENV, dict(pu.HOSTSIM_ENV, B200BWA_NO_MMAP="1")):
+            assert not pu.first_diff(ref, pu.engine_sam(c1, hostsim, env=env)), (opts, env)
+        n_lines[" ".join(opts)] = len(set(l.split(b"\t")[0] for l in pu.sam_body(ref) if not l.startswith(b"@")))
+    assert n_lines[""] == 56 and n_lines["-1"] == 29, n_lines
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_paired_names_must_match(hostsim, workdir):
     """Mate files that are out of step: mem_sam_pe ends the reference's run on the first pair whose reads carry different
     names (bwa/bwamem_pair.c:355,385; it exits with status 1).  The engine returns 1 with the same message instead of
