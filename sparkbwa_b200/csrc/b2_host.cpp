@@ -284,6 +284,22 @@ int b2_parse_mem_args(int argc, char** argv, B2MemArgs* m) {
     if (!opt0.pen_clip3) opt->pen_clip3 *= opt->a;
     if (!opt0.pen_unpaired) opt->pen_unpaired *= opt->a;
   }
+  // Values outside the options' domain.  With a match score of zero or less the reference dies in its first local
+  // alignment (an assertion / a division by zero: bwa/ksw.c:348, :218); inside a JVM that must be a status, not a signal.
+  // A negative -m reads as "no mate rescue" there (the loop bound of bwa/bwamem_pair.c:267 is never met): the same as 0.
+  if (opt->a <= 0) {
+    fprintf(stderr, "[E::main_mem] the matching score (-A) must be positive\n");
+    return 1;
+  }
+  if (opt->max_matesw < 0) opt->max_matesw = 0;
+  // Negative penalties, band width or seed length and a non-positive -c: the reference either dies (-w -1: abort, -c 0:
+  // division by zero) or runs on with values its loops were not written for (-c -1 keeps no seed at all, -B -3 rewards
+  // mismatches).  The kernels' packed cells and counts assume the documented domain, so these are refused up front.
+  if (opt->b < 0 || opt->o_del < 0 || opt->o_ins < 0 || opt->e_del < 0 || opt->e_ins < 0 || opt->w < 0 || opt->min_seed_len < 0 ||
+      opt->max_occ <= 0) {
+    fprintf(stderr, "[E::main_mem] option value outside its domain (-B -O -E -w -k must not be negative, -c must be positive)\n");
+    return 1;
+  }
   b2_fill_scmat(opt->a, opt->b, opt->mat);
   return 0;
 }

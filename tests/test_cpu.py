@@ -304,6 +304,24 @@ def test_malformed_records_end_the_input_like_the_reference(hostsim, workdir):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_option_values_outside_their_domain(hostsim, workdir):
+    """Where the reference dies of a signal (-A 0: assertion in ksw_align2; -c 0: division by zero; -w -1: abort) or runs
+    on with values its loops were not written for, the engine returns status 1 with a message -- a signal would take the
+    executor JVM down.  A negative -m reads as `no mate rescue` in the reference (bwa/bwamem_pair.c:267) and here."""
+    c = pu.make_case(workdir, "pe_small")
+    env = dict(os.environ, **pu.HOSTSIM_ENV)
+    for bad in (["-A", "0"], ["-A", "-1"], ["-c", "0"], ["-c", "-1"], ["-w", "-1"], ["-k", "-3"], ["-B", "-3"], ["-O", "-2"], ["-E", "-1"]):
+        r = subprocess.run([hostsim, "mem"] + bad + [c["ref"]] + c["fq"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+        assert r.returncode == 1 and b"[E::main_mem]" in r.stderr, (bad, r.returncode)
+        assert not [l for l in r.stdout.splitlines() if not l.startswith(b"@")], bad
+    for opts in (["-A", "0"], ["-c", "0"], ["-w", "-1"]):   # what the reference does with them
+        o = subprocess.run([pu.ORACLE, "mem"] + opts + [c["ref"]] + c["fq"], stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+        assert o.returncode < 0 or o.returncode > 1, (opts, o.returncode)
+    for same in (["-m", "-1"], ["-m", "-5"], ["-k", "0"], ["-E", "0"], ["-w", "0"], ["-B", "0"], ["-O", "0"], ["-c", "1"]):
+        assert not pu.first_diff(pu.oracle_sam(c, extra=same), pu.engine_sam(c, hostsim, extra=same, env=pu.HOSTSIM_ENV)), same
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_paired_names_must_match(hostsim, workdir):
     """Mate files that are out of step: mem_sam_pe ends the reference's run on the first pair whose reads carry different
     names (bwa/bwamem_pair.c:355,385; it exits with status 1).  The engine returns 1 with the same message instead of
