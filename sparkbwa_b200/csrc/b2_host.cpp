@@ -511,6 +511,7 @@ struct B2SeqReader::Impl {
   const unsigned char* data = 0;          // current buffer (store.data() or the mapping)
   size_t begin = 0, end = 0;
   bool is_eof = false;
+  std::string io_err;
   int last_char = 0;
   const unsigned char* map = 0;
   size_t map_size = 0;
@@ -724,6 +725,11 @@ struct B2SeqReader::Impl {
     if (map || is_eof) { is_eof = true; return false; }
     begin = 0;
     int n = gzread(fp, store.data(), (unsigned)store.size());
+    if (n < 0 && io_err.empty()) {
+      int errnum = 0;
+      const char* msg = gzerror(fp, &errnum);
+      io_err = std::string("[gzread] ") + (errnum == Z_ERRNO ? strerror(errno) : (msg ? msg : "read error"));
+    }
     end = n > 0 ? (size_t)n : 0;
     data = store.data();
     if (end == 0) { is_eof = true; return false; }
@@ -828,7 +834,11 @@ int B2SeqReader::open(const char* fn) {
 }
 void B2SeqReader::close() {
   impl_->pre_shutdown();
-  if (impl_->fp) { gzclose(impl_->fp); impl_->fp = 0; }
+  if (impl_->fp) {   // a .gz cut off in mid-stream shows up here (Z_BUF_ERROR): fatal in the reference (err_gzclose, bwa/utils.c:284-289)
+    const int r = gzclose(impl_->fp);
+    impl_->fp = 0;
+    if (r != Z_OK && impl_->io_err.empty()) impl_->io_err = std::string("[gzclose] ") + (r == Z_ERRNO ? strerror(errno) : zError(r));
+  }
   if (impl_->map) { munmap((void*)impl_->map, impl_->map_size); impl_->map = 0; impl_->data = 0; impl_->begin = impl_->end = 0; }
 }
 int B2SeqReader::next() {  // string-returning form: same record stream as next_view
@@ -861,6 +871,7 @@ void B2SeqReader::advance(size_t k) { impl_->cur_i += k; }
 const unsigned char* B2SeqReader::map_base() const { return impl_->map; }
 void B2SeqReader::view_of(const unsigned char* base, const B2Rec& r, B2RecView* v) { Impl::rec_view(base, r, v); }
 const std::string& B2SeqReader::name() const { return impl_->name; }
+const std::string& B2SeqReader::io_error() const { return impl_->io_err; }
 const std::string& B2SeqReader::comment() const { return impl_->comment; }
 const std::string& B2SeqReader::seq() const { return impl_->seq; }
 const std::string& B2SeqReader::qual() const { return impl_->qual; }
@@ -1513,6 +1524,11 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
       cv_dev[to_dev].notify_all();
     }
     std::lock_guard<std::mutex> lk(mu);
+    {  // a read error is fatal in the reference (err_gzread exits): the run fails, the output keeps its header only
+      const std::string& e1 = ks.io_error();
+      const std::string& e2 = have2 ? ks2.io_error() : e1;
+      if (!e1.empty() || !e2.empty()) { failed = true; if (errmsg.empty()) errmsg = !e1.empty() ? e1 : e2; }
+    }
     read_done = true;
     wake_all();
   });
@@ -1765,6 +1781,13 @@ int b2_mem_main(int argc, char** argv, const char* out_path, const char* pg_cmdl
   // a failed run leaves the header alone: the batches behind it were written at their final offsets as they finished, so
   // the reserved range has holes (and, mapped, its fallocate()d length)
   if (rc && positioned && ftruncate(out_fd, (off_t)hdr_bytes) != 0) {}
+  if (!rc) {   // the reference closes its inputs after the last batch is out and exits with 1 if that fails: output complete, status 1
+    ks.close();
+    if (have2) ks2.close();
+    const std::string& e = !ks.io_error().empty() || !have2 ? ks.io_error() : ks2.io_error();
+    if (!e.empty()) { rc = 1; errmsg = e; }
+  }
+  if (rc && m.verbose >= 1 && !errmsg.empty() && errmsg[0] == '[') fprintf(stderr, "%s\n", errmsg.c_str());
   if (rc) {
     std::string em = errmsg;
     for (B2Engine* e : engs) if (em.empty() && e->last_error()[0]) em = e->last_error();

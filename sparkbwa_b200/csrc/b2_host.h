@@ -68,6 +68,9 @@ class B2SeqReader {  // kseq_read semantics, bwa/kseq.h:175-215
   const std::string& comment() const;
   const std::string& seq() const;
   const std::string& qual() const;
+  // "" or the message of a failed gzread (a corrupt or cut-off .gz, a directory): fatal in the reference (err_gzread,
+  // bwa/utils.c:214-225); the reader reports end of input and the caller turns this into status 1
+  const std::string& io_error() const;
  private:
   struct Impl;
   Impl* impl_;

@@ -322,6 +322,30 @@ def test_option_values_outside_their_domain(hostsim, workdir):
 
 
 @pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
+def test_input_read_errors_are_fatal_like_the_reference(hostsim, workdir):
+    """err_gzread / err_gzclose (bwa/utils.c:214-225,284-289) end the reference's run with status 1: a .gz cut off in
+    mid-stream is aligned as far as it decodes and then fails at gzclose (complete output, status 1); a directory given
+    as a read file fails at the first gzread.  The engine used to report success on both."""
+    import gzip
+    c = pu.make_case(workdir, "pe_small")
+    env = dict(os.environ, **pu.HOSTSIM_ENV)
+    gz = os.path.join(c["dir"], "r_1_cut.fq.gz")
+    with open(c["fq"][0], "rb") as fi, gzip.open(gz + ".full", "wb", compresslevel=1) as fo:
+        fo.write(fi.read())
+    with open(gz + ".full", "rb") as fi, open(gz, "wb") as fo:
+        fo.write(fi.read()[:9000])
+    o = subprocess.run([pu.ORACLE, "mem", c["ref"], gz], stdout=subprocess.PIPE, stderr=subprocess.PIPE)
+    assert o.returncode == 1 and b"[gzclose]" in o.stderr
+    out = os.path.join(c["dir"], "cut.sam")
+    e = subprocess.run([hostsim, "mem", "-f", out, c["ref"], gz], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert e.returncode == 1 and b"[gzclose]" in e.stderr, e.stderr[-300:]
+    ours = pu.sam_body(out)
+    assert ours == [l for l in o.stdout.splitlines(True) if not l.startswith(b"@PG")] and len(ours) > 50
+    e = subprocess.run([hostsim, "mem", "-f", out, c["ref"], c["dir"]], stdout=subprocess.PIPE, stderr=subprocess.PIPE, env=env)
+    assert e.returncode == 1 and b"[gzread]" in e.stderr
+
+
+@pytest.mark.skipif(not pu.have_oracle(), reason="oracle/_ref not built")
 def test_paired_names_must_match(hostsim, workdir):
     """Mate files that are out of step: mem_sam_pe ends the reference's run on the first pair whose reads carry different
     names (bwa/bwamem_pair.c:355,385; it exits with status 1).  The engine returns 1 with the same message instead of
